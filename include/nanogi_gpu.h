@@ -127,8 +127,12 @@ typedef struct NgiRenderParams {
     int32_t accumulate;          /* render_device only: 1 = add into film, 0 = overwrite      */
     uint64_t seed;               /* Philox key                                                */
     uint32_t wave_capacity;      /* path slots in flight; 0 = module default                  */
-    uint32_t reserved0;
+    uint32_t flags;              /* NGI_RENDER_* bits                                          */
 } NgiRenderParams;
+
+/* time every trace-kernel launch with CUDA events (fills NgiRenderStats.trace_kernel_seconds);
+ * the wavefront loop is then launched kernel by kernel instead of as a CUDA graph */
+#define NGI_RENDER_TIME_KERNELS 1u
 
 typedef struct NgiRenderStats {
     uint64_t paths;              /* samples processed                                         */

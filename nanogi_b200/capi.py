@@ -60,7 +60,7 @@ class NgiRenderParams(C.Structure):
         ("struct_size", C.c_uint32), ("renderer", C.c_int32),
         ("num_samples", C.c_int64), ("sample_offset", C.c_int64), ("film_norm_samples", C.c_int64),
         ("max_num_vertices", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("accumulate", C.c_int32),
-        ("seed", C.c_uint64), ("wave_capacity", C.c_uint32), ("reserved0", C.c_uint32),
+        ("seed", C.c_uint64), ("wave_capacity", C.c_uint32), ("flags", C.c_uint32),
     ]
 
 
@@ -164,9 +164,6 @@ def make_prim(**kw) -> NgiPrimitive:
     p.first_tri = -1
     p.d_tex = -1
     p.g_tex = -1
-    p.s_eta1 = 1.0
-    p.s_eta2 = 1.0
-    p.e_aspect = 1.0
     for k, v in kw.items():
         if isinstance(getattr(p, k), C.Array):
             setattr(p, k, d3(*[float(x) for x in v]))
@@ -298,7 +295,7 @@ class GpuScene:
         return out
 
     def _params(self, renderer, num_samples, width, height, max_num_vertices=-1, seed=1, sample_offset=0,
-                film_norm_samples=None, wave_capacity=0, accumulate=0) -> NgiRenderParams:
+                film_norm_samples=None, wave_capacity=0, accumulate=0, flags=0) -> NgiRenderParams:
         p = NgiRenderParams()
         p.struct_size = C.sizeof(NgiRenderParams)
         p.renderer = RENDERERS[renderer] if isinstance(renderer, str) else int(renderer)
@@ -310,6 +307,7 @@ class GpuScene:
         p.accumulate = int(accumulate)
         p.seed = int(seed)
         p.wave_capacity = int(wave_capacity)
+        p.flags = int(flags)
         return p
 
     def render(self, renderer, num_samples, width, height, **kw):

@@ -1,0 +1,253 @@
+// ngi_build.h — per-item bodies of the GPU BVH build kernels.
+//
+// Replaces Embree's scene commit (reference include/nanogi/rt.hpp:2085-2143: rtcNewScene / rtcNewTriangleMesh /
+// rtcCommit). Pipeline, all on the device:
+//   1. triangle records + padded AABBs + scene bounds            (k_tri_setup)
+//   2. 63-bit Morton codes of the AABB centres                    (k_morton)        -> cub radix sort
+//   3. Karras 2012 LBVH topology, one thread per inner node       (k_karras)
+//   4. bottom-up refit with one atomic flag per inner node        (k_refit)
+//   5. 64-byte two-child traversal nodes (BVH2, cross-check)      (k_pack2)
+//   6. top-down collapse to compressed 8-wide nodes, level by level with atomically allocated child /
+//      triangle ranges (k_collapse8); octant slot assignment + outward-rounded 8-bit quantisation.
+#pragma once
+#include "ngi_math.h"
+
+struct NgiBuildTask { int node2; unsigned node8; };
+
+// ---- 1. triangle record + padded box --------------------------------------------------------------
+// record = (v0.xyz | id) (e1.xyz) (e2.xyz) with e1 = v1 - v0, e2 = v2 - v0 as single IEEE subtractions (the
+// oracle precomputes the same). Slots >= n_real are degenerate filler triangles (never hit: det == 0).
+NGI_HD void ngi_tri_setup(const float* __restrict__ positions, unsigned i, unsigned n_real, float pad, f3 anchor,
+                          float4* __restrict__ rec, float4* __restrict__ lo, float4* __restrict__ hi) {
+    if (i < n_real) {
+        const float* p = positions + 9 * (size_t)i;
+        const f3 v0 = mk3(p[0], p[1], p[2]), v1 = mk3(p[3], p[4], p[5]), v2 = mk3(p[6], p[7], p[8]);
+        rec[3 * (size_t)i + 0] = make_float4(v0.x, v0.y, v0.z, u2f(i));
+        rec[3 * (size_t)i + 1] = make_float4(NGI_SUB(v1.x, v0.x), NGI_SUB(v1.y, v0.y), NGI_SUB(v1.z, v0.z), 0.0f);
+        rec[3 * (size_t)i + 2] = make_float4(NGI_SUB(v2.x, v0.x), NGI_SUB(v2.y, v0.y), NGI_SUB(v2.z, v0.z), 0.0f);
+        lo[i] = make_float4(fminf(v0.x, fminf(v1.x, v2.x)) - pad, fminf(v0.y, fminf(v1.y, v2.y)) - pad, fminf(v0.z, fminf(v1.z, v2.z)) - pad, 0.0f);
+        hi[i] = make_float4(fmaxf(v0.x, fmaxf(v1.x, v2.x)) + pad, fmaxf(v0.y, fmaxf(v1.y, v2.y)) + pad, fmaxf(v0.z, fmaxf(v1.z, v2.z)) + pad, 0.0f);
+    } else {
+        rec[3 * (size_t)i + 0] = make_float4(anchor.x, anchor.y, anchor.z, u2f(0xFFFFFFFFu));
+        rec[3 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        rec[3 * (size_t)i + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        lo[i] = make_float4(anchor.x - pad, anchor.y - pad, anchor.z - pad, 0.0f);
+        hi[i] = make_float4(anchor.x + pad, anchor.y + pad, anchor.z + pad, 0.0f);
+    }
+}
+
+// ---- 2. Morton -----------------------------------------------------------------------------------
+NGI_HD unsigned long long ngi_expand21(unsigned long long v) {
+    v &= 0x1FFFFFull;
+    v = (v | (v << 32)) & 0x1F00000000FFFFull;
+    v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+    v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+    v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+NGI_HD unsigned long long ngi_morton63(f3 c, f3 smin, f3 sinv) {
+    const float fx = fminf(fmaxf((c.x - smin.x) * sinv.x, 0.0f), 1.0f);
+    const float fy = fminf(fmaxf((c.y - smin.y) * sinv.y, 0.0f), 1.0f);
+    const float fz = fminf(fmaxf((c.z - smin.z) * sinv.z, 0.0f), 1.0f);
+    const unsigned long long x = (unsigned long long)(fx * 2097151.0f);
+    const unsigned long long y = (unsigned long long)(fy * 2097151.0f);
+    const unsigned long long z = (unsigned long long)(fz * 2097151.0f);
+    return (ngi_expand21(x) << 2) | (ngi_expand21(y) << 1) | ngi_expand21(z);
+}
+
+// ---- 3. Karras topology --------------------------------------------------------------------------
+// Nodes are numbered 0..n-2 (inner) and n-1..2n-2 (leaf k = n-1+k, k = position in Morton order).
+NGI_HD int ngi_delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + ngi_clz32((unsigned)i ^ (unsigned)j);
+    return ngi_clz64(a ^ b);
+}
+NGI_HD void ngi_karras_node(const unsigned long long* __restrict__ keys, int n, int i, int& left, int& right, int& first, int& last) {
+    const int d = (ngi_delta(keys, n, i, i + 1) - ngi_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = ngi_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (ngi_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (ngi_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = ngi_delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (ngi_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + (d < 0 ? d : 0);
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    left = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    first = lo; last = hi;
+}
+
+// ---- 5. BVH2 traversal node ----------------------------------------------------------------------
+NGI_HD void ngi_pack2(const float4* __restrict__ lo, const float4* __restrict__ hi, const int* __restrict__ left,
+                      const int* __restrict__ right, int n, int i, float4* __restrict__ out) {
+    const int l = left[i], r = right[i];
+    const float4 l0 = lo[l], l1 = hi[l], r0 = lo[r], r1 = hi[r];
+    const int lc = l >= n - 1 ? ~(l - (n - 1)) : l;
+    const int rc = r >= n - 1 ? ~(r - (n - 1)) : r;
+    out[4 * (size_t)i + 0] = make_float4(l0.x, l0.y, l0.z, l1.x);
+    out[4 * (size_t)i + 1] = make_float4(l1.y, l1.z, r0.x, r0.y);
+    out[4 * (size_t)i + 2] = make_float4(r0.z, r1.x, r1.y, r1.z);
+    out[4 * (size_t)i + 3] = make_float4(u2f((unsigned)lc), u2f((unsigned)rc), 0.0f, 0.0f);
+}
+
+// ---- 6. collapse to BVH8 -------------------------------------------------------------------------
+#define NGI_LEAF_MAX_TRIS 3
+
+struct NgiCollapseCtx {
+    // BVH2 (node numbering as above)
+    const float4* lo; const float4* hi;      // [2n-1] padded boxes
+    const int* left; const int* right;       // [n-1]
+    const uint2* range;                      // [n-1] (first, last) Morton positions of the subtree
+    const float4* tris2;                     // [n][3] Morton-ordered triangle records
+    int n;
+    // BVH8 output
+    uint4* nodes8;                           // [<= n][5]
+    float4* tris8;                           // [n][3]
+    unsigned* counters;                      // [0] = nodes allocated, [1] = triangles allocated, [2] = next-level task count
+    NgiBuildTask* out_tasks;
+};
+
+NGI_HD unsigned ngi_atomic_add(unsigned* p, unsigned v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    const unsigned o = *p; *p = o + v; return o;
+#endif
+}
+
+NGI_HD unsigned ngi_pack4(const unsigned* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); }
+
+NGI_HD float ngi_half_area(float4 lo, float4 hi) {
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTask task) {
+    const int n = c.n;
+    int child[8];
+    int cnt = 2;
+    child[0] = c.left[task.node2];
+    child[1] = c.right[task.node2];
+    // greedily open the inner child with the largest surface area until 8 children
+    while (cnt < 8) {
+        int best = -1; float bestA = -1.0f;
+        for (int k = 0; k < cnt; k++) {
+            const int nd = child[k];
+            if (nd >= n - 1) continue;  // single-triangle leaf
+            const uint2 r = c.range[nd];
+            if ((int)(r.y - r.x) + 1 <= NGI_LEAF_MAX_TRIS) continue;  // small subtree stays one leaf slot
+            const float a = ngi_half_area(c.lo[nd], c.hi[nd]);
+            if (a > bestA) { bestA = a; best = k; }
+        }
+        if (best < 0) break;
+        const int nd = child[best];
+        child[best] = c.left[nd];
+        child[cnt++] = c.right[nd];
+    }
+    // node frame
+    const float4 nlo = c.lo[task.node2], nhi = c.hi[task.node2];
+    const float plo[3] = {nlo.x, nlo.y, nlo.z}, phi[3] = {nhi.x, nhi.y, nhi.z};
+    int eb[3]; double scale[3];
+    for (int a = 0; a < 3; a++) {
+        const double ext = (double)phi[a] - (double)plo[a];
+        int e = -126;
+        if (ext > 0) {
+            int k; (void)frexp(ext / 255.0, &k);  // ext/255 = m * 2^k, m in [0.5, 1)  =>  2^k * 255 >= ext
+            e = k;
+        }
+        if (e < -126) e = -126;
+        if (e > 127) e = 127;
+        while (e < 127 && ((double)phi[a] - (double)plo[a]) > 255.0 * ldexp(1.0, e)) e++;
+        eb[a] = e + 127;
+        scale[a] = ldexp(1.0, e);
+    }
+    // classify children
+    bool inner[8]; int ntri[8]; int first[8];
+    unsigned nInner = 0, nTris = 0;
+    float cx[8], cy[8], cz[8];
+    for (int k = 0; k < cnt; k++) {
+        const int nd = child[k];
+        if (nd >= n - 1) { inner[k] = false; ntri[k] = 1; first[k] = nd - (n - 1); }
+        else {
+            const uint2 r = c.range[nd];
+            const int m = (int)(r.y - r.x) + 1;
+            if (m <= NGI_LEAF_MAX_TRIS) { inner[k] = false; ntri[k] = m; first[k] = (int)r.x; }
+            else { inner[k] = true; ntri[k] = 0; first[k] = 0; }
+        }
+        if (inner[k]) nInner++; else nTris += (unsigned)ntri[k];
+        const float4 l = c.lo[nd], h = c.hi[nd];
+        cx[k] = 0.5f * (l.x + h.x) - 0.5f * (nlo.x + nhi.x);
+        cy[k] = 0.5f * (l.y + h.y) - 0.5f * (nlo.y + nhi.y);
+        cz[k] = 0.5f * (l.z + h.z) - 0.5f * (nlo.z + nhi.z);
+    }
+    const unsigned childBase = nInner ? ngi_atomic_add(&c.counters[0], nInner) : 0u;
+    const unsigned triBase = nTris ? ngi_atomic_add(&c.counters[1], nTris) : 0u;
+    const unsigned taskBase = nInner ? ngi_atomic_add(&c.counters[2], nInner) : 0u;
+    // greedy octant slot assignment: slot bit a set <=> child lies towards +axis a
+    int slotOf[8]; bool slotUsed[8]; bool done[8];
+    for (int k = 0; k < 8; k++) { slotUsed[k] = false; done[k] = false; slotOf[k] = -1; }
+    for (int it = 0; it < cnt; it++) {
+        float bestC = -3.0e38f; int bk = -1, bs = -1;
+        for (int k = 0; k < cnt; k++) {
+            if (done[k]) continue;
+            for (int s = 0; s < 8; s++) {
+                if (slotUsed[s]) continue;
+                const float cost = ((s & 1) ? cx[k] : -cx[k]) + ((s & 2) ? cy[k] : -cy[k]) + ((s & 4) ? cz[k] : -cz[k]);
+                if (cost > bestC) { bestC = cost; bk = k; bs = s; }
+            }
+        }
+        done[bk] = true; slotUsed[bs] = true; slotOf[bk] = bs;
+    }
+    int childAt[8];
+    for (int s = 0; s < 8; s++) childAt[s] = -1;
+    for (int k = 0; k < cnt; k++) childAt[slotOf[k]] = k;
+
+    unsigned meta[8], q[6][8];
+    unsigned imask = 0, innerRank = 0, triOff = 0;
+    for (int s = 0; s < 8; s++) {
+        meta[s] = 0;
+        for (int a = 0; a < 6; a++) q[a][s] = 0;
+        const int k = childAt[s];
+        if (k < 0) continue;
+        const int nd = child[k];
+        const float4 l = c.lo[nd], h = c.hi[nd];
+        const float clo[3] = {l.x, l.y, l.z}, chi[3] = {h.x, h.y, h.z};
+        for (int a = 0; a < 3; a++) {
+            double ql = floor(((double)clo[a] - (double)plo[a]) / scale[a]);
+            double qh = ceil(((double)chi[a] - (double)plo[a]) / scale[a]);
+            if (ql < 0) ql = 0; if (ql > 255) ql = 255;
+            if (qh < 0) qh = 0; if (qh > 255) qh = 255;
+            q[a][s] = (unsigned)ql; q[3 + a][s] = (unsigned)qh;
+        }
+        if (inner[k]) {
+            imask |= 1u << s;
+            meta[s] = (1u << 5) | (24u + (unsigned)s);
+            NgiBuildTask t; t.node2 = nd; t.node8 = childBase + innerRank;
+            c.out_tasks[taskBase + innerRank] = t;
+            innerRank++;
+        } else {
+            meta[s] = (((1u << ntri[k]) - 1u) << 5) | triOff;
+            for (int j = 0; j < ntri[k]; j++) {
+                const size_t src = (size_t)(first[k] + j) * 3, dst = (size_t)(triBase + triOff + j) * 3;
+                c.tris8[dst] = c.tris2[src]; c.tris8[dst + 1] = c.tris2[src + 1]; c.tris8[dst + 2] = c.tris2[src + 2];
+            }
+            triOff += (unsigned)ntri[k];
+        }
+    }
+    uint4* out = c.nodes8 + 5 * (size_t)task.node8;
+    out[0] = make_uint4(f2u(nlo.x), f2u(nlo.y), f2u(nlo.z), (unsigned)eb[0] | ((unsigned)eb[1] << 8) | ((unsigned)eb[2] << 16) | (imask << 24));
+    out[1] = make_uint4(childBase, triBase, ngi_pack4(meta), ngi_pack4(meta + 4));
+    out[2] = make_uint4(ngi_pack4(q[0]), ngi_pack4(q[0] + 4), ngi_pack4(q[1]), ngi_pack4(q[1] + 4));
+    out[3] = make_uint4(ngi_pack4(q[2]), ngi_pack4(q[2] + 4), ngi_pack4(q[3]), ngi_pack4(q[3] + 4));
+    out[4] = make_uint4(ngi_pack4(q[4]), ngi_pack4(q[4] + 4), ngi_pack4(q[5]), ngi_pack4(q[5] + 4));
+}

@@ -1,0 +1,247 @@
+// ngi_bvh.h — ray/triangle test and the two traversal kernels' per-ray bodies.
+//
+// Replaces Embree's rtcIntersect as called from Scene::Intersect / Scene::Visible
+// (reference include/nanogi/rt.hpp:2162-2261, rtcIntersect at :2182). Geometry contract:
+//   * float32 Moeller-Trumbore with ONE explicit expression tree (NGI_FMA/NGI_MUL/... are single IEEE
+//     roundings; the CPU oracle evaluates the identical tree) -> bit-identical (t, u, v);
+//   * no back-face culling (rt.hpp:2174-2178), accept iff tmin < t < tmax (strict);
+//   * closest hit = lexicographic minimum of (t, global triangle id): order-free, so any conservative
+//     acceleration structure returns the same answer; node culling is inclusive (t_box <= t_best);
+//   * boxes are padded at build time, the BVH is a pure filter.
+//
+// Two structures are traversed:
+//   BVH8  (product)  compressed 8-wide nodes, 80 B = 5 x 16-byte loads, quantised child boxes
+//                    (layout after Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal on GPUs
+//                    Through Compressed Wide BVHs", HPG 2017), 48-byte triangles = 3 x 16-byte loads;
+//   BVH2  (cross-check) the GPU-built LBVH the BVH8 is collapsed from, 64-byte two-child nodes.
+#pragma once
+#include "ngi_math.h"
+
+struct NgiHitRec { float t, u, v; unsigned tri; };
+#define NGI_MISS 0xFFFFFFFFu
+
+// triangle record: a = (v0.xyz, id bits), b = (e1.xyz, -), c = (e2.xyz, -) with e1 = v1 - v0, e2 = v2 - v0
+NGI_HD bool ngi_tri_test(const float4 a, const float4 b, const float4 c, const f3 o, const f3 d, const float tmin, const float tmax,
+                         float& t, float& u, float& v) {
+    // P = d x e2
+    const float px = NGI_FMA(d.y, c.z, -NGI_MUL(d.z, c.y));
+    const float py = NGI_FMA(d.z, c.x, -NGI_MUL(d.x, c.z));
+    const float pz = NGI_FMA(d.x, c.y, -NGI_MUL(d.y, c.x));
+    const float det = NGI_FMA(b.x, px, NGI_FMA(b.y, py, NGI_MUL(b.z, pz)));
+    if (!(det != 0.0f)) return false;
+    const float inv = NGI_RCP(det);
+    const float tx = NGI_SUB(o.x, a.x), ty = NGI_SUB(o.y, a.y), tz = NGI_SUB(o.z, a.z);
+    const float uu = NGI_MUL(NGI_FMA(tx, px, NGI_FMA(ty, py, NGI_MUL(tz, pz))), inv);
+    if (!(uu >= 0.0f && uu <= 1.0f)) return false;
+    // Q = T x e1
+    const float qx = NGI_FMA(ty, b.z, -NGI_MUL(tz, b.y));
+    const float qy = NGI_FMA(tz, b.x, -NGI_MUL(tx, b.z));
+    const float qz = NGI_FMA(tx, b.y, -NGI_MUL(ty, b.x));
+    const float vv = NGI_MUL(NGI_FMA(d.x, qx, NGI_FMA(d.y, qy, NGI_MUL(d.z, qz))), inv);
+    if (!(vv >= 0.0f && NGI_ADD(uu, vv) <= 1.0f)) return false;
+    const float tt = NGI_MUL(NGI_FMA(c.x, qx, NGI_FMA(c.y, qy, NGI_MUL(c.z, qz))), inv);
+    if (!(tt > tmin && tt < tmax)) return false;
+    t = tt; u = uu; v = vv;
+    return true;
+}
+
+// explicit closest-hit reduction: (t, id) lexicographic
+NGI_HD void ngi_accept(NgiHitRec& best, float t, float u, float v, unsigned id) {
+    if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.u = u; best.v = v; best.tri = id; }
+}
+
+NGI_HD float ngi_safe_rcp_dir(float d) {
+    // a zero / denormal component becomes +-2^-80 (keeps 0 * inf NaNs out of the slab test)
+    const float eps = 8.27180613e-25f;
+    const float dd = fabsf(d) > eps ? d : copysignf(eps, d);
+    return 1.0f / dd;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BVH2 (LBVH) — 64-byte nodes: both child boxes + child links. child >= 0: inner node, child < 0: leaf
+// holding the single triangle ~child (index into the Morton-sorted triangle array).
+//   n0 = (c0.min.xyz, c0.max.x)  n1 = (c0.max.yz, c1.min.xy)  n2 = (c1.min.z, c1.max.xyz)  n3 = (left, right, -, -)
+// ------------------------------------------------------------------------------------------------
+template <bool ANY_HIT>
+NGI_HD bool ngi_trace_bvh2(const float4* __restrict__ nodes, const float4* __restrict__ tris, const f3 o, const f3 d,
+                           const float tmin, const float tmax, NgiHitRec& out) {
+    const float ix = ngi_safe_rcp_dir(d.x), iy = ngi_safe_rcp_dir(d.y), iz = ngi_safe_rcp_dir(d.z);
+    NgiHitRec best; best.t = tmax; best.u = 0; best.v = 0; best.tri = NGI_MISS;
+    bool found = false;
+    int stack[64];
+    int sp = 0;
+    int cur = 0;
+    while (true) {
+        if (cur >= 0) {
+            const float4 n0 = ngi_ldg(nodes + 4 * (size_t)cur), n1 = ngi_ldg(nodes + 4 * (size_t)cur + 1);
+            const float4 n2 = ngi_ldg(nodes + 4 * (size_t)cur + 2), n3 = ngi_ldg(nodes + 4 * (size_t)cur + 3);
+            const float limit = found ? best.t : tmax;
+            float t0, t1, a, b;
+            // child 0
+            a = (n0.x - o.x) * ix; b = (n0.w - o.x) * ix; t0 = fminf(a, b); t1 = fmaxf(a, b);
+            a = (n0.y - o.y) * iy; b = (n1.x - o.y) * iy; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+            a = (n0.z - o.z) * iz; b = (n1.y - o.z) * iz; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+            const float c0n = fmaxf(t0, tmin); const bool h0 = c0n <= fminf(t1, limit);
+            // child 1
+            a = (n1.z - o.x) * ix; b = (n2.y - o.x) * ix; t0 = fminf(a, b); t1 = fmaxf(a, b);
+            a = (n1.w - o.y) * iy; b = (n2.z - o.y) * iy; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+            a = (n2.x - o.z) * iz; b = (n2.w - o.z) * iz; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+            const float c1n = fmaxf(t0, tmin); const bool h1 = c1n <= fminf(t1, limit);
+            const int left = (int)f2u(n3.x), right = (int)f2u(n3.y);
+            if (h0 && h1) {
+                const bool swp = c1n < c0n;
+                stack[sp++] = swp ? left : right;
+                cur = swp ? right : left;
+                continue;
+            }
+            if (h0) { cur = left; continue; }
+            if (h1) { cur = right; continue; }
+        } else {
+            const size_t ti = (size_t)(~cur);
+            const float4 a = ngi_ldg(tris + 3 * ti), b = ngi_ldg(tris + 3 * ti + 1), c = ngi_ldg(tris + 3 * ti + 2);
+            float t, u, v;
+            if (ngi_tri_test(a, b, c, o, d, tmin, tmax, t, u, v)) {
+                if (ANY_HIT) { out.t = t; out.u = u; out.v = v; out.tri = 0; return true; }
+                ngi_accept(best, t, u, v, f2u(a.w));
+                found = true;
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    out = best;
+    if (!found) { out.t = 0; out.tri = NGI_MISS; }
+    return found;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BVH8 — compressed wide node, 80 bytes = 5 x uint4:
+//   n0 = (p.x, p.y, p.z as float bits,  ex | ey<<8 | ez<<16 | imask<<24)       e* = biased float exponents
+//   n1 = (child_base, tri_base, meta[0..3], meta[4..7])
+//   n2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])
+//   n3 = (qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7])
+//   n4 = (qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7])
+// child box = p + q * 2^(e-127) per axis, q in [0,255] rounded outward.
+// meta[i]: 0 = empty slot; inner child: 0b001'11sss (low5 = 24 + slot); leaf: (unary triangle count) << 5 |
+// offset of its first triangle relative to tri_base (0..23). imask bit i = slot i is an inner child.
+// Inner children are stored contiguously from child_base in slot order. Children sit in slots so that
+// (slot ^ octant) approximates front-to-back order (slot bit0/1/2 = child lies towards +x/+y/+z).
+// ------------------------------------------------------------------------------------------------
+#define NGI_BVH8_STACK 40
+
+NGI_HD unsigned ngi_byte(unsigned w, int i) { return (w >> (8 * i)) & 0xFFu; }
+
+template <bool ANY_HIT>
+NGI_HD bool ngi_trace_bvh8(const uint4* __restrict__ nodes, const float4* __restrict__ tris, const f3 o, const f3 d,
+                           const float tmin, const float tmax, NgiHitRec& out) {
+    const float idx = ngi_safe_rcp_dir(d.x), idy = ngi_safe_rcp_dir(d.y), idz = ngi_safe_rcp_dir(d.z);
+    // signs are taken from the clamped reciprocals so that -0.0f components stay self-consistent
+    const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
+    const unsigned octinv = (negx ? 0u : 1u) | (negy ? 0u : 2u) | (negz ? 0u : 4u);
+    NgiHitRec best; best.t = tmax; best.u = 0; best.v = 0; best.tri = NGI_MISS;
+    bool found = false;
+
+    uint2 stack[NGI_BVH8_STACK];
+    int sp = 0;
+    uint2 ngroup = make_uint2(0u, 0x80000000u);  // root: base 0, pseudo-slot 7
+    uint2 tgroup = make_uint2(0u, 0u);
+
+    while (true) {
+        if (ngroup.y > 0x00FFFFFFu) {
+            const unsigned hits = ngroup.y;
+            const unsigned imask = ngroup.y & 0xFFu;
+            const int bit = ngi_bfind(hits);
+            ngroup.y &= ~(1u << bit);
+            if (ngroup.y > 0x00FFFFFFu) {
+                if (sp < NGI_BVH8_STACK) stack[sp++] = ngroup;
+            }
+            const unsigned slot = ((unsigned)(bit - 24) ^ octinv) & 7u;
+            const unsigned rel = (unsigned)ngi_popc(imask & ~(0xFFFFFFFFu << slot));
+            const size_t ni = (size_t)ngroup.x + rel;
+
+            const uint4 n0 = ngi_ldg(nodes + 5 * ni), n1 = ngi_ldg(nodes + 5 * ni + 1), n2 = ngi_ldg(nodes + 5 * ni + 2);
+            const uint4 n3 = ngi_ldg(nodes + 5 * ni + 3), n4 = ngi_ldg(nodes + 5 * ni + 4);
+
+            const float sx = u2f((n0.w & 0xFFu) << 23) * idx;
+            const float sy = u2f(((n0.w >> 8) & 0xFFu) << 23) * idy;
+            const float sz = u2f(((n0.w >> 16) & 0xFFu) << 23) * idz;
+            const float bx = (u2f(n0.x) - o.x) * idx, by = (u2f(n0.y) - o.y) * idy, bz = (u2f(n0.z) - o.z) * idz;
+            const float limit = found ? best.t : tmax;
+
+            unsigned hitmask = 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const unsigned meta4 = h ? n1.w : n1.z;
+                // near / far plane words per axis, chosen by the ray's sign
+                const unsigned lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
+                const unsigned hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
+                const unsigned nx = negx ? hix : lox, fx = negx ? lox : hix;
+                const unsigned ny = negy ? hiy : loy, fy = negy ? loy : hiy;
+                const unsigned nz = negz ? hiz : loz, fz = negz ? loz : hiz;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const unsigned meta = ngi_byte(meta4, i);
+                    const float tnx = fmaf((float)ngi_byte(nx, i), sx, bx), tfx = fmaf((float)ngi_byte(fx, i), sx, bx);
+                    const float tny = fmaf((float)ngi_byte(ny, i), sy, by), tfy = fmaf((float)ngi_byte(fy, i), sy, by);
+                    const float tnz = fmaf((float)ngi_byte(nz, i), sz, bz), tfz = fmaf((float)ngi_byte(fz, i), sz, bz);
+                    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+                    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, limit));
+                    if (meta != 0u && tn <= tf) {
+                        const bool inner = (meta & 0x18u) == 0x18u;
+                        const unsigned bits = inner ? 1u : (meta >> 5);
+                        const unsigned pos = inner ? ((meta ^ octinv) & 31u) : (meta & 31u);
+                        hitmask |= bits << pos;
+                    }
+                }
+            }
+            ngroup.x = n1.x;
+            ngroup.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
+            tgroup.x = n1.y;
+            tgroup.y = hitmask & 0x00FFFFFFu;
+        } else {
+            tgroup = ngroup;
+            ngroup = make_uint2(0u, 0u);
+        }
+
+        while (tgroup.y != 0u) {
+            const int bit = ngi_bfind(tgroup.y);
+            tgroup.y &= ~(1u << bit);
+            const size_t ti = (size_t)tgroup.x + (unsigned)bit;
+            const float4 a = ngi_ldg(tris + 3 * ti), b = ngi_ldg(tris + 3 * ti + 1), c = ngi_ldg(tris + 3 * ti + 2);
+            float t, u, v;
+            if (ngi_tri_test(a, b, c, o, d, tmin, tmax, t, u, v)) {
+                if (ANY_HIT) { out.t = t; out.u = u; out.v = v; out.tri = 0; return true; }
+                ngi_accept(best, t, u, v, f2u(a.w));
+                found = true;
+            }
+        }
+
+        if (ngroup.y <= 0x00FFFFFFu) {
+            if (sp == 0) break;
+            ngroup = stack[--sp];
+        }
+    }
+    out = best;
+    if (!found) { out.t = 0; out.tri = NGI_MISS; }
+    return found;
+}
+
+// O(n) reference loop over the same triangle records (test aid: proves the BVHs are pure filters)
+template <bool ANY_HIT>
+NGI_HD bool ngi_trace_brute(const float4* __restrict__ tris, const unsigned n, const f3 o, const f3 d, const float tmin,
+                            const float tmax, NgiHitRec& out) {
+    NgiHitRec best; best.t = tmax; best.u = 0; best.v = 0; best.tri = NGI_MISS;
+    bool found = false;
+    for (unsigned i = 0; i < n; i++) {
+        const float4 a = ngi_ldg(tris + 3 * (size_t)i), b = ngi_ldg(tris + 3 * (size_t)i + 1), c = ngi_ldg(tris + 3 * (size_t)i + 2);
+        float t, u, v;
+        if (ngi_tri_test(a, b, c, o, d, tmin, tmax, t, u, v)) {
+            if (ANY_HIT) { out.t = t; out.u = u; out.v = v; out.tri = 0; return true; }
+            ngi_accept(best, t, u, v, f2u(a.w));
+            found = true;
+        }
+    }
+    out = best;
+    if (!found) { out.t = 0; out.tri = NGI_MISS; }
+    return found;
+}

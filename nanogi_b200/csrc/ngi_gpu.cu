@@ -1,0 +1,693 @@
+// ngi_gpu.cu — CUDA kernels (sm_100a) and the C ABI of include/nanogi_gpu.h.
+//
+// Every kernel is a thin grid wrapper around a per-item body in ngi_build.h / ngi_bvh.h / ngi_wave.h.
+// There is no CPU path in this library: without a CUDA device every entry point fails with
+// NGI_ERR_NO_DEVICE.
+//
+// Kernel inventory
+//   build   : k_bounds, k_tri_setup, k_morton, cub::DeviceRadixSort, k_gather_sorted, k_karras, k_refit,
+//             k_pack2, k_collapse8 (one launch per BVH8 level), k_shade_upload is a plain memcpy
+//   queries : k_trace<ACCEL, ANY_HIT>
+//   render  : k_iter_begin, k_logic, k_extend, k_shadow   (one wavefront iteration = these four)
+//   tests   : k_eval_bsdf
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/nanogi_gpu.h"
+#include "ngi_build.h"
+#include "ngi_bvh.h"
+#include "ngi_scene_host.h"
+#include "ngi_wave.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define NGI_CUDA(call)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            return set_err(e__ == cudaErrorMemoryAllocation ? NGI_ERR_OUT_OF_MEMORY : NGI_ERR_CUDA,     \
+                           std::string(#call) + ": " + cudaGetErrorString(e__));                        \
+        }                                                                                               \
+    } while (0)
+
+constexpr int kBlock = 256;
+inline unsigned grid_for(size_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+
+// ================================================================================================
+// build kernels
+// ================================================================================================
+__device__ __forceinline__ int float_to_ordered(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__host__ __device__ __forceinline__ float ordered_to_float(int i) {
+    const int j = i >= 0 ? i : i ^ 0x7FFFFFFF;
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(j);
+#else
+    float f; memcpy(&f, &j, 4); return f;
+#endif
+}
+
+// scene bounds over the raw vertex array: block reduction + 6 atomics per block
+__global__ void __launch_bounds__(kBlock) k_bounds(const float* __restrict__ positions, size_t n_verts, int* __restrict__ bounds /*[6] ordered ints*/) {
+    float mn[3] = {NGI_INF_F, NGI_INF_F, NGI_INF_F}, mx[3] = {-NGI_INF_F, -NGI_INF_F, -NGI_INF_F};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_verts; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const float v = positions[3 * i + k]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        for (int off = 16; off > 0; off >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xFFFFFFFFu, mn[k], off));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xFFFFFFFFu, mx[k], off));
+        }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { atomicMin(bounds + k, float_to_ordered(mn[k])); atomicMax(bounds + 3 + k, float_to_ordered(mx[k])); }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_tri_setup(const float* __restrict__ positions, unsigned n, unsigned n_real, float pad, f3 anchor,
+                                                      float4* __restrict__ rec, float4* __restrict__ lo, float4* __restrict__ hi) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ngi_tri_setup(positions, i, n_real, pad, anchor, rec, lo, hi);
+}
+
+__global__ void __launch_bounds__(kBlock) k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, unsigned n, f3 mmin, f3 sinv,
+                                                   unsigned long long* __restrict__ keys, unsigned* __restrict__ vals) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = lo[i], b = hi[i];
+    keys[i] = ngi_morton63(mk3(0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z)), mmin, sinv);
+    vals[i] = i;
+}
+
+__global__ void __launch_bounds__(kBlock) k_gather_sorted(const unsigned* __restrict__ order, unsigned n, const float4* __restrict__ rec_in,
+                                                          const float4* __restrict__ tlo, const float4* __restrict__ thi,
+                                                          float4* __restrict__ tris2, float4* __restrict__ lo, float4* __restrict__ hi) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned i = order[k];
+    tris2[3 * (size_t)k + 0] = rec_in[3 * (size_t)i + 0];
+    tris2[3 * (size_t)k + 1] = rec_in[3 * (size_t)i + 1];
+    tris2[3 * (size_t)k + 2] = rec_in[3 * (size_t)i + 2];
+    lo[n - 1 + k] = tlo[i];
+    hi[n - 1 + k] = thi[i];
+}
+
+__global__ void __launch_bounds__(kBlock) k_karras(const unsigned long long* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
+                                                   uint2* __restrict__ range, int* __restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int l, r, f, la;
+    ngi_karras_node(keys, n, i, l, r, f, la);
+    left[i] = l; right[i] = r; range[i] = make_uint2((unsigned)f, (unsigned)la);
+    parent[l] = i; parent[r] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+// bottom-up refit: the second thread to arrive at an inner node computes its box
+__global__ void __launch_bounds__(kBlock) k_refit(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent,
+                                                  unsigned* __restrict__ flags, float4* lo, float4* hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cur = parent[n - 1 + i];
+    while (cur >= 0) {
+        __threadfence();
+        if (atomicAdd(flags + cur, 1u) == 0u) return;
+        const int l = left[cur], r = right[cur];
+        const float4 a0 = __ldcg(lo + l), a1 = __ldcg(hi + l), b0 = __ldcg(lo + r), b1 = __ldcg(hi + r);
+        lo[cur] = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), 0.0f);
+        hi[cur] = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.0f);
+        cur = parent[cur];
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_pack2(const float4* __restrict__ lo, const float4* __restrict__ hi, const int* __restrict__ left,
+                                                  const int* __restrict__ right, int n, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) ngi_pack2(lo, hi, left, right, n, i, out);
+}
+
+__global__ void __launch_bounds__(128) k_collapse8(NgiCollapseCtx ctx, const NgiBuildTask* __restrict__ tasks, unsigned n_tasks) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tasks) ngi_collapse_node(ctx, tasks[i]);
+}
+
+// ================================================================================================
+// ray-query kernels (ngi_gpu_trace*)
+// ================================================================================================
+template <int ACCEL, bool ANY_HIT>
+__global__ void __launch_bounds__(kBlock) k_trace(NgiDevScene sc, const NgiRay* __restrict__ rays, size_t n, NgiHit* __restrict__ hits) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i), r1 = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i + 1);
+    const f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
+    NgiHitRec h;
+    bool hit;
+    if (ACCEL == 0) hit = ngi_trace_bvh8<ANY_HIT>(sc.nodes8, sc.tris8, o, d, r0.w, r1.w, h);
+    else if (ACCEL == 1) hit = ngi_trace_bvh2<ANY_HIT>(sc.nodes2, sc.tris2, o, d, r0.w, r1.w, h);
+    else hit = ngi_trace_brute<ANY_HIT>(sc.tris2, sc.n_tris, o, d, r0.w, r1.w, h);
+    float4 out;
+    out.x = hit ? h.t : 0.0f; out.y = hit ? h.u : 0.0f; out.z = hit ? h.v : 0.0f;
+    out.w = __uint_as_float(hit ? (ANY_HIT ? 0u : h.tri) : NGI_NO_HIT);
+    reinterpret_cast<float4*>(hits)[i] = out;
+}
+
+// ================================================================================================
+// wavefront kernels
+// ================================================================================================
+struct NgiRenderCounters {
+    unsigned long long next_sample;
+    unsigned long long total_extend;
+    unsigned long long total_shadow;
+    unsigned long long iterations;
+    unsigned iter[2];   // [0] shadow entries, [1] extend rays of the iteration in flight
+    unsigned last[2];   // snapshot of the previous iteration (read by the host for termination)
+};
+
+__global__ void k_iter_begin(NgiRenderCounters* c) {
+    c->total_shadow += c->iter[0];
+    c->total_extend += c->iter[1];
+    c->last[0] = c->iter[0];
+    c->last[1] = c->iter[1];
+    c->iter[0] = 0u;
+    c->iter[1] = 0u;
+    c->iterations += 1ull;
+}
+
+__global__ void __launch_bounds__(kBlock) k_logic(NgiDevScene sc, NgiWaveParams wp) {
+    const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < wp.capacity) ngi_logic_step(sc, wp, slot);
+}
+__global__ void __launch_bounds__(kBlock) k_extend(NgiDevScene sc, NgiWaveParams wp) {
+    const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < wp.capacity) ngi_extend_step(sc, wp, slot);
+}
+__global__ void __launch_bounds__(kBlock) k_shadow(NgiDevScene sc, NgiWaveParams wp) {
+    const unsigned n = wp.iter_counters[0];
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_shadow_step(sc, wp, e);
+}
+
+__global__ void __launch_bounds__(kBlock) k_eval_bsdf(NgiDevScene sc, const float* __restrict__ q, const float* __restrict__ wo_in, size_t n,
+                                                      int force_degenerated, float* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = q + 16 * i;
+    const NgiDevPrim& P = sc.prims[(int)a[0]];
+    const int type = (int)a[1];
+    NgiGeom g; g.sn = mk3(a[2], a[3], a[4]); g.gn = mk3(a[5], a[6], a[7]);
+    ngi_tangent_space(g);
+    const f3 wi = mk3(a[8], a[9], a[10]);
+    f3 wo = mk3(0.0f); bool valid = true;
+    if (a[14] != 0.0f) wo = mk3(wo_in[3 * i], wo_in[3 * i + 1], wo_in[3 * i + 2]);
+    else valid = ngi_sample_bsdf(P, type, g, wi, a[11], a[12], a[13], wo);
+    float pdf = 0.0f; f3 fs = mk3(0.0f);
+    if (valid) fs = ngi_eval_bsdf(P, type, g, wi, wo, force_degenerated != 0, pdf);
+    float* o = out + 8 * i;
+    o[0] = wo.x; o[1] = wo.y; o[2] = wo.z; o[3] = fs.x; o[4] = fs.y; o[5] = fs.z; o[6] = pdf; o[7] = valid ? 1.0f : 0.0f;
+}
+
+// ================================================================================================
+// scene handle
+// ================================================================================================
+struct Scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    NgiDevScene dev{};
+    NgiSceneInfo info{};
+    std::vector<void*> allocs;
+    // wavefront state cache (allocated on first render, re-used while the capacity fits)
+    unsigned wave_capacity = 0;
+    void* wave_mem = nullptr;
+    NgiRenderCounters* counters = nullptr;
+    NgiRenderCounters* counters_host = nullptr;  // pinned
+    cudaGraphExec_t graph_exec = nullptr;
+    NgiWaveParams graph_wp{};
+    int graph_iters = 0;
+    std::vector<cudaEvent_t> events;
+
+    ~Scene() {
+        cudaSetDevice(device);
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        for (auto e : events) cudaEventDestroy(e);
+        for (void* p : allocs) cudaFree(p);
+        if (wave_mem) cudaFree(wave_mem);
+        if (counters) cudaFree(counters);
+        if (counters_host) cudaFreeHost(counters_host);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+template <class T>
+int dev_alloc(Scene* s, T** out, size_t count, bool keep) {
+    void* p = nullptr;
+    NGI_CUDA(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    if (keep) { s->allocs.push_back(p); s->info.device_bytes += count * sizeof(T); }
+    *out = (T*)p;
+    return NGI_OK;
+}
+
+int build_scene(Scene* s, const NgiSceneDesc* desc) {
+    NgiHostArrays ha;
+    if (!ngi_prepare_scene(desc, ha)) return set_err(ha.error.find("not supported") != std::string::npos ? NGI_ERR_UNSUPPORTED : NGI_ERR_INVALID_ARGUMENT, ha.error);
+    cudaStream_t st = s->stream;
+    const unsigned nr = ha.n_real;
+    const unsigned n = nr < 2 ? 2 : nr;
+
+    cudaEvent_t ev0, ev1;
+    NGI_CUDA(cudaEventCreate(&ev0));
+    NGI_CUDA(cudaEventCreate(&ev1));
+
+    // ---- upload ----
+    float* d_pos = nullptr;
+    int rc;
+    if ((rc = dev_alloc(s, &d_pos, (size_t)std::max(nr, 1u) * 9, false))) return rc;
+    if (nr) NGI_CUDA(cudaMemcpyAsync(d_pos, desc->positions, (size_t)nr * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    float4* d_shade = nullptr; NgiDevPrim* d_prims = nullptr; unsigned* d_lights = nullptr; float* d_cdf = nullptr;
+    if ((rc = dev_alloc(s, &d_shade, ha.shade_tris.size(), true))) return rc;
+    if ((rc = dev_alloc(s, &d_prims, ha.prims.size(), true))) return rc;
+    if ((rc = dev_alloc(s, &d_lights, ha.light_prims.size(), true))) return rc;
+    if ((rc = dev_alloc(s, &d_cdf, ha.cdf.size(), true))) return rc;
+    if (!ha.shade_tris.empty()) NGI_CUDA(cudaMemcpyAsync(d_shade, ha.shade_tris.data(), ha.shade_tris.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    NGI_CUDA(cudaMemcpyAsync(d_prims, ha.prims.data(), ha.prims.size() * sizeof(NgiDevPrim), cudaMemcpyHostToDevice, st));
+    if (!ha.light_prims.empty()) NGI_CUDA(cudaMemcpyAsync(d_lights, ha.light_prims.data(), ha.light_prims.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    if (!ha.cdf.empty()) NGI_CUDA(cudaMemcpyAsync(d_cdf, ha.cdf.data(), ha.cdf.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+
+    NGI_CUDA(cudaEventRecord(ev0, st));
+    // ---- 0. bounds ----
+    int* d_bounds = nullptr;
+    if ((rc = dev_alloc(s, &d_bounds, 6, false))) return rc;
+    float smin[3] = {0, 0, 0}, smax[3] = {0, 0, 0};
+    if (nr) {
+        const int init[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+        NGI_CUDA(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        k_bounds<<<std::min(grid_for((size_t)nr * 3), 148u * 8u), kBlock, 0, st>>>(d_pos, (size_t)nr * 3, d_bounds);
+        int hb[6];
+        NGI_CUDA(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
+        NGI_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < 3; k++) { smin[k] = ordered_to_float(hb[k]); smax[k] = ordered_to_float(hb[3 + k]); }
+    }
+    const float pad = ngi_box_pad(smin, smax, ha.sensor);
+    const f3 anchor = mk3(smin[0], smin[1], smin[2]);
+
+    // ---- 1. triangle records + boxes ----
+    float4 *d_rec = nullptr, *d_tlo = nullptr, *d_thi = nullptr;
+    if ((rc = dev_alloc(s, &d_rec, (size_t)n * 3, false))) return rc;
+    if ((rc = dev_alloc(s, &d_tlo, n, false))) return rc;
+    if ((rc = dev_alloc(s, &d_thi, n, false))) return rc;
+    k_tri_setup<<<grid_for(n), kBlock, 0, st>>>(d_pos, n, nr, pad, anchor, d_rec, d_tlo, d_thi);
+
+    // ---- 2. Morton + sort ----
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; unsigned *d_vals = nullptr, *d_vals2 = nullptr;
+    if ((rc = dev_alloc(s, &d_keys, n, false))) return rc;
+    if ((rc = dev_alloc(s, &d_keys2, n, false))) return rc;
+    if ((rc = dev_alloc(s, &d_vals, n, false))) return rc;
+    if ((rc = dev_alloc(s, &d_vals2, n, false))) return rc;
+    const f3 mmin = mk3(smin[0] - pad, smin[1] - pad, smin[2] - pad);
+    f3 sinv;
+    sinv.x = 1.0f / fmaxf(smax[0] - smin[0] + 2 * pad, 1e-30f);
+    sinv.y = 1.0f / fmaxf(smax[1] - smin[1] + 2 * pad, 1e-30f);
+    sinv.z = 1.0f / fmaxf(smax[2] - smin[2] + 2 * pad, 1e-30f);
+    k_morton<<<grid_for(n), kBlock, 0, st>>>(d_tlo, d_thi, n, mmin, sinv, d_keys, d_vals);
+    size_t tmp_bytes = 0;
+    NGI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, st));
+    unsigned char* d_tmp = nullptr;
+    if ((rc = dev_alloc(s, &d_tmp, tmp_bytes, false))) return rc;
+    NGI_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, st));
+
+    // ---- 3-5. LBVH ----
+    float4 *d_tris2 = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_nodes2 = nullptr;
+    int *d_left = nullptr, *d_right = nullptr, *d_parent = nullptr; uint2* d_range = nullptr; unsigned* d_flags = nullptr;
+    if ((rc = dev_alloc(s, &d_tris2, (size_t)n * 3, true))) return rc;
+    if ((rc = dev_alloc(s, &d_lo, 2 * (size_t)n - 1, false))) return rc;
+    if ((rc = dev_alloc(s, &d_hi, 2 * (size_t)n - 1, false))) return rc;
+    if ((rc = dev_alloc(s, &d_nodes2, (size_t)(n - 1) * 4, true))) return rc;
+    if ((rc = dev_alloc(s, &d_left, n - 1, false))) return rc;
+    if ((rc = dev_alloc(s, &d_right, n - 1, false))) return rc;
+    if ((rc = dev_alloc(s, &d_parent, 2 * (size_t)n - 1, false))) return rc;
+    if ((rc = dev_alloc(s, &d_range, n - 1, false))) return rc;
+    if ((rc = dev_alloc(s, &d_flags, n - 1, false))) return rc;
+    k_gather_sorted<<<grid_for(n), kBlock, 0, st>>>(d_vals2, n, d_rec, d_tlo, d_thi, d_tris2, d_lo, d_hi);
+    k_karras<<<grid_for(n - 1), kBlock, 0, st>>>(d_keys2, (int)n, d_left, d_right, d_range, d_parent);
+    NGI_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)(n - 1) * sizeof(unsigned), st));
+    k_refit<<<grid_for(n), kBlock, 0, st>>>((int)n, d_left, d_right, d_parent, d_flags, d_lo, d_hi);
+    k_pack2<<<grid_for(n - 1), kBlock, 0, st>>>(d_lo, d_hi, d_left, d_right, (int)n, d_nodes2);
+
+    // ---- 6. collapse to BVH8, one launch per level ----
+    uint4* d_nodes8_tmp = nullptr; float4* d_tris8 = nullptr; unsigned* d_cnt = nullptr; NgiBuildTask *d_q0 = nullptr, *d_q1 = nullptr;
+    if ((rc = dev_alloc(s, &d_nodes8_tmp, (size_t)n * 5, false))) return rc;
+    if ((rc = dev_alloc(s, &d_tris8, (size_t)n * 3, true))) return rc;
+    if ((rc = dev_alloc(s, &d_cnt, 4, false))) return rc;
+    if ((rc = dev_alloc(s, &d_q0, n, false))) return rc;
+    if ((rc = dev_alloc(s, &d_q1, n, false))) return rc;
+    {
+        const unsigned init[4] = {1u, 0u, 0u, 0u};
+        NGI_CUDA(cudaMemcpyAsync(d_cnt, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        const NgiBuildTask root = {0, 0u};
+        NGI_CUDA(cudaMemcpyAsync(d_q0, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+    }
+    NgiCollapseCtx ctx;
+    ctx.lo = d_lo; ctx.hi = d_hi; ctx.left = d_left; ctx.right = d_right; ctx.range = d_range; ctx.tris2 = d_tris2; ctx.n = (int)n;
+    ctx.nodes8 = d_nodes8_tmp; ctx.tris8 = d_tris8; ctx.counters = d_cnt;
+    unsigned n_tasks = 1, depth = 0;
+    unsigned hc[4] = {1, 0, 0, 0};
+    NgiBuildTask *qin = d_q0, *qout = d_q1;
+    while (n_tasks > 0) {
+        depth++;
+        ctx.out_tasks = qout;
+        NGI_CUDA(cudaMemsetAsync(d_cnt + 2, 0, sizeof(unsigned), st));
+        k_collapse8<<<grid_for(n_tasks, 128), 128, 0, st>>>(ctx, qin, n_tasks);
+        NGI_CUDA(cudaMemcpyAsync(hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        NGI_CUDA(cudaStreamSynchronize(st));
+        n_tasks = hc[2];
+        std::swap(qin, qout);
+        if (depth > 4096) return set_err(NGI_ERR_CUDA, "BVH8 collapse did not terminate");
+    }
+    NGI_CUDA(cudaGetLastError());
+    if (hc[1] != n) return set_err(NGI_ERR_CUDA, "BVH8 collapse lost triangles: " + std::to_string(hc[1]) + " of " + std::to_string(n));
+    if (depth > NGI_BVH8_STACK) return set_err(NGI_ERR_UNSUPPORTED, "BVH8 depth " + std::to_string(depth) + " exceeds the traversal stack");
+    const unsigned n_nodes8 = hc[0];
+    uint4* d_nodes8 = nullptr;
+    if ((rc = dev_alloc(s, &d_nodes8, (size_t)n_nodes8 * 5, true))) return rc;
+    NGI_CUDA(cudaMemcpyAsync(d_nodes8, d_nodes8_tmp, (size_t)n_nodes8 * 5 * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
+    NGI_CUDA(cudaEventRecord(ev1, st));
+    NGI_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    NGI_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+
+    for (void* p : {(void*)d_pos, (void*)d_bounds, (void*)d_rec, (void*)d_tlo, (void*)d_thi, (void*)d_keys, (void*)d_keys2, (void*)d_vals, (void*)d_vals2,
+                    (void*)d_tmp, (void*)d_lo, (void*)d_hi, (void*)d_left, (void*)d_right, (void*)d_parent, (void*)d_range, (void*)d_flags,
+                    (void*)d_nodes8_tmp, (void*)d_cnt, (void*)d_q0, (void*)d_q1})
+        cudaFree(p);
+
+    NgiDevScene& d = s->dev;
+    d.nodes8 = d_nodes8; d.tris8 = d_tris8; d.nodes2 = d_nodes2; d.tris2 = d_tris2;
+    d.shade_tris = d_shade; d.prims = d_prims; d.light_prims = d_lights; d.cdf = d_cdf;
+    d.n_tris = n; d.n_lights = (unsigned)ha.light_prims.size(); d.sensor = ha.sensor;
+    s->info.num_tris = nr; s->info.bvh8_nodes = n_nodes8; s->info.bvh2_nodes = n - 1;
+    s->info.build_gpu_seconds = ms * 1e-3;
+    for (int k = 0; k < 3; k++) { s->info.scene_min[k] = smin[k]; s->info.scene_max[k] = smax[k]; }
+    s->info.num_lights = d.n_lights; s->info.bvh8_max_depth = depth;
+    return NGI_OK;
+}
+
+// ---- wavefront state ---------------------------------------------------------------------------
+int ensure_wave(Scene* s, unsigned P) {
+    if (s->wave_capacity == P && s->wave_mem) return NGI_OK;
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+    if (s->wave_mem) { cudaFree(s->wave_mem); s->wave_mem = nullptr; }
+    // per slot: sample 8 + thr_pix 16 + p 24 + dir_info 16 + hit 16 = 80 B; shadow queue 2 entries x 48 B
+    const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96);
+    NGI_CUDA(cudaMalloc(&s->wave_mem, bytes));
+    if (!s->counters) NGI_CUDA(cudaMalloc((void**)&s->counters, sizeof(NgiRenderCounters)));
+    if (!s->counters_host) NGI_CUDA(cudaMallocHost((void**)&s->counters_host, sizeof(NgiRenderCounters)));
+    s->wave_capacity = P;
+    return NGI_OK;
+}
+
+void carve_wave(Scene* s, NgiWaveParams& wp) {
+    const size_t P = s->wave_capacity;
+    unsigned char* p = (unsigned char*)s->wave_mem;
+    wp.thr_pix = (float4*)p; p += P * 16;
+    wp.dir_info = (float4*)p; p += P * 16;
+    wp.hit = (float4*)p; p += P * 16;
+    wp.shadow_q = (float4*)p; p += P * 96;
+    wp.sample = (unsigned long long*)p; p += P * 8;
+    wp.px = (double*)p; p += P * 8;
+    wp.py = (double*)p; p += P * 8;
+    wp.pz = (double*)p; p += P * 8;
+    wp.iter_counters = s->counters->iter;
+    wp.next_sample = &s->counters->next_sample;
+    wp.capacity = (unsigned)P;
+}
+
+bool same_wp(const NgiWaveParams& a, const NgiWaveParams& b) { return memcmp(&a, &b, sizeof(a)) == 0; }
+
+int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool timed, size_t& ev_used) {
+    const unsigned P = wp.capacity;
+    k_iter_begin<<<1, 1, 0, st>>>(s->counters);
+    k_logic<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
+    if (timed) {
+        while (s->events.size() < ev_used + 2) { cudaEvent_t e; NGI_CUDA(cudaEventCreate(&e)); s->events.push_back(e); }
+        NGI_CUDA(cudaEventRecord(s->events[ev_used], st));
+    }
+    k_extend<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
+    if (wp.renderer == NGI_RENDERER_PTDIRECT) k_shadow<<<std::min(grid_for((size_t)P * 2), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
+    if (timed) { NGI_CUDA(cudaEventRecord(s->events[ev_used + 1], st)); ev_used += 2; }
+    return NGI_OK;
+}
+
+int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream_t st, NgiRenderStats* stats) {
+    if (rp->struct_size != sizeof(NgiRenderParams)) return set_err(NGI_ERR_INVALID_ARGUMENT, "NgiRenderParams.struct_size mismatch (ABI)");
+    if (rp->renderer != NGI_RENDERER_PT && rp->renderer != NGI_RENDERER_PTDIRECT)
+        return set_err(NGI_ERR_UNSUPPORTED, "renderer not supported by this build (only pt and ptdirect are on the GPU path)");
+    if (rp->width <= 0 || rp->height <= 0 || rp->num_samples < 0 || rp->sample_offset < 0) return set_err(NGI_ERR_INVALID_ARGUMENT, "invalid width/height/num_samples");
+    const size_t npx = (size_t)rp->width * rp->height;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!rp->accumulate) NGI_CUDA(cudaMemsetAsync(film_dev, 0, npx * 3 * sizeof(float), st));
+    if (rp->num_samples == 0 || (rp->max_num_vertices != -1 && rp->max_num_vertices < 2)) {
+        // MaxNumVertices <= 1: the loop exits before the first direction is sampled (src/nanogi.cpp:485)
+        NGI_CUDA(cudaStreamSynchronize(st));
+        if (stats) stats->paths = (uint64_t)rp->num_samples;
+        return NGI_OK;
+    }
+    unsigned P = rp->wave_capacity ? rp->wave_capacity : (1u << 21);
+    P = std::max(P, 1024u);
+    if ((unsigned long long)rp->num_samples < P) P = std::max(1024u, (unsigned)((rp->num_samples + 255) / 256 * 256));
+    int rc = ensure_wave(s, P);
+    if (rc) return rc;
+
+    NgiWaveParams wp;
+    memset(&wp, 0, sizeof(wp));
+    carve_wave(s, wp);
+    wp.film = film_dev;
+    wp.renderer = rp->renderer; wp.max_verts = rp->max_num_vertices; wp.width = rp->width; wp.height = rp->height;
+    wp.sample_end = (unsigned long long)(rp->sample_offset + rp->num_samples);
+    wp.seed_lo = (unsigned)rp->seed; wp.seed_hi = (unsigned)(rp->seed >> 32);
+    wp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
+
+    NgiRenderCounters init;
+    memset(&init, 0, sizeof(init));
+    init.next_sample = (unsigned long long)rp->sample_offset;
+    *s->counters_host = init;
+    NGI_CUDA(cudaMemcpyAsync(s->counters, s->counters_host, sizeof(init), cudaMemcpyHostToDevice, st));
+    NGI_CUDA(cudaMemsetAsync(wp.dir_info, 0, (size_t)P * 16, st));   // every slot starts idle
+
+    cudaEvent_t ev0, ev1;
+    NGI_CUDA(cudaEventCreate(&ev0));
+    NGI_CUDA(cudaEventCreate(&ev1));
+    NGI_CUDA(cudaEventRecord(ev0, st));
+
+    const bool timed = (rp->flags & NGI_RENDER_TIME_KERNELS) != 0;
+    const int kItersPerBatch = 8;
+    const int kernels_per_iter = rp->renderer == NGI_RENDERER_PTDIRECT ? 4 : 3;
+    size_t ev_used = 0;
+    uint64_t launches = 0;
+    double trace_ms = 0.0;
+
+    if (!timed) {
+        // the batch of kItersPerBatch iterations is captured once into a CUDA graph and replayed
+        if (!s->graph_exec || !same_wp(s->graph_wp, wp) || s->graph_iters != kItersPerBatch) {
+            if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+            cudaGraph_t graph;
+            NGI_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            for (int i = 0; i < kItersPerBatch; i++) { size_t dummy = 0; rc = launch_iteration(s, wp, st, false, dummy); if (rc) { cudaStreamEndCapture(st, &graph); return rc; } }
+            NGI_CUDA(cudaStreamEndCapture(st, &graph));
+            NGI_CUDA(cudaGraphInstantiate(&s->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            s->graph_wp = wp; s->graph_iters = kItersPerBatch;
+        }
+    }
+    // expected number of iterations ~ (rays per path) * N / P; poll the counters once per batch
+    while (true) {
+        if (timed) {
+            for (int i = 0; i < kItersPerBatch; i++) { rc = launch_iteration(s, wp, st, true, ev_used); if (rc) return rc; }
+        } else {
+            NGI_CUDA(cudaGraphLaunch(s->graph_exec, st));
+        }
+        launches += (uint64_t)kItersPerBatch * kernels_per_iter;
+        NGI_CUDA(cudaMemcpyAsync(s->counters_host, s->counters, sizeof(NgiRenderCounters), cudaMemcpyDeviceToHost, st));
+        NGI_CUDA(cudaStreamSynchronize(st));
+        if (timed) {
+            for (size_t i = 0; i + 1 < ev_used; i += 2) { float ms = 0; NGI_CUDA(cudaEventElapsedTime(&ms, s->events[i], s->events[i + 1])); trace_ms += ms; }
+            ev_used = 0;
+        }
+        const NgiRenderCounters& c = *s->counters_host;
+        if (c.next_sample >= wp.sample_end && c.iter[0] == 0 && c.iter[1] == 0) break;
+    }
+    NGI_CUDA(cudaEventRecord(ev1, st));
+    NGI_CUDA(cudaStreamSynchronize(st));
+    NGI_CUDA(cudaGetLastError());
+    float ms = 0;
+    NGI_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (stats) {
+        const NgiRenderCounters& c = *s->counters_host;
+        stats->paths = (uint64_t)rp->num_samples;
+        stats->extend_rays = c.total_extend + c.iter[1];
+        stats->shadow_rays = c.total_shadow + c.iter[0];
+        stats->wave_iterations = c.iterations;
+        stats->kernel_launches = launches;
+        stats->gpu_seconds = ms * 1e-3;
+        stats->trace_kernel_seconds = trace_ms * 1e-3;
+    }
+    return NGI_OK;
+}
+
+template <int ACCEL>
+void launch_trace(Scene* s, const NgiRay* rays, size_t n, NgiHit* hits, int any_hit, cudaStream_t st) {
+    if (any_hit) k_trace<ACCEL, true><<<grid_for(n), kBlock, 0, st>>>(s->dev, rays, n, hits);
+    else k_trace<ACCEL, false><<<grid_for(n), kBlock, 0, st>>>(s->dev, rays, n, hits);
+}
+
+int trace_impl(Scene* s, const NgiRay* rays_dev, size_t n, NgiHit* hits_dev, int any_hit, int accel, double* seconds) {
+    if (accel < 0 || accel > 2) return set_err(NGI_ERR_INVALID_ARGUMENT, "accel must be 0 (BVH8), 1 (BVH2) or 2 (brute force)");
+    cudaStream_t st = s->stream;
+    cudaEvent_t ev0, ev1;
+    NGI_CUDA(cudaEventCreate(&ev0));
+    NGI_CUDA(cudaEventCreate(&ev1));
+    NGI_CUDA(cudaEventRecord(ev0, st));
+    if (n) {
+        if (accel == 0) launch_trace<0>(s, rays_dev, n, hits_dev, any_hit, st);
+        else if (accel == 1) launch_trace<1>(s, rays_dev, n, hits_dev, any_hit, st);
+        else launch_trace<2>(s, rays_dev, n, hits_dev, any_hit, st);
+    }
+    NGI_CUDA(cudaEventRecord(ev1, st));
+    NGI_CUDA(cudaStreamSynchronize(st));
+    NGI_CUDA(cudaGetLastError());
+    float ms = 0;
+    NGI_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (seconds) *seconds = ms * 1e-3;
+    return NGI_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int ngi_gpu_abi_version(void) { return 1; }
+
+const char* ngi_gpu_last_error(void) { return g_err.c_str(); }
+
+int ngi_gpu_device_count(void) {
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return set_err(NGI_ERR_NO_DEVICE, "no CUDA device available (this module has no CPU fallback)"); }
+    return n;
+}
+
+int ngi_gpu_scene_create(const NgiSceneDesc* desc, int device, void** out_scene) {
+    if (!desc || !out_scene) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    *out_scene = nullptr;
+    const int nd = ngi_gpu_device_count();
+    if (nd < 0) return nd;
+    if (device < 0 || device >= nd) return set_err(NGI_ERR_INVALID_ARGUMENT, "device index out of range");
+    NGI_CUDA(cudaSetDevice(device));
+    Scene* s = new Scene;
+    s->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete s; return set_err(NGI_ERR_CUDA, cudaGetErrorString(e)); }
+    const int rc = build_scene(s, desc);
+    if (rc != NGI_OK) { delete s; return rc; }
+    *out_scene = s;
+    return NGI_OK;
+}
+
+int ngi_gpu_scene_info(void* scene, NgiSceneInfo* out) {
+    if (!scene || !out) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    *out = ((Scene*)scene)->info;
+    return NGI_OK;
+}
+
+void ngi_gpu_scene_destroy(void* scene) { delete (Scene*)scene; }
+
+int ngi_gpu_render_device(void* scene, const NgiRenderParams* params, void* film_rgb_device, void* cuda_stream, NgiRenderStats* out_stats) {
+    if (!scene || !params || !film_rgb_device) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    Scene* s = (Scene*)scene;
+    NGI_CUDA(cudaSetDevice(s->device));
+    return render_impl(s, params, (float*)film_rgb_device, cuda_stream ? (cudaStream_t)cuda_stream : s->stream, out_stats);
+}
+
+int ngi_gpu_render(void* scene, const NgiRenderParams* params, float* film_rgb_host, NgiRenderStats* out_stats) {
+    if (!scene || !params || !film_rgb_host) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    Scene* s = (Scene*)scene;
+    NGI_CUDA(cudaSetDevice(s->device));
+    if (params->width <= 0 || params->height <= 0) return set_err(NGI_ERR_INVALID_ARGUMENT, "invalid width/height");
+    const size_t bytes = (size_t)params->width * params->height * 3 * sizeof(float);
+    float* d_film = nullptr;
+    NGI_CUDA(cudaMalloc((void**)&d_film, bytes));
+    NgiRenderParams p = *params;
+    p.accumulate = 0;
+    int rc = render_impl(s, &p, d_film, s->stream, out_stats);
+    if (rc == NGI_OK) {
+        cudaError_t e = cudaMemcpyAsync(film_rgb_host, d_film, bytes, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = set_err(NGI_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_film);
+    return rc;
+}
+
+int ngi_gpu_trace_device(void* scene, const void* rays_device, uint64_t n, void* hits_device, int any_hit, int accel, double* out_seconds) {
+    if (!scene || (n && (!rays_device || !hits_device))) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    Scene* s = (Scene*)scene;
+    NGI_CUDA(cudaSetDevice(s->device));
+    return trace_impl(s, (const NgiRay*)rays_device, (size_t)n, (NgiHit*)hits_device, any_hit, accel, out_seconds);
+}
+
+int ngi_gpu_trace(void* scene, const NgiRay* rays_host, uint64_t n, NgiHit* hits_host, int any_hit, int accel) {
+    if (!scene || (n && (!rays_host || !hits_host))) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    Scene* s = (Scene*)scene;
+    NGI_CUDA(cudaSetDevice(s->device));
+    if (n == 0) return NGI_OK;
+    NgiRay* d_rays = nullptr; NgiHit* d_hits = nullptr;
+    NGI_CUDA(cudaMalloc((void**)&d_rays, n * sizeof(NgiRay)));
+    cudaError_t e = cudaMalloc((void**)&d_hits, n * sizeof(NgiHit));
+    if (e != cudaSuccess) { cudaFree(d_rays); return set_err(NGI_ERR_OUT_OF_MEMORY, cudaGetErrorString(e)); }
+    int rc = NGI_OK;
+    e = cudaMemcpyAsync(d_rays, rays_host, n * sizeof(NgiRay), cudaMemcpyHostToDevice, s->stream);
+    if (e != cudaSuccess) rc = set_err(NGI_ERR_CUDA, cudaGetErrorString(e));
+    if (rc == NGI_OK) rc = trace_impl(s, d_rays, (size_t)n, d_hits, any_hit, accel, nullptr);
+    if (rc == NGI_OK) {
+        e = cudaMemcpy(hits_host, d_hits, n * sizeof(NgiHit), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_err(NGI_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_rays); cudaFree(d_hits);
+    return rc;
+}
+
+int ngi_gpu_eval_bsdf(void* scene, const float* queries_host, const float* wo_in_host, uint64_t n, int force_degenerated, float* out_host) {
+    if (!scene || (n && (!queries_host || !wo_in_host || !out_host))) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    Scene* s = (Scene*)scene;
+    NGI_CUDA(cudaSetDevice(s->device));
+    if (n == 0) return NGI_OK;
+    float *d_q = nullptr, *d_wo = nullptr, *d_out = nullptr;
+    NGI_CUDA(cudaMalloc((void**)&d_q, n * 16 * sizeof(float)));
+    NGI_CUDA(cudaMalloc((void**)&d_wo, n * 3 * sizeof(float)));
+    NGI_CUDA(cudaMalloc((void**)&d_out, n * 8 * sizeof(float)));
+    NGI_CUDA(cudaMemcpyAsync(d_q, queries_host, n * 16 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    NGI_CUDA(cudaMemcpyAsync(d_wo, wo_in_host, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    k_eval_bsdf<<<grid_for(n), kBlock, 0, s->stream>>>(s->dev, d_q, d_wo, (size_t)n, force_degenerated, d_out);
+    NGI_CUDA(cudaMemcpyAsync(out_host, d_out, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    NGI_CUDA(cudaStreamSynchronize(s->stream));
+    NGI_CUDA(cudaGetLastError());
+    cudaFree(d_q); cudaFree(d_wo); cudaFree(d_out);
+    return NGI_OK;
+}
+
+}  // extern "C"

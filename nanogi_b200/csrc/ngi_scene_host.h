@@ -1,0 +1,130 @@
+// ngi_scene_host.h — host-side preparation of the device scene from the POD NgiSceneDesc.
+//
+// Loader-side derivations the reference performs in Scene::Load before the Embree commit:
+//   * sensor = last E primitive, light list in YAML order      (reference include/nanogi/rt.hpp:1606-1615)
+//   * per-light triangle-area CDF + InvArea, computed in fp64   (rt.hpp:1747-1765, basic.hpp:448-461)
+//   * directional-light bounding disk                           (rt.hpp:2067-2073)
+// plus the narrowing of the fp64 parameters to the fp32 device structs. Pure host C++ (no CUDA calls):
+// ngi_capi.cu uploads the arrays; tests/hostsim reuses them for the CPU simulator.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nanogi_gpu.h"
+#include "ngi_shade.h"
+
+struct NgiHostArrays {
+    std::vector<float4> shade_tris;     // [n_real][5]
+    std::vector<NgiDevPrim> prims;
+    std::vector<unsigned> light_prims;
+    std::vector<float> cdf;
+    NgiDevSensor sensor;
+    unsigned n_real = 0;
+    std::string error;
+};
+
+inline f3 ngi_f3_from(const double* v) { return mk3((float)v[0], (float)v[1], (float)v[2]); }
+
+inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out) {
+    if (!d || d->struct_size != sizeof(NgiSceneDesc)) { out.error = "NgiSceneDesc.struct_size mismatch (ABI)"; return false; }
+    if (d->num_tris > 0 && (!d->positions || !d->normals)) { out.error = "positions / normals are NULL"; return false; }
+    if (d->num_prims == 0 || !d->prims) { out.error = "scene has no primitives"; return false; }
+    if (d->num_tris >= 0x7FFFFFF0ull) { out.error = "too many triangles (max 2^31 - 16)"; return false; }
+    const size_t n = (size_t)d->num_tris;
+    out.n_real = (unsigned)n;
+    std::vector<int> triPrim(n, -1);
+    out.prims.resize(d->num_prims);
+    int sensor = -1;
+    double bmin[3] = {1e300, 1e300, 1e300}, bmax[3] = {-1e300, -1e300, -1e300};
+    for (size_t i = 0; i < n * 3; i++)
+        for (int k = 0; k < 3; k++) {
+            const double v = d->positions[i * 3 + k];
+            if (v < bmin[k]) bmin[k] = v;
+            if (v > bmax[k]) bmax[k] = v;
+        }
+    for (uint32_t i = 0; i < d->num_prims; i++) {
+        const NgiPrimitive& s = d->prims[i];
+        NgiDevPrim p;
+        std::memset(&p, 0, sizeof(p));
+        p.type = s.type;
+        p.first_tri = s.first_tri; p.num_tris = s.first_tri >= 0 ? s.num_tris : 0;
+        p.l_type = s.l_type; p.s_type = s.s_type; p.cdf_offset = -1;
+        if (p.first_tri >= 0 && ((size_t)p.first_tri + (size_t)p.num_tris > n || p.num_tris < 0)) { out.error = "primitive triangle range out of bounds"; return false; }
+        if (s.d_tex >= 0 || s.g_tex >= 0) { out.error = "TexR textures are not supported yet (SURVEY 8f)"; return false; }
+        p.d_r = ngi_f3_from(s.d_r);
+        p.g_r = ngi_f3_from(s.g_r); p.g_eta = ngi_f3_from(s.g_eta); p.g_k = ngi_f3_from(s.g_k); p.g_rough = (float)s.g_roughness;
+        p.s_r = ngi_f3_from(s.s_r); p.s_eta1 = (float)s.s_eta1; p.s_eta2 = (float)s.s_eta2;
+        p.l_le = ngi_f3_from(s.l_le); p.l_vec = ngi_f3_from(s.l_vec);
+        for (int t = 0; t < p.num_tris; t++) triPrim[(size_t)p.first_tri + t] = (int)i;
+        if (s.type & NGI_TYPE_E) {
+            if (s.e_type != NGI_E_PINHOLE) { out.error = "E.area sensors are not supported yet (SURVEY 8f)"; return false; }
+            sensor = (int)i;                                                           // rt.hpp:1606-1610 (last one wins)
+        }
+        if (s.type & NGI_TYPE_L) {
+            out.light_prims.push_back(i);                                              // rt.hpp:1612-1615
+            if (s.l_type == NGI_L_AREA) {
+                if (p.num_tris <= 0) { out.error = "Area light must be associated with mesh"; return false; }   // rt.hpp:1826-1830
+                // CreateTriangleAreaDist, rt.hpp:1747-1765 (fp64), Distribution1D::Normalize basic.hpp:453-461
+                std::vector<double> cdf(1, 0.0);
+                double sumArea = 0;
+                for (int t = 0; t < p.num_tris; t++) {
+                    const float* q = d->positions + ((size_t)p.first_tri + t) * 9;
+                    const double e1[3] = {(double)q[3] - q[0], (double)q[4] - q[1], (double)q[5] - q[2]};
+                    const double e2[3] = {(double)q[6] - q[0], (double)q[7] - q[1], (double)q[8] - q[2]};
+                    const double cx = e1[1] * e2[2] - e2[1] * e1[2], cy = e1[2] * e2[0] - e2[2] * e1[0], cz = e1[0] * e2[1] - e2[0] * e1[1];
+                    const double area = std::sqrt(cx * cx + cy * cy + cz * cz) * 0.5;
+                    cdf.push_back(cdf.back() + area);
+                    sumArea += area;
+                }
+                const double invSum = 1.0 / cdf.back();
+                p.cdf_offset = (int)out.cdf.size();
+                for (double v : cdf) out.cdf.push_back((float)(v * invSum));
+                p.l_inv_area = (float)(1.0 / sumArea);
+            } else if (s.l_type == NGI_L_DIRECTIONAL) {                                // rt.hpp:2067-2073
+                double c[3], r2 = 0;
+                for (int k = 0; k < 3; k++) { c[k] = (bmax[k] + bmin[k]) * 0.5; r2 += (c[k] - bmax[k]) * (c[k] - bmax[k]); }
+                const double radius = std::sqrt(r2) * 1.01;
+                p.l_center = mk3((float)c[0], (float)c[1], (float)c[2]);
+                p.l_radius = (float)radius;
+                p.l_inv_area = (float)(1.0 / (2.0 * 3.14159265358979323846 * radius * radius));
+            }
+        }
+        out.prims[i] = p;
+    }
+    if (sensor < 0) { out.error = "scene has no sensor (E) primitive"; return false; }
+    {
+        const NgiPrimitive& s = d->prims[sensor];
+        NgiDevSensor& E = out.sensor;
+        E.px = s.e_position[0]; E.py = s.e_position[1]; E.pz = s.e_position[2];
+        E.vx = ngi_f3_from(s.e_vx); E.vy = ngi_f3_from(s.e_vy); E.vz = ngi_f3_from(s.e_vz);
+        const double tanFov = std::tan(s.e_fov * 0.5);
+        E.tan_fov = (float)tanFov;
+        E.aspect = (float)s.e_aspect;
+        E.inv_a = (float)(1.0 / (tanFov * tanFov * s.e_aspect * 4.0));                  // rt.hpp:974
+        E.prim = sensor;
+    }
+    out.shade_tris.resize(n * 5);
+    for (size_t t = 0; t < n; t++) {
+        if (triPrim[t] < 0) { out.error = "triangle " + std::to_string(t) + " belongs to no primitive"; return false; }
+        const float* p = d->positions + t * 9;
+        const float* q = d->normals + t * 9;
+        float4* r = &out.shade_tris[t * 5];
+        r[0] = make_float4(p[0], p[1], p[2], p[3]);
+        r[1] = make_float4(p[4], p[5], p[6], p[7]);
+        r[2] = make_float4(p[8], q[0], q[1], q[2]);
+        r[3] = make_float4(q[3], q[4], q[5], q[6]);
+        r[4] = make_float4(q[7], q[8], u2f((unsigned)triPrim[t]), 0.0f);
+    }
+    return true;
+}
+
+// conservative box padding: the triangle test's rounding is ~ulp(|o - v0|), so every
+// triangle box grows by 2^-16 of the largest coordinate magnitude in play (scene bounds, sensor position)
+inline float ngi_box_pad(const float smin[3], const float smax[3], const NgiDevSensor& E) {
+    float mag = 1e-30f;
+    for (int k = 0; k < 3; k++) { mag = fmaxf(mag, fabsf(smin[k])); mag = fmaxf(mag, fabsf(smax[k])); }
+    mag = fmaxf(mag, (float)fmax(fabs(E.px), fmax(fabs(E.py), fabs(E.pz))));
+    return mag * (1.0f / 65536.0f);
+}

@@ -1,0 +1,276 @@
+// ngi_wave.h — per-slot body of the wavefront "logic" stage.
+//
+// Replaces the per-sample loops ProcessSample_PT (reference src/nanogi.cpp:446-607) and
+// ProcessSample_PTDirect (src/nanogi.cpp:609-802) plus the sample scheduler of RenderProcess
+// (src/nanogi.cpp:225-440). One reference loop iteration is split at the ray query:
+//
+//   logic(slot):   [tail of iteration k]   miss -> end | pt: emission on L hit (:566-577) | RR (:581-591) |
+//                                          vertex update (:597-603) | vertex cap (:485 / :647)
+//                  [head of iteration k+1] ptdirect: NEE sample -> shadow queue (:654-712) |
+//                                          SampleDirection + fs/pdf (:492-544 / :716-754) -> extend ray
+//                  a slot whose path ended pulls the next sample index and starts at the eye vertex
+//   extend(slot):  Scene::Intersect's ray query (include/nanogi/rt.hpp:2162-2182)   [trace kernel]
+//   shadow(entry): Scene::Visible (rt.hpp:2251-2261) + film accumulation (:706)     [trace kernel]
+//
+// Random numbers: Philox4x32-10, key = seed, counter = (sample index, vertex index, block):
+//   block 0 = {direction u0, direction u1, uComp, RR}, block 1 = {light pick, light u0, light u1, -}.
+// The vertex position is carried in fp64 and advanced as p += d * (double)t exactly like the reference
+// (rt.hpp:2197), then narrowed to fp32 for the ray query (rt.hpp:2166-2168); everything else is fp32.
+#pragma once
+#include "ngi_bvh.h"
+#include "ngi_shade.h"
+
+#define NGI_INFO_ALIVE 1u
+#define NGI_INFO_RR_SURVIVE 2u
+
+struct NgiWaveParams {
+    // path state, SoA, one entry per slot
+    unsigned long long* sample;   // sample index (Philox counter)
+    float4* thr_pix;              // throughput.xyz, pixel index (int bits)
+    double* px; double* py; double* pz;   // current vertex position (fp64)
+    float4* dir_info;             // extend-ray direction.xyz, info bits (alive | rr_survive<<1 | numVertices<<8)
+    float4* hit;                  // t, u, v, global triangle id (written by the extend kernel)
+    // shadow queue: 3 x float4 per entry = (o.xyz, tmax) (d.xyz, pixel) (C.xyz, -)
+    float4* shadow_q;
+    unsigned* iter_counters;      // [0] shadow entries this iteration, [1] extend rays this iteration
+    unsigned long long* next_sample;
+    float* film;                  // [H][W][3], row 0 = bottom
+    unsigned capacity;            // slots
+    int renderer;                 // 0 pt, 1 ptdirect
+    int max_verts;
+    int width, height;
+    unsigned long long sample_end;   // exclusive
+    unsigned seed_lo, seed_hi;
+    float film_scale;             // W*H / film_norm_samples (src/nanogi.cpp:436), folded into every splat
+};
+
+// ---- atomics / queue allocation (warp-aggregated on the device) ---------------------------------
+NGI_HD unsigned long long ngi_fetch_sample(unsigned long long* ctr) {
+#if defined(__CUDA_ARCH__)
+    const unsigned mask = __activemask();
+    const int leader = __ffs((int)mask) - 1;
+    const int lane = (int)(threadIdx.x & 31u);
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(ctr, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+#else
+    return (*ctr)++;
+#endif
+}
+NGI_HD unsigned ngi_queue_alloc(unsigned* ctr) {
+#if defined(__CUDA_ARCH__)
+    const unsigned mask = __activemask();
+    const int leader = __ffs((int)mask) - 1;
+    const int lane = (int)(threadIdx.x & 31u);
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(ctr, (unsigned)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+#else
+    return (*ctr)++;
+#endif
+}
+NGI_HD void ngi_film_add(float* film, const int pixel, const f3 c) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(film + 3 * (size_t)pixel + 0, c.x);
+    atomicAdd(film + 3 * (size_t)pixel + 1, c.y);
+    atomicAdd(film + 3 * (size_t)pixel + 2, c.z);
+#else
+    film[3 * (size_t)pixel + 0] += c.x; film[3 * (size_t)pixel + 1] += c.y; film[3 * (size_t)pixel + 2] += c.z;
+#endif
+}
+
+NGI_HD void ngi_push_shadow(const NgiWaveParams& wp, const f3 o, const f3 d, const float tmax, const f3 C, const int pixel) {
+    const unsigned e = ngi_queue_alloc(wp.iter_counters + 0);
+    float4* q = wp.shadow_q + 3 * (size_t)e;
+    q[0] = make_float4(o.x, o.y, o.z, tmax);
+    q[1] = make_float4(d.x, d.y, d.z, u2f((unsigned)pixel));
+    q[2] = make_float4(C.x, C.y, C.z, 0.0f);
+}
+
+// ---- fp64 view of the traced fp32 direction: d + U(-1/2, 1/2) * ulp(d) per component ---------------
+NGI_HD double ngi_dither1(const float d, const unsigned r10) {
+    const unsigned e = f2u(d) & 0x7F800000u;
+    const float ulp = e > (24u << 23) ? u2f(e - (23u << 23)) : 0.0f;
+    return (double)d + ((double)r10 * (1.0 / 1024.0) - 0.5 + (0.5 / 1024.0)) * (double)ulp;
+}
+NGI_HD void ngi_dither_direction(const f3 d, const float4 hit, double& dx, double& dy, double& dz) {
+    unsigned h = (f2u(hit.x) * 0x9E3779B1u) ^ (f2u(hit.y) * 0x85EBCA77u) ^ (f2u(hit.z) * 0xC2B2AE3Du) ^ f2u(hit.w);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    dx = ngi_dither1(d.x, h & 1023u);
+    dy = ngi_dither1(d.y, (h >> 10) & 1023u);
+    dz = ngi_dither1(d.z, (h >> 20) & 1023u);
+}
+
+// ---- surface reconstruction of a hit, rt.hpp:2190-2233 ------------------------------------------
+NGI_HD int ngi_reconstruct(const NgiDevScene& sc, const unsigned tri, const float u, const float v, NgiGeom& g) {
+    const float4* r = sc.shade_tris + 5 * (size_t)tri;
+    const float4 r0 = ngi_ldg(r), r1 = ngi_ldg(r + 1), r2 = ngi_ldg(r + 2), r3 = ngi_ldg(r + 3), r4 = ngi_ldg(r + 4);
+    const f3 p1 = mk3(r0.x, r0.y, r0.z), p2 = mk3(r0.w, r1.x, r1.y), p3 = mk3(r1.z, r1.w, r2.x);
+    const f3 n1 = mk3(r2.y, r2.z, r2.w), n2 = mk3(r3.x, r3.y, r3.z), n3 = mk3(r3.w, r4.x, r4.y);
+    g.gn = normalize(cross(p2 - p1, p3 - p1));                                                // :2206
+    const float w = 1.0f - u - v;                                                             // (1.0f - u - v) in float, :2212
+    g.sn = normalize(n1 * w + n2 * u + n3 * v);
+    if (g.sn.x != g.sn.x || g.sn.y != g.sn.y || g.sn.z != g.sn.z) g.sn = g.gn;               // NaN fallback, :2213-2218
+    ngi_tangent_space(g);                                                                     // :2233
+    return (int)f2u(r4.z);
+}
+
+// ---- the logic stage for one slot --------------------------------------------------------------
+NGI_HD_NOINLINE void ngi_logic_step(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
+    const float4 di = wp.dir_info[slot];
+    const unsigned info = f2u(di.w);
+    const NgiDevSensor& E = sc.sensor;
+
+    f3 thr = mk3(1.0f);
+    int pixel = -1;
+    unsigned long long sample = 0;
+    int nverts = 1;
+    int type = NGI_E;
+    NgiGeom g; g.sn = g.gn = g.dpdu = g.dpdv = mk3(0.0f);
+    f3 wi = mk3(0.0f);
+    double px = 0, py = 0, pz = 0;
+    int primIdx = -1;
+    bool have_vertex = false;
+
+    if (info & NGI_INFO_ALIVE) {
+        const float4 h = wp.hit[slot];
+        const unsigned tri = f2u(h.w);
+        if (tri != NGI_MISS) {                                                                // miss -> break, nanogi.cpp:557 / :767
+            const f3 d = mk3(di.x, di.y, di.z);
+            const float4 tp = wp.thr_pix[slot];
+            thr = mk3(tp.x, tp.y, tp.z);
+            pixel = (int)f2u(tp.w);
+            // isect.geom.p = ray.o + ray.d * (double)tfar, rt.hpp:2197. In the reference ray.d is the fp64
+            // direction whose fp32 ROUNDING was traced (rt.hpp:2169-2171): the reconstructed point is off the
+            // traced ray by (d64 - d32) * t, which together with the absolute 1e-4 epsilon decides how often
+            // the next ray re-hits its own surface (measured on the Cornell box: 5.3 % of bounce rays with
+            // that term, 5.0 % without). The device direction only exists in fp32, so the rounding residual
+            // is re-created as a uniform +-ulp/2 dither hashed from the hit record (tests/test_sim_parity.py).
+            double ddx, ddy, ddz;
+            ngi_dither_direction(d, h, ddx, ddy, ddz);
+            px = wp.px[slot] + ddx * (double)h.x;
+            py = wp.py[slot] + ddy * (double)h.x;
+            pz = wp.pz[slot] + ddz * (double)h.x;
+            primIdx = ngi_reconstruct(sc, tri, h.y, h.z, g);
+            const NgiDevPrim& P = sc.prims[primIdx];
+            if (wp.renderer == 0 && (P.type & NGI_L) && P.l_type == NGI_LT_AREA) {            // nanogi.cpp:566-577
+                // EvaluateDirection(L.area): Le iff cos_sn(-d) > 0 (rt.hpp:922-927); EvaluatePosition(area) = 1
+                if (dot(g.sn, -d) > 0.0f) ngi_film_add(wp.film, pixel, thr * P.l_le * wp.film_scale);
+            }
+            if (info & NGI_INFO_RR_SURVIVE) {                                                 // nanogi.cpp:581-591
+                nverts = (int)(info >> 8) + 1;                                                // :603
+                if (!(wp.max_verts != -1 && nverts >= wp.max_verts)) {                        // :485 / :647
+                    thr = thr * 2.0f;                                                         // throughput /= rrProb
+                    type = P.type & ~NGI_EMITTER;                                             // :601
+                    wi = -d;                                                                  // :602
+                    sample = wp.sample[slot];
+                    have_vertex = true;
+                }
+            }
+        }
+    }
+
+    for (int pass = 0; pass < 2; pass++) {
+        if (!have_vertex) {
+            // the slot's path ended: start the next sample at the eye vertex (nanogi.cpp:450-479 / :613-641)
+            sample = ngi_fetch_sample(wp.next_sample);
+            if (sample >= wp.sample_end) break;
+            thr = mk3(1.0f);       // EvaluatePosition / pdfPE / pdfE = 1 for the pinhole
+            nverts = 1; type = NGI_E; pixel = -1;
+            px = E.px; py = E.py; pz = E.pz;
+            primIdx = E.prim;
+        }
+        const unsigned vtx = (unsigned)(nverts - 1);
+        const bool eye = (type == NGI_E);
+        const NgiDevPrim& P = sc.prims[primIdx];
+
+        // ---- direct light sampling (ptdirect), nanogi.cpp:654-712 ----
+        if (wp.renderer == 1 && sc.n_lights > 0) {
+            unsigned rb[4];
+            philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), vtx, 1u, wp.seed_lo, wp.seed_hi, rb);
+            const NgiLightSample ls = ngi_sample_light(sc, u01(rb[0]), u01(rb[1]), u01(rb[2]));
+            if (ls.valid) {
+                const f3 diff = mk3((float)((double)ls.p.x - px), (float)((double)ls.p.y - py), (float)((double)ls.p.z - pz));
+                const float dist2 = dot(diff, diff);
+                const float dist = sqrtf(dist2);
+                const f3 ppL = diff / dist;                                                   // :680
+                f3 fsE; int index = pixel;
+                float g1 = 1.0f;
+                if (eye) {
+                    float rx = 0.0f, ry = 0.0f;
+                    const float we = ngi_pinhole_importance(E, ppL, rx, ry);                  // :681 (type E)
+                    fsE = mk3(we);
+                    index = ngi_pixel_index(rx, ry, wp.width, wp.height);                     // :698-703
+                } else {
+                    float pdfUnused;
+                    fsE = ngi_eval_bsdf(P, type, g, wi, ppL, false, pdfUnused);               // :681
+                    g1 = fabsf(dot(g.sn, ppL));                                               // GeometryTerm, rt.hpp:2371
+                }
+                f3 fsL = ls.le;                                                               // :682
+                float g2 = 1.0f;
+                if (!ls.degenerate) {
+                    const float cl = dot(ls.n, -ppL);
+                    if (cl <= 0.0f) fsL = mk3(0.0f);                                          // rt.hpp:922-927
+                    g2 = fabsf(cl);                                                           // rt.hpp:2372
+                }
+                const float G = g1 * g2 / dist2;                                              // :683
+                const f3 C = thr * fsE * fsL * (G / ls.pdf);                                  // :686 (V applied by the shadow kernel)
+                if (!is_zero(C)) {
+                    const f3 o = mk3((float)px, (float)py, (float)pz);                        // rt.hpp:2166-2168
+                    ngi_push_shadow(wp, o, ppL, dist * (1.0f - NGI_EPS_F), C * wp.film_scale, index);         // rt.hpp:2260
+                }
+            }
+        }
+
+        // ---- sample the next direction, nanogi.cpp:492-544 / :716-754 ----
+        unsigned ra[4];
+        philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), vtx, 0u, wp.seed_lo, wp.seed_hi, ra);
+        f3 wo;
+        bool ok;
+        if (eye) {
+            wo = ngi_pinhole_sample(E, u01(ra[0]), u01(ra[1]));
+            float rx, ry, ct;
+            ok = ngi_raster_position(E, wo, rx, ry, ct);                                      // :504-523 / :728-733
+            if (ok) pixel = ngi_pixel_index(rx, ry, wp.width, wp.height);
+            // fs / pdfD = We / pdf = 1 exactly (same expression on both sides)
+        } else {
+            ok = ngi_sample_bsdf(P, type, g, wi, u01(ra[0]), u01(ra[1]), u01(ra[2]), wo);
+            if (ok) {
+                float pdfD;
+                const f3 fs = ngi_eval_bsdf(P, type, g, wi, wo, true, pdfD);                  // :531 / :741
+                if (is_zero(fs)) ok = false;                                                  // :532 / :742
+                else thr = thr * (fs / pdfD);                                                 // :544 / :754
+            }
+        }
+        if (ok) {
+            const unsigned survive = (u01(ra[3]) > 0.5f) ? 0u : NGI_INFO_RR_SURVIVE;          // :583-587, decided up front
+            wp.sample[slot] = sample;
+            wp.thr_pix[slot] = make_float4(thr.x, thr.y, thr.z, u2f((unsigned)pixel));
+            wp.px[slot] = px; wp.py[slot] = py; wp.pz[slot] = pz;
+            wp.dir_info[slot] = make_float4(wo.x, wo.y, wo.z, u2f(NGI_INFO_ALIVE | survive | ((unsigned)nverts << 8)));
+            (void)ngi_queue_alloc(wp.iter_counters + 1);                                      // exact extend-ray count
+            return;
+        }
+        have_vertex = false;  // path ended at this vertex; the slot restarts with a fresh sample
+    }
+    wp.dir_info[slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));                               // idle slot
+}
+
+// ---- extend / shadow bodies (BVH8 = product path) -----------------------------------------------
+NGI_HD void ngi_extend_step(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
+    const float4 di = wp.dir_info[slot];
+    if (!(f2u(di.w) & NGI_INFO_ALIVE)) return;
+    const f3 o = mk3((float)wp.px[slot], (float)wp.py[slot], (float)wp.pz[slot]);             // rt.hpp:2166-2168
+    NgiHitRec h;
+    ngi_trace_bvh8<false>(sc.nodes8, sc.tris8, o, mk3(di.x, di.y, di.z), NGI_EPS_F, NGI_INF_F, h);   // rt.hpp:2246-2249
+    wp.hit[slot] = make_float4(h.t, h.u, h.v, u2f(h.tri));
+}
+NGI_HD void ngi_shadow_step(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned e) {
+    const float4* q = wp.shadow_q + 3 * (size_t)e;
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+    NgiHitRec h;
+    const bool occluded = ngi_trace_bvh8<true>(sc.nodes8, sc.tris8, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), NGI_EPS_F, q0.w, h);
+    if (!occluded) ngi_film_add(wp.film, (int)f2u(q1.w), mk3(q2.x, q2.y, q2.z));             // nanogi.cpp:706
+}

@@ -277,13 +277,15 @@ def furnace(rho: float = 0.5, le: float = 1.0) -> Spec:
 
 
 def light_over_plane(le: float = 5.0, height: float = 1.0, half: float = 0.5, rho: float = 0.8) -> Spec:
-    """One square light (side 2*half, facing down) at y = height over a large diffuse floor; camera looks down at it."""
+    """One square light (side 2*half, facing down) at y = height over a large diffuse floor. A narrow-fov camera
+    below the light looks at the floor point under the light's centre, where the radiance with -m 3 is
+    rho * Le * F,  F = 4/pi * X * atan(X),  X = half / sqrt(half^2 + height^2)  (parallel-square form factor)."""
     light = [[[half, height, -half], [half, height, half], [-half, height, half], [-half, height, -half]]]
     floor = [[[-20, 0, -20], [-20, 0, 20], [20, 0, 20], [20, 0, -20]]]
     return [
         mesh_prim(["L", "D"], quads_to_tris(light), name="light", L={"type": "area", "Le": [le] * 3}, D={"R": [0, 0, 0]}),
         mesh_prim(["D"], quads_to_tris(floor), name="floor", D={"R": [rho] * 3}),
-        pinhole(eye=[0, 3.0, 0.0], center=[0, 0, 0], up=[0, 0, -1], fov_deg=40),
+        pinhole(eye=[2.0, 0.8 * height, 0.0], center=[0, 0, 0], up=[0, 1, 0], fov_deg=2),
     ]
 
 

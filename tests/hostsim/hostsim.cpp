@@ -1,0 +1,220 @@
+// hostsim.cpp — TEST-ONLY single-threaded simulator of the device code.
+//
+// This container has no GPU, so the per-item bodies of every CUDA kernel (nanogi_b200/csrc/ngi_*.h, all
+// `__host__ __device__`) are also compiled here with g++ and driven by plain loops in the order the
+// kernels run. It lets `-m "not gpu"` tests check the device algorithms (LBVH build, BVH8 collapse and
+// traversal, fp32 shading, wavefront logic, Philox streams) against the oracle before any GPU time is
+// spent. It is NOT part of the product and is NOT a CPU fallback: libnanogi_gpu.so never links it and
+// nothing outside tests/ loads it. Compile with -ffp-contract=off (see tests/hostsim/Makefile).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../nanogi_b200/csrc/ngi_build.h"
+#include "../../nanogi_b200/csrc/ngi_bvh.h"
+#include "../../nanogi_b200/csrc/ngi_scene_host.h"
+#include "../../nanogi_b200/csrc/ngi_wave.h"
+
+namespace {
+
+struct SimScene {
+    NgiHostArrays ha;
+    unsigned n = 0;  // padded triangle count
+    std::vector<float4> rec_in, lo, hi;        // input order records, node boxes [2n-1]
+    std::vector<float4> tris2, nodes2, tris8;
+    std::vector<uint4> nodes8;
+    std::vector<int> left, right;
+    std::vector<uint2> range;
+    unsigned n_nodes8 = 0, depth8 = 0;
+    float smin[3], smax[3], pad = 0;
+    NgiDevScene dev;
+};
+
+thread_local std::string g_err;
+
+void refit(SimScene& s, int node) {
+    // iterative post-order over inner nodes
+    const int n = (int)s.n;
+    std::vector<int> order; order.reserve(n);
+    std::vector<int> st{node};
+    while (!st.empty()) {
+        int c = st.back(); st.pop_back();
+        if (c >= n - 1) continue;
+        order.push_back(c);
+        st.push_back(s.left[c]); st.push_back(s.right[c]);
+    }
+    for (auto it = order.rbegin(); it != order.rend(); ++it) {
+        const int c = *it, l = s.left[c], r = s.right[c];
+        s.lo[c] = make_float4(fminf(s.lo[l].x, s.lo[r].x), fminf(s.lo[l].y, s.lo[r].y), fminf(s.lo[l].z, s.lo[r].z), 0);
+        s.hi[c] = make_float4(fmaxf(s.hi[l].x, s.hi[r].x), fmaxf(s.hi[l].y, s.hi[r].y), fmaxf(s.hi[l].z, s.hi[r].z), 0);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) const char* sim_last_error() { return g_err.c_str(); }
+
+__attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc* desc) {
+    SimScene* s = new SimScene;
+    if (!ngi_prepare_scene(desc, s->ha)) { g_err = s->ha.error; delete s; return nullptr; }
+    const unsigned nr = s->ha.n_real;
+    const unsigned n = nr < 2 ? 2 : nr;
+    s->n = n;
+    for (int k = 0; k < 3; k++) { s->smin[k] = 3.0e38f; s->smax[k] = -3.0e38f; }
+    for (size_t i = 0; i < (size_t)nr * 3; i++)
+        for (int k = 0; k < 3; k++) { s->smin[k] = fminf(s->smin[k], desc->positions[i * 3 + k]); s->smax[k] = fmaxf(s->smax[k], desc->positions[i * 3 + k]); }
+    if (nr == 0) for (int k = 0; k < 3; k++) { s->smin[k] = 0; s->smax[k] = 0; }
+    s->pad = ngi_box_pad(s->smin, s->smax, s->ha.sensor);
+    const f3 anchor = mk3(s->smin[0], s->smin[1], s->smin[2]);
+    s->rec_in.resize((size_t)n * 3);
+    std::vector<float4> tlo(n), thi(n);
+    for (unsigned i = 0; i < n; i++) ngi_tri_setup(desc->positions, i, nr, s->pad, anchor, s->rec_in.data(), tlo.data(), thi.data());
+    // Morton + sort
+    const f3 mmin = mk3(s->smin[0] - s->pad, s->smin[1] - s->pad, s->smin[2] - s->pad);
+    f3 sinv;
+    sinv.x = 1.0f / fmaxf(s->smax[0] - s->smin[0] + 2 * s->pad, 1e-30f);
+    sinv.y = 1.0f / fmaxf(s->smax[1] - s->smin[1] + 2 * s->pad, 1e-30f);
+    sinv.z = 1.0f / fmaxf(s->smax[2] - s->smin[2] + 2 * s->pad, 1e-30f);
+    std::vector<unsigned long long> keys(n);
+    for (unsigned i = 0; i < n; i++) {
+        const f3 c = mk3(0.5f * (tlo[i].x + thi[i].x), 0.5f * (tlo[i].y + thi[i].y), 0.5f * (tlo[i].z + thi[i].z));
+        keys[i] = ngi_morton63(c, mmin, sinv);
+    }
+    std::vector<unsigned> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return keys[a] < keys[b]; });
+    std::vector<unsigned long long> skeys(n);
+    s->tris2.resize((size_t)n * 3);
+    s->lo.resize(2 * (size_t)n - 1); s->hi.resize(2 * (size_t)n - 1);
+    for (unsigned k = 0; k < n; k++) {
+        const unsigned i = order[k];
+        skeys[k] = keys[i];
+        for (int j = 0; j < 3; j++) s->tris2[(size_t)k * 3 + j] = s->rec_in[(size_t)i * 3 + j];
+        s->lo[n - 1 + k] = tlo[i]; s->hi[n - 1 + k] = thi[i];
+    }
+    // Karras
+    s->left.resize(n - 1); s->right.resize(n - 1); s->range.resize(n - 1);
+    for (int i = 0; i < (int)n - 1; i++) {
+        int l, r, f, la;
+        ngi_karras_node(skeys.data(), (int)n, i, l, r, f, la);
+        s->left[i] = l; s->right[i] = r; s->range[i] = make_uint2((unsigned)f, (unsigned)la);
+    }
+    refit(*s, 0);
+    s->nodes2.resize((size_t)(n - 1) * 4);
+    for (int i = 0; i < (int)n - 1; i++) ngi_pack2(s->lo.data(), s->hi.data(), s->left.data(), s->right.data(), (int)n, i, s->nodes2.data());
+    // collapse
+    s->nodes8.assign((size_t)n * 5, make_uint4(0, 0, 0, 0));
+    s->tris8.resize((size_t)n * 3);
+    unsigned counters[3] = {1, 0, 0};
+    std::vector<NgiBuildTask> cur{{0, 0u}}, next(n);
+    NgiCollapseCtx c;
+    c.lo = s->lo.data(); c.hi = s->hi.data(); c.left = s->left.data(); c.right = s->right.data(); c.range = s->range.data();
+    c.tris2 = s->tris2.data(); c.n = (int)n; c.nodes8 = s->nodes8.data(); c.tris8 = s->tris8.data(); c.counters = counters;
+    unsigned depth = 0;
+    while (!cur.empty()) {
+        depth++;
+        counters[2] = 0;
+        c.out_tasks = next.data();
+        for (auto& t : cur) ngi_collapse_node(c, t);
+        cur.assign(next.begin(), next.begin() + counters[2]);
+    }
+    s->n_nodes8 = counters[0];
+    s->depth8 = depth;
+    if (counters[1] != n) { g_err = "collapse lost triangles: " + std::to_string(counters[1]) + " of " + std::to_string(n); delete s; return nullptr; }
+    NgiDevScene& d = s->dev;
+    d.nodes8 = s->nodes8.data(); d.tris8 = s->tris8.data(); d.nodes2 = s->nodes2.data(); d.tris2 = s->tris2.data();
+    d.shade_tris = s->ha.shade_tris.data(); d.prims = s->ha.prims.data(); d.light_prims = s->ha.light_prims.data();
+    d.cdf = s->ha.cdf.data(); d.n_tris = n; d.n_lights = (unsigned)s->ha.light_prims.size(); d.sensor = s->ha.sensor;
+    return s;
+}
+
+__attribute__((visibility("default"))) void sim_scene_destroy(void* h) { delete (SimScene*)h; }
+
+// out = {n padded, nodes8, depth8, nodes2, pad}
+__attribute__((visibility("default"))) void sim_scene_info(void* h, double* out) {
+    SimScene* s = (SimScene*)h;
+    out[0] = s->n; out[1] = s->n_nodes8; out[2] = s->depth8; out[3] = s->n - 1; out[4] = s->pad;
+}
+
+__attribute__((visibility("default"))) int sim_trace(void* h, const NgiRay* rays, uint64_t n, NgiHit* hits, int any_hit, int accel) {
+    SimScene* s = (SimScene*)h;
+    for (uint64_t i = 0; i < n; i++) {
+        const NgiRay& r = rays[i];
+        const f3 o = mk3(r.o[0], r.o[1], r.o[2]), d = mk3(r.d[0], r.d[1], r.d[2]);
+        NgiHitRec hr; bool hit;
+        if (accel == 0) hit = any_hit ? ngi_trace_bvh8<true>(s->dev.nodes8, s->dev.tris8, o, d, r.tmin, r.tmax, hr) : ngi_trace_bvh8<false>(s->dev.nodes8, s->dev.tris8, o, d, r.tmin, r.tmax, hr);
+        else if (accel == 1) hit = any_hit ? ngi_trace_bvh2<true>(s->dev.nodes2, s->dev.tris2, o, d, r.tmin, r.tmax, hr) : ngi_trace_bvh2<false>(s->dev.nodes2, s->dev.tris2, o, d, r.tmin, r.tmax, hr);
+        else hit = any_hit ? ngi_trace_brute<true>(s->dev.tris2, s->n, o, d, r.tmin, r.tmax, hr) : ngi_trace_brute<false>(s->dev.tris2, s->n, o, d, r.tmin, r.tmax, hr);
+        NgiHit out; out.t = hit ? hr.t : 0.0f; out.u = hit ? hr.u : 0.0f; out.v = hit ? hr.v : 0.0f;
+        out.tri = hit ? (any_hit ? 0u : hr.tri) : NGI_NO_HIT;
+        hits[i] = out;
+    }
+    return 0;
+}
+
+// the wavefront loop, kernels run in the order k_iter_begin, k_logic, k_extend, k_shadow
+// stats = {paths, extend rays, shadow rays, iterations}
+__attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderParams* rp, float* film, double* stats) {
+    SimScene* s = (SimScene*)h;
+    const size_t npx = (size_t)rp->width * rp->height;
+    std::fill(film, film + npx * 3, 0.0f);
+    if (stats) std::fill(stats, stats + 4, 0.0);
+    if (rp->max_num_vertices != -1 && rp->max_num_vertices < 2) return 0;
+    const unsigned P = rp->wave_capacity ? rp->wave_capacity : 4096;
+    std::vector<unsigned long long> sample(P);
+    std::vector<float4> thr_pix(P), dir_info(P, make_float4(0, 0, 0, 0)), hit(P), shadow_q((size_t)P * 2 * 3);
+    std::vector<double> px(P), py(P), pz(P);
+    unsigned iter_counters[2] = {0, 0};
+    unsigned long long next_sample = (unsigned long long)rp->sample_offset;
+    NgiWaveParams wp;
+    wp.sample = sample.data(); wp.thr_pix = thr_pix.data(); wp.px = px.data(); wp.py = py.data(); wp.pz = pz.data();
+    wp.dir_info = dir_info.data(); wp.hit = hit.data(); wp.shadow_q = shadow_q.data(); wp.iter_counters = iter_counters;
+    wp.next_sample = &next_sample; wp.film = film; wp.capacity = P; wp.renderer = rp->renderer; wp.max_verts = rp->max_num_vertices;
+    wp.width = rp->width; wp.height = rp->height; wp.sample_end = (unsigned long long)(rp->sample_offset + rp->num_samples);
+    wp.seed_lo = (unsigned)rp->seed; wp.seed_hi = (unsigned)(rp->seed >> 32);
+    wp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
+    unsigned long long extend = 0, shadow = 0, iters = 0;
+    while (true) {
+        iter_counters[0] = iter_counters[1] = 0;
+        for (unsigned i = 0; i < P; i++) ngi_logic_step(s->dev, wp, i);
+        extend += iter_counters[1]; shadow += iter_counters[0];
+        iters++;
+        if (iter_counters[1] == 0 && iter_counters[0] == 0 && next_sample >= wp.sample_end) break;
+        for (unsigned i = 0; i < P; i++) ngi_extend_step(s->dev, wp, i);
+        for (unsigned e = 0; e < iter_counters[0]; e++) ngi_shadow_step(s->dev, wp, e);
+    }
+    if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)extend; stats[2] = (double)shadow; stats[3] = (double)iters; }
+    return 0;
+}
+
+// same contract as ngi_gpu_eval_bsdf
+__attribute__((visibility("default"))) int sim_eval_bsdf(void* h, const float* q, const float* wo_in, uint64_t n, int force_degenerated, float* out) {
+    SimScene* s = (SimScene*)h;
+    for (uint64_t i = 0; i < n; i++) {
+        const float* a = q + 16 * i;
+        const NgiDevPrim& P = s->dev.prims[(int)a[0]];
+        const int type = (int)a[1];
+        NgiGeom g; g.sn = mk3(a[2], a[3], a[4]); g.gn = mk3(a[5], a[6], a[7]);
+        ngi_tangent_space(g);
+        const f3 wi = mk3(a[8], a[9], a[10]);
+        f3 wo = mk3(0.0f); bool valid = true;
+        if (a[14] != 0.0f) wo = mk3(wo_in[3 * i], wo_in[3 * i + 1], wo_in[3 * i + 2]);
+        else valid = ngi_sample_bsdf(P, type, g, wi, a[11], a[12], a[13], wo);
+        float pdf = 0; f3 fs = mk3(0.0f);
+        if (valid) fs = ngi_eval_bsdf(P, type, g, wi, wo, force_degenerated != 0, pdf);
+        float* o = out + 8 * i;
+        o[0] = wo.x; o[1] = wo.y; o[2] = wo.z; o[3] = fs.x; o[4] = fs.y; o[5] = fs.z; o[6] = pdf; o[7] = valid ? 1.0f : 0.0f;
+    }
+    return 0;
+}
+
+__attribute__((visibility("default"))) void sim_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}
+
+}  // extern "C"

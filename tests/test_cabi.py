@@ -1,0 +1,70 @@
+"""The C-ABI libraries load and export every symbol the headers declare (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from nanogi_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(r"NGI_API\s+[\w\s\*]+?\b(ngi_\w+)\s*\(", text)))
+
+
+def test_host_library_exports_header_symbols():
+    names = _declared("nanogi_host.h")
+    assert sorted(names) == sorted(capi.HOST_SYMBOLS)
+    lib = ctypes.CDLL(capi.HOST_LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_gpu_library_exports_header_symbols():
+    names = _declared("nanogi_gpu.h")
+    assert sorted(names) == sorted(capi.GPU_SYMBOLS)
+    if not os.path.exists(capi.GPU_LIB_PATH):
+        pytest.skip("libnanogi_gpu.so not built yet (needs nvcc): run __graft_entry__.build()")
+    lib = ctypes.CDLL(capi.GPU_LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.ngi_gpu_abi_version.restype = ctypes.c_int
+    assert lib.ngi_gpu_abi_version() == 1
+
+
+def test_struct_sizes_match_the_header():
+    """ctypes mirrors vs the C compiler's layout (sizes printed by a tiny C program)."""
+    import subprocess, tempfile
+    src = r'''
+#include <stdio.h>
+#include "nanogi_gpu.h"
+#include "nanogi_host.h"
+int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(NgiPrimitive), sizeof(NgiSceneDesc), sizeof(NgiRenderParams),
+  sizeof(NgiRenderStats), sizeof(NgiSceneInfo), sizeof(NgiRay), sizeof(NgiHit), sizeof(NgiCliOptions)); return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    expect = [ctypes.sizeof(t) for t in (capi.NgiPrimitive, capi.NgiSceneDesc, capi.NgiRenderParams, capi.NgiRenderStats, capi.NgiSceneInfo)]
+    assert sizes[:5] == expect
+    assert sizes[5] == capi.RAY_DTYPE.itemsize and sizes[6] == capi.HIT_DTYPE.itemsize and sizes[7] == ctypes.sizeof(capi.NgiCliOptions)
+
+
+def test_gpu_path_fails_loudly_without_a_device():
+    """No CPU fallback: without a CUDA device scene_create returns NGI_ERR_NO_DEVICE."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    if not os.path.exists(capi.GPU_LIB_PATH):
+        pytest.skip("libnanogi_gpu.so not built")
+    from nanogi_b200 import scenes
+    sd = scenes.to_scene_data(scenes.cornell_box(), 1.0)
+    with pytest.raises(capi.NgiError, match="no CUDA device"):
+        capi.GpuScene(sd, 0)
+    assert capi.device_count() == -2

@@ -1,0 +1,147 @@
+"""Parity tests proper: libnanogi_gpu.so (CUDA, sm_100a) through the C ABI vs the oracle, on the B200."""
+import numpy as np
+import pytest
+
+from nanogi_b200 import capi, scenes
+from oracle import pyoracle
+from tests import parity_common as pc
+from tests.conftest import scaled_spec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu_cornell(cornell):
+    s = capi.GpuScene(cornell, 0)
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def gpu_c2(cornell_spheres):
+    s = capi.GpuScene(cornell_spheres, 0)
+    yield s
+    s.close()
+
+
+def test_extension_is_loaded_and_device_present():
+    assert capi.device_count() >= 1
+    import ctypes
+    assert ctypes.CDLL(capi.GPU_LIB_PATH).ngi_gpu_abi_version() == 1
+
+
+@pytest.mark.parametrize("name", ["cornell", "cornell_spheres", "furnace"])
+def test_trace_bit_exact(name, request):
+    sd = request.getfixturevalue(name)
+    g = capi.GpuScene(sd, 0)
+    pc.check_trace_bit_exact(g, sd, n_random=200000, cam=256)
+    pc.check_trace_edge_cases(g, sd)
+    info = g.info()
+    assert info.num_tris == sd.num_tris and info.bvh8_nodes >= 1 and info.bvh8_max_depth <= 40
+    g.close()
+
+
+def test_trace_bit_exact_100k_triangles():
+    """GPU LBVH + BVH8 on a ~123k-triangle mesh scene; BVH8 / BVH2 vs the oracle's SAH BVH, plus GPU brute force on a subset."""
+    sd = scenes.to_scene_data(scenes.instanced_spheres(seed=1, subdiv=4, grid=(3, 2, 4)), 16 / 9)
+    g = capi.GpuScene(sd, 0)
+    pc.check_trace_bit_exact(g, sd, n_random=300000, cam=384, accels=(0, 1))
+    rays = scenes.random_rays(sd, 4096, 21)
+    assert np.array_equal(g.trace(rays, False, 0), g.trace(rays, False, 2))
+    g.close()
+
+
+def test_degenerate_scenes():
+    cam = scenes.pinhole(eye=[0, 0, 5], center=[0, 0, 0], up=[0, 1, 0], fov_deg=40)
+    tri = np.array([[[-1, -1, 0], [1, -1, 0], [0, 1, 0]]], dtype=np.float64)
+    light = scenes.mesh_prim(["L", "D"], tri, name="l", L={"type": "area", "Le": [1, 1, 1]}, D={"R": [0, 0, 0]})
+    for spec in ([light, cam], [scenes.mesh_prim(["D"], np.repeat(tri, 9, axis=0), name="dup", D={"R": [1, 1, 1]}), light, cam]):
+        sd = scenes.to_scene_data(spec, 1.0)
+        g = capi.GpuScene(sd, 0)
+        pc.check_trace_bit_exact(g, sd, n_random=5000, cam=32)
+        g.close()
+    pt_light = {"type": ["L"], "mesh": None, "params": {"L": {"type": "point", "Le": [1, 1, 1], "position": [0, 1, 0]}}}
+    sd = scenes.to_scene_data([pt_light, cam], 1.0)
+    g = capi.GpuScene(sd, 0)
+    assert (g.trace(scenes.camera_rays(sd, 8, 8))["tri"] == capi.NO_HIT).all()
+    film, st = g.render("ptdirect", 1000, 8, 8, seed=1)
+    assert st.extend_rays == 1000 and np.isfinite(film).all()
+    g.close()
+
+
+@pytest.mark.parametrize("prim,type_bit", [(4, capi.TYPE_D), (8, capi.TYPE_G), (9, capi.TYPE_S)])
+def test_bsdf_parity(gpu_c2, cornell_spheres, prim, type_bit):
+    pc.check_bsdf_parity(gpu_c2, cornell_spheres, prim, type_bit, n=3000)
+
+
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect"])
+@pytest.mark.parametrize("m", [-1, 3])
+def test_replay_small_scale(renderer, m):
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_spheres(), 0.01), 1.0)
+    g = capi.GpuScene(sd, 0)
+    pc.check_replay(g, sd, renderer, n=200000, w=96, h=96, m=m)
+    g.close()
+
+
+def test_gpu_equals_simulator_sample_for_sample(cornell):
+    """The CUDA kernels and the CPU-stepped device code are the same program: identical ray counts, films equal to fp32 sum order."""
+    from tests.hostsim import pysim
+    g = capi.GpuScene(cornell, 0)
+    sim = pysim.SimScene(cornell)
+    for renderer in ("pt", "ptdirect"):
+        fg, sg = g.render(renderer, 30000, 32, 32, seed=12, max_num_vertices=8)
+        fs, ss = sim.render(renderer, 30000, 32, 32, seed=12, max_num_vertices=8)
+        assert sg.extend_rays == ss["extend_rays"] and sg.shadow_rays == ss["shadow_rays"]
+        assert np.allclose(fg, fs, rtol=2e-3, atol=1e-5 * fs.max())
+    g.close()
+
+
+@pytest.mark.parametrize("renderer,m,expect", [("pt", -1, 2.0), ("pt", 2, 1.0), ("pt", 4, 1.75), ("ptdirect", 3, 1.5), ("ptdirect", -1, 2.0)])
+def test_furnace(renderer, m, expect):
+    pc.check_furnace(lambda sd: capi.GpuScene(sd, 0), renderer, m, expect, n=1 << 22, tol=0.004 if renderer == "pt" else 0.02)
+
+
+def test_self_intersection_rate_matches_reference_arithmetic():
+    sd = scenes.to_scene_data(scaled_spec(scenes.furnace(0.5, 1.0), 250.0, 500.0), 1.0)
+    orc, g = pyoracle.OracleScene(sd), capi.GpuScene(sd, 0)
+    fo, _ = orc.render("pt", 1 << 22, 8, 8, max_num_vertices=3, seed=1)
+    fg, _ = g.render("pt", 1 << 24, 8, 8, max_num_vertices=3, seed=2)
+    a_o, a_g = (1.5 - fo.mean()) * 2, (1.5 - float(fg.mean())) * 2
+    assert abs(a_g - a_o) < 0.001, (a_g, a_o)
+    g.close()
+
+
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect"])
+def test_image_statistics_cornell_c1(gpu_cornell, cornell, renderer):
+    """C1 (Cornell box, -m 8): K = 8 seeds per side, 64 spp as in BASELINE config 0 at 64x64."""
+    pc.check_image_statistics(gpu_cornell, cornell, renderer, w=64, h=64, spp=64, seeds=8, m=8, block=16)
+
+
+def test_image_statistics_c2(gpu_c2, cornell_spheres):
+    pc.check_image_statistics(gpu_c2, cornell_spheres, "ptdirect", w=64, h=64, spp=128, seeds=8, m=-1, block=16)
+
+
+def test_sharding_and_wave_capacity(gpu_cornell):
+    pc.check_sharding(gpu_cornell)
+    a, sa = gpu_cornell.render("ptdirect", 100000, 32, 32, seed=4, wave_capacity=4096)
+    b, sb = gpu_cornell.render("ptdirect", 100000, 32, 32, seed=4, wave_capacity=1 << 20)
+    assert sa.extend_rays == sb.extend_rays and sa.shadow_rays == sb.shadow_rays
+    assert np.allclose(a, b, rtol=1e-3, atol=1e-5 * a.max())
+
+
+def test_timed_and_graph_paths_agree(gpu_cornell):
+    a, sa = gpu_cornell.render("ptdirect", 300000, 32, 32, seed=8)
+    b, sb = gpu_cornell.render("ptdirect", 300000, 32, 32, seed=8, flags=1)
+    assert sa.extend_rays == sb.extend_rays and sb.trace_kernel_seconds > 0 and sa.trace_kernel_seconds == 0
+    assert np.allclose(a, b, rtol=1e-3, atol=1e-5 * a.max())
+
+
+def test_error_paths(gpu_cornell):
+    with pytest.raises(capi.NgiError, match="not supported"):
+        gpu_cornell.render(2, 10, 4, 4)           # lt is not on the GPU path
+    with pytest.raises(capi.NgiError):
+        gpu_cornell.render("pt", 10, 0, 4)
+    film, st = gpu_cornell.render("pt", 0, 4, 4)
+    assert np.all(film == 0)
+    film, st = gpu_cornell.render("pt", 1000, 4, 4, max_num_vertices=1)   # loop exits before any ray (src/nanogi.cpp:485)
+    assert np.all(film == 0) and st.extend_rays == 0

@@ -1,0 +1,162 @@
+"""Host front end (C++): YAML subset, OBJ loader, Scene::Load mirror, CLI parser, film writers."""
+import math
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from nanogi_b200 import capi, scenes
+from tests.conftest import REFERENCE
+
+os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+
+
+def test_cli_defaults_match_reference_table():
+    o = capi.parse_cli(["nanogi", "pt", "scene.yml"])
+    # reference src/nanogi.cpp:2003-2019
+    assert o.renderer == b"pt" and o.scene == b"scene.yml" and o.result == b"render.hdr"
+    assert o.num_samples == 10000000 and o.max_num_vertices == -1 and o.width == 1280 and o.height == 720
+    assert o.grain_size == 10000 and o.progress_update_interval == 100000 and o.render_time == -1
+    assert o.progress_image_update_interval == -1 and o.progress_image_update_format == b"progress/{{count}}.png"
+    assert o.has_num_threads == 0 and o.gpus == 1
+
+
+def test_cli_positional_and_short_options():
+    o = capi.parse_cli(["nanogi", "ptdirect", "s.yml", "out.exr", "1920", "1080", "-n", "2123366400", "-m", "8", "-j", "-1"])
+    assert (o.renderer, o.scene, o.result, o.width, o.height) == (b"ptdirect", b"s.yml", b"out.exr", 1920, 1080)
+    assert o.num_samples == 2123366400 and o.max_num_vertices == 8 and o.num_threads == -1 and o.has_num_threads
+    # -h is --height (help is --help only), long options with '='
+    o = capi.parse_cli(["nanogi", "-r", "pt", "-i", "a.yml", "-o", "b.png", "-w", "64", "-h", "32", "--num-samples=5", "--gpus", "8", "--seed", "42"])
+    assert (o.width, o.height, o.num_samples, o.gpus, o.seed, o.has_seed) == (64, 32, 5, 8, 42, 1)
+    assert capi.parse_cli(["nanogi"]).help == 1 and capi.parse_cli(["nanogi", "--help"]).help == 1
+    with pytest.raises(capi.NgiError, match="renderer"):
+        capi.parse_cli(["nanogi", "-n", "10"])
+    with pytest.raises(capi.NgiError, match="unrecognised"):
+        capi.parse_cli(["nanogi", "pt", "--bogus", "1"])
+    with pytest.raises(capi.NgiError, match="invalid"):
+        capi.parse_cli(["nanogi", "pt", "s.yml", "o.hdr", "abc"])
+
+
+def test_scene_files_round_trip(tmp_path):
+    spec = scenes.cornell_spheres()
+    path = scenes.write_scene_files(spec, str(tmp_path))
+    sd_file = capi.load_scene_file(path, 1.5)
+    sd_mem = scenes.to_scene_data(spec, 1.5)
+    assert sd_file.num_tris == sd_mem.num_tris == 38 + 2 * 1280
+    assert np.array_equal(sd_file.positions, sd_mem.positions)
+    assert np.allclose(sd_file.normals, sd_mem.normals, atol=1e-6)
+    assert len(sd_file.prims) == len(sd_mem.prims)
+    for a, b in zip(sd_file.prims, sd_mem.prims):
+        for f, _ in capi.NgiPrimitive._fields_:
+            va, vb = getattr(a, f), getattr(b, f)
+            if hasattr(va, "__len__"):
+                assert np.allclose(list(va), list(vb), rtol=1e-12, atol=1e-12), f
+            else:
+                assert va == pytest.approx(vb, rel=1e-12, abs=1e-12), f
+    assert sd_file.sensor_prim() == len(spec) - 1 and sd_file.light_prims() == [0]
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference fixtures only exist in the build container")
+def test_loads_reference_fixtures():
+    sd = capi.load_scene_file(os.path.join(REFERENCE, "utils/runc/data/cornelbox/scene.yml"), 1.0)
+    assert sd.num_tris == 38 and len(sd.prims) == 9                      # 38 triangles after triangulation
+    assert [p.num_tris for p in sd.prims[:8]] == [2, 2, 4, 2, 2, 2, 12, 12]
+    assert sd.prims[0].type == capi.TYPE_L | capi.TYPE_D and list(sd.prims[0].l_le) == [10, 10, 10]
+    cam = sd.prims[8]
+    assert cam.type == capi.TYPE_E and cam.e_type == capi.E_PINHOLE and list(cam.e_position) == [278, 273, -800]
+    assert abs(cam.e_fov - math.radians(39.3077)) < 1e-12 and list(cam.e_vz) == [0, 0, -1]
+    # our generated Cornell box is the same scene (same published data; the fixture carries float noise)
+    gen = scenes.to_scene_data(scenes.cornell_box(), 1.0)
+    assert np.allclose(np.sort(sd.positions.reshape(-1, 3), axis=0), np.sort(gen.positions.reshape(-1, 3), axis=0), atol=2e-3)
+    sd2 = capi.load_scene_file(os.path.join(REFERENCE, "utils/runc/data/scene.yml"), 16 / 9)
+    assert sd2.num_tris == 3 * 1280 + 3 * 2
+    assert [p.type for p in sd2.prims] == [capi.TYPE_L | capi.TYPE_D, capi.TYPE_G, capi.TYPE_D, capi.TYPE_S, capi.TYPE_D, capi.TYPE_D, capi.TYPE_E]
+    assert sd2.prims[1].g_roughness == 0.1 and sd2.prims[3].s_type == capi.S_FRESNEL and sd2.prims[3].s_eta2 == 2
+    n = sd2.normals[sd2.prims[1].first_tri:sd2.prims[1].first_tri + 1280].reshape(-1, 3)
+    assert np.allclose(np.linalg.norm(n, axis=1), 1, atol=1e-3)
+
+
+def test_yaml_and_loader_errors(tmp_path):
+    def write(text, name="scene.yml"):
+        p = tmp_path / name
+        p.write_text(text)
+        return str(p)
+    with pytest.raises(capi.NgiError, match="version"):
+        capi.load_scene_file(write("version: 9\nscene:\n  primitives: []\n"), 1.0)
+    with pytest.raises(capi.NgiError, match="Invalid primitive type"):
+        capi.load_scene_file(write("version: 5\nscene:\n  primitives:\n    - type: [L, E]\n      params: {}\n"), 1.0)
+    with pytest.raises(capi.NgiError):
+        capi.load_scene_file(str(tmp_path / "missing.yml"), 1.0)
+    # mesh without normals and without postprocess: clean error instead of the reference's null dereference (rt.hpp:1688)
+    (tmp_path / "t.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    y = "version: 5\nscene:\n  primitives:\n    - type: [D]\n      mesh:\n        path: t.obj\n      params:\n        D:\n          R: [1, 1, 1]\n"
+    with pytest.raises(capi.NgiError, match="no normals"):
+        capi.load_scene_file(write(y), 1.0)
+    y2 = y.replace("        path: t.obj\n", "        path: t.obj\n        postprocess:\n          generate_normals: true\n          generate_smooth_normals: false\n")
+    y2 += "    - type: [E]\n      params:\n        E:\n          type: pinhole\n          pinhole:\n            We: [1,1,1]\n            view: {eye: [0,0,3], center: [0,0,0], up: [0,1,0]}\n            perspective:\n              fov: 45\n"
+    sd = capi.load_scene_file(write(y2), 2.0)
+    assert sd.num_tris == 1 and np.allclose(sd.normals[0], [[0, 0, 1]] * 3) and sd.prims[1].e_aspect == 2.0
+
+
+def test_obj_features(tmp_path):
+    (tmp_path / "m.obj").write_text(
+        "# quad + negative indices + vt\no first\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+        "f 1/1/1 2/2/1 3/3/1 4/4/1\nf -4/-4/-1 -3/-3/-1 -2/-2/-1\no second\nv 5 5 5\nv 6 5 5\nv 5 6 5\nf 5//1 6//1 7//1\n")
+    y = ("version: 4\nscene:\n  primitives:\n    - type: [D]\n      mesh:\n        path: 'm.obj'\n      params:\n        D:\n          R: [0.5, 0.5, 0.5]\n"
+         "    - type: [E]\n      params:\n        E:\n          type: pinhole\n          pinhole:\n            We: [1, 1, 1]\n            view:\n"
+         "              eye: [0, 0, 3]\n              center: [0, 0, 0]\n              up: [0, 1, 0]\n            perspective:\n              fov: 45\n")
+    (tmp_path / "scene.yml").write_text(y)
+    sd = capi.load_scene_file(str(tmp_path / "scene.yml"), 1.0)
+    assert sd.num_tris == 3                                # quad -> fan (0,1,2),(0,2,3) + one triangle; 2nd object ignored (mMeshes[0])
+    assert np.array_equal(sd.positions[1], [[0, 0, 0], [1, 1, 0], [0, 1, 0]])
+    assert sd.texcoords is not None and np.array_equal(sd.texcoords[0], [[0, 0], [1, 0], [1, 1]])
+
+
+def _ramp(w, h):
+    y, x = np.mgrid[0:h, 0:w]
+    f = np.stack([x / w * 4.0, y / h * 0.5, np.full_like(x, 0.25, dtype=np.float64)], axis=-1).astype(np.float32)
+    f[0, 0] = [100.0, 0.001, 0.0]
+    return f
+
+
+def test_exr_writer(tmp_path):
+    import cv2
+    f = _ramp(37, 21)     # not a multiple of the 16-line ZIP blocks
+    p = str(tmp_path / "out" / "a.exr")
+    capi.save_image(p, f)  # also creates the directory (basic.hpp:510-521)
+    img = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+    assert img is not None and img.shape == (21, 37, 3) and img.dtype == np.float32
+    # cv2 returns BGR, top row first; the film's row 0 is the bottom scanline (basic.hpp:583-589)
+    assert np.array_equal(img[::-1, :, ::-1], f)
+    raw = open(p, "rb").read()
+    assert raw[:4] == bytes([0x76, 0x2F, 0x31, 0x01]) and b"channels\x00chlist\x00" in raw
+    i = raw.index(b"chlist\x00") + 7 + 4
+    assert raw[i:i + 2] == b"B\x00" and struct.unpack("<i", raw[i + 2:i + 6])[0] == 2     # B first, FLOAT
+
+
+def test_hdr_writer(tmp_path):
+    import cv2
+    f = _ramp(32, 16)
+    p = str(tmp_path / "a.hdr")
+    capi.save_image(p, f)
+    img = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+    assert img is not None and img.shape == (16, 32, 3)
+    got = img[::-1, :, ::-1]
+    # RGBE keeps 8 bits of mantissa relative to the pixel's largest channel
+    mx = np.maximum(f.max(axis=2, keepdims=True), 1e-30)
+    assert np.all(np.abs(got - f) <= mx / 128.0 + 1e-6)
+
+
+def test_png_writer(tmp_path):
+    import cv2
+    f = _ramp(20, 10)
+    p = str(tmp_path / "a.png")
+    capi.save_image(p, f)
+    img = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+    assert img.shape == (10, 20, 3) and img.dtype == np.uint8
+    expect = np.clip((np.power(f.astype(np.float64), 1 / 2.2) * 255.0).astype(np.int64), 0, 255).astype(np.uint8)   # basic.hpp:633-646
+    assert np.array_equal(img[::-1, :, ::-1], expect)
+    with pytest.raises(capi.NgiError):
+        capi.save_image(str(tmp_path / "a.bmp"), f)
