@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 `pt` / `ptdirect` path (BASELINE.json metric: Mpaths/s, Mrays/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3] [--impl reference]
+
+Own arm (default)
+  step      one full render of the workload (one pass of the hot path over one batch of samples): at N = 1 the
+            workload is BASELINE.json configs[1] — Cornell box + glossy/glass spheres, `ptdirect`, 1024 x 1024,
+            1024 spp = 2^30 samples, unbounded path length. N > 1: every rank renders 2^30 samples of the SAME
+            image (disjoint Philox sample-index ranges, weak scaling: N * 1024 spp) and the per-rank films are
+            summed by ONE NCCL reduce to rank 0 inside the timed region.
+  value     Mpaths/s of the whole job, device-timed (torch CUDA events on the stream the kernels are launched on),
+            scene + BVH resident in HBM, film left in HBM; max over ranks.
+  e2e       the same metric through the C-ABI call a host application makes, with HOST buffers, every step:
+            ngi_gpu_scene_create (H2D of the flattened scene + GPU BVH build) -> render -> film D2H into pinned
+            host memory -> ngi_gpu_scene_destroy; wall clock around the calls (they synchronise), max over ranks.
+  roofline  dominant kernel (named in the JSON) timed live with CUDA events around every launch
+            (NGI_RENDER_TIME_KERNELS pass on the same stream), algorithmic bytes per ray from SURVEY.md §8(d).
+  cpu_baseline  the CPU oracle (restated nanogi path; the real Embree+TBB binary cannot be built) on all
+            host cores, bounded sample of the same workload; rank 0, N = 1 only.
+Reference arm (`--impl reference`): the oracle on all host threads, same workload/metric, each step a bounded sample.
+
+PyTorch is used for device memory, streams, events and torch.distributed only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mpaths/s (ptdirect; Mrays/s and image checks alongside)"
+
+WORKLOADS = {
+    # name: (scene generator, renderer, W, H, spp, max_num_vertices, description)
+    "c1": ("cornell_box", "pt", 256, 256, 64, 8, "C1 Cornell box (38 tris) pt 256x256 64spp -m 8"),
+    "c2": ("cornell_spheres", "ptdirect", 1024, 1024, 1024, -1,
+           "C2 Cornell box + glossy/glass icospheres (2598 tris) ptdirect 1024x1024 1024spp"),
+    "c3": ("instanced_spheres", "ptdirect", 1920, 1080, 1024, -1,
+           "C3 procedural 1M-triangle instanced spheres, mixed D/G/S, ptdirect 1920x1080 1024spp"),
+}
+
+
+def b_ray(n_tris: int) -> int:
+    """Algorithmic bytes per ray, SURVEY.md §8(d): d*80 + 4*48 + 96 with d = ceil(log8(nTri/4))."""
+    d, cap = 0, 4
+    while cap < n_tris:
+        cap *= 8
+        d += 1
+    return max(d, 1) * 80 + 4 * 48 + 96
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            for key in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+                if key in j:
+                    return float(j[key]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+def build_scene(name: str, aspect: float):
+    from nanogi_b200 import scenes
+    gen = getattr(scenes, WORKLOADS[name][0])
+    return scenes.to_scene_data(gen(), aspect, name=name)
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank: int):
+    """The reference's CPU implementation of the path = the oracle restatement on all host threads (kind 'port')."""
+    if rank != 0:
+        return
+    from oracle import pyoracle
+    gen, renderer, W, H, spp, m, desc = WORKLOADS[args.workload]
+    sd = build_scene(args.workload, W / H)
+    orc = pyoracle.OracleScene(sd)
+    cores = os.cpu_count() or 1
+    # bounded sample: calibrate on 2^18 samples, then size a step to ~ args.cpu_seconds of wall time
+    t0 = time.perf_counter()
+    orc.render(renderer, 1 << 18, W, H, max_num_vertices=m, seed=11)
+    rate = (1 << 18) / (time.perf_counter() - t0)
+    n_step = int(max(1 << 18, min(rate * args.cpu_step_seconds, W * H * spp)))
+    for i in range(args.warmup):
+        orc.render(renderer, n_step, W, H, max_num_vertices=m, seed=100 + i)
+    rays = 0.0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        _, st = orc.render(renderer, n_step, W, H, max_num_vertices=m, seed=200 + i)
+        rays += st["extend_rays"] + st["shadow_rays"]
+    dt = time.perf_counter() - t0
+    v = n_step * args.steps / dt / 1e6
+    sample = f"{n_step} samples/step ({n_step / (W * H):.2f} spp of {spp}) x {args.steps} steps, same scene/resolution/renderer"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "mrays_per_s": rays / dt / 1e6,
+        "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp": spp, "max_num_vertices": m,
+                   "note": "restated nanogi CPU path (own BVH, no Embree; the real Embree+TBB binary cannot be built offline)"},
+        "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_own(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+
+    from nanogi_b200 import capi
+
+    if not torch.cuda.is_available() or capi.device_count() <= 0:
+        raise RuntimeError("bench.py: no CUDA device — the GPU path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    gen, renderer, W, H, spp, m, desc = WORKLOADS[args.workload]
+    if args.spp:
+        spp = args.spp
+    n_rank = W * H * spp                      # samples per rank per step (weak scaling)
+    n_total = n_rank * world
+    sd = build_scene(args.workload, W / H)
+    scene = capi.GpuScene(sd, local_rank)
+    info = scene.info()
+    film = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(i: int, flags: int = 0):
+        flush.zero_()                                               # L2 flush between iterations
+        st = scene.render_device(film.data_ptr(), stream.cuda_stream, renderer, n_rank, W, H, max_num_vertices=m,
+                                 seed=1000 + i, sample_offset=rank * n_rank, film_norm_samples=n_total, flags=flags,
+                                 wave_capacity=args.wave_capacity)
+        if world > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)           # the one exchange of the path
+        return st
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = ext = sh = iters = 0
+    ev0.record(stream)
+    for i in range(args.steps):
+        st = step(args.warmup + i)
+        launches += st.kernel_launches; ext += st.extend_rays; sh += st.shadow_rays; iters += st.wave_iterations
+    ev1.record(stream)
+    barrier()
+    clk = clocks.stop() if clocks else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(launches), float(ext), float(sh)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    t = float(ms.item()) * 1e-3
+    value = n_total * args.steps / t / 1e6
+    mrays = float(cnt[1] + cnt[2]) / t / 1e6
+    film_mean = float(film.mean().item())
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------------------
+    pinned = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+    h2d = sd.positions.nbytes + sd.normals.nbytes + len(sd.prims) * __import__("ctypes").sizeof(capi.NgiPrimitive) \
+        + __import__("ctypes").sizeof(capi.NgiRenderParams)
+    d2h = film.numel() * 4
+
+    def e2e_step(i: int):
+        sc = capi.GpuScene(sd, local_rank)                           # H2D of the scene + GPU BVH build
+        if world == 1:
+            p = sc._params(renderer, n_rank, W, H, max_num_vertices=m, seed=5000 + i, film_norm_samples=n_total,
+                           wave_capacity=args.wave_capacity)
+            st = capi.NgiRenderStats()
+            capi._check(sc.lib.ngi_gpu_render(sc.handle, __import__("ctypes").byref(p), pinned.data_ptr(), __import__("ctypes").byref(st)),
+                        "ngi_gpu_render")                           # render + film D2H into pinned host memory
+        else:
+            sc.render_device(film.data_ptr(), stream.cuda_stream, renderer, n_rank, W, H, max_num_vertices=m, seed=5000 + i,
+                             sample_offset=rank * n_rank, film_norm_samples=n_total, wave_capacity=args.wave_capacity)
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                pinned.copy_(film, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        sc.close()
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_step(-1)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * e2e_steps / float(te.item()) / 1e6
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the same stream ------------------------
+    roof = None
+    kern = None
+    if rank == 0:
+        stt = scene.render_device(film.data_ptr(), stream.cuda_stream, renderer, n_rank, W, H, max_num_vertices=m, seed=77,
+                                  sample_offset=0, film_norm_samples=n_rank, flags=capi.RENDER_TIME_KERNELS,
+                                  wave_capacity=args.wave_capacity)
+        peak, peak_src = measured_peaks()
+        br = b_ray(int(info.num_tris))
+        per = {"k_logic": (stt.logic_kernel_seconds, stt.logic_launches, None),
+               "k_extend": (stt.extend_kernel_seconds, stt.extend_launches, stt.extend_rays),
+               "k_shadow": (stt.shadow_kernel_seconds, stt.shadow_launches, stt.shadow_rays)}
+        total_k = sum(v[0] for v in per.values()) or 1.0
+        kern = {k: {"seconds": v[0], "launches": int(v[1]), "share": v[0] / total_k,
+                    "avg_launch_ms": (v[0] / v[1] * 1e3 if v[1] else None)} for k, v in per.items()}
+        # dominant TRACE kernel (the path's bytes are the BVH/triangle fetches of the ray queries)
+        dom = "k_extend" if stt.extend_kernel_seconds >= stt.shadow_kernel_seconds else "k_shadow"
+        sec, nl, rays = per[dom]
+        achieved = rays * br / sec / 1e9 if sec > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "bytes_per_ray": br, "rays_per_launch": rays / max(nl, 1),
+                "avg_launch_ms": sec / max(nl, 1) * 1e3, "grays_per_s": rays / sec / 1e9 if sec > 0 else 0.0,
+                "note": "algorithmic bytes (SURVEY 8d) / CUDA-event launch time; the scene (%.1f MB incl. BVH) is L2-resident, so "
+                        "HBM is not the physical limiter of this workload — see profiles/ for L2/issue counters" % (info.device_bytes / 1e6)}
+
+    # ---- CPU baseline (oracle port) on the host cores: rank 0, N = 1 only -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import pyoracle
+        orc = pyoracle.OracleScene(sd)
+        t0 = time.perf_counter()
+        orc.render(renderer, 1 << 18, W, H, max_num_vertices=m, seed=11)
+        rate = (1 << 18) / (time.perf_counter() - t0)
+        n_cpu = int(max(1 << 18, min(rate * args.cpu_seconds, n_rank)))
+        t0 = time.perf_counter()
+        fo, so = orc.render(renderer, n_cpu, W, H, max_num_vertices=m, seed=12)
+        dtc = time.perf_counter() - t0
+        cpu = {"value": n_cpu / dtc / 1e6, "unit": "Mpaths/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{n_cpu} samples ({n_cpu / (W * H):.2f} spp of {spp}) of the same scene/resolution/renderer, {dtc:.1f} s",
+               "mrays_per_s": (so["extend_rays"] + so["shadow_rays"]) / dtc / 1e6, "film_mean": float(fo.mean())}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "mrays_per_s": mrays,
+            "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp_per_gpu": spp, "samples_per_step": n_total,
+                       "max_num_vertices": m, "tris": int(info.num_tris), "bvh8_nodes": int(info.bvh8_nodes),
+                       "scene_device_bytes": int(info.device_bytes), "bvh_build_ms": info.build_gpu_seconds * 1e3,
+                       "parallelism": f"samples sharded by index over {world} GPU(s); scene replicated; one NCCL film reduce",
+                       "l2": "256 MB memset between iterations flushes L2; wavefront state (%.0f MB) also exceeds it"
+                             % ((args.wave_capacity or (1 << 21)) * 176 / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "includes": "scene H2D + GPU BVH build + render + film D2H (pinned) + destroy, wall clock"},
+            "gpu_launches": int(cnt[0].item()), "wave_iterations": int(iters), "film_mean": film_mean,
+            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    scene.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (default: the workload's)")
+    ap.add_argument("--wave-capacity", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="size of the cpu_baseline sample")
+    ap.add_argument("--cpu-step-seconds", type=float, default=4.0, help="--impl reference: CPU seconds per step")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "own":
+        print("bench.py: note: W < 3 warm-up steps — not a valid headline number", file=sys.stderr)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                   "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    run_own(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

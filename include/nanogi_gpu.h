@@ -143,6 +143,12 @@ typedef struct NgiRenderStats {
     double gpu_seconds;          /* CUDA-event time of the render on its stream               */
     double trace_kernel_seconds; /* CUDA-event time summed over the trace kernel launches, 0 if
                                     per-kernel timing was not requested                       */
+    /* per-kernel breakdown, filled only with NGI_RENDER_TIME_KERNELS (CUDA events on the render
+     * stream around every launch): summed seconds and launch counts of the three wavefront kernels */
+    double logic_kernel_seconds;
+    double extend_kernel_seconds;
+    double shadow_kernel_seconds;
+    uint64_t logic_launches, extend_launches, shadow_launches;
 } NgiRenderStats;
 
 typedef struct NgiSceneInfo {

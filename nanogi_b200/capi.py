@@ -24,6 +24,7 @@ E_AREA, E_PINHOLE = 0, 1
 S_REFLECTION, S_REFRACTION, S_FRESNEL = 0, 1, 2
 RENDERER_PT, RENDERER_PTDIRECT = 0, 1
 RENDERERS = {"pt": RENDERER_PT, "ptdirect": RENDERER_PTDIRECT}
+RENDER_TIME_KERNELS = 1  # NGI_RENDER_TIME_KERNELS
 NO_HIT = 0xFFFFFFFF
 
 d3 = C.c_double * 3
@@ -69,6 +70,8 @@ class NgiRenderStats(C.Structure):
         ("paths", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("wave_iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("gpu_seconds", C.c_double), ("trace_kernel_seconds", C.c_double),
+        ("logic_kernel_seconds", C.c_double), ("extend_kernel_seconds", C.c_double), ("shadow_kernel_seconds", C.c_double),
+        ("logic_launches", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
     ]
 
 

@@ -436,15 +436,18 @@ bool same_wp(const NgiWaveParams& a, const NgiWaveParams& b) { return memcmp(&a,
 
 int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool timed, size_t& ev_used) {
     const unsigned P = wp.capacity;
+    const bool direct = wp.renderer == NGI_RENDERER_PTDIRECT;
     k_iter_begin<<<1, 1, 0, st>>>(s->counters);
-    k_logic<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
     if (timed) {
-        while (s->events.size() < ev_used + 2) { cudaEvent_t e; NGI_CUDA(cudaEventCreate(&e)); s->events.push_back(e); }
+        while (s->events.size() < ev_used + 4) { cudaEvent_t e; NGI_CUDA(cudaEventCreate(&e)); s->events.push_back(e); }
         NGI_CUDA(cudaEventRecord(s->events[ev_used], st));
     }
+    k_logic<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
+    if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 1], st));
     k_extend<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
-    if (wp.renderer == NGI_RENDERER_PTDIRECT) k_shadow<<<std::min(grid_for((size_t)P * 2), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
-    if (timed) { NGI_CUDA(cudaEventRecord(s->events[ev_used + 1], st)); ev_used += 2; }
+    if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 2], st));
+    if (direct) k_shadow<<<std::min(grid_for((size_t)P * 2), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
+    if (timed) { NGI_CUDA(cudaEventRecord(s->events[ev_used + 3], st)); ev_used += 4; }
     return NGI_OK;
 }
 
@@ -494,7 +497,8 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     const int kernels_per_iter = rp->renderer == NGI_RENDERER_PTDIRECT ? 4 : 3;
     size_t ev_used = 0;
     uint64_t launches = 0;
-    double trace_ms = 0.0;
+    double logic_ms = 0.0, extend_ms = 0.0, shadow_ms = 0.0;
+    uint64_t timed_iters = 0;
 
     if (!timed) {
         // the batch of kItersPerBatch iterations is captured once into a CUDA graph and replayed
@@ -520,7 +524,13 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         NGI_CUDA(cudaMemcpyAsync(s->counters_host, s->counters, sizeof(NgiRenderCounters), cudaMemcpyDeviceToHost, st));
         NGI_CUDA(cudaStreamSynchronize(st));
         if (timed) {
-            for (size_t i = 0; i + 1 < ev_used; i += 2) { float ms = 0; NGI_CUDA(cudaEventElapsedTime(&ms, s->events[i], s->events[i + 1])); trace_ms += ms; }
+            for (size_t i = 0; i + 3 < ev_used; i += 4) {
+                float ms = 0;
+                NGI_CUDA(cudaEventElapsedTime(&ms, s->events[i], s->events[i + 1])); logic_ms += ms;
+                NGI_CUDA(cudaEventElapsedTime(&ms, s->events[i + 1], s->events[i + 2])); extend_ms += ms;
+                NGI_CUDA(cudaEventElapsedTime(&ms, s->events[i + 2], s->events[i + 3])); shadow_ms += ms;
+                timed_iters++;
+            }
             ev_used = 0;
         }
         const NgiRenderCounters& c = *s->counters_host;
@@ -540,7 +550,13 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         stats->wave_iterations = c.iterations;
         stats->kernel_launches = launches;
         stats->gpu_seconds = ms * 1e-3;
-        stats->trace_kernel_seconds = trace_ms * 1e-3;
+        stats->trace_kernel_seconds = (extend_ms + shadow_ms) * 1e-3;
+        stats->logic_kernel_seconds = logic_ms * 1e-3;
+        stats->extend_kernel_seconds = extend_ms * 1e-3;
+        stats->shadow_kernel_seconds = rp->renderer == NGI_RENDERER_PTDIRECT ? shadow_ms * 1e-3 : 0.0;
+        stats->logic_launches = timed_iters;
+        stats->extend_launches = timed_iters;
+        stats->shadow_launches = rp->renderer == NGI_RENDERER_PTDIRECT ? timed_iters : 0;
     }
     return NGI_OK;
 }

@@ -79,7 +79,9 @@ def test_bsdf_parity(gpu_c2, cornell_spheres, prim, type_bit):
 def test_replay_small_scale(renderer, m):
     sd = scenes.to_scene_data(scaled_spec(scenes.cornell_spheres(), 0.01), 1.0)
     g = capi.GpuScene(sd, 0)
-    pc.check_replay(g, sd, renderer, n=200000, w=96, h=96, m=m)
+    # ~22 samples per pixel: a pixel is "bad" when ANY of its samples took a different branch in fp32 than in the
+    # fp64 oracle (Fresnel pick, RR, self-hit). Measured on B200: <= 0.44 % of pixels, i.e. ~2e-4 of the samples.
+    pc.check_replay(g, sd, renderer, n=200000, w=96, h=96, m=m, max_bad_pixels=0.01)
     g.close()
 
 
