@@ -128,16 +128,99 @@ NGI_HD bool ngi_trace_bvh2(const float4* __restrict__ nodes, const float4* __res
 // (slot ^ octant) approximates front-to-back order (slot bit0/1/2 = child lies towards +x/+y/+z).
 // ------------------------------------------------------------------------------------------------
 #define NGI_BVH8_STACK 40
+#define NGI_BVH8_MAX_DEPTH 32     /* enforced by the build; traversal stacks are sized from it */
 
 NGI_HD unsigned ngi_byte(unsigned w, int i) { return (w >> (8 * i)) & 0xFFu; }
 
+// exact byte -> float without the XU pipe: I2F.U8 runs at 16 lanes/clk/SM and was the busiest pipe of the
+// first traversal kernel (profiles/r01_ncu_c2_steady.txt: XU 71 %). PRMT builds 2^23 + q in one ALU op, the
+// FADD of -2^23 is exact, so the value is bit-identical to (float)q.
+NGI_HD float ngi_qf(unsigned w, int i) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (unsigned)i)) - 8388608.0f;
+#else
+    return (float)((w >> (8 * i)) & 0xFFu);
+#endif
+}
+
+// per-ray constants of a BVH8 traversal
+struct NgiRayCtx {
+    f3 o, d;
+    float idx, idy, idz;      // clamped reciprocal direction
+    float tmin;
+    unsigned octinv;          // 7 - octant of the direction
+    bool negx, negy, negz;    // taken from the clamped reciprocals so that -0.0f components stay self-consistent
+};
+
+NGI_HD void ngi_ray_ctx(NgiRayCtx& r, const f3 o, const f3 d, const float tmin) {
+    r.o = o; r.d = d; r.tmin = tmin;
+    r.idx = ngi_safe_rcp_dir(d.x); r.idy = ngi_safe_rcp_dir(d.y); r.idz = ngi_safe_rcp_dir(d.z);
+    r.negx = r.idx < 0.0f; r.negy = r.idy < 0.0f; r.negz = r.idz < 0.0f;
+    r.octinv = (r.negx ? 0u : 1u) | (r.negy ? 0u : 2u) | (r.negz ? 0u : 4u);
+}
+
+// One node step: pops the front-most inner child of `ngroup`, (the caller pushes what is left of the group),
+// intersects its 8 quantised child boxes with the ray and returns the new node group / triangle group.
+NGI_HD void ngi_bvh8_pop_child(uint2& ngroup, const unsigned octinv, size_t& ni) {
+    const unsigned imask = ngroup.y & 0xFFu;
+    const int bit = ngi_bfind(ngroup.y);
+    ngroup.y &= ~(1u << bit);
+    const unsigned slot = ((unsigned)(bit - 24) ^ octinv) & 7u;
+    const unsigned rel = (unsigned)ngi_popc(imask & ~(0xFFFFFFFFu << slot));
+    ni = (size_t)ngroup.x + rel;
+}
+
+NGI_HD void ngi_bvh8_node_step(const uint4* __restrict__ nodes, const size_t ni, const NgiRayCtx& r, const float limit,
+                               uint2& ngroup, uint2& tgroup) {
+    const uint4 n0 = ngi_ldg(nodes + 5 * ni), n1 = ngi_ldg(nodes + 5 * ni + 1), n2 = ngi_ldg(nodes + 5 * ni + 2);
+    const uint4 n3 = ngi_ldg(nodes + 5 * ni + 3), n4 = ngi_ldg(nodes + 5 * ni + 4);
+
+    const float sx = u2f((n0.w & 0xFFu) << 23) * r.idx;
+    const float sy = u2f(((n0.w >> 8) & 0xFFu) << 23) * r.idy;
+    const float sz = u2f(((n0.w >> 16) & 0xFFu) << 23) * r.idz;
+    const float bx = (u2f(n0.x) - r.o.x) * r.idx, by = (u2f(n0.y) - r.o.y) * r.idy, bz = (u2f(n0.z) - r.o.z) * r.idz;
+    const unsigned octinv = r.octinv;
+
+    unsigned hitmask = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const unsigned meta4 = h ? n1.w : n1.z;
+        // near / far plane words per axis, chosen by the ray's sign
+        const unsigned lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
+        const unsigned hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
+        const unsigned nx = r.negx ? hix : lox, fx = r.negx ? lox : hix;
+        const unsigned ny = r.negy ? hiy : loy, fy = r.negy ? loy : hiy;
+        const unsigned nz = r.negz ? hiz : loz, fz = r.negz ? loz : hiz;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned meta = ngi_byte(meta4, i);
+            const float tnx = fmaf(ngi_qf(nx, i), sx, bx), tfx = fmaf(ngi_qf(fx, i), sx, bx);
+            const float tny = fmaf(ngi_qf(ny, i), sy, by), tfy = fmaf(ngi_qf(fy, i), sy, by);
+            const float tnz = fmaf(ngi_qf(nz, i), sz, bz), tfz = fmaf(ngi_qf(fz, i), sz, bz);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, limit));
+            if (meta != 0u && tn <= tf) {
+                const bool inner = (meta & 0x18u) == 0x18u;
+                const unsigned bits = inner ? 1u : (meta >> 5);
+                const unsigned pos = inner ? ((meta ^ octinv) & 31u) : (meta & 31u);
+                hitmask |= bits << pos;
+            }
+        }
+    }
+    ngroup.x = n1.x;
+    ngroup.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
+    tgroup.x = n1.y;
+    tgroup.y = hitmask & 0x00FFFFFFu;
+}
+
+// per-ray traversal (one thread = one ray, no cooperation): the reference form of the algorithm. The product
+// kernels in ngi_gpu.cu run the warp-cooperative version (ngi_trace_warp.cuh) over the same building blocks;
+// because the closest hit is an order-free reduction both return bit-identical results.
 template <bool ANY_HIT>
 NGI_HD bool ngi_trace_bvh8(const uint4* __restrict__ nodes, const float4* __restrict__ tris, const f3 o, const f3 d,
                            const float tmin, const float tmax, NgiHitRec& out) {
-    const float idx = ngi_safe_rcp_dir(d.x), idy = ngi_safe_rcp_dir(d.y), idz = ngi_safe_rcp_dir(d.z);
-    // signs are taken from the clamped reciprocals so that -0.0f components stay self-consistent
-    const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
-    const unsigned octinv = (negx ? 0u : 1u) | (negy ? 0u : 2u) | (negz ? 0u : 4u);
+    NgiRayCtx r;
+    ngi_ray_ctx(r, o, d, tmin);
     NgiHitRec best; best.t = tmax; best.u = 0; best.v = 0; best.tri = NGI_MISS;
     bool found = false;
 
@@ -148,56 +231,12 @@ NGI_HD bool ngi_trace_bvh8(const uint4* __restrict__ nodes, const float4* __rest
 
     while (true) {
         if (ngroup.y > 0x00FFFFFFu) {
-            const unsigned hits = ngroup.y;
-            const unsigned imask = ngroup.y & 0xFFu;
-            const int bit = ngi_bfind(hits);
-            ngroup.y &= ~(1u << bit);
+            size_t ni;
+            ngi_bvh8_pop_child(ngroup, r.octinv, ni);
             if (ngroup.y > 0x00FFFFFFu) {
                 if (sp < NGI_BVH8_STACK) stack[sp++] = ngroup;
             }
-            const unsigned slot = ((unsigned)(bit - 24) ^ octinv) & 7u;
-            const unsigned rel = (unsigned)ngi_popc(imask & ~(0xFFFFFFFFu << slot));
-            const size_t ni = (size_t)ngroup.x + rel;
-
-            const uint4 n0 = ngi_ldg(nodes + 5 * ni), n1 = ngi_ldg(nodes + 5 * ni + 1), n2 = ngi_ldg(nodes + 5 * ni + 2);
-            const uint4 n3 = ngi_ldg(nodes + 5 * ni + 3), n4 = ngi_ldg(nodes + 5 * ni + 4);
-
-            const float sx = u2f((n0.w & 0xFFu) << 23) * idx;
-            const float sy = u2f(((n0.w >> 8) & 0xFFu) << 23) * idy;
-            const float sz = u2f(((n0.w >> 16) & 0xFFu) << 23) * idz;
-            const float bx = (u2f(n0.x) - o.x) * idx, by = (u2f(n0.y) - o.y) * idy, bz = (u2f(n0.z) - o.z) * idz;
-            const float limit = found ? best.t : tmax;
-
-            unsigned hitmask = 0;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const unsigned meta4 = h ? n1.w : n1.z;
-                // near / far plane words per axis, chosen by the ray's sign
-                const unsigned lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
-                const unsigned hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
-                const unsigned nx = negx ? hix : lox, fx = negx ? lox : hix;
-                const unsigned ny = negy ? hiy : loy, fy = negy ? loy : hiy;
-                const unsigned nz = negz ? hiz : loz, fz = negz ? loz : hiz;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const unsigned meta = ngi_byte(meta4, i);
-                    const float tnx = fmaf((float)ngi_byte(nx, i), sx, bx), tfx = fmaf((float)ngi_byte(fx, i), sx, bx);
-                    const float tny = fmaf((float)ngi_byte(ny, i), sy, by), tfy = fmaf((float)ngi_byte(fy, i), sy, by);
-                    const float tnz = fmaf((float)ngi_byte(nz, i), sz, bz), tfz = fmaf((float)ngi_byte(fz, i), sz, bz);
-                    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-                    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, limit));
-                    if (meta != 0u && tn <= tf) {
-                        const bool inner = (meta & 0x18u) == 0x18u;
-                        const unsigned bits = inner ? 1u : (meta >> 5);
-                        const unsigned pos = inner ? ((meta ^ octinv) & 31u) : (meta & 31u);
-                        hitmask |= bits << pos;
-                    }
-                }
-            }
-            ngroup.x = n1.x;
-            ngroup.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
-            tgroup.x = n1.y;
-            tgroup.y = hitmask & 0x00FFFFFFu;
+            ngi_bvh8_node_step(nodes, ni, r, best.t, ngroup, tgroup);   // best.t == tmax until a hit is found
         } else {
             tgroup = ngroup;
             ngroup = make_uint2(0u, 0u);

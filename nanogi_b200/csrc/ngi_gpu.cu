@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -25,6 +26,7 @@
 #include "ngi_bvh.h"
 #include "ngi_scene_host.h"
 #include "ngi_wave.h"
+#include "ngi_trace_warp.cuh"
 
 namespace {
 
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(128) k_collapse8(NgiCollapseCtx ctx, const Ngi
 // ================================================================================================
 // ray-query kernels (ngi_gpu_trace*)
 // ================================================================================================
+// BVH2 / brute force: cross-check structures, one thread per ray
 template <int ACCEL, bool ANY_HIT>
 __global__ void __launch_bounds__(kBlock) k_trace(NgiDevScene sc, const NgiRay* __restrict__ rays, size_t n, NgiHit* __restrict__ hits) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -154,13 +157,35 @@ __global__ void __launch_bounds__(kBlock) k_trace(NgiDevScene sc, const NgiRay* 
     const f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
     NgiHitRec h;
     bool hit;
-    if (ACCEL == 0) hit = ngi_trace_bvh8<ANY_HIT>(sc.nodes8, sc.tris8, o, d, r0.w, r1.w, h);
-    else if (ACCEL == 1) hit = ngi_trace_bvh2<ANY_HIT>(sc.nodes2, sc.tris2, o, d, r0.w, r1.w, h);
+    if (ACCEL == 1) hit = ngi_trace_bvh2<ANY_HIT>(sc.nodes2, sc.tris2, o, d, r0.w, r1.w, h);
     else hit = ngi_trace_brute<ANY_HIT>(sc.tris2, sc.n_tris, o, d, r0.w, r1.w, h);
     float4 out;
     out.x = hit ? h.t : 0.0f; out.y = hit ? h.u : 0.0f; out.z = hit ? h.v : 0.0f;
     out.w = __uint_as_float(hit ? (ANY_HIT ? 0u : h.tri) : NGI_NO_HIT);
     reinterpret_cast<float4*>(hits)[i] = out;
+}
+
+// BVH8 (product): persistent warps with dynamic fetch, see ngi_trace_warp.cuh
+template <bool ANY_HIT>
+struct QuerySource {
+    const float4* rays; float4* hits; unsigned n; unsigned* cur;
+    __device__ __forceinline__ unsigned count() const { return n; }
+    __device__ __forceinline__ unsigned* cursor() const { return cur; }
+    __device__ __forceinline__ unsigned load(unsigned i, f3& o, f3& d, float& tmin, float& tmax) const {
+        const float4 r0 = __ldg(rays + 2 * (size_t)i), r1 = __ldg(rays + 2 * (size_t)i + 1);
+        o = mk3(r0.x, r0.y, r0.z); d = mk3(r1.x, r1.y, r1.z); tmin = r0.w; tmax = r1.w;
+        return i;
+    }
+    __device__ __forceinline__ void store(unsigned i, bool found, const NgiHitRec& h) const {
+        float4 out;
+        if (ANY_HIT) out = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(found ? 0u : NGI_NO_HIT));
+        else out = found ? make_float4(h.t, h.u, h.v, __uint_as_float(h.tri)) : make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(NGI_NO_HIT));
+        hits[i] = out;
+    }
+};
+template <bool ANY_HIT>
+__global__ void __launch_bounds__(kBlock) k_trace8(NgiDevScene sc, QuerySource<ANY_HIT> src, NgiTraceTuning tune) {
+    ngi_trace_warp<ANY_HIT>(sc.nodes8, sc.tris8, src, tune);
 }
 
 // ================================================================================================
@@ -173,6 +198,8 @@ struct NgiRenderCounters {
     unsigned long long iterations;
     unsigned iter[2];   // [0] shadow entries, [1] extend rays of the iteration in flight
     unsigned last[2];   // snapshot of the previous iteration (read by the host for termination)
+    unsigned fetch[2];  // dynamic-fetch cursors of the persistent trace kernels ([0] shadow, [1] extend)
+    unsigned pad[2];
 };
 
 __global__ void k_iter_begin(NgiRenderCounters* c) {
@@ -182,6 +209,8 @@ __global__ void k_iter_begin(NgiRenderCounters* c) {
     c->last[1] = c->iter[1];
     c->iter[0] = 0u;
     c->iter[1] = 0u;
+    c->fetch[0] = 0u;
+    c->fetch[1] = 0u;
     c->iterations += 1ull;
 }
 
@@ -189,13 +218,47 @@ __global__ void __launch_bounds__(kBlock) k_logic(NgiDevScene sc, NgiWaveParams 
     const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot < wp.capacity) ngi_logic_step(sc, wp, slot);
 }
-__global__ void __launch_bounds__(kBlock) k_extend(NgiDevScene sc, NgiWaveParams wp) {
-    const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < wp.capacity) ngi_extend_step(sc, wp, slot);
+// Scene::Intersect's ray query (rt.hpp:2162-2182) for the compacted extend queue of this iteration
+struct ExtendSource {
+    NgiWaveParams wp;
+    __device__ __forceinline__ unsigned count() const { return wp.iter_counters[1]; }
+    __device__ __forceinline__ unsigned* cursor() const { return wp.fetch_cursors + 1; }
+    __device__ __forceinline__ unsigned load(unsigned i, f3& o, f3& d, float& tmin, float& tmax) const {
+        const unsigned slot = wp.extend_q[i];
+        const float4 di = wp.dir_info[slot];
+        o = mk3((float)wp.px[slot], (float)wp.py[slot], (float)wp.pz[slot]);                 // rt.hpp:2166-2168
+        d = mk3(di.x, di.y, di.z); tmin = NGI_EPS_F; tmax = NGI_INF_F;                        // rt.hpp:2246-2249
+        return slot;
+    }
+    __device__ __forceinline__ void store(unsigned slot, bool found, const NgiHitRec& h) const {
+        wp.hit[slot] = found ? make_float4(h.t, h.u, h.v, u2f(h.tri)) : make_float4(0.0f, 0.0f, 0.0f, u2f(NGI_MISS));
+    }
+};
+// Scene::Visible (rt.hpp:2251-2261) for the shadow queue + film accumulation (src/nanogi.cpp:706)
+struct ShadowSource {
+    NgiWaveParams wp;
+    __device__ __forceinline__ unsigned count() const { return wp.iter_counters[0]; }
+    __device__ __forceinline__ unsigned* cursor() const { return wp.fetch_cursors + 0; }
+    __device__ __forceinline__ unsigned load(unsigned e, f3& o, f3& d, float& tmin, float& tmax) const {
+        const float4* q = wp.shadow_q + 3 * (size_t)e;
+        const float4 q0 = q[0], q1 = q[1];
+        o = mk3(q0.x, q0.y, q0.z); d = mk3(q1.x, q1.y, q1.z); tmin = NGI_EPS_F; tmax = q0.w;
+        return e;
+    }
+    __device__ __forceinline__ void store(unsigned e, bool occluded, const NgiHitRec&) const {
+        if (occluded) return;
+        const float4* q = wp.shadow_q + 3 * (size_t)e;
+        const float4 q1 = q[1], q2 = q[2];
+        ngi_film_add(wp.film, (int)f2u(q1.w), mk3(q2.x, q2.y, q2.z));
+    }
+};
+__global__ void __launch_bounds__(kBlock) k_extend(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
+    ExtendSource src; src.wp = wp;
+    ngi_trace_warp<false>(sc.nodes8, sc.tris8, src, tune);
 }
-__global__ void __launch_bounds__(kBlock) k_shadow(NgiDevScene sc, NgiWaveParams wp) {
-    const unsigned n = wp.iter_counters[0];
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_shadow_step(sc, wp, e);
+__global__ void __launch_bounds__(kBlock) k_shadow(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
+    ShadowSource src; src.wp = wp;
+    ngi_trace_warp<true>(sc.nodes8, sc.tris8, src, tune);
 }
 
 __global__ void __launch_bounds__(kBlock) k_eval_bsdf(NgiDevScene sc, const float* __restrict__ q, const float* __restrict__ wo_in, size_t n,
@@ -235,6 +298,10 @@ struct Scene {
     NgiWaveParams graph_wp{};
     int graph_iters = 0;
     std::vector<cudaEvent_t> events;
+    // persistent trace kernels: grid = SM count x resident CTAs per SM (queried once per kernel)
+    NgiTraceTuning tune{8, 8};
+    unsigned grid_extend = 0, grid_shadow = 0, grid_trace[2] = {0, 0};
+    unsigned* trace_cursor = nullptr;
 
     ~Scene() {
         cudaSetDevice(device);
@@ -243,6 +310,7 @@ struct Scene {
         for (void* p : allocs) cudaFree(p);
         if (wave_mem) cudaFree(wave_mem);
         if (counters) cudaFree(counters);
+        if (trace_cursor) cudaFree(trace_cursor);
         if (counters_host) cudaFreeHost(counters_host);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -254,6 +322,28 @@ int dev_alloc(Scene* s, T** out, size_t count, bool keep) {
     NGI_CUDA(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
     if (keep) { s->allocs.push_back(p); s->info.device_bytes += count * sizeof(T); }
     *out = (T*)p;
+    return NGI_OK;
+}
+
+template <class K>
+int persistent_grid(K kernel, unsigned* out) {
+    int dev = 0, sms = 0, per_sm = 0;
+    NGI_CUDA(cudaGetDevice(&dev));
+    NGI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    NGI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0));
+    *out = (unsigned)(sms * (per_sm > 0 ? per_sm : 1));
+    return NGI_OK;
+}
+
+int init_trace_launch(Scene* s) {
+    int rc;
+    if ((rc = persistent_grid(k_extend, &s->grid_extend))) return rc;
+    if ((rc = persistent_grid(k_shadow, &s->grid_shadow))) return rc;
+    if ((rc = persistent_grid(k_trace8<false>, &s->grid_trace[0]))) return rc;
+    if ((rc = persistent_grid(k_trace8<true>, &s->grid_trace[1]))) return rc;
+    NGI_CUDA(cudaMalloc((void**)&s->trace_cursor, sizeof(unsigned)));
+    if (const char* e = getenv("NGI_TRACE_REFILL_MIN")) s->tune.refill_min = atoi(e);
+    if (const char* e = getenv("NGI_TRACE_TRI_MIN")) s->tune.tri_min = atoi(e);
     return NGI_OK;
 }
 
@@ -375,7 +465,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     }
     NGI_CUDA(cudaGetLastError());
     if (hc[1] != n) return set_err(NGI_ERR_CUDA, "BVH8 collapse lost triangles: " + std::to_string(hc[1]) + " of " + std::to_string(n));
-    if (depth > NGI_BVH8_STACK) return set_err(NGI_ERR_UNSUPPORTED, "BVH8 depth " + std::to_string(depth) + " exceeds the traversal stack");
+    if (depth > NGI_BVH8_MAX_DEPTH) return set_err(NGI_ERR_UNSUPPORTED, "BVH8 depth " + std::to_string(depth) + " exceeds the traversal stack");
     const unsigned n_nodes8 = hc[0];
     uint4* d_nodes8 = nullptr;
     if ((rc = dev_alloc(s, &d_nodes8, (size_t)n_nodes8 * 5, true))) return rc;
@@ -399,7 +489,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     s->info.build_gpu_seconds = ms * 1e-3;
     for (int k = 0; k < 3; k++) { s->info.scene_min[k] = smin[k]; s->info.scene_max[k] = smax[k]; }
     s->info.num_lights = d.n_lights; s->info.bvh8_max_depth = depth;
-    return NGI_OK;
+    return init_trace_launch(s);
 }
 
 // ---- wavefront state ---------------------------------------------------------------------------
@@ -408,7 +498,7 @@ int ensure_wave(Scene* s, unsigned P) {
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     if (s->wave_mem) { cudaFree(s->wave_mem); s->wave_mem = nullptr; }
     // per slot: sample 8 + thr_pix 16 + p 24 + dir_info 16 + hit 16 = 80 B; shadow queue 2 entries x 48 B
-    const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96);
+    const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96 + 4);
     NGI_CUDA(cudaMalloc(&s->wave_mem, bytes));
     if (!s->counters) NGI_CUDA(cudaMalloc((void**)&s->counters, sizeof(NgiRenderCounters)));
     if (!s->counters_host) NGI_CUDA(cudaMallocHost((void**)&s->counters_host, sizeof(NgiRenderCounters)));
@@ -427,7 +517,9 @@ void carve_wave(Scene* s, NgiWaveParams& wp) {
     wp.px = (double*)p; p += P * 8;
     wp.py = (double*)p; p += P * 8;
     wp.pz = (double*)p; p += P * 8;
+    wp.extend_q = (unsigned*)p; p += P * 4;
     wp.iter_counters = s->counters->iter;
+    wp.fetch_cursors = s->counters->fetch;
     wp.next_sample = &s->counters->next_sample;
     wp.capacity = (unsigned)P;
 }
@@ -444,9 +536,9 @@ int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool ti
     }
     k_logic<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
     if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 1], st));
-    k_extend<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
+    k_extend<<<s->grid_extend, kBlock, 0, st>>>(s->dev, wp, s->tune);
     if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 2], st));
-    if (direct) k_shadow<<<std::min(grid_for((size_t)P * 2), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
+    if (direct) k_shadow<<<s->grid_shadow, kBlock, 0, st>>>(s->dev, wp, s->tune);
     if (timed) { NGI_CUDA(cudaEventRecord(s->events[ev_used + 3], st)); ev_used += 4; }
     return NGI_OK;
 }
@@ -567,15 +659,26 @@ void launch_trace(Scene* s, const NgiRay* rays, size_t n, NgiHit* hits, int any_
     else k_trace<ACCEL, false><<<grid_for(n), kBlock, 0, st>>>(s->dev, rays, n, hits);
 }
 
+template <bool ANY_HIT>
+void launch_trace8(Scene* s, const NgiRay* rays, size_t n, NgiHit* hits, cudaStream_t st) {
+    QuerySource<ANY_HIT> src;
+    src.rays = reinterpret_cast<const float4*>(rays); src.hits = reinterpret_cast<float4*>(hits); src.n = (unsigned)n; src.cur = s->trace_cursor;
+    const unsigned need = grid_for(n);
+    const unsigned grid = std::min(s->grid_trace[ANY_HIT ? 1 : 0], need);
+    k_trace8<ANY_HIT><<<grid, kBlock, 0, st>>>(s->dev, src, s->tune);
+}
+
 int trace_impl(Scene* s, const NgiRay* rays_dev, size_t n, NgiHit* hits_dev, int any_hit, int accel, double* seconds) {
     if (accel < 0 || accel > 2) return set_err(NGI_ERR_INVALID_ARGUMENT, "accel must be 0 (BVH8), 1 (BVH2) or 2 (brute force)");
     cudaStream_t st = s->stream;
     cudaEvent_t ev0, ev1;
     NGI_CUDA(cudaEventCreate(&ev0));
     NGI_CUDA(cudaEventCreate(&ev1));
+    if (n >= 0xFFFFFF00ull) return set_err(NGI_ERR_INVALID_ARGUMENT, "at most 2^32 - 256 rays per call");
+    if (accel == 0) NGI_CUDA(cudaMemsetAsync(s->trace_cursor, 0, sizeof(unsigned), st));
     NGI_CUDA(cudaEventRecord(ev0, st));
     if (n) {
-        if (accel == 0) launch_trace<0>(s, rays_dev, n, hits_dev, any_hit, st);
+        if (accel == 0) { if (any_hit) launch_trace8<true>(s, rays_dev, n, hits_dev, st); else launch_trace8<false>(s, rays_dev, n, hits_dev, st); }
         else if (accel == 1) launch_trace<1>(s, rays_dev, n, hits_dev, any_hit, st);
         else launch_trace<2>(s, rays_dev, n, hits_dev, any_hit, st);
     }

@@ -1,0 +1,151 @@
+// ngi_trace_warp.cuh — warp-cooperative BVH8 traversal: the product form of the ray-query kernels.
+//
+// Replaces the per-ray calls Scene::Intersect / Scene::Visible -> rtcIntersect (reference
+// include/nanogi/rt.hpp:2162-2261) for whole queues of rays.
+//
+// Why not "one thread = one ray to completion": the first version of k_extend ran with 6.0 of 32 lanes
+// active on average (profiles/r01_ncu_c2_steady.txt) — rays of one warp need very different numbers of
+// node steps and triangle tests, the compiler's reconvergence points let lanes drift between the node
+// code and the triangle code, and a warp lives as long as its slowest ray. Here instead (after Aila & Laine
+// 2009 "Understanding the efficiency of ray traversal on GPUs" and Ylitie, Karras, Laine 2017):
+//   * persistent warps: grid = SM count x resident CTAs, every warp pulls rays from the queue in chunks
+//     (one global atomic per 128 rays) and hands them to lanes as they go idle (dynamic fetch);
+//   * the loop body is warp-uniform and phase-structured — all lanes reconverge (__syncwarp) before the
+//     node phase (one 8-wide node step per lane per round) and before the triangle phase (one triangle
+//     test per lane per trip) — so each phase issues once for all lanes that need it;
+//   * triangle postponing: when only a few lanes have triangles left while most could be doing node
+//     steps, the leftover triangle group is pushed on the lane's stack and handled later.
+// The closest hit is the order-free lexicographic minimum of (t, triangle id) and occlusion is an
+// existence test, so the visiting order (and therefore all of the above) cannot change any result: the
+// kernels stay bit-exact against the oracle and against the per-ray form ngi_trace_bvh8.
+#pragma once
+#include "ngi_bvh.h"
+
+#define NGI_WARP_STACK 48          /* >= NGI_BVH8_MAX_DEPTH (node groups) + NGI_POSTPONE_MAX_SP (postponed triangle groups) */
+#define NGI_POSTPONE_MAX_SP 16
+#define NGI_FETCH_CHUNK 128u
+
+struct NgiTraceTuning {
+    int refill_min;     // refill idle lanes when at least this many are idle (or all are)
+    int tri_min;        // postpone the triangle phase when fewer lanes than this have triangles pending
+};
+
+// Source concept:
+//   unsigned count() const;                       number of rays in the queue
+//   unsigned* cursor() const;                     global fetch cursor (zeroed before the launch)
+//   unsigned load(unsigned i, f3& o, f3& d, float& tmin, float& tmax);   returns a token handed back to store()
+//   void store(unsigned token, bool found, const NgiHitRec& h);
+template <bool ANY_HIT, class Source>
+__device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Source src,
+                                               const NgiTraceTuning tune) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned n = src.count();
+
+    // warp-uniform fetch state
+    unsigned chunk_next = 0, chunk_end = 0;
+    bool exhausted = (n == 0);
+
+    // per-lane ray state
+    bool active = false;
+    unsigned item = 0;
+    NgiRayCtx r;
+    float tmax = 0.0f;
+    NgiHitRec best; best.t = 0; best.u = 0; best.v = 0; best.tri = NGI_MISS;
+    bool found = false;
+    uint2 stack[NGI_WARP_STACK];
+    int sp = 0;
+    int defer = 0;            // consecutive postponements of this lane's triangle group (starvation guard)
+    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+
+    while (true) {
+        __syncwarp();
+        // ---------------- dynamic fetch ----------------
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle != 0u) {
+            const int nidle = __popc(idle);
+            if (!exhausted && (nidle >= tune.refill_min || idle == FULL)) {
+                if (chunk_next >= chunk_end) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(src.cursor(), NGI_FETCH_CHUNK);
+                    base = __shfl_sync(FULL, base, 0);
+                    chunk_next = base;
+                    chunk_end = base + NGI_FETCH_CHUNK < n ? base + NGI_FETCH_CHUNK : n;
+                    if (base >= n) { exhausted = true; chunk_next = chunk_end = 0; }
+                }
+                if (!exhausted) {
+                    const unsigned my = chunk_next + (unsigned)__popc(idle & lt_mask);
+                    if (!active && my < chunk_end) {
+                        f3 o, d; float tmin;
+                        item = src.load(my, o, d, tmin, tmax);
+                        ngi_ray_ctx(r, o, d, tmin);
+                        best.t = tmax; best.u = 0; best.v = 0; best.tri = NGI_MISS;
+                        found = false; sp = 0; defer = 0;
+                        ngroup = make_uint2(0u, 0x80000000u);   // root: base 0, pseudo-slot 7
+                        tgroup = make_uint2(0u, 0u);
+                        active = true;
+                    }
+                    chunk_next = chunk_next + (unsigned)nidle < chunk_end ? chunk_next + (unsigned)nidle : chunk_end;
+                }
+            }
+            if (exhausted && __ballot_sync(FULL, active) == 0u) break;
+        }
+
+        // ---------------- node phase: one node step per lane ----------------
+        if (active) {
+            if (ngroup.y > 0x00FFFFFFu) {
+                size_t ni;
+                ngi_bvh8_pop_child(ngroup, r.octinv, ni);
+                if (ngroup.y > 0x00FFFFFFu && sp < NGI_WARP_STACK) stack[sp++] = ngroup;   // never full: the build bounds the depth
+                ngi_bvh8_node_step(nodes, ni, r, best.t, ngroup, tgroup);
+            } else {
+                tgroup = ngroup;                                      // a postponed triangle group came off the stack
+                ngroup = make_uint2(0u, 0u);
+            }
+        }
+        __syncwarp();
+
+        // ---------------- triangle phase: one triangle per lane per trip ----------------
+        while (true) {
+            const bool has = active && tgroup.y != 0u;
+            const unsigned m = __ballot_sync(FULL, has);
+            if (m == 0u) break;
+            if (__popc(m) < tune.tri_min) {
+                // few lanes busy: postpone if more lanes could be doing node steps instead
+                const unsigned node_ready = __ballot_sync(FULL, active && ngroup.y > 0x00FFFFFFu);
+                const unsigned starved = __ballot_sync(FULL, has && defer >= 2);
+                if (__popc(node_ready) > __popc(m) && starved == 0u) {
+                    if (has && sp < NGI_POSTPONE_MAX_SP) { stack[sp++] = tgroup; tgroup.y = 0u; defer++; }
+                    if (__ballot_sync(FULL, active && tgroup.y != 0u) == 0u) break;
+                }
+            }
+            if (active && tgroup.y != 0u) {
+                const int bit = ngi_bfind(tgroup.y);
+                tgroup.y &= ~(1u << bit);
+                defer = 0;
+                const size_t ti = (size_t)tgroup.x + (unsigned)bit;
+                const float4 a = ngi_ldg(tris + 3 * ti), b = ngi_ldg(tris + 3 * ti + 1), c = ngi_ldg(tris + 3 * ti + 2);
+                float t, u, v;
+                if (ngi_tri_test(a, b, c, r.o, r.d, r.tmin, tmax, t, u, v)) {
+                    if (ANY_HIT) {
+                        found = true; tgroup.y = 0u; ngroup.y = 0u; sp = 0;   // occluded: this ray is finished
+                    } else {
+                        ngi_accept(best, t, u, v, f2u(a.w));
+                        found = true;
+                    }
+                }
+            }
+        }
+
+        // ---------------- pop / retire ----------------
+        if (active && ngroup.y <= 0x00FFFFFFu) {
+            if (sp == 0) {
+                src.store(item, found, best);
+                active = false;
+            } else {
+                ngroup = stack[--sp];
+            }
+        }
+    }
+}

@@ -32,7 +32,9 @@ struct NgiWaveParams {
     float4* hit;                  // t, u, v, global triangle id (written by the extend kernel)
     // shadow queue: 3 x float4 per entry = (o.xyz, tmax) (d.xyz, pixel) (C.xyz, -)
     float4* shadow_q;
+    unsigned* extend_q;           // slot ids of the extend rays of this iteration (compacted by the logic stage)
     unsigned* iter_counters;      // [0] shadow entries this iteration, [1] extend rays this iteration
+    unsigned* fetch_cursors;      // [0] shadow, [1] extend: dynamic-fetch cursors of the persistent trace kernels
     unsigned long long* next_sample;
     float* film;                  // [H][W][3], row 0 = bottom
     unsigned capacity;            // slots
@@ -250,7 +252,7 @@ NGI_HD_NOINLINE void ngi_logic_step(const NgiDevScene& sc, const NgiWaveParams& 
             wp.thr_pix[slot] = make_float4(thr.x, thr.y, thr.z, u2f((unsigned)pixel));
             wp.px[slot] = px; wp.py[slot] = py; wp.pz[slot] = pz;
             wp.dir_info[slot] = make_float4(wo.x, wo.y, wo.z, u2f(NGI_INFO_ALIVE | survive | ((unsigned)nverts << 8)));
-            (void)ngi_queue_alloc(wp.iter_counters + 1);                                      // exact extend-ray count
+            wp.extend_q[ngi_queue_alloc(wp.iter_counters + 1)] = slot;                        // compacted extend queue (+ exact ray count)
             return;
         }
         have_vertex = false;  // path ended at this vertex; the slot restarts with a fresh sample

@@ -169,11 +169,13 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
     std::vector<unsigned long long> sample(P);
     std::vector<float4> thr_pix(P), dir_info(P, make_float4(0, 0, 0, 0)), hit(P), shadow_q((size_t)P * 2 * 3);
     std::vector<double> px(P), py(P), pz(P);
-    unsigned iter_counters[2] = {0, 0};
+    unsigned iter_counters[2] = {0, 0}, fetch_cursors[2] = {0, 0};
+    std::vector<unsigned> extend_q(P);
     unsigned long long next_sample = (unsigned long long)rp->sample_offset;
     NgiWaveParams wp;
     wp.sample = sample.data(); wp.thr_pix = thr_pix.data(); wp.px = px.data(); wp.py = py.data(); wp.pz = pz.data();
     wp.dir_info = dir_info.data(); wp.hit = hit.data(); wp.shadow_q = shadow_q.data(); wp.iter_counters = iter_counters;
+    wp.extend_q = extend_q.data(); wp.fetch_cursors = fetch_cursors;
     wp.next_sample = &next_sample; wp.film = film; wp.capacity = P; wp.renderer = rp->renderer; wp.max_verts = rp->max_num_vertices;
     wp.width = rp->width; wp.height = rp->height; wp.sample_end = (unsigned long long)(rp->sample_offset + rp->num_samples);
     wp.seed_lo = (unsigned)rp->seed; wp.seed_hi = (unsigned)(rp->seed >> 32);
@@ -185,7 +187,7 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
         extend += iter_counters[1]; shadow += iter_counters[0];
         iters++;
         if (iter_counters[1] == 0 && iter_counters[0] == 0 && next_sample >= wp.sample_end) break;
-        for (unsigned i = 0; i < P; i++) ngi_extend_step(s->dev, wp, i);
+        for (unsigned q = 0; q < iter_counters[1]; q++) ngi_extend_step(s->dev, wp, extend_q[q]);   // compacted extend queue
         for (unsigned e = 0; e < iter_counters[0]; e++) ngi_shadow_step(s->dev, wp, e);
     }
     if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)extend; stats[2] = (double)shadow; stats[3] = (double)iters; }
