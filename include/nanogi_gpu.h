@@ -133,6 +133,9 @@ typedef struct NgiRenderParams {
 /* time every trace-kernel launch with CUDA events (fills NgiRenderStats.trace_kernel_seconds);
  * the wavefront loop is then launched kernel by kernel instead of as a CUDA graph */
 #define NGI_RENDER_TIME_KERNELS 1u
+/* cross-check: run the two trace stages as one-thread-per-ray kernels instead of the warp-cooperative
+ * persistent kernels (same building blocks, results identical up to the film's summation order) */
+#define NGI_RENDER_PER_RAY_TRACE 2u
 
 typedef struct NgiRenderStats {
     uint64_t paths;              /* samples processed                                         */

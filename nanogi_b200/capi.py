@@ -25,6 +25,7 @@ S_REFLECTION, S_REFRACTION, S_FRESNEL = 0, 1, 2
 RENDERER_PT, RENDERER_PTDIRECT = 0, 1
 RENDERERS = {"pt": RENDERER_PT, "ptdirect": RENDERER_PTDIRECT}
 RENDER_TIME_KERNELS = 1  # NGI_RENDER_TIME_KERNELS
+RENDER_PER_RAY_TRACE = 2  # NGI_RENDER_PER_RAY_TRACE
 NO_HIT = 0xFFFFFFFF
 
 d3 = C.c_double * 3

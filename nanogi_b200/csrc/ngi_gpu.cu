@@ -252,6 +252,15 @@ struct ShadowSource {
         ngi_film_add(wp.film, (int)f2u(q1.w), mk3(q2.x, q2.y, q2.z));
     }
 };
+// per-ray forms of the two trace stages (NGI_RENDER_PER_RAY_TRACE): cross-check only, see tests/test_gpu_parity.py
+__global__ void __launch_bounds__(kBlock) k_extend_per_ray(NgiDevScene sc, NgiWaveParams wp) {
+    const unsigned n = wp.iter_counters[1];
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) ngi_extend_step(sc, wp, wp.extend_q[q]);
+}
+__global__ void __launch_bounds__(kBlock) k_shadow_per_ray(NgiDevScene sc, NgiWaveParams wp) {
+    const unsigned n = wp.iter_counters[0];
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_shadow_step(sc, wp, e);
+}
 __global__ void __launch_bounds__(kBlock) k_extend(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
     ExtendSource src; src.wp = wp;
     ngi_trace_warp<false>(sc.nodes8, sc.tris8, src, tune);
@@ -299,7 +308,7 @@ struct Scene {
     int graph_iters = 0;
     std::vector<cudaEvent_t> events;
     // persistent trace kernels: grid = SM count x resident CTAs per SM (queried once per kernel)
-    NgiTraceTuning tune{8, 8};
+    NgiTraceTuning tune{4, 8};   // best of the sweep in profiles/r01_sweep_trace.txt
     unsigned grid_extend = 0, grid_shadow = 0, grid_trace[2] = {0, 0};
     unsigned* trace_cursor = nullptr;
 
@@ -526,7 +535,7 @@ void carve_wave(Scene* s, NgiWaveParams& wp) {
 
 bool same_wp(const NgiWaveParams& a, const NgiWaveParams& b) { return memcmp(&a, &b, sizeof(a)) == 0; }
 
-int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool timed, size_t& ev_used) {
+int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool timed, size_t& ev_used, bool per_ray = false) {
     const unsigned P = wp.capacity;
     const bool direct = wp.renderer == NGI_RENDERER_PTDIRECT;
     k_iter_begin<<<1, 1, 0, st>>>(s->counters);
@@ -536,9 +545,11 @@ int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool ti
     }
     k_logic<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
     if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 1], st));
-    k_extend<<<s->grid_extend, kBlock, 0, st>>>(s->dev, wp, s->tune);
+    if (per_ray) k_extend_per_ray<<<std::min(grid_for(P), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
+    else k_extend<<<s->grid_extend, kBlock, 0, st>>>(s->dev, wp, s->tune);
     if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 2], st));
-    if (direct) k_shadow<<<s->grid_shadow, kBlock, 0, st>>>(s->dev, wp, s->tune);
+    if (direct && per_ray) k_shadow_per_ray<<<std::min(grid_for((size_t)P * 2), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
+    else if (direct) k_shadow<<<s->grid_shadow, kBlock, 0, st>>>(s->dev, wp, s->tune);
     if (timed) { NGI_CUDA(cudaEventRecord(s->events[ev_used + 3], st)); ev_used += 4; }
     return NGI_OK;
 }
@@ -584,7 +595,8 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     NGI_CUDA(cudaEventCreate(&ev1));
     NGI_CUDA(cudaEventRecord(ev0, st));
 
-    const bool timed = (rp->flags & NGI_RENDER_TIME_KERNELS) != 0;
+    const bool per_ray = (rp->flags & NGI_RENDER_PER_RAY_TRACE) != 0;
+    const bool timed = (rp->flags & NGI_RENDER_TIME_KERNELS) != 0 || per_ray;
     const int kItersPerBatch = 8;
     const int kernels_per_iter = rp->renderer == NGI_RENDERER_PTDIRECT ? 4 : 3;
     size_t ev_used = 0;
@@ -608,7 +620,7 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     // expected number of iterations ~ (rays per path) * N / P; poll the counters once per batch
     while (true) {
         if (timed) {
-            for (int i = 0; i < kItersPerBatch; i++) { rc = launch_iteration(s, wp, st, true, ev_used); if (rc) return rc; }
+            for (int i = 0; i < kItersPerBatch; i++) { rc = launch_iteration(s, wp, st, true, ev_used, per_ray); if (rc) return rc; }
         } else {
             NGI_CUDA(cudaGraphLaunch(s->graph_exec, st));
         }

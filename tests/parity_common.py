@@ -154,10 +154,15 @@ def check_image_statistics(backend, sd, renderer, w=32, h=32, spp=256, seeds=6, 
     go, gg = fo.mean(axis=(1, 2, 3)), fg.mean(axis=(1, 2, 3))
     zt = (gg.mean() - go.mean()) / math.sqrt(go.var(ddof=1) / seeds + gg.var(ddof=1) / seeds)
     assert abs(zt) < 4.0, f"{renderer}: image mean differs, z = {zt:.2f} ({gg.mean()} vs {go.mean()})"
-    # relative RMSE of single renders against the pooled reference: equal noise level on both sides
+    # relative RMSE of single renders against the pooled reference: equal noise level on both sides. Scenes with
+    # glossy / specular lobes produce rare fireflies that dominate a plain RMSE over a handful of seeds (the oracle's
+    # own value moves by 2x between runs because its mt19937 streams depend on thread scheduling), so the statistic
+    # is taken on films clamped at 20x the pooled mean — identical treatment on both sides.
     ref = np.concatenate([fo, fg]).mean(0)
+    cap = 20.0 * ref.mean()
+    refc = np.minimum(ref, cap)
     def rel_rmse(f):
-        return math.sqrt(((f - ref) ** 2).mean()) / ref.mean()
+        return math.sqrt(((np.minimum(f, cap) - refc) ** 2).mean()) / refc.mean()
     ro = np.mean([rel_rmse(f) for f in fo]); rg = np.mean([rel_rmse(f) for f in fg])
     assert abs(rg - ro) < 0.25 * ro, f"{renderer}: relRMSE {rg:.4f} vs oracle {ro:.4f}"
     return float(np.abs(z).max()), ro, rg

@@ -88,19 +88,24 @@ def test_replay_small_scale(renderer, m):
 def test_gpu_equals_simulator_sample_for_sample(cornell):
     """The CUDA kernels and the CPU-stepped device code are the same program. The triangle test is bit-identical
     (explicit roundings); the shading arithmetic is not (nvcc contracts a*b+c into FMAs, the host build of the
-    same headers uses -ffp-contract=off), so a handful of paths per 10^5 may take a different branch: ray counts
-    agree to 1e-4 relative and the films agree except on the pixels those paths land in."""
+    same headers uses -ffp-contract=off). Away from the fp32 self-intersection regime (scene scaled to unit size)
+    a last-bit difference almost never changes a branch: ray counts agree to 1e-4 and <= 1 % of the pixels differ.
+    At Cornell scale (coordinates ~550, absolute epsilon 1e-4 ~ 1.6 ulp) a last-bit change of a shadow-ray direction
+    flips grazing self-hits, so ~0.2 % of the samples (measured: 7 % of the pixels at 29 spp) differ — same counts."""
     from tests.hostsim import pysim
-    g = capi.GpuScene(cornell, 0)
-    sim = pysim.SimScene(cornell)
-    for renderer in ("pt", "ptdirect"):
-        fg, sg = g.render(renderer, 30000, 32, 32, seed=12, max_num_vertices=8)
-        fs, ss = sim.render(renderer, 30000, 32, 32, seed=12, max_num_vertices=8)
-        assert abs(sg.extend_rays - ss["extend_rays"]) <= max(2, 1e-4 * ss["extend_rays"]), (sg.extend_rays, ss["extend_rays"])
-        assert abs(sg.shadow_rays - ss["shadow_rays"]) <= max(2, 1e-4 * ss["shadow_rays"]), (sg.shadow_rays, ss["shadow_rays"])
-        close = np.isclose(fg, fs, rtol=2e-3, atol=1e-5 * fs.max()).all(axis=2)
-        assert (~close).mean() <= 0.005, f"{renderer}: {(~close).sum()} pixels differ"
-    g.close()
+    small = scenes.to_scene_data(scaled_spec(scenes.cornell_box(), 0.01), 1.0)
+    for sd, max_bad in ((small, 0.01), (cornell, 0.15)):
+        g = capi.GpuScene(sd, 0)
+        sim = pysim.SimScene(sd)
+        for renderer in ("pt", "ptdirect"):
+            fg, sg = g.render(renderer, 30000, 32, 32, seed=12, max_num_vertices=8)
+            fs, ss = sim.render(renderer, 30000, 32, 32, seed=12, max_num_vertices=8)
+            assert abs(sg.extend_rays - ss["extend_rays"]) <= max(2, 1e-4 * ss["extend_rays"]), (sg.extend_rays, ss["extend_rays"])
+            assert abs(sg.shadow_rays - ss["shadow_rays"]) <= max(2, 1e-4 * ss["shadow_rays"]), (sg.shadow_rays, ss["shadow_rays"])
+            close = np.isclose(fg, fs, rtol=2e-3, atol=1e-5 * fs.max()).all(axis=2)
+            assert (~close).mean() <= max_bad, f"{renderer}: {(~close).sum()} pixels differ"
+            assert abs(fg.mean() - fs.mean()) < 0.01 * fs.mean()
+        g.close()
 
 
 @pytest.mark.parametrize("renderer,m,expect", [("pt", -1, 2.0), ("pt", 2, 1.0), ("pt", 4, 1.75), ("ptdirect", 3, 1.5), ("ptdirect", -1, 2.0)])
@@ -152,3 +157,14 @@ def test_error_paths(gpu_cornell):
     assert np.all(film == 0)
     film, st = gpu_cornell.render("pt", 1000, 4, 4, max_num_vertices=1)   # loop exits before any ray (src/nanogi.cpp:485)
     assert np.all(film == 0) and st.extend_rays == 0
+
+
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect"])
+def test_warp_cooperative_trace_equals_per_ray_trace(gpu_c2, renderer):
+    """The persistent warp-cooperative trace kernels (dynamic fetch, postponing) and the one-thread-per-ray form
+    visit nodes in different orders but reduce to the same closest hit / occlusion: identical ray counts and
+    films equal up to the order of the film's fp32 atomic adds."""
+    a, sa = gpu_c2.render(renderer, 400000, 64, 64, seed=21)
+    b, sb = gpu_c2.render(renderer, 400000, 64, 64, seed=21, flags=capi.RENDER_PER_RAY_TRACE)
+    assert sa.extend_rays == sb.extend_rays and sa.shadow_rays == sb.shadow_rays
+    assert np.allclose(a, b, rtol=1e-4, atol=1e-6 * b.max())
