@@ -154,22 +154,27 @@ NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTa
         child[best] = c.left[nd];
         child[cnt++] = c.right[nd];
     }
-    // node frame
+    // node frame: origin one quantisation step below the node box and 252 steps of usable range, so that the
+    // outward-rounded planes (widened by 2^-7 step, see below) never need clamping on either side
     const float4 nlo = c.lo[task.node2], nhi = c.hi[task.node2];
-    const float plo[3] = {nlo.x, nlo.y, nlo.z}, phi[3] = {nhi.x, nhi.y, nhi.z};
+    const float blo[3] = {nlo.x, nlo.y, nlo.z}, phi[3] = {nhi.x, nhi.y, nhi.z};
+    float plo[3];
     int eb[3]; double scale[3];
     for (int a = 0; a < 3; a++) {
-        const double ext = (double)phi[a] - (double)plo[a];
+        const double ext = (double)phi[a] - (double)blo[a];
         int e = -126;
         if (ext > 0) {
-            int k; (void)frexp(ext / 255.0, &k);  // ext/255 = m * 2^k, m in [0.5, 1)  =>  2^k * 255 >= ext
+            int k; (void)frexp(ext / 252.0, &k);  // ext/252 = m * 2^k, m in [0.5, 1)  =>  2^k * 252 >= ext
             e = k;
         }
         if (e < -126) e = -126;
-        if (e > 127) e = 127;
-        while (e < 127 && ((double)phi[a] - (double)plo[a]) > 255.0 * ldexp(1.0, e)) e++;
+        if (e > 112) e = 112;   // the traversal forms 2^(e+15) as a float exponent
+        while (e < 112 && ext > 252.0 * ldexp(1.0, e)) e++;
         eb[a] = e + 127;
         scale[a] = ldexp(1.0, e);
+        float o = (float)((double)blo[a] - scale[a]);
+        if ((double)o > (double)blo[a] - scale[a]) o = nextafterf(o, -NGI_INF_F);   // round the origin downwards
+        plo[a] = o;
     }
     // classify children
     bool inner[8]; int ntri[8]; int first[8];
@@ -223,10 +228,13 @@ NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTa
         const float4 l = c.lo[nd], h = c.hi[nd];
         const float clo[3] = {l.x, l.y, l.z}, chi[3] = {h.x, h.y, h.z};
         for (int a = 0; a < 3; a++) {
-            double ql = floor(((double)clo[a] - (double)plo[a]) / scale[a]);
-            double qh = ceil(((double)chi[a] - (double)plo[a]) / scale[a]);
-            if (ql < 0) ql = 0; if (ql > 255) ql = 255;
-            if (qh < 0) qh = 0; if (qh > 255) qh = 255;
+            // outward rounding, widened by 2^-7 step: covers the <= 2^-9 step decode error of ngi_q1 (ngi_bvh.h)
+            double ql = floor(((double)clo[a] - (double)plo[a]) / scale[a] - 0.0078125);
+            double qh = ceil(((double)chi[a] - (double)plo[a]) / scale[a] + 0.0078125);
+            if (ql < 0) ql = 0;
+            if (ql > 255) ql = 255;
+            if (qh < 0) qh = 0;
+            if (qh > 255) qh = 255;
             q[a][s] = (unsigned)ql; q[3 + a][s] = (unsigned)qh;
         }
         if (inner[k]) {
@@ -245,7 +253,7 @@ NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTa
         }
     }
     uint4* out = c.nodes8 + 5 * (size_t)task.node8;
-    out[0] = make_uint4(f2u(nlo.x), f2u(nlo.y), f2u(nlo.z), (unsigned)eb[0] | ((unsigned)eb[1] << 8) | ((unsigned)eb[2] << 16) | (imask << 24));
+    out[0] = make_uint4(f2u(plo[0]), f2u(plo[1]), f2u(plo[2]), (unsigned)eb[0] | ((unsigned)eb[1] << 8) | ((unsigned)eb[2] << 16) | (imask << 24));
     out[1] = make_uint4(childBase, triBase, ngi_pack4(meta), ngi_pack4(meta + 4));
     out[2] = make_uint4(ngi_pack4(q[0]), ngi_pack4(q[0] + 4), ngi_pack4(q[1]), ngi_pack4(q[1] + 4));
     out[3] = make_uint4(ngi_pack4(q[2]), ngi_pack4(q[2] + 4), ngi_pack4(q[3]), ngi_pack4(q[3] + 4));

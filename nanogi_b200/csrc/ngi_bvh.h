@@ -132,14 +132,28 @@ NGI_HD bool ngi_trace_bvh2(const float4* __restrict__ nodes, const float4* __res
 
 NGI_HD unsigned ngi_byte(unsigned w, int i) { return (w >> (8 * i)) & 0xFFu; }
 
-// exact byte -> float without the XU pipe: I2F.U8 runs at 16 lanes/clk/SM and was the busiest pipe of the
-// first traversal kernel (profiles/r01_ncu_c2_steady.txt: XU 71 %). PRMT builds 2^23 + q in one ALU op, the
-// FADD of -2^23 is exact, so the value is bit-identical to (float)q.
-NGI_HD float ngi_qf(unsigned w, int i) {
+// Quantised plane -> float without a conversion instruction. I2F.U8 runs on the XU pipe at 16 lanes/clk/SM and
+// was the busiest pipe of the first traversal kernel (profiles/r01_ncu_c2_steady.txt: XU 71 %). Instead one PRMT
+// drops byte i of `w` into mantissa bits 8..15 of 1.0f:  Q = 1 + q * 2^-15  (exact), and the plane distance
+//     t = q * s + b  =  Q * (2^15 s) + (b - 2^15 s)
+// costs that PRMT and one FMA per plane; (b - 2^15 s) is formed once per axis per node. Its rounding error is at
+// most 2^-24 |b - 2^15 s| <= 2^-9 quantisation steps (plus the 2^-24 |b| every slab test has and the box padding
+// covers); the build widens every quantised plane by 2^-7 step (ngi_collapse_node) so the decode stays conservative.
+NGI_HD float ngi_q1(unsigned w, int i) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (unsigned)i)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | ((unsigned)i << 4)));
 #else
-    return (float)((w >> (8 * i)) & 0xFFu);
+    return u2f(0x3F800000u | (((w >> (8 * i)) & 0xFFu) << 8));
+#endif
+}
+// per byte: 0xFF if the byte's top bit is set, else 0x00
+NGI_HD unsigned ngi_sext_s8x4(unsigned x) {
+#if defined(__CUDA_ARCH__)
+    unsigned r;
+    asm("prmt.b32 %0, %1, 0, 0x0000ba98;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return ((x >> 7) & 0x01010101u) * 0xFFu;
 #endif
 }
 
@@ -175,16 +189,22 @@ NGI_HD void ngi_bvh8_node_step(const uint4* __restrict__ nodes, const size_t ni,
     const uint4 n0 = ngi_ldg(nodes + 5 * ni), n1 = ngi_ldg(nodes + 5 * ni + 1), n2 = ngi_ldg(nodes + 5 * ni + 2);
     const uint4 n3 = ngi_ldg(nodes + 5 * ni + 3), n4 = ngi_ldg(nodes + 5 * ni + 4);
 
-    const float sx = u2f((n0.w & 0xFFu) << 23) * r.idx;
-    const float sy = u2f(((n0.w >> 8) & 0xFFu) << 23) * r.idy;
-    const float sz = u2f(((n0.w >> 16) & 0xFFu) << 23) * r.idz;
-    const float bx = (u2f(n0.x) - r.o.x) * r.idx, by = (u2f(n0.y) - r.o.y) * r.idy, bz = (u2f(n0.z) - r.o.z) * r.idz;
-    const unsigned octinv = r.octinv;
+    // per-axis scale 2^(e+15) / d and offset (p - o) / d - 2^(e+15) / d   (see ngi_q1)
+    const float sx = u2f(((n0.w & 0xFFu) + 15u) << 23) * r.idx;
+    const float sy = u2f((((n0.w >> 8) & 0xFFu) + 15u) << 23) * r.idy;
+    const float sz = u2f((((n0.w >> 16) & 0xFFu) + 15u) << 23) * r.idz;
+    const float bx = (u2f(n0.x) - r.o.x) * r.idx - sx, by = (u2f(n0.y) - r.o.y) * r.idy - sy, bz = (u2f(n0.z) - r.o.z) * r.idz - sz;
+    const unsigned octinv4 = r.octinv * 0x01010101u;
 
     unsigned hitmask = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const unsigned meta4 = h ? n1.w : n1.z;
+        // 4 children at a time (Ylitie et al. 2017): bit position and bit pattern each child contributes
+        const unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const unsigned inner_mask4 = ngi_sext_s8x4(is_inner4 << 3);
+        const unsigned bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+        const unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
         // near / far plane words per axis, chosen by the ray's sign
         const unsigned lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
         const unsigned hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
@@ -193,18 +213,12 @@ NGI_HD void ngi_bvh8_node_step(const uint4* __restrict__ nodes, const size_t ni,
         const unsigned nz = r.negz ? hiz : loz, fz = r.negz ? loz : hiz;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const unsigned meta = ngi_byte(meta4, i);
-            const float tnx = fmaf(ngi_qf(nx, i), sx, bx), tfx = fmaf(ngi_qf(fx, i), sx, bx);
-            const float tny = fmaf(ngi_qf(ny, i), sy, by), tfy = fmaf(ngi_qf(fy, i), sy, by);
-            const float tnz = fmaf(ngi_qf(nz, i), sz, bz), tfz = fmaf(ngi_qf(fz, i), sz, bz);
+            const float tnx = fmaf(ngi_q1(nx, i), sx, bx), tfx = fmaf(ngi_q1(fx, i), sx, bx);
+            const float tny = fmaf(ngi_q1(ny, i), sy, by), tfy = fmaf(ngi_q1(fy, i), sy, by);
+            const float tnz = fmaf(ngi_q1(nz, i), sz, bz), tfz = fmaf(ngi_q1(fz, i), sz, bz);
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, limit));
-            if (meta != 0u && tn <= tf) {
-                const bool inner = (meta & 0x18u) == 0x18u;
-                const unsigned bits = inner ? 1u : (meta >> 5);
-                const unsigned pos = inner ? ((meta ^ octinv) & 31u) : (meta & 31u);
-                hitmask |= bits << pos;
-            }
+            if (tn <= tf) hitmask |= ngi_byte(child_bits4, i) << ngi_byte(bit_index4, i);   // empty slots have no bits
         }
     }
     ngroup.x = n1.x;
