@@ -224,8 +224,12 @@ def run_own(args, rank: int, local_rank: int, world: int):
         + __import__("ctypes").sizeof(capi.NgiRenderParams)
     d2h = film.numel() * 4
 
+    e2e_parts = {"create_s": 0.0, "render_s": 0.0, "destroy_s": 0.0}
+
     def e2e_step(i: int):
+        ta = time.perf_counter()
         sc = capi.GpuScene(sd, local_rank)                           # H2D of the scene + GPU BVH build
+        tb = time.perf_counter()
         if world == 1:
             p = sc._params(renderer, n_rank, W, H, max_num_vertices=m, seed=5000 + i, film_norm_samples=n_total,
                            wave_capacity=args.wave_capacity)
@@ -239,7 +243,11 @@ def run_own(args, rank: int, local_rank: int, world: int):
             if rank == 0:
                 pinned.copy_(film, non_blocking=True)
             torch.cuda.synchronize(dev)
+        tc = time.perf_counter()
         sc.close()
+        td = time.perf_counter()
+        if i >= 0:
+            e2e_parts["create_s"] += tb - ta; e2e_parts["render_s"] += tc - tb; e2e_parts["destroy_s"] += td - tc
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_step(-1)
@@ -306,7 +314,8 @@ def run_own(args, rank: int, local_rank: int, world: int):
                        "l2": "256 MB memset between iterations flushes L2; wavefront state (%.0f MB) also exceeds it"
                              % ((args.wave_capacity or (1 << 21)) * 176 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "includes": "scene H2D + GPU BVH build + render + film D2H (pinned) + destroy, wall clock"},
+                    "steps": e2e_steps, "includes": "scene H2D + GPU BVH build + render + film D2H (pinned) + destroy, wall clock",
+                    "breakdown_s_per_step": {k: v / e2e_steps for k, v in e2e_parts.items()}},
             "gpu_launches": int(cnt[0].item()), "wave_iterations": int(iters), "film_mean": film_mean,
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clk,
         }

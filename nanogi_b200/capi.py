@@ -15,6 +15,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 GPU_LIB_PATH = os.path.join(_HERE, "libnanogi_gpu.so")
+if os.environ.get("NGI_GPU_LIB"):   # A/B experiments with alternative builds of the SAME CUDA module (tools/)
+    GPU_LIB_PATH = os.environ["NGI_GPU_LIB"]
 HOST_LIB_PATH = os.path.join(_HERE, "libnanogi_host.so")
 
 # ---- enums (include/nanogi_gpu.h) -------------------------------------------------------------

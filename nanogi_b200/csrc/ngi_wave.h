@@ -119,145 +119,163 @@ NGI_HD int ngi_reconstruct(const NgiDevScene& sc, const unsigned tri, const floa
     return (int)f2u(r4.z);
 }
 
-// ---- the logic stage for one slot --------------------------------------------------------------
-NGI_HD_NOINLINE void ngi_logic_step(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
+// ---- the logic stage ---------------------------------------------------------------------------
+// Split in three per-slot functions so that the CUDA kernel can regroup the slots of a block between them
+// (block-local compaction: dense warps per stage, see k_logic in ngi_gpu.cu) while the CPU simulator simply
+// calls them back to back (ngi_logic_step):
+//   classify  tail of reference iteration k that needs no surface geometry: miss / RR / vertex cap; `pt` adds
+//             the emission of a hit light here. Returns whether the path continues at a surface vertex.
+//   surface   head of iteration k+1 at a surface vertex: reconstruct, NEE, BSDF sample. Returns false when the
+//             path ends at this vertex (the slot is then regenerated by `eye` in the same logic stage).
+//   eye       starts the next sample at the eye vertex: NEE to the light-sample's pixel, camera ray.
+#define NGI_CLASS_REGENERATE 0
+#define NGI_CLASS_SURFACE 1
+
+// one path vertex: optional NEE (ptdirect), direction sampling, extend-ray emission. `eye` is a literal at every
+// call site, so the two flavours are specialised by the compiler.
+NGI_HD bool ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot, const bool eye,
+                       const unsigned long long sample, f3 thr, int pixel, const int nverts, const int type,
+                       const NgiGeom& g, const f3 wi, const double px, const double py, const double pz, const int primIdx) {
+    const NgiDevSensor& E = sc.sensor;
+    const unsigned vtx = (unsigned)(nverts - 1);
+    const NgiDevPrim& P = sc.prims[primIdx];
+
+    // ---- direct light sampling (ptdirect), nanogi.cpp:654-712 ----
+    if (wp.renderer == 1 && sc.n_lights > 0) {
+        unsigned rb[4];
+        philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), vtx, 1u, wp.seed_lo, wp.seed_hi, rb);
+        const NgiLightSample ls = ngi_sample_light(sc, u01(rb[0]), u01(rb[1]), u01(rb[2]));
+        if (ls.valid) {
+            const f3 diff = mk3((float)((double)ls.p.x - px), (float)((double)ls.p.y - py), (float)((double)ls.p.z - pz));
+            const float dist2 = dot(diff, diff);
+            const float dist = sqrtf(dist2);
+            const f3 ppL = diff / dist;                                                   // :680
+            f3 fsE; int index = pixel;
+            float g1 = 1.0f;
+            if (eye) {
+                float rx = 0.0f, ry = 0.0f;
+                const float we = ngi_pinhole_importance(E, ppL, rx, ry);                  // :681 (type E)
+                fsE = mk3(we);
+                index = ngi_pixel_index(rx, ry, wp.width, wp.height);                     // :698-703
+            } else {
+                float pdfUnused;
+                fsE = ngi_eval_bsdf(P, type, g, wi, ppL, false, pdfUnused);               // :681
+                g1 = fabsf(dot(g.sn, ppL));                                               // GeometryTerm, rt.hpp:2371
+            }
+            f3 fsL = ls.le;                                                               // :682
+            float g2 = 1.0f;
+            if (!ls.degenerate) {
+                const float cl = dot(ls.n, -ppL);
+                if (cl <= 0.0f) fsL = mk3(0.0f);                                          // rt.hpp:922-927
+                g2 = fabsf(cl);                                                           // rt.hpp:2372
+            }
+            const float G = g1 * g2 / dist2;                                              // :683
+            const f3 C = thr * fsE * fsL * (G / ls.pdf);                                  // :686 (V applied by the shadow kernel)
+            if (!is_zero(C)) {
+                const f3 o = mk3((float)px, (float)py, (float)pz);                        // rt.hpp:2166-2168
+                ngi_push_shadow(wp, o, ppL, dist * (1.0f - NGI_EPS_F), C * wp.film_scale, index);         // rt.hpp:2260
+            }
+        }
+    }
+
+    // ---- sample the next direction, nanogi.cpp:492-544 / :716-754 ----
+    unsigned ra[4];
+    philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), vtx, 0u, wp.seed_lo, wp.seed_hi, ra);
+    f3 wo;
+    bool ok;
+    if (eye) {
+        wo = ngi_pinhole_sample(E, u01(ra[0]), u01(ra[1]));
+        float rx, ry, ct;
+        ok = ngi_raster_position(E, wo, rx, ry, ct);                                      // :504-523 / :728-733
+        if (ok) pixel = ngi_pixel_index(rx, ry, wp.width, wp.height);
+        // fs / pdfD = We / pdf = 1 exactly (same expression on both sides)
+    } else {
+        ok = ngi_sample_bsdf(P, type, g, wi, u01(ra[0]), u01(ra[1]), u01(ra[2]), wo);
+        if (ok) {
+            float pdfD;
+            const f3 fs = ngi_eval_bsdf(P, type, g, wi, wo, true, pdfD);                  // :531 / :741
+            if (is_zero(fs)) ok = false;                                                  // :532 / :742
+            else thr = thr * (fs / pdfD);                                                 // :544 / :754
+        }
+    }
+    if (!ok) return false;
+    const unsigned survive = (u01(ra[3]) > 0.5f) ? 0u : NGI_INFO_RR_SURVIVE;              // :583-587, decided up front
+    wp.sample[slot] = sample;
+    wp.thr_pix[slot] = make_float4(thr.x, thr.y, thr.z, u2f((unsigned)pixel));
+    wp.px[slot] = px; wp.py[slot] = py; wp.pz[slot] = pz;
+    wp.dir_info[slot] = make_float4(wo.x, wo.y, wo.z, u2f(NGI_INFO_ALIVE | survive | ((unsigned)nverts << 8)));
+    wp.extend_q[ngi_queue_alloc(wp.iter_counters + 1)] = slot;                            // compacted extend queue (+ exact ray count)
+    return true;
+}
+
+NGI_HD int ngi_logic_classify(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
     const float4 di = wp.dir_info[slot];
     const unsigned info = f2u(di.w);
-    const NgiDevSensor& E = sc.sensor;
-
-    f3 thr = mk3(1.0f);
-    int pixel = -1;
-    unsigned long long sample = 0;
-    int nverts = 1;
-    int type = NGI_E;
-    NgiGeom g; g.sn = g.gn = g.dpdu = g.dpdv = mk3(0.0f);
-    f3 wi = mk3(0.0f);
-    double px = 0, py = 0, pz = 0;
-    int primIdx = -1;
-    bool have_vertex = false;
-
-    if (info & NGI_INFO_ALIVE) {
-        const float4 h = wp.hit[slot];
-        const unsigned tri = f2u(h.w);
-        if (tri != NGI_MISS) {                                                                // miss -> break, nanogi.cpp:557 / :767
+    if (!(info & NGI_INFO_ALIVE)) return NGI_CLASS_REGENERATE;
+    const float4 h = wp.hit[slot];
+    const unsigned tri = f2u(h.w);
+    if (tri == NGI_MISS) return NGI_CLASS_REGENERATE;                                         // miss -> break, nanogi.cpp:557 / :767
+    if (wp.renderer == 0) {                                                                   // nanogi.cpp:566-577
+        const int primIdx = (int)f2u(ngi_ldg(sc.shade_tris + 5 * (size_t)tri + 4).z);
+        const NgiDevPrim& P = sc.prims[primIdx];
+        if ((P.type & NGI_L) && P.l_type == NGI_LT_AREA) {
+            // EvaluateDirection(L.area): Le iff cos_sn(-d) > 0 (rt.hpp:922-927); EvaluatePosition(area) = 1
+            NgiGeom g;
+            ngi_reconstruct(sc, tri, h.y, h.z, g);
             const f3 d = mk3(di.x, di.y, di.z);
-            const float4 tp = wp.thr_pix[slot];
-            thr = mk3(tp.x, tp.y, tp.z);
-            pixel = (int)f2u(tp.w);
-            // isect.geom.p = ray.o + ray.d * (double)tfar, rt.hpp:2197. In the reference ray.d is the fp64
-            // direction whose fp32 ROUNDING was traced (rt.hpp:2169-2171): the reconstructed point is off the
-            // traced ray by (d64 - d32) * t, which together with the absolute 1e-4 epsilon decides how often
-            // the next ray re-hits its own surface (measured on the Cornell box: 5.3 % of bounce rays with
-            // that term, 5.0 % without). The device direction only exists in fp32, so the rounding residual
-            // is re-created as a uniform +-ulp/2 dither hashed from the hit record (tests/test_sim_parity.py).
-            double ddx, ddy, ddz;
-            ngi_dither_direction(d, h, ddx, ddy, ddz);
-            px = wp.px[slot] + ddx * (double)h.x;
-            py = wp.py[slot] + ddy * (double)h.x;
-            pz = wp.pz[slot] + ddz * (double)h.x;
-            primIdx = ngi_reconstruct(sc, tri, h.y, h.z, g);
-            const NgiDevPrim& P = sc.prims[primIdx];
-            if (wp.renderer == 0 && (P.type & NGI_L) && P.l_type == NGI_LT_AREA) {            // nanogi.cpp:566-577
-                // EvaluateDirection(L.area): Le iff cos_sn(-d) > 0 (rt.hpp:922-927); EvaluatePosition(area) = 1
-                if (dot(g.sn, -d) > 0.0f) ngi_film_add(wp.film, pixel, thr * P.l_le * wp.film_scale);
-            }
-            if (info & NGI_INFO_RR_SURVIVE) {                                                 // nanogi.cpp:581-591
-                nverts = (int)(info >> 8) + 1;                                                // :603
-                if (!(wp.max_verts != -1 && nverts >= wp.max_verts)) {                        // :485 / :647
-                    thr = thr * 2.0f;                                                         // throughput /= rrProb
-                    type = P.type & ~NGI_EMITTER;                                             // :601
-                    wi = -d;                                                                  // :602
-                    sample = wp.sample[slot];
-                    have_vertex = true;
-                }
+            if (dot(g.sn, -d) > 0.0f) {
+                const float4 tp = wp.thr_pix[slot];
+                ngi_film_add(wp.film, (int)f2u(tp.w), mk3(tp.x, tp.y, tp.z) * P.l_le * wp.film_scale);
             }
         }
     }
+    if (!(info & NGI_INFO_RR_SURVIVE)) return NGI_CLASS_REGENERATE;                           // nanogi.cpp:581-591
+    const int nverts = (int)(info >> 8) + 1;                                                  // :603
+    if (wp.max_verts != -1 && nverts >= wp.max_verts) return NGI_CLASS_REGENERATE;            // :485 / :647
+    return NGI_CLASS_SURFACE;
+}
 
-    for (int pass = 0; pass < 2; pass++) {
-        if (!have_vertex) {
-            // the slot's path ended: start the next sample at the eye vertex (nanogi.cpp:450-479 / :613-641)
-            sample = ngi_fetch_sample(wp.next_sample);
-            if (sample >= wp.sample_end) break;
-            thr = mk3(1.0f);       // EvaluatePosition / pdfPE / pdfE = 1 for the pinhole
-            nverts = 1; type = NGI_E; pixel = -1;
-            px = E.px; py = E.py; pz = E.pz;
-            primIdx = E.prim;
-        }
-        const unsigned vtx = (unsigned)(nverts - 1);
-        const bool eye = (type == NGI_E);
-        const NgiDevPrim& P = sc.prims[primIdx];
+NGI_HD bool ngi_logic_surface(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
+    const float4 di = wp.dir_info[slot];
+    const unsigned info = f2u(di.w);
+    const float4 h = wp.hit[slot];
+    const f3 d = mk3(di.x, di.y, di.z);
+    const float4 tp = wp.thr_pix[slot];
+    // isect.geom.p = ray.o + ray.d * (double)tfar, rt.hpp:2197. In the reference ray.d is the fp64
+    // direction whose fp32 ROUNDING was traced (rt.hpp:2169-2171): the reconstructed point is off the
+    // traced ray by (d64 - d32) * t, which together with the absolute 1e-4 epsilon decides how often
+    // the next ray re-hits its own surface (measured on the Cornell box: 5.3 % of bounce rays with
+    // that term, 5.0 % without). The device direction only exists in fp32, so the rounding residual
+    // is re-created as a uniform +-ulp/2 dither hashed from the hit record (tests/test_sim_parity.py).
+    double ddx, ddy, ddz;
+    ngi_dither_direction(d, h, ddx, ddy, ddz);
+    const double px = wp.px[slot] + ddx * (double)h.x;
+    const double py = wp.py[slot] + ddy * (double)h.x;
+    const double pz = wp.pz[slot] + ddz * (double)h.x;
+    NgiGeom g;
+    const int primIdx = ngi_reconstruct(sc, f2u(h.w), h.y, h.z, g);
+    const int nverts = (int)(info >> 8) + 1;                                                  // :603
+    const f3 thr = mk3(tp.x, tp.y, tp.z) * 2.0f;                                              // throughput /= rrProb, :591
+    const int type = sc.prims[primIdx].type & ~NGI_EMITTER;                                   // :601
+    return ngi_vertex(sc, wp, slot, false, wp.sample[slot], thr, (int)f2u(tp.w), nverts, type, g, -d /* :602 */, px, py, pz, primIdx);
+}
 
-        // ---- direct light sampling (ptdirect), nanogi.cpp:654-712 ----
-        if (wp.renderer == 1 && sc.n_lights > 0) {
-            unsigned rb[4];
-            philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), vtx, 1u, wp.seed_lo, wp.seed_hi, rb);
-            const NgiLightSample ls = ngi_sample_light(sc, u01(rb[0]), u01(rb[1]), u01(rb[2]));
-            if (ls.valid) {
-                const f3 diff = mk3((float)((double)ls.p.x - px), (float)((double)ls.p.y - py), (float)((double)ls.p.z - pz));
-                const float dist2 = dot(diff, diff);
-                const float dist = sqrtf(dist2);
-                const f3 ppL = diff / dist;                                                   // :680
-                f3 fsE; int index = pixel;
-                float g1 = 1.0f;
-                if (eye) {
-                    float rx = 0.0f, ry = 0.0f;
-                    const float we = ngi_pinhole_importance(E, ppL, rx, ry);                  // :681 (type E)
-                    fsE = mk3(we);
-                    index = ngi_pixel_index(rx, ry, wp.width, wp.height);                     // :698-703
-                } else {
-                    float pdfUnused;
-                    fsE = ngi_eval_bsdf(P, type, g, wi, ppL, false, pdfUnused);               // :681
-                    g1 = fabsf(dot(g.sn, ppL));                                               // GeometryTerm, rt.hpp:2371
-                }
-                f3 fsL = ls.le;                                                               // :682
-                float g2 = 1.0f;
-                if (!ls.degenerate) {
-                    const float cl = dot(ls.n, -ppL);
-                    if (cl <= 0.0f) fsL = mk3(0.0f);                                          // rt.hpp:922-927
-                    g2 = fabsf(cl);                                                           // rt.hpp:2372
-                }
-                const float G = g1 * g2 / dist2;                                              // :683
-                const f3 C = thr * fsE * fsL * (G / ls.pdf);                                  // :686 (V applied by the shadow kernel)
-                if (!is_zero(C)) {
-                    const f3 o = mk3((float)px, (float)py, (float)pz);                        // rt.hpp:2166-2168
-                    ngi_push_shadow(wp, o, ppL, dist * (1.0f - NGI_EPS_F), C * wp.film_scale, index);         // rt.hpp:2260
-                }
-            }
-        }
-
-        // ---- sample the next direction, nanogi.cpp:492-544 / :716-754 ----
-        unsigned ra[4];
-        philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), vtx, 0u, wp.seed_lo, wp.seed_hi, ra);
-        f3 wo;
-        bool ok;
-        if (eye) {
-            wo = ngi_pinhole_sample(E, u01(ra[0]), u01(ra[1]));
-            float rx, ry, ct;
-            ok = ngi_raster_position(E, wo, rx, ry, ct);                                      // :504-523 / :728-733
-            if (ok) pixel = ngi_pixel_index(rx, ry, wp.width, wp.height);
-            // fs / pdfD = We / pdf = 1 exactly (same expression on both sides)
-        } else {
-            ok = ngi_sample_bsdf(P, type, g, wi, u01(ra[0]), u01(ra[1]), u01(ra[2]), wo);
-            if (ok) {
-                float pdfD;
-                const f3 fs = ngi_eval_bsdf(P, type, g, wi, wo, true, pdfD);                  // :531 / :741
-                if (is_zero(fs)) ok = false;                                                  // :532 / :742
-                else thr = thr * (fs / pdfD);                                                 // :544 / :754
-            }
-        }
-        if (ok) {
-            const unsigned survive = (u01(ra[3]) > 0.5f) ? 0u : NGI_INFO_RR_SURVIVE;          // :583-587, decided up front
-            wp.sample[slot] = sample;
-            wp.thr_pix[slot] = make_float4(thr.x, thr.y, thr.z, u2f((unsigned)pixel));
-            wp.px[slot] = px; wp.py[slot] = py; wp.pz[slot] = pz;
-            wp.dir_info[slot] = make_float4(wo.x, wo.y, wo.z, u2f(NGI_INFO_ALIVE | survive | ((unsigned)nverts << 8)));
-            wp.extend_q[ngi_queue_alloc(wp.iter_counters + 1)] = slot;                        // compacted extend queue (+ exact ray count)
-            return;
-        }
-        have_vertex = false;  // path ended at this vertex; the slot restarts with a fresh sample
+// the slot's path ended: start the next sample at the eye vertex (nanogi.cpp:450-479 / :613-641)
+NGI_HD void ngi_logic_eye(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
+    const NgiDevSensor& E = sc.sensor;
+    const unsigned long long sample = ngi_fetch_sample(wp.next_sample);
+    if (sample < wp.sample_end) {
+        NgiGeom g; g.sn = g.gn = g.dpdu = g.dpdv = mk3(0.0f);
+        // EvaluatePosition / pdfPE / pdfE = 1 for the pinhole
+        if (ngi_vertex(sc, wp, slot, true, sample, mk3(1.0f), -1, 1, NGI_E, g, mk3(0.0f), E.px, E.py, E.pz, E.prim)) return;
     }
     wp.dir_info[slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));                               // idle slot
+}
+
+// all three for one slot (the CPU simulator's order; the CUDA kernel regroups slots between the stages)
+NGI_HD_NOINLINE void ngi_logic_step(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
+    if (ngi_logic_classify(sc, wp, slot) == NGI_CLASS_SURFACE && ngi_logic_surface(sc, wp, slot)) return;
+    ngi_logic_eye(sc, wp, slot);
 }
 
 // ---- extend / shadow bodies (BVH8 = product path) -----------------------------------------------
