@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -333,6 +334,28 @@ __global__ void __launch_bounds__(kBlock) k_eval_bsdf(NgiDevScene sc, const floa
 // ================================================================================================
 // scene handle
 // ================================================================================================
+// The path-state buffer (176 B + queues per slot, 369 MB at the default 2 Mi slots) is scene independent, and
+// cudaMalloc / cudaFree of that size cost 0.1-0.3 s: a released buffer is parked per device and handed to the
+// next scene handle that asks for the same capacity (the e2e path creates one handle per render).
+struct WaveCacheEntry { void* mem = nullptr; unsigned capacity = 0; };
+std::mutex g_wave_mutex;
+WaveCacheEntry g_wave_cache[64];
+
+void* wave_cache_take(int device, unsigned P) {
+    std::lock_guard<std::mutex> lock(g_wave_mutex);
+    if (device < 0 || device >= 64) return nullptr;
+    WaveCacheEntry& e = g_wave_cache[device];
+    if (e.mem && e.capacity == P) { void* m = e.mem; e.mem = nullptr; e.capacity = 0; return m; }
+    return nullptr;
+}
+void wave_cache_put(int device, void* mem, unsigned P) {
+    std::lock_guard<std::mutex> lock(g_wave_mutex);
+    if (device < 0 || device >= 64) { cudaFree(mem); return; }
+    WaveCacheEntry& e = g_wave_cache[device];
+    if (e.mem) cudaFree(e.mem);
+    e.mem = mem; e.capacity = P;
+}
+
 struct Scene {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -358,7 +381,7 @@ struct Scene {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (auto e : events) cudaEventDestroy(e);
         for (void* p : allocs) cudaFree(p);
-        if (wave_mem) cudaFree(wave_mem);
+        if (wave_mem) wave_cache_put(device, wave_mem, wave_capacity);
         if (counters) cudaFree(counters);
         if (trace_cursor) cudaFree(trace_cursor);
         if (counters_host) cudaFreeHost(counters_host);
@@ -546,10 +569,11 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
 int ensure_wave(Scene* s, unsigned P) {
     if (s->wave_capacity == P && s->wave_mem) return NGI_OK;
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
-    if (s->wave_mem) { cudaFree(s->wave_mem); s->wave_mem = nullptr; }
+    if (s->wave_mem) { wave_cache_put(s->device, s->wave_mem, s->wave_capacity); s->wave_mem = nullptr; }
     // per slot: sample 8 + thr_pix 16 + p 24 + dir_info 16 + hit 16 = 80 B; shadow queue 2 entries x 48 B
     const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96 + 4);
-    NGI_CUDA(cudaMalloc(&s->wave_mem, bytes));
+    s->wave_mem = wave_cache_take(s->device, P);
+    if (!s->wave_mem) NGI_CUDA(cudaMalloc(&s->wave_mem, bytes));
     if (!s->counters) NGI_CUDA(cudaMalloc((void**)&s->counters, sizeof(NgiRenderCounters)));
     if (!s->counters_host) NGI_CUDA(cudaMallocHost((void**)&s->counters_host, sizeof(NgiRenderCounters)));
     s->wave_capacity = P;

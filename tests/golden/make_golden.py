@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures of tests/golden/ from the CPU oracle (oracle/oracle.cpp).
+
+The reference ships no tests, golden vectors or numeric images and cannot be built or imported here
+(SURVEY.md §8c), so these fixtures are NOT reference outputs: they pin the oracle restatement itself (a change of the
+oracle's behaviour shows up as a diff here) and give the GPU tests fixed, machine-independent vectors.
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from nanogi_b200 import capi, scenes  # noqa: E402
+from oracle import pyoracle  # noqa: E402
+from tests import parity_common as pc  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    for name in ("cornell_box", "cornell_spheres"):
+        sd = scenes.to_scene_data(getattr(scenes, name)(), 1.0)
+        orc = pyoracle.OracleScene(sd)
+        rays = np.concatenate([scenes.camera_rays(sd, 16, 16), scenes.random_rays(sd, 768, 3)])
+        occ = scenes.random_rays(sd, 512, 4, occlusion=True)
+        hits = orc.trace(rays, 0)
+        brute = orc.trace(rays, 2)
+        assert np.array_equal(hits, brute), "oracle BVH differs from its own brute force"
+        occ_hits = orc.trace(occ, 1)
+        films = {}
+        for renderer in ("pt", "ptdirect"):
+            for m in (-1, 4):
+                f, st = orc.render(renderer, 4096, 16, 16, max_num_vertices=m, seed=3, rng_mode=1, num_threads=1)
+                films[f"film_{renderer}_{m}"] = f
+                films[f"rays_{renderer}_{m}"] = np.array([st["extend_rays"], st["shadow_rays"]])
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), rays=rays, hits=hits, occ=occ, occ_tri=occ_hits["tri"], **films)
+        print(name, "hit rate", float((hits["tri"] != capi.NO_HIT).mean()), "occluded", float((occ_hits["tri"] == 0).mean()))
+    # BSDF tables on the C2 scene: D wall, G conductor sphere, S fresnel sphere
+    sd = scenes.to_scene_data(scenes.cornell_spheres(), 1.0)
+    orc = pyoracle.OracleScene(sd)
+    tab = {}
+    for prim, bit in pc.bsdf_test_prims(sd):
+        q = pc.bsdf_queries(sd, prim, bit, 256, seed=17)
+        wo, fs, pdf, ok = pc.oracle_bsdf_table(orc, q)
+        tab[f"q_{prim}_{bit}"] = q; tab[f"wo_{prim}_{bit}"] = wo; tab[f"fs_{prim}_{bit}"] = fs; tab[f"pdf_{prim}_{bit}"] = pdf; tab[f"ok_{prim}_{bit}"] = ok
+    np.savez_compressed(os.path.join(OUT, "bsdf_tables.npz"), **tab)
+    print("bsdf tables", sorted(k for k in tab if k.startswith("q_")))
+
+
+if __name__ == "__main__":
+    main()

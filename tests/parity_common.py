@@ -82,6 +82,28 @@ def bsdf_queries(sd, prim, type_bit, n, seed):
     return q
 
 
+BSDF_TEST_PRIMS = [(4, capi.TYPE_D), (8, capi.TYPE_G), (9, capi.TYPE_S)]   # C2: a diffuse wall, the conductor, the glass sphere
+
+
+def bsdf_test_prims(sd):
+    return BSDF_TEST_PRIMS
+
+
+def oracle_bsdf_table(orc, q):
+    """SampleDirection + EvaluateDirection(+PDF) of the oracle for a query block (golden fixture format)."""
+    n = q.shape[0]
+    wo = np.zeros((n, 3)); fs = np.zeros((n, 3)); pdf = np.zeros(n); ok = np.zeros(n, bool)
+    for i in range(n):
+        prim, bit = int(q[i, 0]), int(q[i, 1])
+        sn, gn, wi = q[i, 2:5].astype(np.float64), q[i, 5:8].astype(np.float64), q[i, 8:11].astype(np.float64)
+        w, wrote = orc.sample_direction(prim, bit, sn, gn, wi, float(q[i, 11]), float(q[i, 12]), float(q[i, 13]))
+        ok[i] = wrote
+        if wrote:
+            wo[i] = w
+            fs[i], pdf[i] = orc.evaluate_direction(prim, bit, sn, gn, wi, w, True, True)
+    return wo, fs, pdf, ok
+
+
 def check_bsdf_parity(backend, sd, prim, type_bit, n=4000, seed=0, rtol=2e-3):
     orc = pyoracle.OracleScene(sd)
     q = bsdf_queries(sd, prim, type_bit, n, seed)

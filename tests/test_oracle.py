@@ -1,6 +1,6 @@
 """The oracle pinned against known answers we derived analytically (the reference ships no
 tests or golden vectors, so these are the anchors; golden fixtures generated from the oracle live in
-tests/golden and are checked by test_golden.py)."""
+tests/golden and are checked by tests/test_golden.py)."""
 import math
 
 import numpy as np
