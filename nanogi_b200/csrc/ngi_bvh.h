@@ -54,7 +54,11 @@ NGI_HD float ngi_safe_rcp_dir(float d) {
     // a zero / denormal component becomes +-2^-80 (keeps 0 * inf NaNs out of the slab test)
     const float eps = 8.27180613e-25f;
     const float dd = fabsf(d) > eps ? d : copysignf(eps, d);
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(dd);
+#else
     return 1.0f / dd;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -139,9 +143,12 @@ NGI_HD unsigned ngi_byte(unsigned w, int i) { return (w >> (8 * i)) & 0xFFu; }
 // costs that PRMT and one FMA per plane; (b - 2^15 s) is formed once per axis per node. Its rounding error is at
 // most 2^-24 |b - 2^15 s| <= 2^-9 quantisation steps (plus the 2^-24 |b| every slab test has and the box padding
 // covers); the build widens every quantised plane by 2^-7 step (ngi_collapse_node) so the decode stays conservative.
-NGI_HD float ngi_q1(unsigned w, int i) {
+// `one` must be the bit pattern of 1.0f held in a REGISTER the compiler cannot constant-fold (the product kernels
+// pass it as a kernel parameter, NgiTraceTuning::one_bits): PRMT takes one immediate, and with a literal here ptxas
+// keeps the literal and materialises the four selectors in registers instead (+40 moves per node step).
+NGI_HD float ngi_q1(unsigned w, int i, unsigned one) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | ((unsigned)i << 4)));
+    return __uint_as_float(__byte_perm(w, one, 0x7604u | ((unsigned)i << 4)));
 #else
     return u2f(0x3F800000u | (((w >> (8 * i)) & 0xFFu) << 8));
 #endif
@@ -163,6 +170,7 @@ struct NgiRayCtx {
     float idx, idy, idz;      // clamped reciprocal direction
     float tmin;
     unsigned octinv;          // 7 - octant of the direction
+    unsigned one;             // 0x3F800000, see ngi_q1
     bool negx, negy, negz;    // taken from the clamped reciprocals so that -0.0f components stay self-consistent
 };
 
@@ -171,6 +179,7 @@ NGI_HD void ngi_ray_ctx(NgiRayCtx& r, const f3 o, const f3 d, const float tmin) 
     r.idx = ngi_safe_rcp_dir(d.x); r.idy = ngi_safe_rcp_dir(d.y); r.idz = ngi_safe_rcp_dir(d.z);
     r.negx = r.idx < 0.0f; r.negy = r.idy < 0.0f; r.negz = r.idz < 0.0f;
     r.octinv = (r.negx ? 0u : 1u) | (r.negy ? 0u : 2u) | (r.negz ? 0u : 4u);
+    r.one = 0x3F800000u;
 }
 
 // One node step: pops the front-most inner child of `ngroup`, (the caller pushes what is left of the group),
@@ -195,6 +204,7 @@ NGI_HD void ngi_bvh8_node_step(const uint4* __restrict__ nodes, const size_t ni,
     const float sz = u2f((((n0.w >> 16) & 0xFFu) + 15u) << 23) * r.idz;
     const float bx = (u2f(n0.x) - r.o.x) * r.idx - sx, by = (u2f(n0.y) - r.o.y) * r.idy - sy, bz = (u2f(n0.z) - r.o.z) * r.idz - sz;
     const unsigned octinv4 = r.octinv * 0x01010101u;
+    const unsigned one = r.one;
 
     unsigned hitmask = 0;
 #pragma unroll
@@ -213,9 +223,9 @@ NGI_HD void ngi_bvh8_node_step(const uint4* __restrict__ nodes, const size_t ni,
         const unsigned nz = r.negz ? hiz : loz, fz = r.negz ? loz : hiz;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const float tnx = fmaf(ngi_q1(nx, i), sx, bx), tfx = fmaf(ngi_q1(fx, i), sx, bx);
-            const float tny = fmaf(ngi_q1(ny, i), sy, by), tfy = fmaf(ngi_q1(fy, i), sy, by);
-            const float tnz = fmaf(ngi_q1(nz, i), sz, bz), tfz = fmaf(ngi_q1(fz, i), sz, bz);
+            const float tnx = fmaf(ngi_q1(nx, i, one), sx, bx), tfx = fmaf(ngi_q1(fx, i, one), sx, bx);
+            const float tny = fmaf(ngi_q1(ny, i, one), sy, by), tfy = fmaf(ngi_q1(fy, i, one), sy, by);
+            const float tnz = fmaf(ngi_q1(nz, i, one), sz, bz), tfz = fmaf(ngi_q1(fz, i, one), sz, bz);
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, limit));
             if (tn <= tf) hitmask |= ngi_byte(child_bits4, i) << ngi_byte(bit_index4, i);   // empty slots have no bits

@@ -28,6 +28,7 @@
 struct NgiTraceTuning {
     int refill_min;     // refill idle lanes when at least this many are idle (or all are)
     int tri_min;        // postpone the triangle phase when fewer lanes than this have triangles pending
+    unsigned one_bits;  // 0x3F800000 as a run-time value (keeps it in a register for PRMT, see ngi_q1)
 };
 
 // Source concept:
@@ -80,6 +81,7 @@ __device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, 
                         f3 o, d; float tmin;
                         item = src.load(my, o, d, tmin, tmax);
                         ngi_ray_ctx(r, o, d, tmin);
+                        r.one = tune.one_bits;
                         best.t = tmax; best.u = 0; best.v = 0; best.tri = NGI_MISS;
                         found = false; sp = 0; defer = 0;
                         ngroup = make_uint2(0u, 0x80000000u);   // root: base 0, pseudo-slot 7
