@@ -4,8 +4,12 @@
 // rtcCommit). Pipeline, all on the device:
 //   1. triangle records + padded AABBs + scene bounds            (k_tri_setup)
 //   2. 63-bit Morton codes of the AABB centres                    (k_morton)        -> cub radix sort
-//   3. Karras 2012 LBVH topology, one thread per inner node       (k_karras)
-//   4. bottom-up refit with one atomic flag per inner node        (k_refit)
+//   3. binary topology over the Morton order by PLOC — parallel locally-ordered clustering (Meister & Bittner
+//      2017): every round each cluster looks NGI_PLOC_RADIUS neighbours left and right for the partner that
+//      minimises the surface area of the union, mutual nearest neighbours merge, the cluster array is compacted
+//      (k_ploc_nearest, k_ploc_flag, cub scan, k_ploc_merge). Node boxes come out of the merges (no refit).
+//      An LBVH (Karras 2012, ngi_karras_node) was the first version; its traversal cost on the 1M-triangle scene
+//      was ~3.3x the Cornell box's per ray, mostly from the room's large triangles inflating Morton-adjacent nodes.
 //   5. 64-byte two-child traversal nodes (BVH2, cross-check)      (k_pack2)
 //   6. top-down collapse to compressed 8-wide nodes, level by level with atomically allocated child /
 //      triangle ranges (k_collapse8); octant slot assignment + outward-rounded 8-bit quantisation.
@@ -87,6 +91,64 @@ NGI_HD void ngi_karras_node(const unsigned long long* __restrict__ keys, int n, 
     first = lo; last = hi;
 }
 
+// ---- 3b. PLOC ------------------------------------------------------------------------------------
+// Node numbering: inner nodes 0..n-2 with the ROOT = 0 (ids are handed out downwards from n-2, the last merge
+// gets 0), leaf k = n-1+k (k = position in Morton order). cnt[] = triangles below an inner node.
+#define NGI_PLOC_RADIUS 16
+
+NGI_HD float ngi_union_half_area(const float4 a0, const float4 a1, const float4 b0, const float4 b1) {
+    const float dx = fmaxf(a1.x, b1.x) - fminf(a0.x, b0.x), dy = fmaxf(a1.y, b1.y) - fminf(a0.y, b0.y), dz = fmaxf(a1.z, b1.z) - fminf(a0.z, b0.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+// nearest neighbour of cluster i inside the window; ties -> lowest index (guarantees a mutual pair every round)
+NGI_HD int ngi_ploc_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, const int C, const int i) {
+    const float4 a0 = clo[i], a1 = chi[i];
+    int best = -1;
+    float bestA = NGI_INF_F;
+    const int j0 = i - NGI_PLOC_RADIUS < 0 ? 0 : i - NGI_PLOC_RADIUS;
+    const int j1 = i + NGI_PLOC_RADIUS > C - 1 ? C - 1 : i + NGI_PLOC_RADIUS;
+    for (int j = j0; j <= j1; j++) {
+        if (j == i) continue;
+        const float A = ngi_union_half_area(a0, a1, clo[j], chi[j]);
+        if (A < bestA || best < 0) { bestA = A; best = j; }
+    }
+    return best;
+}
+// 1 = cluster i survives the round (alone or as the merged pair), 0 = it is absorbed by its lower-index partner
+NGI_HD unsigned ngi_ploc_keep(const int* __restrict__ nn, const int i) {
+    const int j = nn[i];
+    return (j >= 0 && nn[j] == i && j < i) ? 0u : 1u;
+}
+struct NgiPlocCtx {
+    const int* nn; const unsigned* pos;          // nearest neighbour, exclusive scan of the keep flags
+    const int* cid_in; const float4* clo_in; const float4* chi_in;
+    int* cid_out; float4* clo_out; float4* chi_out;
+    float4* lo; float4* hi;                      // [2n-1] node boxes
+    int* left; int* right; unsigned* cnt;        // [n-1]
+    int n;                                       // leaves
+    int next_id;                                 // id of the first merge of this round (ids go downwards)
+};
+NGI_HD void ngi_ploc_merge(const NgiPlocCtx& c, const int i) {
+    const int j = c.nn[i];
+    const bool mutual = j >= 0 && c.nn[j] == i;
+    if (mutual && j < i) return;                 // absorbed
+    const unsigned p = c.pos[i];
+    if (mutual) {
+        const int rank = j - (int)c.pos[j];      // absorbed clusters in front of j = merges in front of this one
+        const int id = c.next_id - rank;
+        const int a = c.cid_in[i], b = c.cid_in[j];
+        const float4 a0 = c.clo_in[i], a1 = c.chi_in[i], b0 = c.clo_in[j], b1 = c.chi_in[j];
+        const float4 u0 = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), 0.0f);
+        const float4 u1 = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.0f);
+        c.left[id] = a; c.right[id] = b;
+        c.cnt[id] = (a >= c.n - 1 ? 1u : c.cnt[a]) + (b >= c.n - 1 ? 1u : c.cnt[b]);
+        c.lo[id] = u0; c.hi[id] = u1;
+        c.cid_out[p] = id; c.clo_out[p] = u0; c.chi_out[p] = u1;
+    } else {
+        c.cid_out[p] = c.cid_in[i]; c.clo_out[p] = c.clo_in[i]; c.chi_out[p] = c.chi_in[i];
+    }
+}
+
 // ---- 5. BVH2 traversal node ----------------------------------------------------------------------
 NGI_HD void ngi_pack2(const float4* __restrict__ lo, const float4* __restrict__ hi, const int* __restrict__ left,
                       const int* __restrict__ right, int n, int i, float4* __restrict__ out) {
@@ -107,7 +169,7 @@ struct NgiCollapseCtx {
     // BVH2 (node numbering as above)
     const float4* lo; const float4* hi;      // [2n-1] padded boxes
     const int* left; const int* right;       // [n-1]
-    const uint2* range;                      // [n-1] (first, last) Morton positions of the subtree
+    const unsigned* cnt;                     // [n-1] triangles below an inner node
     const float4* tris2;                     // [n][3] Morton-ordered triangle records
     int n;
     // BVH8 output
@@ -144,8 +206,7 @@ NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTa
         for (int k = 0; k < cnt; k++) {
             const int nd = child[k];
             if (nd >= n - 1) continue;  // single-triangle leaf
-            const uint2 r = c.range[nd];
-            if ((int)(r.y - r.x) + 1 <= NGI_LEAF_MAX_TRIS) continue;  // small subtree stays one leaf slot
+            if (c.cnt[nd] <= NGI_LEAF_MAX_TRIS) continue;  // small subtree stays one leaf slot
             const float a = ngi_half_area(c.lo[nd], c.hi[nd]);
             if (a > bestA) { bestA = a; best = k; }
         }
@@ -177,18 +238,23 @@ NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTa
         plo[a] = o;
     }
     // classify children
-    bool inner[8]; int ntri[8]; int first[8];
+    bool inner[8]; int ntri[8]; int leafTri[8][NGI_LEAF_MAX_TRIS];
     unsigned nInner = 0, nTris = 0;
     float cx[8], cy[8], cz[8];
     for (int k = 0; k < cnt; k++) {
         const int nd = child[k];
-        if (nd >= n - 1) { inner[k] = false; ntri[k] = 1; first[k] = nd - (n - 1); }
-        else {
-            const uint2 r = c.range[nd];
-            const int m = (int)(r.y - r.x) + 1;
-            if (m <= NGI_LEAF_MAX_TRIS) { inner[k] = false; ntri[k] = m; first[k] = (int)r.x; }
-            else { inner[k] = true; ntri[k] = 0; first[k] = 0; }
-        }
+        if (nd >= n - 1) { inner[k] = false; ntri[k] = 1; leafTri[k][0] = nd - (n - 1); }
+        else if (c.cnt[nd] <= NGI_LEAF_MAX_TRIS) {
+            // gather the (at most NGI_LEAF_MAX_TRIS) leaves of the small subtree, left first
+            inner[k] = false; ntri[k] = 0;
+            int st[NGI_LEAF_MAX_TRIS + 1]; int sp = 0;
+            st[sp++] = nd;
+            while (sp > 0) {
+                const int x = st[--sp];
+                if (x >= n - 1) leafTri[k][ntri[k]++] = x - (n - 1);
+                else { st[sp++] = c.right[x]; st[sp++] = c.left[x]; }
+            }
+        } else { inner[k] = true; ntri[k] = 0; }
         if (inner[k]) nInner++; else nTris += (unsigned)ntri[k];
         const float4 l = c.lo[nd], h = c.hi[nd];
         cx[k] = 0.5f * (l.x + h.x) - 0.5f * (nlo.x + nhi.x);
@@ -246,7 +312,7 @@ NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTa
         } else {
             meta[s] = (((1u << ntri[k]) - 1u) << 5) | triOff;
             for (int j = 0; j < ntri[k]; j++) {
-                const size_t src = (size_t)(first[k] + j) * 3, dst = (size_t)(triBase + triOff + j) * 3;
+                const size_t src = (size_t)leafTri[k][j] * 3, dst = (size_t)(triBase + triOff + j) * 3;
                 c.tris8[dst] = c.tris2[src]; c.tris8[dst + 1] = c.tris2[src + 1]; c.tris8[dst + 2] = c.tris2[src + 2];
             }
             triOff += (unsigned)ntri[k];

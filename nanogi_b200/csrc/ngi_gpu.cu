@@ -5,8 +5,8 @@
 // NGI_ERR_NO_DEVICE.
 //
 // Kernel inventory
-//   build   : k_bounds, k_tri_setup, k_morton, cub::DeviceRadixSort, k_gather_sorted, k_karras, k_refit,
-//             k_pack2, k_collapse8 (one launch per BVH8 level), k_shade_upload is a plain memcpy
+//   build   : k_bounds, k_tri_setup, k_morton, cub::DeviceRadixSort, k_gather_sorted, PLOC rounds (k_ploc_nearest,
+//             k_ploc_flag, cub::DeviceScan, k_ploc_merge), k_pack2, k_collapse8 (one launch per BVH8 level), k_shade_upload is a plain memcpy
 //   queries : k_trace<ACCEL, ANY_HIT>
 //   render  : k_iter_begin, k_logic, k_extend, k_shadow   (one wavefront iteration = these four)
 //   tests   : k_eval_bsdf
@@ -21,6 +21,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "../../include/nanogi_gpu.h"
 #include "ngi_build.h"
@@ -110,32 +111,26 @@ __global__ void __launch_bounds__(kBlock) k_gather_sorted(const unsigned* __rest
     hi[n - 1 + k] = thi[i];
 }
 
-__global__ void __launch_bounds__(kBlock) k_karras(const unsigned long long* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
-                                                   uint2* __restrict__ range, int* __restrict__ parent) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int l, r, f, la;
-    ngi_karras_node(keys, n, i, l, r, f, la);
-    left[i] = l; right[i] = r; range[i] = make_uint2((unsigned)f, (unsigned)la);
-    parent[l] = i; parent[r] = i;
-    if (i == 0) parent[0] = -1;
+// ---- PLOC rounds (ngi_build.h) ----
+__global__ void __launch_bounds__(kBlock) k_ploc_init(int n, const float4* __restrict__ lo, const float4* __restrict__ hi, int* __restrict__ cid,
+                                                      float4* __restrict__ clo, float4* __restrict__ chi) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    cid[k] = n - 1 + k; clo[k] = lo[n - 1 + k]; chi[k] = hi[n - 1 + k];
 }
-
-// bottom-up refit: the second thread to arrive at an inner node computes its box
-__global__ void __launch_bounds__(kBlock) k_refit(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent,
-                                                  unsigned* __restrict__ flags, float4* lo, float4* hi) {
+__global__ void __launch_bounds__(kBlock) k_ploc_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, int C, int* __restrict__ nn) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int cur = parent[n - 1 + i];
-    while (cur >= 0) {
-        __threadfence();
-        if (atomicAdd(flags + cur, 1u) == 0u) return;
-        const int l = left[cur], r = right[cur];
-        const float4 a0 = __ldcg(lo + l), a1 = __ldcg(hi + l), b0 = __ldcg(lo + r), b1 = __ldcg(hi + r);
-        lo[cur] = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), 0.0f);
-        hi[cur] = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.0f);
-        cur = parent[cur];
-    }
+    if (i < C) nn[i] = ngi_ploc_nearest(clo, chi, C, i);
+}
+__global__ void __launch_bounds__(kBlock) k_ploc_flag(const int* __restrict__ nn, int C, unsigned* __restrict__ keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) keep[i] = ngi_ploc_keep(nn, i);
+}
+__global__ void __launch_bounds__(kBlock) k_ploc_merge(NgiPlocCtx c, int C, const unsigned* __restrict__ keep, unsigned* __restrict__ new_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C) return;
+    ngi_ploc_merge(c, i);
+    if (i == C - 1) *new_count = c.pos[i] + keep[i];
 }
 
 __global__ void __launch_bounds__(kBlock) k_pack2(const float4* __restrict__ lo, const float4* __restrict__ hi, const int* __restrict__ left,
@@ -488,22 +483,56 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     if ((rc = dev_alloc(s, &d_tmp, tmp_bytes, false))) return rc;
     NGI_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, st));
 
-    // ---- 3-5. LBVH ----
+    // ---- 3-5. binary BVH by PLOC over the Morton order ----
     float4 *d_tris2 = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_nodes2 = nullptr;
-    int *d_left = nullptr, *d_right = nullptr, *d_parent = nullptr; uint2* d_range = nullptr; unsigned* d_flags = nullptr;
+    int *d_left = nullptr, *d_right = nullptr; unsigned* d_ncnt = nullptr;
     if ((rc = dev_alloc(s, &d_tris2, (size_t)n * 3, true))) return rc;
     if ((rc = dev_alloc(s, &d_lo, 2 * (size_t)n - 1, false))) return rc;
     if ((rc = dev_alloc(s, &d_hi, 2 * (size_t)n - 1, false))) return rc;
     if ((rc = dev_alloc(s, &d_nodes2, (size_t)(n - 1) * 4, true))) return rc;
     if ((rc = dev_alloc(s, &d_left, n - 1, false))) return rc;
     if ((rc = dev_alloc(s, &d_right, n - 1, false))) return rc;
-    if ((rc = dev_alloc(s, &d_parent, 2 * (size_t)n - 1, false))) return rc;
-    if ((rc = dev_alloc(s, &d_range, n - 1, false))) return rc;
-    if ((rc = dev_alloc(s, &d_flags, n - 1, false))) return rc;
+    if ((rc = dev_alloc(s, &d_ncnt, n - 1, false))) return rc;
     k_gather_sorted<<<grid_for(n), kBlock, 0, st>>>(d_vals2, n, d_rec, d_tlo, d_thi, d_tris2, d_lo, d_hi);
-    k_karras<<<grid_for(n - 1), kBlock, 0, st>>>(d_keys2, (int)n, d_left, d_right, d_range, d_parent);
-    NGI_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)(n - 1) * sizeof(unsigned), st));
-    k_refit<<<grid_for(n), kBlock, 0, st>>>((int)n, d_left, d_right, d_parent, d_flags, d_lo, d_hi);
+    // the sort buffers are dead now; cluster arrays ping-pong
+    int *d_cid[2] = {nullptr, nullptr}, *d_nn = nullptr; float4 *d_clo[2] = {nullptr, nullptr}, *d_chi[2] = {nullptr, nullptr};
+    unsigned *d_keep = nullptr, *d_spos = nullptr, *d_newc = nullptr; unsigned char* d_scan_tmp = nullptr;
+    for (int k = 0; k < 2; k++) {
+        if ((rc = dev_alloc(s, &d_cid[k], n, false))) return rc;
+        if ((rc = dev_alloc(s, &d_clo[k], n, false))) return rc;
+        if ((rc = dev_alloc(s, &d_chi[k], n, false))) return rc;
+    }
+    if ((rc = dev_alloc(s, &d_nn, n, false))) return rc;
+    if ((rc = dev_alloc(s, &d_keep, n, false))) return rc;
+    if ((rc = dev_alloc(s, &d_spos, n, false))) return rc;
+    if ((rc = dev_alloc(s, &d_newc, 1, false))) return rc;
+    size_t scan_bytes = 0;
+    NGI_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_keep, d_spos, (int)n, st));
+    if ((rc = dev_alloc(s, &d_scan_tmp, scan_bytes, false))) return rc;
+    k_ploc_init<<<grid_for(n), kBlock, 0, st>>>((int)n, d_lo, d_hi, d_cid[0], d_clo[0], d_chi[0]);
+    {
+        unsigned C = n, merges_done = 0, rounds = 0;
+        int cur = 0;
+        while (C > 1) {
+            k_ploc_nearest<<<grid_for(C), kBlock, 0, st>>>(d_clo[cur], d_chi[cur], (int)C, d_nn);
+            k_ploc_flag<<<grid_for(C), kBlock, 0, st>>>(d_nn, (int)C, d_keep);
+            NGI_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_bytes, d_keep, d_spos, (int)C, st));
+            NgiPlocCtx pc;
+            pc.nn = d_nn; pc.pos = d_spos; pc.cid_in = d_cid[cur]; pc.clo_in = d_clo[cur]; pc.chi_in = d_chi[cur];
+            pc.cid_out = d_cid[cur ^ 1]; pc.clo_out = d_clo[cur ^ 1]; pc.chi_out = d_chi[cur ^ 1];
+            pc.lo = d_lo; pc.hi = d_hi; pc.left = d_left; pc.right = d_right; pc.cnt = d_ncnt; pc.n = (int)n;
+            pc.next_id = (int)(n - 2) - (int)merges_done;
+            k_ploc_merge<<<grid_for(C), kBlock, 0, st>>>(pc, (int)C, d_keep, d_newc);
+            unsigned newC = 0;
+            NGI_CUDA(cudaMemcpyAsync(&newC, d_newc, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            NGI_CUDA(cudaStreamSynchronize(st));
+            if (newC == 0 || newC >= C) return set_err(NGI_ERR_CUDA, "PLOC made no progress");
+            merges_done += C - newC;
+            C = newC; cur ^= 1;
+            if (++rounds > 100000) return set_err(NGI_ERR_CUDA, "PLOC did not terminate");
+        }
+        if (merges_done != n - 1) return set_err(NGI_ERR_CUDA, "PLOC merge count mismatch");
+    }
     k_pack2<<<grid_for(n - 1), kBlock, 0, st>>>(d_lo, d_hi, d_left, d_right, (int)n, d_nodes2);
 
     // ---- 6. collapse to BVH8, one launch per level ----
@@ -520,7 +549,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
         NGI_CUDA(cudaMemcpyAsync(d_q0, &root, sizeof(root), cudaMemcpyHostToDevice, st));
     }
     NgiCollapseCtx ctx;
-    ctx.lo = d_lo; ctx.hi = d_hi; ctx.left = d_left; ctx.right = d_right; ctx.range = d_range; ctx.tris2 = d_tris2; ctx.n = (int)n;
+    ctx.lo = d_lo; ctx.hi = d_hi; ctx.left = d_left; ctx.right = d_right; ctx.cnt = d_ncnt; ctx.tris2 = d_tris2; ctx.n = (int)n;
     ctx.nodes8 = d_nodes8_tmp; ctx.tris8 = d_tris8; ctx.counters = d_cnt;
     unsigned n_tasks = 1, depth = 0;
     unsigned hc[4] = {1, 0, 0, 0};
@@ -550,7 +579,8 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
 
     for (void* p : {(void*)d_pos, (void*)d_bounds, (void*)d_rec, (void*)d_tlo, (void*)d_thi, (void*)d_keys, (void*)d_keys2, (void*)d_vals, (void*)d_vals2,
-                    (void*)d_tmp, (void*)d_lo, (void*)d_hi, (void*)d_left, (void*)d_right, (void*)d_parent, (void*)d_range, (void*)d_flags,
+                    (void*)d_tmp, (void*)d_lo, (void*)d_hi, (void*)d_left, (void*)d_right, (void*)d_ncnt, (void*)d_cid[0], (void*)d_cid[1],
+                    (void*)d_clo[0], (void*)d_clo[1], (void*)d_chi[0], (void*)d_chi[1], (void*)d_nn, (void*)d_keep, (void*)d_spos, (void*)d_newc, (void*)d_scan_tmp,
                     (void*)d_nodes8_tmp, (void*)d_cnt, (void*)d_q0, (void*)d_q1})
         cudaFree(p);
 

@@ -27,31 +27,13 @@ struct SimScene {
     std::vector<float4> tris2, nodes2, tris8;
     std::vector<uint4> nodes8;
     std::vector<int> left, right;
-    std::vector<uint2> range;
+    std::vector<unsigned> cnt;
     unsigned n_nodes8 = 0, depth8 = 0;
     float smin[3], smax[3], pad = 0;
     NgiDevScene dev;
 };
 
 thread_local std::string g_err;
-
-void refit(SimScene& s, int node) {
-    // iterative post-order over inner nodes
-    const int n = (int)s.n;
-    std::vector<int> order; order.reserve(n);
-    std::vector<int> st{node};
-    while (!st.empty()) {
-        int c = st.back(); st.pop_back();
-        if (c >= n - 1) continue;
-        order.push_back(c);
-        st.push_back(s.left[c]); st.push_back(s.right[c]);
-    }
-    for (auto it = order.rbegin(); it != order.rend(); ++it) {
-        const int c = *it, l = s.left[c], r = s.right[c];
-        s.lo[c] = make_float4(fminf(s.lo[l].x, s.lo[r].x), fminf(s.lo[l].y, s.lo[r].y), fminf(s.lo[l].z, s.lo[r].z), 0);
-        s.hi[c] = make_float4(fmaxf(s.hi[l].x, s.hi[r].x), fmaxf(s.hi[l].y, s.hi[r].y), fmaxf(s.hi[l].z, s.hi[r].z), 0);
-    }
-}
 
 }  // namespace
 
@@ -97,14 +79,28 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
         for (int j = 0; j < 3; j++) s->tris2[(size_t)k * 3 + j] = s->rec_in[(size_t)i * 3 + j];
         s->lo[n - 1 + k] = tlo[i]; s->hi[n - 1 + k] = thi[i];
     }
-    // Karras
-    s->left.resize(n - 1); s->right.resize(n - 1); s->range.resize(n - 1);
-    for (int i = 0; i < (int)n - 1; i++) {
-        int l, r, f, la;
-        ngi_karras_node(skeys.data(), (int)n, i, l, r, f, la);
-        s->left[i] = l; s->right[i] = r; s->range[i] = make_uint2((unsigned)f, (unsigned)la);
+    // PLOC rounds, same per-item functions as the CUDA kernels (k_ploc_*)
+    s->left.assign(n - 1, 0); s->right.assign(n - 1, 0); s->cnt.assign(n - 1, 0u);
+    {
+        std::vector<int> cid[2] = {std::vector<int>(n), std::vector<int>(n)}, nn(n);
+        std::vector<float4> clo[2] = {std::vector<float4>(n), std::vector<float4>(n)}, chi[2] = {std::vector<float4>(n), std::vector<float4>(n)};
+        std::vector<unsigned> keep(n), pos(n);
+        for (unsigned k = 0; k < n; k++) { cid[0][k] = (int)(n - 1 + k); clo[0][k] = s->lo[n - 1 + k]; chi[0][k] = s->hi[n - 1 + k]; }
+        unsigned C = n, merges = 0;
+        int cur = 0;
+        while (C > 1) {
+            for (unsigned i = 0; i < C; i++) nn[i] = ngi_ploc_nearest(clo[cur].data(), chi[cur].data(), (int)C, (int)i);
+            unsigned acc = 0;
+            for (unsigned i = 0; i < C; i++) { keep[i] = ngi_ploc_keep(nn.data(), (int)i); pos[i] = acc; acc += keep[i]; }
+            NgiPlocCtx pc;
+            pc.nn = nn.data(); pc.pos = pos.data(); pc.cid_in = cid[cur].data(); pc.clo_in = clo[cur].data(); pc.chi_in = chi[cur].data();
+            pc.cid_out = cid[cur ^ 1].data(); pc.clo_out = clo[cur ^ 1].data(); pc.chi_out = chi[cur ^ 1].data();
+            pc.lo = s->lo.data(); pc.hi = s->hi.data(); pc.left = s->left.data(); pc.right = s->right.data(); pc.cnt = s->cnt.data();
+            pc.n = (int)n; pc.next_id = (int)(n - 2) - (int)merges;
+            for (unsigned i = 0; i < C; i++) ngi_ploc_merge(pc, (int)i);
+            merges += C - acc; C = acc; cur ^= 1;
+        }
     }
-    refit(*s, 0);
     s->nodes2.resize((size_t)(n - 1) * 4);
     for (int i = 0; i < (int)n - 1; i++) ngi_pack2(s->lo.data(), s->hi.data(), s->left.data(), s->right.data(), (int)n, i, s->nodes2.data());
     // collapse
@@ -113,7 +109,7 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
     unsigned counters[3] = {1, 0, 0};
     std::vector<NgiBuildTask> cur{{0, 0u}}, next(n);
     NgiCollapseCtx c;
-    c.lo = s->lo.data(); c.hi = s->hi.data(); c.left = s->left.data(); c.right = s->right.data(); c.range = s->range.data();
+    c.lo = s->lo.data(); c.hi = s->hi.data(); c.left = s->left.data(); c.right = s->right.data(); c.cnt = s->cnt.data();
     c.tris2 = s->tris2.data(); c.n = (int)n; c.nodes8 = s->nodes8.data(); c.tris8 = s->tris8.data(); c.counters = counters;
     unsigned depth = 0;
     while (!cur.empty()) {
