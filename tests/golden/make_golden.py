@@ -30,10 +30,15 @@ def main():
         brute = orc.trace(rays, 2)
         assert np.array_equal(hits, brute), "oracle BVH differs from its own brute force"
         occ_hits = orc.trace(occ, 1)
+        # films: the scene scaled to unit size. At Cornell scale (coordinates ~550, absolute epsilon 1e-4 ~ 1.6 fp32 ulp)
+        # whether a grazing ray re-hits its own surface depends on the last bit of the shading arithmetic, so fp32 device
+        # code and the fp64 oracle agree only statistically there (tests/test_gpu_parity.py); at unit scale sample by sample.
+        from tests.conftest import scaled_spec
+        orc_s = pyoracle.OracleScene(scenes.to_scene_data(scaled_spec(getattr(scenes, name)(), 0.01), 1.0))
         films = {}
         for renderer in ("pt", "ptdirect"):
             for m in (-1, 4):
-                f, st = orc.render(renderer, 4096, 16, 16, max_num_vertices=m, seed=3, rng_mode=1, num_threads=1)
+                f, st = orc_s.render(renderer, 4096, 16, 16, max_num_vertices=m, seed=3, rng_mode=1, num_threads=1)
                 films[f"film_{renderer}_{m}"] = f
                 films[f"rays_{renderer}_{m}"] = np.array([st["extend_rays"], st["shadow_rays"]])
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), rays=rays, hits=hits, occ=occ, occ_tri=occ_hits["tri"], **films)
