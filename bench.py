@@ -270,7 +270,7 @@ def run_own(args, rank: int, local_rank: int, world: int):
                                   wave_capacity=args.wave_capacity)
         peak, peak_src = measured_peaks()
         br = b_ray(int(info.num_tris))
-        per = {"k_logic": (stt.logic_kernel_seconds, stt.logic_launches, None),
+        per = {"logic (k_classify + k_surface + k_eye)": (stt.logic_kernel_seconds, stt.logic_launches, None),
                "k_extend": (stt.extend_kernel_seconds, stt.extend_launches, stt.extend_rays),
                "k_shadow": (stt.shadow_kernel_seconds, stt.shadow_launches, stt.shadow_rays)}
         total_k = sum(v[0] for v in per.values()) or 1.0

@@ -198,7 +198,7 @@ struct NgiRenderCounters {
     unsigned iter[2];   // [0] shadow entries, [1] extend rays of the iteration in flight
     unsigned last[2];   // snapshot of the previous iteration (read by the host for termination)
     unsigned fetch[2];  // dynamic-fetch cursors of the persistent trace kernels ([0] shadow, [1] extend)
-    unsigned pad[2];
+    unsigned stage[4];  // [0] surface queue, [1] regenerate queue, [2] slots to classify (= extend rays of the previous iteration)
 };
 
 __global__ void k_iter_begin(NgiRenderCounters* c) {
@@ -210,51 +210,47 @@ __global__ void k_iter_begin(NgiRenderCounters* c) {
     c->iter[1] = 0u;
     c->fetch[0] = 0u;
     c->fetch[1] = 0u;
+    // the slots to classify are the ones that traced an extend ray in the previous iteration; the first iteration
+    // classifies every slot (the host presets stage[2] = capacity and the extend queue = 0..capacity-1, all idle)
+    if (c->iterations > 0ull) c->stage[2] = c->last[1];
+    c->stage[0] = 0u;
+    c->stage[1] = 0u;
     c->iterations += 1ull;
 }
 
-// Logic stage with block-local compaction. One thread first classifies its own slot; the block then regroups its
-// 256 slots into a "surface vertex" list and a "regenerate" list in shared memory and walks each list with dense
-// warps: threads of one warp run the same stage (BSDF work vs. camera-ray work) instead of diverging per lane —
-// the first version of this kernel ran with 15.6 of 32 lanes active (profiles/r01_ncu_c2_steady.txt). Slots live
-// in global SoA arrays, so handing a slot to another thread of the block costs nothing.
-__device__ __forceinline__ void block_list_push(unsigned* list, unsigned* count, bool pred, unsigned value) {
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
-    if (m == 0u) return;
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned base = 0;
-    if (lane == (unsigned)(__ffs((int)m) - 1)) base = atomicAdd(count, (unsigned)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)m) - 1);
-    if (pred) list[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = value;
+// Logic stage = three dense kernels over compacted queues (warp ballot/popc + one atomic per warp, ngi_queue_alloc):
+//   k_classify  every slot that traced an extend ray: miss / RR / vertex cap (+ pt emission) -> surface_q | regen_q
+//   k_surface   surface_q: reconstruct, NEE, BSDF sample -> extend_q (+ shadow_q); paths that end here -> regen_q
+//   k_eye       regen_q: next sample index, eye-vertex NEE, camera ray -> extend_q (+ shadow_q)
+// History (profiles/): one thread per slot doing everything ran 15.6 of 32 lanes; a block-local regrouping through
+// shared memory fixed the lanes (28-29 of 32) but spent 39 % of its stall samples at the two __syncthreads. Separate
+// launches over global queues keep the dense warps and have no barrier.
+constexpr unsigned kStageGrid = 148u * 8u;
+
+__global__ void __launch_bounds__(kBlock) k_classify(NgiDevScene sc, NgiWaveParams wp) {
+    const unsigned n = wp.stage_counters[2];
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const unsigned slot = wp.extend_q[e];
+        if (ngi_logic_classify(sc, wp, slot) == NGI_CLASS_SURFACE) wp.surface_q[ngi_queue_alloc(wp.stage_counters + 0)] = slot;
+        else wp.regen_q[ngi_queue_alloc(wp.stage_counters + 1)] = slot;
+    }
+}
+__global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_surface(NgiDevScene sc, NgiWaveParams wp) {
+    const unsigned n = wp.stage_counters[0];
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const unsigned slot = wp.surface_q[e];
+        if (!ngi_logic_surface(sc, wp, slot)) wp.regen_q[ngi_queue_alloc(wp.stage_counters + 1)] = slot;
+    }
+}
+__global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_eye(NgiDevScene sc, NgiWaveParams wp) {
+    const unsigned n = wp.stage_counters[1];
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_logic_eye(sc, wp, wp.regen_q[e]);
+}
+__global__ void __launch_bounds__(kBlock) k_iota(unsigned* __restrict__ q, unsigned n) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) q[i] = i;
 }
 
-__global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_logic(NgiDevScene sc, NgiWaveParams wp) {
-    __shared__ unsigned s_surface[kBlock], s_regen[kBlock];
-    __shared__ unsigned s_count[2];
-    if (threadIdx.x < 2) s_count[threadIdx.x] = 0u;
-    __syncthreads();
-    // stage 1: classify (+ pt emission)
-    const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = slot < wp.capacity;
-    const int cls = valid ? ngi_logic_classify(sc, wp, slot) : -1;
-    block_list_push(s_surface, &s_count[0], cls == NGI_CLASS_SURFACE, slot);
-    block_list_push(s_regen, &s_count[1], cls == NGI_CLASS_REGENERATE, slot);
-    __syncthreads();
-    // stage 2: surface vertices (paths that end here join the regenerate list)
-    const unsigned n_surface = s_count[0];
-    for (unsigned base = 0; base < n_surface; base += blockDim.x) {       // at most one trip; warp-uniform bounds
-        const unsigned i = base + threadIdx.x;
-        bool ended = false;
-        unsigned sl = 0;
-        if (i < n_surface) { sl = s_surface[i]; ended = !ngi_logic_surface(sc, wp, sl); }
-        __syncwarp();
-        block_list_push(s_regen, &s_count[1], ended, sl);
-    }
-    __syncthreads();
-    // stage 3: regenerate
-    const unsigned n_regen = s_count[1];
-    for (unsigned i = threadIdx.x; i < n_regen; i += blockDim.x) ngi_logic_eye(sc, wp, s_regen[i]);
-}
 // Scene::Intersect's ray query (rt.hpp:2162-2182) for the compacted extend queue of this iteration
 struct ExtendSource {
     NgiWaveParams wp;
@@ -601,7 +597,7 @@ int ensure_wave(Scene* s, unsigned P) {
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     if (s->wave_mem) { wave_cache_put(s->device, s->wave_mem, s->wave_capacity); s->wave_mem = nullptr; }
     // per slot: sample 8 + thr_pix 16 + p 24 + dir_info 16 + hit 16 = 80 B; shadow queue 2 entries x 48 B
-    const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96 + 4);
+    const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96 + 4 + 4 + 4);
     s->wave_mem = wave_cache_take(s->device, P);
     if (!s->wave_mem) NGI_CUDA(cudaMalloc(&s->wave_mem, bytes));
     if (!s->counters) NGI_CUDA(cudaMalloc((void**)&s->counters, sizeof(NgiRenderCounters)));
@@ -622,6 +618,9 @@ void carve_wave(Scene* s, NgiWaveParams& wp) {
     wp.py = (double*)p; p += P * 8;
     wp.pz = (double*)p; p += P * 8;
     wp.extend_q = (unsigned*)p; p += P * 4;
+    wp.surface_q = (unsigned*)p; p += P * 4;
+    wp.regen_q = (unsigned*)p; p += P * 4;
+    wp.stage_counters = s->counters->stage;
     wp.iter_counters = s->counters->iter;
     wp.fetch_cursors = s->counters->fetch;
     wp.next_sample = &s->counters->next_sample;
@@ -638,7 +637,10 @@ int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool ti
         while (s->events.size() < ev_used + 4) { cudaEvent_t e; NGI_CUDA(cudaEventCreate(&e)); s->events.push_back(e); }
         NGI_CUDA(cudaEventRecord(s->events[ev_used], st));
     }
-    k_logic<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
+    const unsigned sg = std::min(grid_for(P), kStageGrid);
+    k_classify<<<sg, kBlock, 0, st>>>(s->dev, wp);
+    k_surface<<<sg, kBlock, 0, st>>>(s->dev, wp);
+    k_eye<<<sg, kBlock, 0, st>>>(s->dev, wp);
     if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 1], st));
     if (per_ray) k_extend_per_ray<<<std::min(grid_for(P), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
     else k_extend<<<s->grid_extend, kBlock, 0, st>>>(s->dev, wp, s->tune);
@@ -681,9 +683,11 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     NgiRenderCounters init;
     memset(&init, 0, sizeof(init));
     init.next_sample = (unsigned long long)rp->sample_offset;
+    init.stage[2] = P;                                                   // first iteration: classify (= regenerate) every slot
     *s->counters_host = init;
     NGI_CUDA(cudaMemcpyAsync(s->counters, s->counters_host, sizeof(init), cudaMemcpyHostToDevice, st));
     NGI_CUDA(cudaMemsetAsync(wp.dir_info, 0, (size_t)P * 16, st));   // every slot starts idle
+    k_iota<<<grid_for(P), kBlock, 0, st>>>(wp.extend_q, P);
 
     cudaEvent_t ev0, ev1;
     NGI_CUDA(cudaEventCreate(&ev0));
@@ -693,7 +697,7 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     const bool per_ray = (rp->flags & NGI_RENDER_PER_RAY_TRACE) != 0;
     const bool timed = (rp->flags & NGI_RENDER_TIME_KERNELS) != 0 || per_ray;
     const int kItersPerBatch = 8;
-    const int kernels_per_iter = rp->renderer == NGI_RENDERER_PTDIRECT ? 4 : 3;
+    const int kernels_per_iter = rp->renderer == NGI_RENDERER_PTDIRECT ? 6 : 5;   // iter_begin, classify, surface, eye, extend (, shadow)
     size_t ev_used = 0;
     uint64_t launches = 0;
     double logic_ms = 0.0, extend_ms = 0.0, shadow_ms = 0.0;

@@ -35,6 +35,9 @@ struct NgiWaveParams {
     unsigned* extend_q;           // slot ids of the extend rays of this iteration (compacted by the logic stage)
     unsigned* iter_counters;      // [0] shadow entries this iteration, [1] extend rays this iteration
     unsigned* fetch_cursors;      // [0] shadow, [1] extend: dynamic-fetch cursors of the persistent trace kernels
+    unsigned* surface_q;          // slots that continue at a surface vertex this iteration (written by the classify stage)
+    unsigned* regen_q;            // slots whose path ended: regenerated from the sample counter by the eye stage
+    unsigned* stage_counters;     // [0] surface_q entries, [1] regen_q entries, [2] slots to classify this iteration
     unsigned long long* next_sample;
     float* film;                  // [H][W][3], row 0 = bottom
     unsigned capacity;            // slots
