@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 `pt` / `ptdirect` path (BASELINE.json metric: Mpaths/s, Mrays/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c4pt] [--impl reference]
 
 Own arm (default)
   step      one full render of the workload (one pass of the hot path over one batch of samples): at N = 1 the
@@ -47,6 +47,10 @@ WORKLOADS = {
            "C2 Cornell box + glossy/glass icospheres (2598 tris) ptdirect 1024x1024 1024spp"),
     "c3": ("instanced_spheres", "ptdirect", 1920, 1080, 1024, -1,
            "C3 procedural 1M-triangle instanced spheres, mixed D/G/S, ptdirect 1920x1080 1024spp"),
+    "c4": ("interior", "ptdirect", 1920, 1080, 4096, -1,
+           "C4 procedural 10M-triangle interior (Sibenik-like layout, 256 small area lights), ptdirect 1920x1080 4096spp"),
+    "c4pt": ("interior", "pt", 1920, 1080, 4096, -1,
+             "C4 procedural 10M-triangle interior (Sibenik-like layout, 256 small area lights), pt 1920x1080 4096spp"),
 }
 
 

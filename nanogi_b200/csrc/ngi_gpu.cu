@@ -198,7 +198,7 @@ struct NgiRenderCounters {
     unsigned iter[2];   // [0] shadow entries, [1] extend rays of the iteration in flight
     unsigned last[2];   // snapshot of the previous iteration (read by the host for termination)
     unsigned fetch[2];  // dynamic-fetch cursors of the persistent trace kernels ([0] shadow, [1] extend)
-    unsigned stage[4];  // [0] surface queue, [1] regenerate queue, [2] slots to classify (= extend rays of the previous iteration)
+    unsigned stage[4];  // [0] surface queue entries, [1] regenerate queue entries
 };
 
 __global__ void k_iter_begin(NgiRenderCounters* c) {
@@ -210,16 +210,13 @@ __global__ void k_iter_begin(NgiRenderCounters* c) {
     c->iter[1] = 0u;
     c->fetch[0] = 0u;
     c->fetch[1] = 0u;
-    // the slots to classify are the ones that traced an extend ray in the previous iteration; the first iteration
-    // classifies every slot (the host presets stage[2] = capacity and the extend queue = 0..capacity-1, all idle)
-    if (c->iterations > 0ull) c->stage[2] = c->last[1];
     c->stage[0] = 0u;
     c->stage[1] = 0u;
     c->iterations += 1ull;
 }
 
 // Logic stage = three dense kernels over compacted queues (warp ballot/popc + one atomic per warp, ngi_queue_alloc):
-//   k_classify  every slot that traced an extend ray: miss / RR / vertex cap (+ pt emission) -> surface_q | regen_q
+//   k_classify  every slot: idle / miss / RR / vertex cap (+ pt emission) -> surface_q | regen_q
 //   k_surface   surface_q: reconstruct, NEE, BSDF sample -> extend_q (+ shadow_q); paths that end here -> regen_q
 //   k_eye       regen_q: next sample index, eye-vertex NEE, camera ray -> extend_q (+ shadow_q)
 // History (profiles/): one thread per slot doing everything ran 15.6 of 32 lanes; a block-local regrouping through
@@ -227,13 +224,28 @@ __global__ void k_iter_begin(NgiRenderCounters* c) {
 // launches over global queues keep the dense warps and have no barrier.
 constexpr unsigned kStageGrid = 148u * 8u;
 
+// One thread per SLOT (coalesced state reads); the block compacts its 256 slots IN SLOT ORDER into the two queues and
+// reserves queue space with one atomic per queue: the queues are sequences of slot-ordered chunks, so the surface / eye
+// kernels read and write the path state almost as coalesced as a slot-indexed kernel would (pushing slot ids in atomic
+// order instead made those kernels 2.3x slower: every state access became a scattered 16-byte touch).
 __global__ void __launch_bounds__(kBlock) k_classify(NgiDevScene sc, NgiWaveParams wp) {
-    const unsigned n = wp.stage_counters[2];
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const unsigned slot = wp.extend_q[e];
-        if (ngi_logic_classify(sc, wp, slot) == NGI_CLASS_SURFACE) wp.surface_q[ngi_queue_alloc(wp.stage_counters + 0)] = slot;
-        else wp.regen_q[ngi_queue_alloc(wp.stage_counters + 1)] = slot;
+    __shared__ unsigned s_warp[2][kBlock / 32];
+    __shared__ unsigned s_base[2];
+    const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int cls = slot < wp.capacity ? ngi_logic_classify(sc, wp, slot) : -1;
+    const unsigned ms = __ballot_sync(0xFFFFFFFFu, cls == NGI_CLASS_SURFACE), mr = __ballot_sync(0xFFFFFFFFu, cls == NGI_CLASS_REGENERATE);
+    if (lane == 0) { s_warp[0][warp] = (unsigned)__popc(ms); s_warp[1][warp] = (unsigned)__popc(mr); }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned acc = 0;
+        for (int w = 0; w < kBlock / 32; w++) { const unsigned c = s_warp[threadIdx.x][w]; s_warp[threadIdx.x][w] = acc; acc += c; }
+        s_base[threadIdx.x] = acc ? atomicAdd(wp.stage_counters + threadIdx.x, acc) : 0u;
     }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1u;
+    if (cls == NGI_CLASS_SURFACE) wp.surface_q[s_base[0] + s_warp[0][warp] + (unsigned)__popc(ms & lt)] = slot;
+    else if (cls == NGI_CLASS_REGENERATE) wp.regen_q[s_base[1] + s_warp[1][warp] + (unsigned)__popc(mr & lt)] = slot;
 }
 __global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_surface(NgiDevScene sc, NgiWaveParams wp) {
     const unsigned n = wp.stage_counters[0];
@@ -246,11 +258,6 @@ __global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_eye(NgiDevScen
     const unsigned n = wp.stage_counters[1];
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_logic_eye(sc, wp, wp.regen_q[e]);
 }
-__global__ void __launch_bounds__(kBlock) k_iota(unsigned* __restrict__ q, unsigned n) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) q[i] = i;
-}
-
 // Scene::Intersect's ray query (rt.hpp:2162-2182) for the compacted extend queue of this iteration
 struct ExtendSource {
     NgiWaveParams wp;
@@ -638,7 +645,7 @@ int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool ti
         NGI_CUDA(cudaEventRecord(s->events[ev_used], st));
     }
     const unsigned sg = std::min(grid_for(P), kStageGrid);
-    k_classify<<<sg, kBlock, 0, st>>>(s->dev, wp);
+    k_classify<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
     k_surface<<<sg, kBlock, 0, st>>>(s->dev, wp);
     k_eye<<<sg, kBlock, 0, st>>>(s->dev, wp);
     if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 1], st));
@@ -683,11 +690,9 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     NgiRenderCounters init;
     memset(&init, 0, sizeof(init));
     init.next_sample = (unsigned long long)rp->sample_offset;
-    init.stage[2] = P;                                                   // first iteration: classify (= regenerate) every slot
     *s->counters_host = init;
     NGI_CUDA(cudaMemcpyAsync(s->counters, s->counters_host, sizeof(init), cudaMemcpyHostToDevice, st));
     NGI_CUDA(cudaMemsetAsync(wp.dir_info, 0, (size_t)P * 16, st));   // every slot starts idle
-    k_iota<<<grid_for(P), kBlock, 0, st>>>(wp.extend_q, P);
 
     cudaEvent_t ev0, ev1;
     NGI_CUDA(cudaEventCreate(&ev0));

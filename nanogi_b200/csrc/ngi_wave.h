@@ -37,7 +37,7 @@ struct NgiWaveParams {
     unsigned* fetch_cursors;      // [0] shadow, [1] extend: dynamic-fetch cursors of the persistent trace kernels
     unsigned* surface_q;          // slots that continue at a surface vertex this iteration (written by the classify stage)
     unsigned* regen_q;            // slots whose path ended: regenerated from the sample counter by the eye stage
-    unsigned* stage_counters;     // [0] surface_q entries, [1] regen_q entries, [2] slots to classify this iteration
+    unsigned* stage_counters;     // [0] surface_q entries, [1] regen_q entries
     unsigned long long* next_sample;
     float* film;                  // [H][W][3], row 0 = bottom
     unsigned capacity;            // slots

@@ -1,4 +1,6 @@
 """Parity tests proper: libnanogi_gpu.so (CUDA, sm_100a) through the C ABI vs the oracle, on the B200."""
+import os
+
 import numpy as np
 import pytest
 
@@ -168,3 +170,21 @@ def test_warp_cooperative_trace_equals_per_ray_trace(gpu_c2, renderer):
     b, sb = gpu_c2.render(renderer, 400000, 64, 64, seed=21, flags=capi.RENDER_PER_RAY_TRACE)
     assert sa.extend_rays == sb.extend_rays and sa.shadow_rays == sb.shadow_rays
     assert np.allclose(a, b, rtol=1e-4, atol=1e-6 * b.max())
+
+
+@pytest.mark.slow
+def test_c5_ray_batches_on_the_1m_triangle_scene():
+    """BASELINE config 5 at reduced count (4 Mi rays per batch; the full 16 Mi run is tools/raybench.py, its output is
+    committed under profiles/): coherent + incoherent, closest hit + occlusion against the 1M-triangle BVH, every ray
+    compared bit for bit with the oracle (primitive id, t, u, v / occlusion flag)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "raybench.py"), "--scene", "c3", "--rays", str(1 << 22)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["tris"] > 900000
+    for name, b in out["batches"].items():
+        assert b["checked"] == b["rays"] and b["mismatches"] == 0, (name, b)
