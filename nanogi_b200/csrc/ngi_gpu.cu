@@ -46,6 +46,9 @@ int set_err(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 constexpr int kBlock = 256;
+#ifndef NGI_SURFACE_MIN_BLOCKS
+#define NGI_SURFACE_MIN_BLOCKS 4
+#endif
 #ifndef NGI_LOGIC_MIN_BLOCKS
 #define NGI_LOGIC_MIN_BLOCKS 4   /* 64 registers + 44 B of spills: latency bound kernel, measured 13 % faster than 3 blocks x 80 registers */
 #endif
@@ -201,7 +204,10 @@ struct NgiRenderCounters {
     unsigned stage[4];  // [0] surface queue entries, [1] regenerate queue entries
 };
 
-__global__ void k_iter_begin(NgiRenderCounters* c) {
+__global__ void k_iter_begin(NgiRenderCounters* c, unsigned long long sample_end) {
+    // the eye kernel of the previous iteration started samples next_sample .. next_sample + stage[1] - 1
+    const unsigned long long ns = c->next_sample + c->stage[1];
+    c->next_sample = ns < sample_end ? ns : sample_end;
     c->total_shadow += c->iter[0];
     c->total_extend += c->iter[1];
     c->last[0] = c->iter[0];
@@ -247,17 +253,68 @@ __global__ void __launch_bounds__(kBlock) k_classify(NgiDevScene sc, NgiWavePara
     if (cls == NGI_CLASS_SURFACE) wp.surface_q[s_base[0] + s_warp[0][warp] + (unsigned)__popc(ms & lt)] = slot;
     else if (cls == NGI_CLASS_REGENERATE) wp.regen_q[s_base[1] + s_warp[1][warp] + (unsigned)__popc(mr & lt)] = slot;
 }
-__global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_surface(NgiDevScene sc, NgiWaveParams wp) {
+// Queue space for a whole block with ONE atomic per queue: every thread passes whether it needs an entry in each of the
+// NQ queues and gets its index back; entries of one block are contiguous and in thread order. (A warp-aggregated atomic
+// per queue and warp — 3 x 35k same-address atomics per launch — was 70 % of the eye kernel's stall samples.)
+template <int NQ>
+__device__ __forceinline__ void block_reserve(unsigned* const (&counters)[NQ], const bool (&need)[NQ], unsigned (&index)[NQ],
+                                              unsigned (*s_warp)[kBlock / 32], unsigned* s_base) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    unsigned m[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        m[q] = __ballot_sync(0xFFFFFFFFu, need[q]);
+        if (lane == 0) s_warp[q][warp] = (unsigned)__popc(m[q]);
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        unsigned acc = 0;
+        for (int w = 0; w < kBlock / 32; w++) { const unsigned c = s_warp[threadIdx.x][w]; s_warp[threadIdx.x][w] = acc; acc += c; }
+        s_base[threadIdx.x] = acc ? atomicAdd(counters[threadIdx.x], acc) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; q++) index[q] = s_base[q] + s_warp[q][warp] + (unsigned)__popc(m[q] & lt);
+    __syncthreads();   // s_warp / s_base are reused by the next trip
+}
+
+__global__ void __launch_bounds__(kBlock, NGI_SURFACE_MIN_BLOCKS) k_surface(NgiDevScene sc, NgiWaveParams wp) {
+    __shared__ unsigned s_warp[3][kBlock / 32];
+    __shared__ unsigned s_base[3];
     const unsigned n = wp.stage_counters[0];
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const unsigned slot = wp.surface_q[e];
-        if (!ngi_logic_surface(sc, wp, slot)) wp.regen_q[ngi_queue_alloc(wp.stage_counters + 1)] = slot;
+    unsigned* const counters[3] = {wp.iter_counters + 0, wp.iter_counters + 1, wp.stage_counters + 1};
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // block-uniform trip count
+        const unsigned e = base + threadIdx.x;
+        NgiVertexOut out; out.shadow = false; out.extend = false;
+        unsigned slot = 0;
+        if (e < n) { slot = wp.surface_q[e]; ngi_logic_surface(sc, wp, slot, out); }
+        const bool need[3] = {out.shadow, out.extend, e < n && !out.extend};                      // a path that ended here is regenerated
+        unsigned idx[3];
+        block_reserve<3>(counters, need, idx, s_warp, s_base);
+        if (need[0]) ngi_write_shadow(wp, idx[0], out);
+        if (need[1]) wp.extend_q[idx[1]] = slot;
+        if (need[2]) wp.regen_q[idx[2]] = slot;
     }
 }
 __global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_eye(NgiDevScene sc, NgiWaveParams wp) {
+    __shared__ unsigned s_warp[2][kBlock / 32];
+    __shared__ unsigned s_base[2];
     const unsigned n = wp.stage_counters[1];
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_logic_eye(sc, wp, wp.regen_q[e]);
+    const unsigned long long first = *wp.next_sample;      // advanced by n in the next k_iter_begin: entry e starts sample first + e
+    unsigned* const counters[2] = {wp.iter_counters + 0, wp.iter_counters + 1};
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned e = base + threadIdx.x;
+        NgiVertexOut out; out.shadow = false; out.extend = false;
+        unsigned slot = 0;
+        if (e < n) { slot = wp.regen_q[e]; ngi_logic_eye(sc, wp, slot, first + e, out); }
+        const bool need[2] = {out.shadow, out.extend};
+        unsigned idx[2];
+        block_reserve<2>(counters, need, idx, s_warp, s_base);
+        if (need[0]) ngi_write_shadow(wp, idx[0], out);
+        if (need[1]) wp.extend_q[idx[1]] = slot;
+    }
 }
+
 // Scene::Intersect's ray query (rt.hpp:2162-2182) for the compacted extend queue of this iteration
 struct ExtendSource {
     NgiWaveParams wp;
@@ -639,7 +696,7 @@ bool same_wp(const NgiWaveParams& a, const NgiWaveParams& b) { return memcmp(&a,
 int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool timed, size_t& ev_used, bool per_ray = false) {
     const unsigned P = wp.capacity;
     const bool direct = wp.renderer == NGI_RENDERER_PTDIRECT;
-    k_iter_begin<<<1, 1, 0, st>>>(s->counters);
+    k_iter_begin<<<1, 1, 0, st>>>(s->counters, wp.sample_end);
     if (timed) {
         while (s->events.size() < ev_used + 4) { cudaEvent_t e; NGI_CUDA(cudaEventCreate(&e)); s->events.push_back(e); }
         NGI_CUDA(cudaEventRecord(s->events[ev_used], st));

@@ -86,12 +86,22 @@ NGI_HD void ngi_film_add(float* film, const int pixel, const f3 c) {
 #endif
 }
 
-NGI_HD void ngi_push_shadow(const NgiWaveParams& wp, const f3 o, const f3 d, const float tmax, const f3 C, const int pixel) {
-    const unsigned e = ngi_queue_alloc(wp.iter_counters + 0);
+// What one path vertex hands to the queues: an optional shadow-queue entry (NEE) and whether the slot traces an
+// extend ray. The per-slot functions only FILL this; the caller allocates the queue entries — the CUDA kernels with
+// one atomic per block and queue (ngi_gpu.cu), the CPU simulator one by one (ngi_emit).
+struct NgiVertexOut {
+    bool shadow, extend;
+    f3 so, sd, sC; float stmax; int spixel;
+};
+NGI_HD void ngi_write_shadow(const NgiWaveParams& wp, const unsigned e, const NgiVertexOut& v) {
     float4* q = wp.shadow_q + 3 * (size_t)e;
-    q[0] = make_float4(o.x, o.y, o.z, tmax);
-    q[1] = make_float4(d.x, d.y, d.z, u2f((unsigned)pixel));
-    q[2] = make_float4(C.x, C.y, C.z, 0.0f);
+    q[0] = make_float4(v.so.x, v.so.y, v.so.z, v.stmax);
+    q[1] = make_float4(v.sd.x, v.sd.y, v.sd.z, u2f((unsigned)v.spixel));
+    q[2] = make_float4(v.sC.x, v.sC.y, v.sC.z, 0.0f);
+}
+NGI_HD void ngi_emit(const NgiWaveParams& wp, const unsigned slot, const NgiVertexOut& v) {
+    if (v.shadow) ngi_write_shadow(wp, ngi_queue_alloc(wp.iter_counters + 0), v);
+    if (v.extend) wp.extend_q[ngi_queue_alloc(wp.iter_counters + 1)] = slot;           // compacted extend queue (+ exact ray count)
 }
 
 // ---- fp64 view of the traced fp32 direction: d + U(-1/2, 1/2) * ulp(d) per component ---------------
@@ -136,9 +146,11 @@ NGI_HD int ngi_reconstruct(const NgiDevScene& sc, const unsigned tri, const floa
 
 // one path vertex: optional NEE (ptdirect), direction sampling, extend-ray emission. `eye` is a literal at every
 // call site, so the two flavours are specialised by the compiler.
-NGI_HD bool ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot, const bool eye,
+NGI_HD void ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot, const bool eye,
                        const unsigned long long sample, f3 thr, int pixel, const int nverts, const int type,
-                       const NgiGeom& g, const f3 wi, const double px, const double py, const double pz, const int primIdx) {
+                       const NgiGeom& g, const f3 wi, const double px, const double py, const double pz, const int primIdx,
+                       NgiVertexOut& out) {
+    out.shadow = false; out.extend = false;
     const NgiDevSensor& E = sc.sensor;
     const unsigned vtx = (unsigned)(nverts - 1);
     const NgiDevPrim& P = sc.prims[primIdx];
@@ -175,8 +187,10 @@ NGI_HD bool ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const uns
             const float G = g1 * g2 / dist2;                                              // :683
             const f3 C = thr * fsE * fsL * (G / ls.pdf);                                  // :686 (V applied by the shadow kernel)
             if (!is_zero(C)) {
-                const f3 o = mk3((float)px, (float)py, (float)pz);                        // rt.hpp:2166-2168
-                ngi_push_shadow(wp, o, ppL, dist * (1.0f - NGI_EPS_F), C * wp.film_scale, index);         // rt.hpp:2260
+                out.shadow = true;
+                out.so = mk3((float)px, (float)py, (float)pz);                            // rt.hpp:2166-2168
+                out.sd = ppL; out.stmax = dist * (1.0f - NGI_EPS_F);                      // rt.hpp:2260
+                out.sC = C * wp.film_scale; out.spixel = index;
             }
         }
     }
@@ -201,14 +215,13 @@ NGI_HD bool ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const uns
             else thr = thr * (fs / pdfD);                                                 // :544 / :754
         }
     }
-    if (!ok) return false;
+    if (!ok) return;
     const unsigned survive = (u01(ra[3]) > 0.5f) ? 0u : NGI_INFO_RR_SURVIVE;              // :583-587, decided up front
     wp.sample[slot] = sample;
     wp.thr_pix[slot] = make_float4(thr.x, thr.y, thr.z, u2f((unsigned)pixel));
     wp.px[slot] = px; wp.py[slot] = py; wp.pz[slot] = pz;
     wp.dir_info[slot] = make_float4(wo.x, wo.y, wo.z, u2f(NGI_INFO_ALIVE | survive | ((unsigned)nverts << 8)));
-    wp.extend_q[ngi_queue_alloc(wp.iter_counters + 1)] = slot;                            // compacted extend queue (+ exact ray count)
-    return true;
+    out.extend = true;
 }
 
 NGI_HD int ngi_logic_classify(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
@@ -238,7 +251,7 @@ NGI_HD int ngi_logic_classify(const NgiDevScene& sc, const NgiWaveParams& wp, co
     return NGI_CLASS_SURFACE;
 }
 
-NGI_HD bool ngi_logic_surface(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
+NGI_HD void ngi_logic_surface(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot, NgiVertexOut& out) {
     const float4 di = wp.dir_info[slot];
     const unsigned info = f2u(di.w);
     const float4 h = wp.hit[slot];
@@ -260,25 +273,34 @@ NGI_HD bool ngi_logic_surface(const NgiDevScene& sc, const NgiWaveParams& wp, co
     const int nverts = (int)(info >> 8) + 1;                                                  // :603
     const f3 thr = mk3(tp.x, tp.y, tp.z) * 2.0f;                                              // throughput /= rrProb, :591
     const int type = sc.prims[primIdx].type & ~NGI_EMITTER;                                   // :601
-    return ngi_vertex(sc, wp, slot, false, wp.sample[slot], thr, (int)f2u(tp.w), nverts, type, g, -d /* :602 */, px, py, pz, primIdx);
+    ngi_vertex(sc, wp, slot, false, wp.sample[slot], thr, (int)f2u(tp.w), nverts, type, g, -d /* :602 */, px, py, pz, primIdx, out);
 }
 
-// the slot's path ended: start the next sample at the eye vertex (nanogi.cpp:450-479 / :613-641)
-NGI_HD void ngi_logic_eye(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
+// the slot's path ended: start sample index `sample` at the eye vertex (nanogi.cpp:450-479 / :613-641); an index
+// past the end of the shard leaves the slot idle. The CUDA eye kernel numbers its queue entries consecutively from
+// the render's sample cursor (no atomics); the simulator draws them from the cursor one at a time.
+NGI_HD void ngi_logic_eye(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot, const unsigned long long sample,
+                          NgiVertexOut& out) {
     const NgiDevSensor& E = sc.sensor;
-    const unsigned long long sample = ngi_fetch_sample(wp.next_sample);
+    out.shadow = false; out.extend = false;
     if (sample < wp.sample_end) {
         NgiGeom g; g.sn = g.gn = g.dpdu = g.dpdv = mk3(0.0f);
         // EvaluatePosition / pdfPE / pdfE = 1 for the pinhole
-        if (ngi_vertex(sc, wp, slot, true, sample, mk3(1.0f), -1, 1, NGI_E, g, mk3(0.0f), E.px, E.py, E.pz, E.prim)) return;
+        ngi_vertex(sc, wp, slot, true, sample, mk3(1.0f), -1, 1, NGI_E, g, mk3(0.0f), E.px, E.py, E.pz, E.prim, out);
     }
-    wp.dir_info[slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));                               // idle slot
+    if (!out.extend) wp.dir_info[slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));           // idle slot
 }
 
-// all three for one slot (the CPU simulator's order; the CUDA kernel regroups slots between the stages)
+// all three for one slot (the CPU simulator's order; the CUDA kernels regroup slots between the stages)
 NGI_HD_NOINLINE void ngi_logic_step(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
-    if (ngi_logic_classify(sc, wp, slot) == NGI_CLASS_SURFACE && ngi_logic_surface(sc, wp, slot)) return;
-    ngi_logic_eye(sc, wp, slot);
+    NgiVertexOut out;
+    if (ngi_logic_classify(sc, wp, slot) == NGI_CLASS_SURFACE) {
+        ngi_logic_surface(sc, wp, slot, out);
+        ngi_emit(wp, slot, out);
+        if (out.extend) return;
+    }
+    ngi_logic_eye(sc, wp, slot, ngi_fetch_sample(wp.next_sample), out);
+    ngi_emit(wp, slot, out);
 }
 
 // ---- extend / shadow bodies (BVH8 = product path) -----------------------------------------------

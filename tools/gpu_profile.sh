@@ -8,6 +8,6 @@ mkdir -p $OUT
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/launches_${TAG}.csv \
     python bench.py --steps 1 --warmup 1 --e2e-steps 1 --workload $WL --spp 8 --no-cpu > $OUT/launches_${TAG}.log 2>&1
 # full capture of the three wavefront kernels, taken well into the steady state of the first render
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_extend|k_shadow|k_classify|k_surface|k_eye' -s $SKIP -c 3 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_extend|k_shadow|k_classify|k_surface|k_eye' -s $SKIP -c 5 \
     -f -o $OUT/prof_${TAG} python bench.py --steps 1 --warmup 1 --e2e-steps 1 --workload $WL --spp $SPP --no-cpu > $OUT/prof_${TAG}.log 2>&1
 ls -la $OUT
