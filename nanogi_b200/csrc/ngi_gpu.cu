@@ -201,12 +201,12 @@ struct NgiRenderCounters {
     unsigned iter[2];   // [0] shadow entries, [1] extend rays of the iteration in flight
     unsigned last[2];   // snapshot of the previous iteration (read by the host for termination)
     unsigned fetch[2];  // dynamic-fetch cursors of the persistent trace kernels ([0] shadow, [1] extend)
-    unsigned stage[4];  // [0..2] surface queue entries per BSDF class, [3] regenerate queue entries
+    unsigned stage[4];  // [0] surface queue entries, [1] regenerate queue entries
 };
 
 __global__ void k_iter_begin(NgiRenderCounters* c, unsigned long long sample_end) {
     // the eye kernel of the previous iteration started samples next_sample .. next_sample + stage[1] - 1
-    const unsigned long long ns = c->next_sample + c->stage[3];
+    const unsigned long long ns = c->next_sample + c->stage[1];
     c->next_sample = ns < sample_end ? ns : sample_end;
     c->total_shadow += c->iter[0];
     c->total_extend += c->iter[1];
@@ -216,7 +216,8 @@ __global__ void k_iter_begin(NgiRenderCounters* c, unsigned long long sample_end
     c->iter[1] = 0u;
     c->fetch[0] = 0u;
     c->fetch[1] = 0u;
-    c->stage[0] = 0u; c->stage[1] = 0u; c->stage[2] = 0u; c->stage[3] = 0u;
+    c->stage[0] = 0u;
+    c->stage[1] = 0u;
     c->iterations += 1ull;
 }
 
@@ -234,35 +235,24 @@ constexpr unsigned kStageGrid = 148u * 8u;
 // kernels read and write the path state almost as coalesced as a slot-indexed kernel would (pushing slot ids in atomic
 // order instead made those kernels 2.3x slower: every state access became a scattered 16-byte touch).
 __global__ void __launch_bounds__(kBlock) k_classify(NgiDevScene sc, NgiWaveParams wp) {
-    constexpr int NQ = NGI_NUM_SURFACE_BINS + 1;             // queue q < 3: surface bin q (D, G, S); q = 3: regenerate
-    __shared__ unsigned s_warp[NQ][kBlock / 32];
-    __shared__ unsigned s_base[NQ];
+    __shared__ unsigned s_warp[2][kBlock / 32];
+    __shared__ unsigned s_base[2];
     const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int cls = slot < wp.capacity ? ngi_logic_classify(sc, wp, slot) : -1;
-    const int q = cls < 0 ? -1 : (cls == NGI_CLASS_REGENERATE ? NGI_NUM_SURFACE_BINS : cls - NGI_CLASS_SURFACE);
-    unsigned m[NQ];
-#pragma unroll
-    for (int k = 0; k < NQ; k++) {
-        m[k] = __ballot_sync(0xFFFFFFFFu, q == k);
-        if (lane == 0) s_warp[k][warp] = (unsigned)__popc(m[k]);
-    }
+    const unsigned ms = __ballot_sync(0xFFFFFFFFu, cls == NGI_CLASS_SURFACE), mr = __ballot_sync(0xFFFFFFFFu, cls == NGI_CLASS_REGENERATE);
+    if (lane == 0) { s_warp[0][warp] = (unsigned)__popc(ms); s_warp[1][warp] = (unsigned)__popc(mr); }
     __syncthreads();
-    if (threadIdx.x < NQ) {
+    if (threadIdx.x < 2) {
         unsigned acc = 0;
         for (int w = 0; w < kBlock / 32; w++) { const unsigned c = s_warp[threadIdx.x][w]; s_warp[threadIdx.x][w] = acc; acc += c; }
         s_base[threadIdx.x] = acc ? atomicAdd(wp.stage_counters + threadIdx.x, acc) : 0u;
     }
     __syncthreads();
     const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int k = 0; k < NQ; k++) {
-        if (q != k) continue;
-        unsigned* dst = k < NGI_NUM_SURFACE_BINS ? wp.surface_q + (size_t)k * wp.capacity : wp.regen_q;
-        dst[s_base[k] + s_warp[k][warp] + (unsigned)__popc(m[k] & lt)] = slot;
-    }
+    if (cls == NGI_CLASS_SURFACE) wp.surface_q[s_base[0] + s_warp[0][warp] + (unsigned)__popc(ms & lt)] = slot;
+    else if (cls == NGI_CLASS_REGENERATE) wp.regen_q[s_base[1] + s_warp[1][warp] + (unsigned)__popc(mr & lt)] = slot;
 }
-
 // Queue space for a whole block with ONE atomic per queue: every thread passes whether it needs an entry in each of the
 // NQ queues and gets its index back; entries of one block are contiguous and in thread order. (A warp-aggregated atomic
 // per queue and warp — 3 x 35k same-address atomics per launch — was 70 % of the eye kernel's stall samples.)
@@ -291,19 +281,14 @@ __device__ __forceinline__ void block_reserve(unsigned* const (&counters)[NQ], c
 __global__ void __launch_bounds__(kBlock, NGI_SURFACE_MIN_BLOCKS) k_surface(NgiDevScene sc, NgiWaveParams wp) {
     __shared__ unsigned s_warp[3][kBlock / 32];
     __shared__ unsigned s_base[3];
-    // the three material bins back to back, each padded to whole warps: a warp shades one BSDF class
-    const unsigned n0 = wp.stage_counters[0], n1 = wp.stage_counters[1], n2 = wp.stage_counters[2];
-    const unsigned p0 = (n0 + 31u) & ~31u, p1 = p0 + ((n1 + 31u) & ~31u), n = p1 + ((n2 + 31u) & ~31u);
-    unsigned* const counters[3] = {wp.iter_counters + 0, wp.iter_counters + 1, wp.stage_counters + 3};
+    const unsigned n = wp.stage_counters[0];
+    unsigned* const counters[3] = {wp.iter_counters + 0, wp.iter_counters + 1, wp.stage_counters + 1};
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // block-uniform trip count
         const unsigned e = base + threadIdx.x;
-        const unsigned bin = e < p0 ? 0u : (e < p1 ? 1u : 2u);
-        const unsigned i = e - (bin == 0u ? 0u : (bin == 1u ? p0 : p1));
-        const bool valid = e < n && i < (bin == 0u ? n0 : (bin == 1u ? n1 : n2));
         NgiVertexOut out; out.shadow = false; out.extend = false;
         unsigned slot = 0;
-        if (valid) { slot = wp.surface_q[(size_t)bin * wp.capacity + i]; ngi_logic_surface(sc, wp, slot, out); }
-        const bool need[3] = {out.shadow, out.extend, valid && !out.extend};                      // a path that ended here is regenerated
+        if (e < n) { slot = wp.surface_q[e]; ngi_logic_surface(sc, wp, slot, out); }
+        const bool need[3] = {out.shadow, out.extend, e < n && !out.extend};                      // a path that ended here is regenerated
         unsigned idx[3];
         block_reserve<3>(counters, need, idx, s_warp, s_base);
         if (need[0]) ngi_write_shadow(wp, idx[0], out);
@@ -314,7 +299,7 @@ __global__ void __launch_bounds__(kBlock, NGI_SURFACE_MIN_BLOCKS) k_surface(NgiD
 __global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_eye(NgiDevScene sc, NgiWaveParams wp) {
     __shared__ unsigned s_warp[2][kBlock / 32];
     __shared__ unsigned s_base[2];
-    const unsigned n = wp.stage_counters[3];
+    const unsigned n = wp.stage_counters[1];
     const unsigned long long first = *wp.next_sample;      // advanced by n in the next k_iter_begin: entry e starts sample first + e
     unsigned* const counters[2] = {wp.iter_counters + 0, wp.iter_counters + 1};
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -676,7 +661,7 @@ int ensure_wave(Scene* s, unsigned P) {
     if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
     if (s->wave_mem) { wave_cache_put(s->device, s->wave_mem, s->wave_capacity); s->wave_mem = nullptr; }
     // per slot: sample 8 + thr_pix 16 + p 24 + dir_info 16 + hit 16 = 80 B; shadow queue 2 entries x 48 B
-    const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96 + 4 + 4 * NGI_NUM_SURFACE_BINS + 4);
+    const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96 + 4 + 4 + 4);
     s->wave_mem = wave_cache_take(s->device, P);
     if (!s->wave_mem) NGI_CUDA(cudaMalloc(&s->wave_mem, bytes));
     if (!s->counters) NGI_CUDA(cudaMalloc((void**)&s->counters, sizeof(NgiRenderCounters)));
@@ -697,7 +682,7 @@ void carve_wave(Scene* s, NgiWaveParams& wp) {
     wp.py = (double*)p; p += P * 8;
     wp.pz = (double*)p; p += P * 8;
     wp.extend_q = (unsigned*)p; p += P * 4;
-    wp.surface_q = (unsigned*)p; p += P * 4 * NGI_NUM_SURFACE_BINS;
+    wp.surface_q = (unsigned*)p; p += P * 4;
     wp.regen_q = (unsigned*)p; p += P * 4;
     wp.stage_counters = s->counters->stage;
     wp.iter_counters = s->counters->iter;

@@ -115,11 +115,7 @@ inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out) {
         r[1] = make_float4(p[4], p[5], p[6], p[7]);
         r[2] = make_float4(p[8], q[0], q[1], q[2]);
         r[3] = make_float4(q[3], q[4], q[5], q[6]);
-        // .w = BSDF class of the primitive (0 D, 1 G, 2 S; precedence D > G > S like rt.hpp:749-900): lets the classify
-        // stage bin surface vertices by material without touching the primitive table
-        const int bt = d->prims[triPrim[t]].type;
-        const unsigned cls = (bt & NGI_TYPE_D) ? 0u : (bt & NGI_TYPE_G) ? 1u : (bt & NGI_TYPE_S) ? 2u : 0u;
-        r[4] = make_float4(q[7], q[8], u2f((unsigned)triPrim[t]), u2f(cls));
+        r[4] = make_float4(q[7], q[8], u2f((unsigned)triPrim[t]), 0.0f);
     }
     return true;
 }

@@ -38,7 +38,7 @@ struct NgiDevSensor {         // E.Pinhole, rt.hpp:422-429
 };
 
 // per-triangle shading record, indexed by GLOBAL triangle id: 5 x float4 = 80 B
-//   r0 = (v0.xyz, v1.x) r1 = (v1.yz, v2.xy) r2 = (v2.z, n0.xyz) r3 = (n1.xyz, n2.x) r4 = (n2.yz, prim bits, BSDF class bits)
+//   r0 = (v0.xyz, v1.x) r1 = (v1.yz, v2.xy) r2 = (v2.z, n0.xyz) r3 = (n1.xyz, n2.x) r4 = (n2.yz, prim bits, -)
 struct NgiDevScene {
     const uint4* nodes8; const float4* tris8;
     const float4* nodes2; const float4* tris2;

@@ -35,9 +35,9 @@ struct NgiWaveParams {
     unsigned* extend_q;           // slot ids of the extend rays of this iteration (compacted by the logic stage)
     unsigned* iter_counters;      // [0] shadow entries this iteration, [1] extend rays this iteration
     unsigned* fetch_cursors;      // [0] shadow, [1] extend: dynamic-fetch cursors of the persistent trace kernels
-    unsigned* surface_q;          // [3][capacity] slots that continue at a surface vertex, binned by BSDF class (D, G, S)
+    unsigned* surface_q;          // slots that continue at a surface vertex this iteration (written by the classify stage)
     unsigned* regen_q;            // slots whose path ended: regenerated from the sample counter by the eye stage
-    unsigned* stage_counters;     // [0..2] surface_q bin entries, [3] regen_q entries
+    unsigned* stage_counters;     // [0] surface_q entries, [1] regen_q entries
     unsigned long long* next_sample;
     float* film;                  // [H][W][3], row 0 = bottom
     unsigned capacity;            // slots
@@ -142,8 +142,7 @@ NGI_HD int ngi_reconstruct(const NgiDevScene& sc, const unsigned tri, const floa
 //             path ends at this vertex (the slot is then regenerated by `eye` in the same logic stage).
 //   eye       starts the next sample at the eye vertex: NEE to the light-sample's pixel, camera ray.
 #define NGI_CLASS_REGENERATE 0
-#define NGI_CLASS_SURFACE 1          /* + BSDF class of the hit primitive: 1 D, 2 G, 3 S */
-#define NGI_NUM_SURFACE_BINS 3
+#define NGI_CLASS_SURFACE 1
 
 // one path vertex: optional NEE (ptdirect), direction sampling, extend-ray emission. `eye` is a literal at every
 // call site, so the two flavours are specialised by the compiler.
@@ -232,9 +231,8 @@ NGI_HD int ngi_logic_classify(const NgiDevScene& sc, const NgiWaveParams& wp, co
     const float4 h = wp.hit[slot];
     const unsigned tri = f2u(h.w);
     if (tri == NGI_MISS) return NGI_CLASS_REGENERATE;                                         // miss -> break, nanogi.cpp:557 / :767
-    const float4 r4 = ngi_ldg(sc.shade_tris + 5 * (size_t)tri + 4);
     if (wp.renderer == 0) {                                                                   // nanogi.cpp:566-577
-        const int primIdx = (int)f2u(r4.z);
+        const int primIdx = (int)f2u(ngi_ldg(sc.shade_tris + 5 * (size_t)tri + 4).z);
         const NgiDevPrim& P = sc.prims[primIdx];
         if ((P.type & NGI_L) && P.l_type == NGI_LT_AREA) {
             // EvaluateDirection(L.area): Le iff cos_sn(-d) > 0 (rt.hpp:922-927); EvaluatePosition(area) = 1
@@ -250,7 +248,7 @@ NGI_HD int ngi_logic_classify(const NgiDevScene& sc, const NgiWaveParams& wp, co
     if (!(info & NGI_INFO_RR_SURVIVE)) return NGI_CLASS_REGENERATE;                           // nanogi.cpp:581-591
     const int nverts = (int)(info >> 8) + 1;                                                  // :603
     if (wp.max_verts != -1 && nverts >= wp.max_verts) return NGI_CLASS_REGENERATE;            // :485 / :647
-    return NGI_CLASS_SURFACE + (int)(f2u(r4.w) % NGI_NUM_SURFACE_BINS);
+    return NGI_CLASS_SURFACE;
 }
 
 NGI_HD void ngi_logic_surface(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot, NgiVertexOut& out) {
@@ -296,7 +294,7 @@ NGI_HD void ngi_logic_eye(const NgiDevScene& sc, const NgiWaveParams& wp, const 
 // all three for one slot (the CPU simulator's order; the CUDA kernels regroup slots between the stages)
 NGI_HD_NOINLINE void ngi_logic_step(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
     NgiVertexOut out;
-    if (ngi_logic_classify(sc, wp, slot) >= NGI_CLASS_SURFACE) {
+    if (ngi_logic_classify(sc, wp, slot) == NGI_CLASS_SURFACE) {
         ngi_logic_surface(sc, wp, slot, out);
         ngi_emit(wp, slot, out);
         if (out.extend) return;
