@@ -427,9 +427,15 @@ struct Scene {
     int graph_iters = 0;
     std::vector<cudaEvent_t> events;
     // persistent trace kernels: grid = SM count x resident CTAs per SM (queried once per kernel)
-    NgiTraceTuning tune{4, 8, 0x3F800000u};   // best of the sweep in profiles/r01_sweep_trace.txt
+    NgiTraceTuning tune{4, 8, 0x3F800000u, 128u};   // best of the sweep in profiles/r01_sweep_trace.txt
     unsigned grid_extend = 0, grid_shadow = 0, grid_trace[2] = {0, 0};
     unsigned* trace_cursor = nullptr;
+    // the extend and shadow kernels of one iteration are independent: the shadow kernel is forked onto a second stream
+    // so that its CTAs fill the SMs the extend kernel's tail leaves idle (each persistent launch ends with a ~70-100 us
+    // tail of a few long rays, profiles/r01_sweep_wave.txt)
+    bool overlap_trace = true;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     ~Scene() {
         cudaSetDevice(device);
@@ -440,6 +446,9 @@ struct Scene {
         if (counters) cudaFree(counters);
         if (trace_cursor) cudaFree(trace_cursor);
         if (counters_host) cudaFreeHost(counters_host);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -470,8 +479,13 @@ int init_trace_launch(Scene* s) {
     if ((rc = persistent_grid(k_trace8<false>, &s->grid_trace[0]))) return rc;
     if ((rc = persistent_grid(k_trace8<true>, &s->grid_trace[1]))) return rc;
     NGI_CUDA(cudaMalloc((void**)&s->trace_cursor, sizeof(unsigned)));
+    NGI_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    NGI_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    NGI_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     if (const char* e = getenv("NGI_TRACE_REFILL_MIN")) s->tune.refill_min = atoi(e);
     if (const char* e = getenv("NGI_TRACE_TRI_MIN")) s->tune.tri_min = atoi(e);
+    if (const char* e = getenv("NGI_TRACE_OVERLAP")) s->overlap_trace = atoi(e) != 0;
+    if (const char* e = getenv("NGI_TRACE_CHUNK")) s->tune.chunk = (unsigned)std::max(1, atoi(e));
     return NGI_OK;
 }
 
@@ -706,6 +720,16 @@ int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool ti
     k_surface<<<sg, kBlock, 0, st>>>(s->dev, wp);
     k_eye<<<sg, kBlock, 0, st>>>(s->dev, wp);
     if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 1], st));
+    if (!timed && direct && s->overlap_trace) {
+        // fork: shadow on stream2, extend on the main stream, join
+        NGI_CUDA(cudaEventRecord(s->ev_fork, st));
+        NGI_CUDA(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
+        k_extend<<<s->grid_extend, kBlock, 0, st>>>(s->dev, wp, s->tune);
+        k_shadow<<<s->grid_shadow, kBlock, 0, s->stream2>>>(s->dev, wp, s->tune);
+        NGI_CUDA(cudaEventRecord(s->ev_join, s->stream2));
+        NGI_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+        return NGI_OK;
+    }
     if (per_ray) k_extend_per_ray<<<std::min(grid_for(P), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
     else k_extend<<<s->grid_extend, kBlock, 0, st>>>(s->dev, wp, s->tune);
     if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 2], st));

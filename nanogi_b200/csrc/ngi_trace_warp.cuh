@@ -9,7 +9,7 @@
 // code and the triangle code, and a warp lives as long as its slowest ray. Here instead (after Aila & Laine
 // 2009 "Understanding the efficiency of ray traversal on GPUs" and Ylitie, Karras, Laine 2017):
 //   * persistent warps: grid = SM count x resident CTAs, every warp pulls rays from the queue in chunks
-//     (one global atomic per 128 rays) and hands them to lanes as they go idle (dynamic fetch);
+//     (one global atomic per chunk of rays) and hands them to lanes as they go idle (dynamic fetch);
 //   * the loop body is warp-uniform and phase-structured — all lanes reconverge (__syncwarp) before the
 //     node phase (one 8-wide node step per lane per round) and before the triangle phase (one triangle
 //     test per lane per trip) — so each phase issues once for all lanes that need it;
@@ -23,12 +23,12 @@
 
 #define NGI_WARP_STACK 48          /* >= NGI_BVH8_MAX_DEPTH (node groups) + NGI_POSTPONE_MAX_SP (postponed triangle groups) */
 #define NGI_POSTPONE_MAX_SP 16
-#define NGI_FETCH_CHUNK 128u
 
 struct NgiTraceTuning {
     int refill_min;     // refill idle lanes when at least this many are idle (or all are)
     int tri_min;        // postpone the triangle phase when fewer lanes than this have triangles pending
     unsigned one_bits;  // 0x3F800000 as a run-time value (keeps it in a register for PRMT, see ngi_q1)
+    unsigned chunk;     // rays a warp takes from the queue per global atomic
 };
 
 // Source concept:
@@ -69,10 +69,10 @@ __device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, 
             if (!exhausted && (nidle >= tune.refill_min || idle == FULL)) {
                 if (chunk_next >= chunk_end) {
                     unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(src.cursor(), NGI_FETCH_CHUNK);
+                    if (lane == 0) base = atomicAdd(src.cursor(), tune.chunk);
                     base = __shfl_sync(FULL, base, 0);
                     chunk_next = base;
-                    chunk_end = base + NGI_FETCH_CHUNK < n ? base + NGI_FETCH_CHUNK : n;
+                    chunk_end = base + tune.chunk < n ? base + tune.chunk : n;
                     if (base >= n) { exhausted = true; chunk_next = chunk_end = 0; }
                 }
                 if (!exhausted) {
