@@ -46,6 +46,10 @@ int set_err(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 constexpr int kBlock = 256;
+#ifndef NGI_TRACE_BLOCK
+#define NGI_TRACE_BLOCK 64   /* persistent trace kernels: small CTAs hand their SM slot back as soon as their 2 warps run dry */
+#endif
+constexpr int kTraceBlock = NGI_TRACE_BLOCK;
 #ifndef NGI_SURFACE_MIN_BLOCKS
 #define NGI_SURFACE_MIN_BLOCKS 4
 #endif
@@ -186,7 +190,7 @@ struct QuerySource {
     }
 };
 template <bool ANY_HIT>
-__global__ void __launch_bounds__(kBlock) k_trace8(NgiDevScene sc, QuerySource<ANY_HIT> src, NgiTraceTuning tune) {
+__global__ void __launch_bounds__(kTraceBlock) k_trace8(NgiDevScene sc, QuerySource<ANY_HIT> src, NgiTraceTuning tune) {
     ngi_trace_warp<ANY_HIT>(sc.nodes8, sc.tris8, src, tune);
 }
 
@@ -358,11 +362,11 @@ __global__ void __launch_bounds__(kBlock) k_shadow_per_ray(NgiDevScene sc, NgiWa
     const unsigned n = wp.iter_counters[0];
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_shadow_step(sc, wp, e);
 }
-__global__ void __launch_bounds__(kBlock) k_extend(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
+__global__ void __launch_bounds__(kTraceBlock) k_extend(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
     ExtendSource src; src.wp = wp;
     ngi_trace_warp<false>(sc.nodes8, sc.tris8, src, tune);
 }
-__global__ void __launch_bounds__(kBlock) k_shadow(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
+__global__ void __launch_bounds__(kTraceBlock) k_shadow(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
     ShadowSource src; src.wp = wp;
     ngi_trace_warp<true>(sc.nodes8, sc.tris8, src, tune);
 }
@@ -427,7 +431,7 @@ struct Scene {
     int graph_iters = 0;
     std::vector<cudaEvent_t> events;
     // persistent trace kernels: grid = SM count x resident CTAs per SM (queried once per kernel)
-    NgiTraceTuning tune{4, 8, 0x3F800000u, 128u};   // best of the sweep in profiles/r01_sweep_trace.txt
+    NgiTraceTuning tune{4, 8, 0x3F800000u, 64u};   // best of the sweep in profiles/r01_sweep_trace.txt
     unsigned grid_extend = 0, grid_shadow = 0, grid_trace[2] = {0, 0};
     unsigned* trace_cursor = nullptr;
     // the extend and shadow kernels of one iteration are independent: the shadow kernel is forked onto a second stream
@@ -467,7 +471,7 @@ int persistent_grid(K kernel, unsigned* out) {
     int dev = 0, sms = 0, per_sm = 0;
     NGI_CUDA(cudaGetDevice(&dev));
     NGI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    NGI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0));
+    NGI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, 0));
     *out = (unsigned)(sms * (per_sm > 0 ? per_sm : 1));
     return NGI_OK;
 }
@@ -724,17 +728,17 @@ int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool ti
         // fork: shadow on stream2, extend on the main stream, join
         NGI_CUDA(cudaEventRecord(s->ev_fork, st));
         NGI_CUDA(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
-        k_extend<<<s->grid_extend, kBlock, 0, st>>>(s->dev, wp, s->tune);
-        k_shadow<<<s->grid_shadow, kBlock, 0, s->stream2>>>(s->dev, wp, s->tune);
+        k_extend<<<s->grid_extend, kTraceBlock, 0, st>>>(s->dev, wp, s->tune);
+        k_shadow<<<s->grid_shadow, kTraceBlock, 0, s->stream2>>>(s->dev, wp, s->tune);
         NGI_CUDA(cudaEventRecord(s->ev_join, s->stream2));
         NGI_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
         return NGI_OK;
     }
     if (per_ray) k_extend_per_ray<<<std::min(grid_for(P), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
-    else k_extend<<<s->grid_extend, kBlock, 0, st>>>(s->dev, wp, s->tune);
+    else k_extend<<<s->grid_extend, kTraceBlock, 0, st>>>(s->dev, wp, s->tune);
     if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 2], st));
     if (direct && per_ray) k_shadow_per_ray<<<std::min(grid_for((size_t)P * 2), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
-    else if (direct) k_shadow<<<s->grid_shadow, kBlock, 0, st>>>(s->dev, wp, s->tune);
+    else if (direct) k_shadow<<<s->grid_shadow, kTraceBlock, 0, st>>>(s->dev, wp, s->tune);
     if (timed) { NGI_CUDA(cudaEventRecord(s->events[ev_used + 3], st)); ev_used += 4; }
     return NGI_OK;
 }
@@ -860,9 +864,9 @@ template <bool ANY_HIT>
 void launch_trace8(Scene* s, const NgiRay* rays, size_t n, NgiHit* hits, cudaStream_t st) {
     QuerySource<ANY_HIT> src;
     src.rays = reinterpret_cast<const float4*>(rays); src.hits = reinterpret_cast<float4*>(hits); src.n = (unsigned)n; src.cur = s->trace_cursor;
-    const unsigned need = grid_for(n);
+    const unsigned need = grid_for(n, kTraceBlock);
     const unsigned grid = std::min(s->grid_trace[ANY_HIT ? 1 : 0], need);
-    k_trace8<ANY_HIT><<<grid, kBlock, 0, st>>>(s->dev, src, s->tune);
+    k_trace8<ANY_HIT><<<grid, kTraceBlock, 0, st>>>(s->dev, src, s->tune);
 }
 
 int trace_impl(Scene* s, const NgiRay* rays_dev, size_t n, NgiHit* hits_dev, int any_hit, int accel, double* seconds) {
