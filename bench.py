@@ -330,6 +330,9 @@ def run_own(args, rank: int, local_rank: int, world: int):
 
 
 def main():
+    # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

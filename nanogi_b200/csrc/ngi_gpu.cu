@@ -397,31 +397,32 @@ __global__ void __launch_bounds__(kBlock) k_eval_bsdf(NgiDevScene sc, const floa
 // cudaMalloc / cudaFree of that size cost 0.1-0.3 s: a released buffer is parked per device and handed to the
 // next scene handle that asks for the same capacity (the e2e path creates one handle per render).
 struct WaveCacheEntry { void* mem = nullptr; unsigned capacity = 0; };
+constexpr int kWaveCacheSlots = 4;
 std::mutex g_wave_mutex;
-WaveCacheEntry g_wave_cache[64];
+WaveCacheEntry g_wave_cache[64][kWaveCacheSlots];
 
 void* wave_cache_take(int device, unsigned P) {
     std::lock_guard<std::mutex> lock(g_wave_mutex);
     if (device < 0 || device >= 64) return nullptr;
-    WaveCacheEntry& e = g_wave_cache[device];
-    if (e.mem && e.capacity == P) { void* m = e.mem; e.mem = nullptr; e.capacity = 0; return m; }
+    for (WaveCacheEntry& e : g_wave_cache[device])
+        if (e.mem && e.capacity == P) { void* m = e.mem; e.mem = nullptr; e.capacity = 0; return m; }
     return nullptr;
 }
 void wave_cache_put(int device, void* mem, unsigned P) {
     std::lock_guard<std::mutex> lock(g_wave_mutex);
-    if (device < 0 || device >= 64) { cudaFree(mem); return; }
-    WaveCacheEntry& e = g_wave_cache[device];
-    if (e.mem) cudaFree(e.mem);
-    e.mem = mem; e.capacity = P;
+    if (device >= 0 && device < 64)
+        for (WaveCacheEntry& e : g_wave_cache[device])
+            if (!e.mem) { e.mem = mem; e.capacity = P; return; }
+    cudaFree(mem);
 }
 
-struct Scene {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    NgiDevScene dev{};
-    NgiSceneInfo info{};
-    std::vector<void*> allocs;
-    // wavefront state cache (allocated on first render, re-used while the capacity fits)
+// One wavefront pipeline: path-state buffer, counters, the captured graph of a batch of iterations and the streams it
+// runs on. A render runs several lanes concurrently on disjoint sample ranges (same film): the kernels of one lane are
+// serially dependent and every persistent trace launch ends in a tail of a few long rays, so a second lane's kernels
+// fill the SMs the first lane leaves idle (and vice versa).
+struct Lane {
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr;
     unsigned wave_capacity = 0;
     void* wave_mem = nullptr;
     NgiRenderCounters* counters = nullptr;
@@ -429,30 +430,43 @@ struct Scene {
     cudaGraphExec_t graph_exec = nullptr;
     NgiWaveParams graph_wp{};
     int graph_iters = 0;
-    std::vector<cudaEvent_t> events;
+    std::vector<cudaEvent_t> events;             // per-kernel timing (NGI_RENDER_TIME_KERNELS)
+    NgiWaveParams wp{};
+    bool running = false;
+};
+
+struct Scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    NgiDevScene dev{};
+    NgiSceneInfo info{};
+    std::vector<void*> allocs;
+    std::vector<Lane> lanes;
+    int num_lanes = 2;
     // persistent trace kernels: grid = SM count x resident CTAs per SM (queried once per kernel)
     NgiTraceTuning tune{4, 8, 0x3F800000u, 64u};   // best of the sweep in profiles/r01_sweep_trace.txt
     unsigned grid_extend = 0, grid_shadow = 0, grid_trace[2] = {0, 0};
     unsigned* trace_cursor = nullptr;
-    // the extend and shadow kernels of one iteration are independent: the shadow kernel is forked onto a second stream
-    // so that its CTAs fill the SMs the extend kernel's tail leaves idle (each persistent launch ends with a ~70-100 us
-    // tail of a few long rays, profiles/r01_sweep_wave.txt)
+    // the extend and shadow kernels of one iteration are independent: the shadow kernel is forked onto the lane's second
+    // stream so that its CTAs fill the SMs the extend kernel's tail leaves idle
     bool overlap_trace = true;
-    cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     ~Scene() {
         cudaSetDevice(device);
-        if (graph_exec) cudaGraphExecDestroy(graph_exec);
-        for (auto e : events) cudaEventDestroy(e);
+        for (Lane& l : lanes) {
+            if (l.graph_exec) cudaGraphExecDestroy(l.graph_exec);
+            for (auto e : l.events) cudaEventDestroy(e);
+            if (l.wave_mem) wave_cache_put(device, l.wave_mem, l.wave_capacity);
+            if (l.counters) cudaFree(l.counters);
+            if (l.counters_host) cudaFreeHost(l.counters_host);
+            if (l.ev_fork) cudaEventDestroy(l.ev_fork);
+            if (l.ev_join) cudaEventDestroy(l.ev_join);
+            if (l.ev_done) cudaEventDestroy(l.ev_done);
+            if (l.stream2) cudaStreamDestroy(l.stream2);
+            if (l.stream) cudaStreamDestroy(l.stream);
+        }
         for (void* p : allocs) cudaFree(p);
-        if (wave_mem) wave_cache_put(device, wave_mem, wave_capacity);
-        if (counters) cudaFree(counters);
         if (trace_cursor) cudaFree(trace_cursor);
-        if (counters_host) cudaFreeHost(counters_host);
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        if (ev_join) cudaEventDestroy(ev_join);
-        if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -483,12 +497,10 @@ int init_trace_launch(Scene* s) {
     if ((rc = persistent_grid(k_trace8<false>, &s->grid_trace[0]))) return rc;
     if ((rc = persistent_grid(k_trace8<true>, &s->grid_trace[1]))) return rc;
     NGI_CUDA(cudaMalloc((void**)&s->trace_cursor, sizeof(unsigned)));
-    NGI_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
-    NGI_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
-    NGI_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     if (const char* e = getenv("NGI_TRACE_REFILL_MIN")) s->tune.refill_min = atoi(e);
     if (const char* e = getenv("NGI_TRACE_TRI_MIN")) s->tune.tri_min = atoi(e);
     if (const char* e = getenv("NGI_TRACE_OVERLAP")) s->overlap_trace = atoi(e) != 0;
+    if (const char* e = getenv("NGI_LANES")) s->num_lanes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("NGI_TRACE_CHUNK")) s->tune.chunk = (unsigned)std::max(1, atoi(e));
     return NGI_OK;
 }
@@ -674,23 +686,30 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
 }
 
 // ---- wavefront state ---------------------------------------------------------------------------
-int ensure_wave(Scene* s, unsigned P) {
-    if (s->wave_capacity == P && s->wave_mem) return NGI_OK;
-    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
-    if (s->wave_mem) { wave_cache_put(s->device, s->wave_mem, s->wave_capacity); s->wave_mem = nullptr; }
-    // per slot: sample 8 + thr_pix 16 + p 24 + dir_info 16 + hit 16 = 80 B; shadow queue 2 entries x 48 B
+int ensure_lane(Scene* s, Lane& l, unsigned P) {
+    if (!l.stream) {
+        NGI_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        NGI_CUDA(cudaStreamCreateWithFlags(&l.stream2, cudaStreamNonBlocking));
+        NGI_CUDA(cudaEventCreateWithFlags(&l.ev_fork, cudaEventDisableTiming));
+        NGI_CUDA(cudaEventCreateWithFlags(&l.ev_join, cudaEventDisableTiming));
+        NGI_CUDA(cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
+        NGI_CUDA(cudaMalloc((void**)&l.counters, sizeof(NgiRenderCounters)));
+        NGI_CUDA(cudaMallocHost((void**)&l.counters_host, sizeof(NgiRenderCounters)));
+    }
+    if (l.wave_capacity == P && l.wave_mem) return NGI_OK;
+    if (l.graph_exec) { cudaGraphExecDestroy(l.graph_exec); l.graph_exec = nullptr; }
+    if (l.wave_mem) { wave_cache_put(s->device, l.wave_mem, l.wave_capacity); l.wave_mem = nullptr; }
+    // per slot: sample 8 + thr_pix 16 + p 24 + dir_info 16 + hit 16 = 80 B; shadow queue 2 entries x 48 B; 3 slot queues
     const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96 + 4 + 4 + 4);
-    s->wave_mem = wave_cache_take(s->device, P);
-    if (!s->wave_mem) NGI_CUDA(cudaMalloc(&s->wave_mem, bytes));
-    if (!s->counters) NGI_CUDA(cudaMalloc((void**)&s->counters, sizeof(NgiRenderCounters)));
-    if (!s->counters_host) NGI_CUDA(cudaMallocHost((void**)&s->counters_host, sizeof(NgiRenderCounters)));
-    s->wave_capacity = P;
+    l.wave_mem = wave_cache_take(s->device, P);
+    if (!l.wave_mem) NGI_CUDA(cudaMalloc(&l.wave_mem, bytes));
+    l.wave_capacity = P;
     return NGI_OK;
 }
 
-void carve_wave(Scene* s, NgiWaveParams& wp) {
-    const size_t P = s->wave_capacity;
-    unsigned char* p = (unsigned char*)s->wave_mem;
+void carve_wave(Lane& l, NgiWaveParams& wp) {
+    const size_t P = l.wave_capacity;
+    unsigned char* p = (unsigned char*)l.wave_mem;
     wp.thr_pix = (float4*)p; p += P * 16;
     wp.dir_info = (float4*)p; p += P * 16;
     wp.hit = (float4*)p; p += P * 16;
@@ -702,44 +721,46 @@ void carve_wave(Scene* s, NgiWaveParams& wp) {
     wp.extend_q = (unsigned*)p; p += P * 4;
     wp.surface_q = (unsigned*)p; p += P * 4;
     wp.regen_q = (unsigned*)p; p += P * 4;
-    wp.stage_counters = s->counters->stage;
-    wp.iter_counters = s->counters->iter;
-    wp.fetch_cursors = s->counters->fetch;
-    wp.next_sample = &s->counters->next_sample;
+    wp.stage_counters = l.counters->stage;
+    wp.iter_counters = l.counters->iter;
+    wp.fetch_cursors = l.counters->fetch;
+    wp.next_sample = &l.counters->next_sample;
     wp.capacity = (unsigned)P;
 }
 
 bool same_wp(const NgiWaveParams& a, const NgiWaveParams& b) { return memcmp(&a, &b, sizeof(a)) == 0; }
 
-int launch_iteration(Scene* s, const NgiWaveParams& wp, cudaStream_t st, bool timed, size_t& ev_used, bool per_ray = false) {
+int launch_iteration(Scene* s, Lane& l, bool timed, size_t& ev_used, bool per_ray = false) {
+    const NgiWaveParams& wp = l.wp;
+    cudaStream_t st = l.stream;
     const unsigned P = wp.capacity;
     const bool direct = wp.renderer == NGI_RENDERER_PTDIRECT;
-    k_iter_begin<<<1, 1, 0, st>>>(s->counters, wp.sample_end);
+    k_iter_begin<<<1, 1, 0, st>>>(l.counters, wp.sample_end);
     if (timed) {
-        while (s->events.size() < ev_used + 4) { cudaEvent_t e; NGI_CUDA(cudaEventCreate(&e)); s->events.push_back(e); }
-        NGI_CUDA(cudaEventRecord(s->events[ev_used], st));
+        while (l.events.size() < ev_used + 4) { cudaEvent_t e; NGI_CUDA(cudaEventCreate(&e)); l.events.push_back(e); }
+        NGI_CUDA(cudaEventRecord(l.events[ev_used], st));
     }
     const unsigned sg = std::min(grid_for(P), kStageGrid);
     k_classify<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
     k_surface<<<sg, kBlock, 0, st>>>(s->dev, wp);
     k_eye<<<sg, kBlock, 0, st>>>(s->dev, wp);
-    if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 1], st));
+    if (timed) NGI_CUDA(cudaEventRecord(l.events[ev_used + 1], st));
     if (!timed && direct && s->overlap_trace) {
-        // fork: shadow on stream2, extend on the main stream, join
-        NGI_CUDA(cudaEventRecord(s->ev_fork, st));
-        NGI_CUDA(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
+        // fork: shadow on stream2, extend on the lane's main stream, join
+        NGI_CUDA(cudaEventRecord(l.ev_fork, st));
+        NGI_CUDA(cudaStreamWaitEvent(l.stream2, l.ev_fork, 0));
         k_extend<<<s->grid_extend, kTraceBlock, 0, st>>>(s->dev, wp, s->tune);
-        k_shadow<<<s->grid_shadow, kTraceBlock, 0, s->stream2>>>(s->dev, wp, s->tune);
-        NGI_CUDA(cudaEventRecord(s->ev_join, s->stream2));
-        NGI_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+        k_shadow<<<s->grid_shadow, kTraceBlock, 0, l.stream2>>>(s->dev, wp, s->tune);
+        NGI_CUDA(cudaEventRecord(l.ev_join, l.stream2));
+        NGI_CUDA(cudaStreamWaitEvent(st, l.ev_join, 0));
         return NGI_OK;
     }
     if (per_ray) k_extend_per_ray<<<std::min(grid_for(P), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
     else k_extend<<<s->grid_extend, kTraceBlock, 0, st>>>(s->dev, wp, s->tune);
-    if (timed) NGI_CUDA(cudaEventRecord(s->events[ev_used + 2], st));
+    if (timed) NGI_CUDA(cudaEventRecord(l.events[ev_used + 2], st));
     if (direct && per_ray) k_shadow_per_ray<<<std::min(grid_for((size_t)P * 2), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
     else if (direct) k_shadow<<<s->grid_shadow, kTraceBlock, 0, st>>>(s->dev, wp, s->tune);
-    if (timed) { NGI_CUDA(cudaEventRecord(s->events[ev_used + 3], st)); ev_used += 4; }
+    if (timed) { NGI_CUDA(cudaEventRecord(l.events[ev_used + 3], st)); ev_used += 4; }
     return NGI_OK;
 }
 
@@ -757,77 +778,98 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         if (stats) stats->paths = (uint64_t)rp->num_samples;
         return NGI_OK;
     }
+    const bool per_ray = (rp->flags & NGI_RENDER_PER_RAY_TRACE) != 0;
+    const bool timed = (rp->flags & NGI_RENDER_TIME_KERNELS) != 0 || per_ray;
     unsigned P = rp->wave_capacity ? rp->wave_capacity : (1u << 21);
     P = std::max(P, 1024u);
     if ((unsigned long long)rp->num_samples < P) P = std::max(1024u, (unsigned)((rp->num_samples + 255) / 256 * 256));
-    int rc = ensure_wave(s, P);
-    if (rc) return rc;
-
-    NgiWaveParams wp;
-    memset(&wp, 0, sizeof(wp));
-    carve_wave(s, wp);
-    wp.film = film_dev;
-    wp.renderer = rp->renderer; wp.max_verts = rp->max_num_vertices; wp.width = rp->width; wp.height = rp->height;
-    wp.sample_end = (unsigned long long)(rp->sample_offset + rp->num_samples);
-    wp.seed_lo = (unsigned)rp->seed; wp.seed_hi = (unsigned)(rp->seed >> 32);
-    wp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
-
-    NgiRenderCounters init;
-    memset(&init, 0, sizeof(init));
-    init.next_sample = (unsigned long long)rp->sample_offset;
-    *s->counters_host = init;
-    NGI_CUDA(cudaMemcpyAsync(s->counters, s->counters_host, sizeof(init), cudaMemcpyHostToDevice, st));
-    NGI_CUDA(cudaMemsetAsync(wp.dir_info, 0, (size_t)P * 16, st));   // every slot starts idle
+    // lanes: concurrent pipelines on disjoint sample ranges; only worth it when every lane gets several waves of work
+    int K = timed ? 1 : s->num_lanes;
+    while (K > 1 && (unsigned long long)rp->num_samples < 4ull * P * (unsigned)K) K--;
+    if ((int)s->lanes.size() < K) s->lanes.resize(K);
+    int rc;
 
     cudaEvent_t ev0, ev1;
     NGI_CUDA(cudaEventCreate(&ev0));
     NGI_CUDA(cudaEventCreate(&ev1));
-    NGI_CUDA(cudaEventRecord(ev0, st));
+    NGI_CUDA(cudaEventRecord(ev0, st));          // also the fork point: the film memset above precedes every lane
 
-    const bool per_ray = (rp->flags & NGI_RENDER_PER_RAY_TRACE) != 0;
-    const bool timed = (rp->flags & NGI_RENDER_TIME_KERNELS) != 0 || per_ray;
     const int kItersPerBatch = 8;
     const int kernels_per_iter = rp->renderer == NGI_RENDERER_PTDIRECT ? 6 : 5;   // iter_begin, classify, surface, eye, extend (, shadow)
+    for (int k = 0; k < K; k++) {
+        Lane& l = s->lanes[k];
+        if ((rc = ensure_lane(s, l, P))) return rc;
+        NgiWaveParams& wp = l.wp;
+        memset(&wp, 0, sizeof(wp));
+        carve_wave(l, wp);
+        wp.film = film_dev;
+        wp.renderer = rp->renderer; wp.max_verts = rp->max_num_vertices; wp.width = rp->width; wp.height = rp->height;
+        const long long lo = rp->num_samples / K * k + std::min<long long>(k, rp->num_samples % K);
+        const long long cnt = rp->num_samples / K + (k < rp->num_samples % K ? 1 : 0);
+        wp.sample_end = (unsigned long long)(rp->sample_offset + lo + cnt);
+        wp.seed_lo = (unsigned)rp->seed; wp.seed_hi = (unsigned)(rp->seed >> 32);
+        wp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
+        NgiRenderCounters init;
+        memset(&init, 0, sizeof(init));
+        init.next_sample = (unsigned long long)(rp->sample_offset + lo);
+        *l.counters_host = init;
+        NGI_CUDA(cudaStreamWaitEvent(l.stream, ev0, 0));
+        NGI_CUDA(cudaMemcpyAsync(l.counters, l.counters_host, sizeof(init), cudaMemcpyHostToDevice, l.stream));
+        NGI_CUDA(cudaMemsetAsync(wp.dir_info, 0, (size_t)P * 16, l.stream));   // every slot starts idle
+        if (!timed && (!l.graph_exec || !same_wp(l.graph_wp, wp) || l.graph_iters != kItersPerBatch)) {
+            // the batch of kItersPerBatch iterations is captured once into a CUDA graph and replayed
+            if (l.graph_exec) { cudaGraphExecDestroy(l.graph_exec); l.graph_exec = nullptr; }
+            cudaGraph_t graph;
+            NGI_CUDA(cudaStreamSynchronize(l.stream));
+            NGI_CUDA(cudaStreamBeginCapture(l.stream, cudaStreamCaptureModeThreadLocal));
+            for (int i = 0; i < kItersPerBatch; i++) { size_t dummy = 0; rc = launch_iteration(s, l, false, dummy); if (rc) { cudaStreamEndCapture(l.stream, &graph); return rc; } }
+            NGI_CUDA(cudaStreamEndCapture(l.stream, &graph));
+            NGI_CUDA(cudaGraphInstantiate(&l.graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            l.graph_wp = wp; l.graph_iters = kItersPerBatch;
+        }
+        l.running = true;
+    }
+
     size_t ev_used = 0;
     uint64_t launches = 0;
     double logic_ms = 0.0, extend_ms = 0.0, shadow_ms = 0.0;
     uint64_t timed_iters = 0;
-
-    if (!timed) {
-        // the batch of kItersPerBatch iterations is captured once into a CUDA graph and replayed
-        if (!s->graph_exec || !same_wp(s->graph_wp, wp) || s->graph_iters != kItersPerBatch) {
-            if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
-            cudaGraph_t graph;
-            NGI_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            for (int i = 0; i < kItersPerBatch; i++) { size_t dummy = 0; rc = launch_iteration(s, wp, st, false, dummy); if (rc) { cudaStreamEndCapture(st, &graph); return rc; } }
-            NGI_CUDA(cudaStreamEndCapture(st, &graph));
-            NGI_CUDA(cudaGraphInstantiate(&s->graph_exec, graph, 0));
-            cudaGraphDestroy(graph);
-            s->graph_wp = wp; s->graph_iters = kItersPerBatch;
-        }
-    }
-    // expected number of iterations ~ (rays per path) * N / P; poll the counters once per batch
-    while (true) {
-        if (timed) {
-            for (int i = 0; i < kItersPerBatch; i++) { rc = launch_iteration(s, wp, st, true, ev_used, per_ray); if (rc) return rc; }
-        } else {
-            NGI_CUDA(cudaGraphLaunch(s->graph_exec, st));
-        }
-        launches += (uint64_t)kItersPerBatch * kernels_per_iter;
-        NGI_CUDA(cudaMemcpyAsync(s->counters_host, s->counters, sizeof(NgiRenderCounters), cudaMemcpyDeviceToHost, st));
-        NGI_CUDA(cudaStreamSynchronize(st));
-        if (timed) {
-            for (size_t i = 0; i + 3 < ev_used; i += 4) {
-                float ms = 0;
-                NGI_CUDA(cudaEventElapsedTime(&ms, s->events[i], s->events[i + 1])); logic_ms += ms;
-                NGI_CUDA(cudaEventElapsedTime(&ms, s->events[i + 1], s->events[i + 2])); extend_ms += ms;
-                NGI_CUDA(cudaEventElapsedTime(&ms, s->events[i + 2], s->events[i + 3])); shadow_ms += ms;
-                timed_iters++;
+    // expected number of iterations ~ (rays per path) * N / P; every lane's counters are polled once per batch
+    int running = K;
+    while (running > 0) {
+        for (int k = 0; k < K; k++) {
+            Lane& l = s->lanes[k];
+            if (!l.running) continue;
+            if (timed) {
+                for (int i = 0; i < kItersPerBatch; i++) { rc = launch_iteration(s, l, true, ev_used, per_ray); if (rc) return rc; }
+            } else {
+                NGI_CUDA(cudaGraphLaunch(l.graph_exec, l.stream));
             }
-            ev_used = 0;
+            launches += (uint64_t)kItersPerBatch * kernels_per_iter;
+            NGI_CUDA(cudaMemcpyAsync(l.counters_host, l.counters, sizeof(NgiRenderCounters), cudaMemcpyDeviceToHost, l.stream));
         }
-        const NgiRenderCounters& c = *s->counters_host;
-        if (c.next_sample >= wp.sample_end && c.iter[0] == 0 && c.iter[1] == 0) break;
+        for (int k = 0; k < K; k++) {
+            Lane& l = s->lanes[k];
+            if (!l.running) continue;
+            NGI_CUDA(cudaStreamSynchronize(l.stream));
+            if (timed) {
+                for (size_t i = 0; i + 3 < ev_used; i += 4) {
+                    float ms = 0;
+                    NGI_CUDA(cudaEventElapsedTime(&ms, l.events[i], l.events[i + 1])); logic_ms += ms;
+                    NGI_CUDA(cudaEventElapsedTime(&ms, l.events[i + 1], l.events[i + 2])); extend_ms += ms;
+                    NGI_CUDA(cudaEventElapsedTime(&ms, l.events[i + 2], l.events[i + 3])); shadow_ms += ms;
+                    timed_iters++;
+                }
+                ev_used = 0;
+            }
+            const NgiRenderCounters& c = *l.counters_host;
+            if (c.next_sample >= l.wp.sample_end && c.iter[0] == 0 && c.iter[1] == 0) {
+                l.running = false; running--;
+                NGI_CUDA(cudaEventRecord(l.ev_done, l.stream));
+                NGI_CUDA(cudaStreamWaitEvent(st, l.ev_done, 0));     // join
+            }
+        }
     }
     NGI_CUDA(cudaEventRecord(ev1, st));
     NGI_CUDA(cudaStreamSynchronize(st));
@@ -836,11 +878,13 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     NGI_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) {
-        const NgiRenderCounters& c = *s->counters_host;
         stats->paths = (uint64_t)rp->num_samples;
-        stats->extend_rays = c.total_extend + c.iter[1];
-        stats->shadow_rays = c.total_shadow + c.iter[0];
-        stats->wave_iterations = c.iterations;
+        for (int k = 0; k < K; k++) {
+            const NgiRenderCounters& c = *s->lanes[k].counters_host;
+            stats->extend_rays += c.total_extend + c.iter[1];
+            stats->shadow_rays += c.total_shadow + c.iter[0];
+            stats->wave_iterations += c.iterations;
+        }
         stats->kernel_launches = launches;
         stats->gpu_seconds = ms * 1e-3;
         stats->trace_kernel_seconds = (extend_ms + shadow_ms) * 1e-3;
