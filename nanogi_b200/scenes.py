@@ -350,7 +350,7 @@ def _displaced_grid(origin, du, dv, nu: int, nv: int, amp: float, rng) -> np.nda
     return quads_to_tris(q)
 
 
-def interior(seed: int = 2, target_tris: int = 10_000_000, n_lights: int = 256) -> Spec:
+def interior(seed: int = 2, target_tris: int = 10_600_000, n_lights: int = 256) -> Spec:
     """Nave + aisles + columns (Sibenik-like layout); walls are displaced subdivided grids to reach target_tris."""
     rng = np.random.default_rng(seed)
     L, Wd, H = 60.0, 24.0, 16.0
@@ -391,7 +391,7 @@ def interior(seed: int = 2, target_tris: int = 10_000_000, n_lights: int = 256) 
             spec.append(mesh_prim(["D"], tris, name=f"wall{i}", D={"R": colr}))
     per_col = col_tris // n_cols
     sides = 8
-    cres = max(2, int(math.sqrt(per_col / sides / 2)))
+    cres = max(2, int(math.sqrt(2 * per_col / sides)))   # each side is a cres x cres/4 grid = cres^2 / 2 triangles
     for c in range(n_cols):
         cx = -L / 2 + (c // 2 + 0.5) * L / (n_cols // 2)
         cz = -Wd / 4 if c % 2 == 0 else Wd / 4
