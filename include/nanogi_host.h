@@ -52,6 +52,11 @@ NGI_API void ngi_host_scene_free(void* scene);
 /* film: float RGB [height][width][3], row 0 = bottom. Format from the extension (.hdr/.exr/.png). */
 NGI_API int ngi_host_save_image(const char* path, const float* film_rgb, int width, int height);
 
+/* Reads a TexR texture image like Texture::Load (reference include/nanogi/rt.hpp:168-258): float RGB, row 0 = TOP.
+ * PNG (8-bit), Radiance .hdr, binary PPM / PFM. Call with rgb_out = NULL to query width / height, then with a buffer
+ * of width*height*3 floats. Returns 0 or -1. */
+NGI_API int ngi_host_load_image(const char* path, int* width, int* height, float* rgb_out, uint64_t capacity_floats);
+
 /* Parses a nanogi command line. Returns 0, or -1 on a usage error (message via ngi_host_last_error). */
 NGI_API int ngi_host_parse_cli(int argc, const char* const* argv, NgiCliOptions* out);
 NGI_API const char* ngi_host_usage(void);

@@ -111,7 +111,7 @@ GPU_SYMBOLS = [
 ]
 HOST_SYMBOLS = [
     "ngi_host_scene_load", "ngi_host_scene_desc", "ngi_host_scene_sensor", "ngi_host_scene_num_lights",
-    "ngi_host_scene_free", "ngi_host_save_image", "ngi_host_parse_cli", "ngi_host_usage", "ngi_host_last_error",
+    "ngi_host_scene_free", "ngi_host_save_image", "ngi_host_load_image", "ngi_host_parse_cli", "ngi_host_usage", "ngi_host_last_error",
 ]
 
 
@@ -124,6 +124,7 @@ class SceneData:
     prims: List[NgiPrimitive]
     texcoords: Optional[np.ndarray] = None    # float32 [nTri, 3, 2]
     name: str = "scene"
+    textures: List[np.ndarray] = field(default_factory=list)   # float32 [H, W, 3] each, row 0 = top (rt.hpp:157-270)
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -145,8 +146,14 @@ class SceneData:
             self.texcoords = np.ascontiguousarray(self.texcoords, dtype=np.float32).reshape(-1, 3, 2)
             d.texcoords = self.texcoords.ctypes.data_as(C.POINTER(C.c_float))
         d.prims = arr
-        d.num_textures = 0
-        self._keep = [arr]
+        self.textures = [np.ascontiguousarray(t, dtype=np.float32) for t in self.textures]
+        tex = (NgiTexture * max(1, len(self.textures)))()
+        for i, t in enumerate(self.textures):
+            tex[i].height, tex[i].width = int(t.shape[0]), int(t.shape[1])
+            tex[i].rgb = t.ctypes.data_as(C.POINTER(C.c_float))
+        d.num_textures = len(self.textures)
+        d.textures = tex if self.textures else None
+        self._keep = [arr, tex]
         return d
 
     def sensor_prim(self) -> int:
@@ -196,6 +203,7 @@ def host_lib():
         lib.ngi_host_scene_free.argtypes = [C.c_void_p]
         lib.ngi_host_scene_free.restype = None
         lib.ngi_host_save_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+        lib.ngi_host_load_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_uint64]
         lib.ngi_host_parse_cli.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(NgiCliOptions)]
         lib.ngi_host_usage.restype = C.c_char_p
         lib.ngi_host_last_error.restype = C.c_char_p
@@ -253,7 +261,11 @@ def load_scene_file(path: str, aspect: float) -> SceneData:
             p = NgiPrimitive()
             C.memmove(C.byref(p), C.byref(d.prims[i]), C.sizeof(NgiPrimitive))
             prims.append(p)
-        return SceneData(pos, nrm, prims, uv, name=os.path.basename(path))
+        textures = []
+        for i in range(d.num_textures):
+            t = d.textures[i]
+            textures.append(np.ctypeslib.as_array(t.rgb, shape=(t.height, t.width, 3)).copy())
+        return SceneData(pos, nrm, prims, uv, name=os.path.basename(path), textures=textures)
     finally:
         lib.ngi_host_scene_free(h)
 
@@ -263,6 +275,18 @@ def save_image(path: str, film: np.ndarray) -> None:
     h, w = film.shape[:2]
     if host_lib().ngi_host_save_image(path.encode(), film.ctypes.data, w, h) != 0:
         raise NgiError(host_lib().ngi_host_last_error().decode())
+
+
+def load_image(path: str) -> np.ndarray:
+    """Texture::Load through the C++ front end: float32 [H, W, 3], row 0 = top."""
+    lib = host_lib()
+    w, h = C.c_int(), C.c_int()
+    if lib.ngi_host_load_image(path.encode(), C.byref(w), C.byref(h), None, 0) != 0:
+        raise NgiError(lib.ngi_host_last_error().decode())
+    out = np.empty((h.value, w.value, 3), np.float32)
+    if lib.ngi_host_load_image(path.encode(), C.byref(w), C.byref(h), out.ctypes.data, out.size) != 0:
+        raise NgiError(lib.ngi_host_last_error().decode())
+    return out
 
 
 def parse_cli(argv: List[str]) -> NgiCliOptions:

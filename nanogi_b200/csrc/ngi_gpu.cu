@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(kBlock) k_eval_bsdf(NgiDevScene sc, const floa
     const int type = (int)a[1];
     NgiGeom g; g.sn = mk3(a[2], a[3], a[4]); g.gn = mk3(a[5], a[6], a[7]);
     ngi_tangent_space(g);
+    g.albedo = ngi_constant_albedo(P, type);
     const f3 wi = mk3(a[8], a[9], a[10]);
     f3 wo = mk3(0.0f); bool valid = true;
     if (a[14] != 0.0f) wo = mk3(wo_in[3 * i], wo_in[3 * i + 1], wo_in[3 * i + 2]);
@@ -530,6 +531,17 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     NGI_CUDA(cudaMemcpyAsync(d_prims, ha.prims.data(), ha.prims.size() * sizeof(NgiDevPrim), cudaMemcpyHostToDevice, st));
     if (!ha.light_prims.empty()) NGI_CUDA(cudaMemcpyAsync(d_lights, ha.light_prims.data(), ha.light_prims.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
     if (!ha.cdf.empty()) NGI_CUDA(cudaMemcpyAsync(d_cdf, ha.cdf.data(), ha.cdf.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    float *d_uv = nullptr, *d_texdata = nullptr; NgiDevTex* d_tex = nullptr;
+    if (!ha.shade_uv.empty()) {
+        if ((rc = dev_alloc(s, &d_uv, ha.shade_uv.size(), true))) return rc;
+        NGI_CUDA(cudaMemcpyAsync(d_uv, ha.shade_uv.data(), ha.shade_uv.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    if (!ha.textures.empty()) {
+        if ((rc = dev_alloc(s, &d_tex, ha.textures.size(), true))) return rc;
+        if ((rc = dev_alloc(s, &d_texdata, ha.tex_data.size(), true))) return rc;
+        NGI_CUDA(cudaMemcpyAsync(d_tex, ha.textures.data(), ha.textures.size() * sizeof(NgiDevTex), cudaMemcpyHostToDevice, st));
+        NGI_CUDA(cudaMemcpyAsync(d_texdata, ha.tex_data.data(), ha.tex_data.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
 
     NGI_CUDA(cudaEventRecord(ev0, st));
     // ---- 0. bounds ----
@@ -677,6 +689,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     NgiDevScene& d = s->dev;
     d.nodes8 = d_nodes8; d.tris8 = d_tris8; d.nodes2 = d_nodes2; d.tris2 = d_tris2;
     d.shade_tris = d_shade; d.prims = d_prims; d.light_prims = d_lights; d.cdf = d_cdf;
+    d.shade_uv = d_uv; d.textures = d_tex; d.tex_data = d_texdata;
     d.n_tris = n; d.n_lights = (unsigned)ha.light_prims.size(); d.sensor = ha.sensor;
     s->info.num_tris = nr; s->info.bvh8_nodes = n_nodes8; s->info.bvh2_nodes = n - 1;
     s->info.build_gpu_seconds = ms * 1e-3;
@@ -780,7 +793,9 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     }
     const bool per_ray = (rp->flags & NGI_RENDER_PER_RAY_TRACE) != 0;
     const bool timed = (rp->flags & NGI_RENDER_TIME_KERNELS) != 0 || per_ray;
-    unsigned P = rp->wave_capacity ? rp->wave_capacity : (1u << 21);
+    // default slot count per lane: 2 Mi, 4 Mi for long renders (profiles/r01_sweep_wave.txt: larger waves amortise the
+    // fixed tail of every launch; small renders prefer the shorter ramp-up and drain)
+    unsigned P = rp->wave_capacity ? rp->wave_capacity : (rp->num_samples >= (1ll << 28) ? (1u << 22) : (1u << 21));
     P = std::max(P, 1024u);
     if ((unsigned long long)rp->num_samples < P) P = std::max(1024u, (unsigned)((rp->num_samples + 255) / 256 * 256));
     // lanes: concurrent pipelines on disjoint sample ranges; only worth it when every lane gets several waves of work

@@ -20,6 +20,9 @@ struct NgiHostArrays {
     std::vector<NgiDevPrim> prims;
     std::vector<unsigned> light_prims;
     std::vector<float> cdf;
+    std::vector<float> shade_uv;        // [n_real][6] or empty
+    std::vector<NgiDevTex> textures;
+    std::vector<float> tex_data;        // concatenated RGB texels
     NgiDevSensor sensor;
     unsigned n_real = 0;
     std::string error;
@@ -52,7 +55,12 @@ inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out) {
         p.first_tri = s.first_tri; p.num_tris = s.first_tri >= 0 ? s.num_tris : 0;
         p.l_type = s.l_type; p.s_type = s.s_type; p.cdf_offset = -1;
         if (p.first_tri >= 0 && ((size_t)p.first_tri + (size_t)p.num_tris > n || p.num_tris < 0)) { out.error = "primitive triangle range out of bounds"; return false; }
-        if (s.d_tex >= 0 || s.g_tex >= 0) { out.error = "TexR textures are not supported yet (SURVEY 8f)"; return false; }
+        p.d_tex = p.g_tex = -1;
+        if (s.d_tex >= 0 || s.g_tex >= 0) {                                            // D.TexR / G.TexR, rt.hpp:1947-1951, :1975-1979
+            if ((s.d_tex >= 0 && (uint32_t)s.d_tex >= d->num_textures) || (s.g_tex >= 0 && (uint32_t)s.g_tex >= d->num_textures)) { out.error = "texture index out of range"; return false; }
+            if (!d->texcoords) { out.error = "a textured primitive needs texture coordinates (NgiSceneDesc.texcoords)"; return false; }
+            p.d_tex = s.d_tex; p.g_tex = s.g_tex;
+        }
         p.d_r = ngi_f3_from(s.d_r);
         p.g_r = ngi_f3_from(s.g_r); p.g_eta = ngi_f3_from(s.g_eta); p.g_k = ngi_f3_from(s.g_k); p.g_rough = (float)s.g_roughness;
         p.s_r = ngi_f3_from(s.s_r); p.s_eta1 = (float)s.s_eta1; p.s_eta2 = (float)s.s_eta2;
@@ -93,6 +101,14 @@ inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out) {
         }
         out.prims[i] = p;
     }
+    for (uint32_t i = 0; i < d->num_textures; i++) {
+        const NgiTexture& t = d->textures[i];
+        if (t.width <= 0 || t.height <= 0 || !t.rgb) { out.error = "invalid texture"; return false; }
+        NgiDevTex T; T.offset = (int)(out.tex_data.size() / 3); T.width = t.width; T.height = t.height; T.pad = 0;
+        out.textures.push_back(T);
+        out.tex_data.insert(out.tex_data.end(), t.rgb, t.rgb + (size_t)t.width * t.height * 3);
+    }
+    if (d->texcoords && d->num_textures > 0) out.shade_uv.assign(d->texcoords, d->texcoords + n * 6);
     if (sensor < 0) { out.error = "scene has no sensor (E) primitive"; return false; }
     {
         const NgiPrimitive& s = d->prims[sensor];

@@ -17,7 +17,7 @@ enum { NGI_ST_REFLECTION = 0, NGI_ST_REFRACTION = 1, NGI_ST_FRESNEL = 2 };
 
 struct NgiDevPrim {           // 144 bytes, 16-byte aligned rows
     int type, first_tri, num_tris, l_type;
-    int s_type, cdf_offset, pad0, pad1;
+    int s_type, cdf_offset, d_tex, g_tex;   // *_tex: index into NgiDevScene::textures, -1 = constant colour
     f3 d_r;   float g_rough;
     f3 g_r;   float s_eta1;
     f3 g_eta; float s_eta2;
@@ -39,6 +39,9 @@ struct NgiDevSensor {         // E.Pinhole, rt.hpp:422-429
 
 // per-triangle shading record, indexed by GLOBAL triangle id: 5 x float4 = 80 B
 //   r0 = (v0.xyz, v1.x) r1 = (v1.yz, v2.xy) r2 = (v2.z, n0.xyz) r3 = (n1.xyz, n2.x) r4 = (n2.yz, prim bits, -)
+// nearest-neighbour RGB texture (Texture, rt.hpp:157-270): texel (x, y) at tex_data[3 * (offset + y * width + x)], row 0 = top
+struct NgiDevTex { int offset, width, height, pad; };
+
 struct NgiDevScene {
     const uint4* nodes8; const float4* tris8;
     const float4* nodes2; const float4* tris2;
@@ -46,13 +49,18 @@ struct NgiDevScene {
     const NgiDevPrim* prims;
     const unsigned* light_prims;
     const float* cdf;          // concatenated per-light normalised CDFs (leading 0 each)
+    const float* shade_uv;     // [n_tris][3 verts][2] texture coordinates by global triangle id, or NULL
+    const NgiDevTex* textures; const float* tex_data;
     unsigned n_tris, n_lights;
     NgiDevSensor sensor;
 };
 
 struct NgiGeom {               // SurfaceGeometry, rt.hpp:282-302 (p lives in fp64 in the path state)
     f3 sn, gn, dpdu, dpdv;
+    f3 albedo;                 // R of the BSDF evaluated at this point: D.R / G.R or their TexR at geom.uv (rt.hpp:1022, :1045)
 };
+// R of the lobe `type` resolves to (precedence D > G like the evaluation itself) without a texture
+NGI_HD f3 ngi_constant_albedo(const NgiDevPrim& P, const int type) { return (type & NGI_D) ? P.d_r : P.g_r; }
 
 // ---- helpers ----------------------------------------------------------------------------------
 // rt.hpp:55-59
@@ -229,7 +237,7 @@ NGI_HD f3 ngi_eval_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& g, c
     if (type & NGI_D) {                                                                       // :1013-1024, :1221-1231
         if (localWi.z <= 0.0f || localWo.z <= 0.0f) return mk3(0.0f);
         pdf = NGI_INV_PI_F;
-        return P.d_r * (NGI_INV_PI_F * snc);
+        return g.albedo * (NGI_INV_PI_F * snc);
     }
     if (type & NGI_G) {                                                                       // :1032-1047, :1239-1251
         if (localWi.z <= 0.0f || localWo.z <= 0.0f) return mk3(0.0f);
@@ -238,7 +246,7 @@ NGI_HD f3 ngi_eval_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& g, c
         const float G = ngi_shadow_masking(localWi, localWo, H);
         const f3 F = ngi_fr_conductor(P.g_eta, P.g_k, dot(localWi, H));
         pdf = D * H.z / (4.0f * dot(localWo, H)) / localWo.z;
-        return P.g_r * F * (D * G / (4.0f * localWi.z) / localWo.z * snc);
+        return g.albedo * F * (D * G / (4.0f * localWi.z) / localWo.z * snc);
     }
     if (type & NGI_S) {
         if (!forceDegenerated) return mk3(0.0f);                                              // :1057-1060, :1261-1264

@@ -118,6 +118,20 @@ NGI_HD void ngi_dither_direction(const f3 d, const float4 hit, double& dx, doubl
     dz = ngi_dither1(d.z, (h >> 20) & 1023u);
 }
 
+// ---- TexR lookup at a hit: geom.uv (rt.hpp:2221-2227, fp64 like the reference so that texel boundaries fall in the
+// same place) and Texture::Evaluate (rt.hpp:262-268: nearest texel, fract wrap) ---------------------------------
+NGI_HD f3 ngi_texture_at_hit(const NgiDevScene& sc, const int tex, const unsigned tri, const float u, const float v) {
+    const float* t = sc.shade_uv + 6 * (size_t)tri;
+    const double w = (double)(1.0f - u - v);
+    const double tu = (double)ngi_ldg(t + 0) * w + (double)ngi_ldg(t + 2) * (double)u + (double)ngi_ldg(t + 4) * (double)v;
+    const double tv = (double)ngi_ldg(t + 1) * w + (double)ngi_ldg(t + 3) * (double)u + (double)ngi_ldg(t + 5) * (double)v;
+    const NgiDevTex T = sc.textures[tex];
+    const int x = clampi((int)((tu - floor(tu)) * T.width), 0, T.width - 1);
+    const int y = clampi((int)((tv - floor(tv)) * T.height), 0, T.height - 1);
+    const float* px = sc.tex_data + 3 * ((size_t)T.offset + (size_t)y * T.width + x);
+    return mk3(ngi_ldg(px), ngi_ldg(px + 1), ngi_ldg(px + 2));
+}
+
 // ---- surface reconstruction of a hit, rt.hpp:2190-2233 ------------------------------------------
 NGI_HD int ngi_reconstruct(const NgiDevScene& sc, const unsigned tri, const float u, const float v, NgiGeom& g) {
     const float4* r = sc.shade_tris + 5 * (size_t)tri;
@@ -272,7 +286,10 @@ NGI_HD void ngi_logic_surface(const NgiDevScene& sc, const NgiWaveParams& wp, co
     const int primIdx = ngi_reconstruct(sc, f2u(h.w), h.y, h.z, g);
     const int nverts = (int)(info >> 8) + 1;                                                  // :603
     const f3 thr = mk3(tp.x, tp.y, tp.z) * 2.0f;                                              // throughput /= rrProb, :591
-    const int type = sc.prims[primIdx].type & ~NGI_EMITTER;                                   // :601
+    const NgiDevPrim& P = sc.prims[primIdx];
+    const int type = P.type & ~NGI_EMITTER;                                                   // :601
+    const int tex = (type & NGI_D) ? P.d_tex : P.g_tex;
+    g.albedo = (tex >= 0 && sc.shade_uv) ? ngi_texture_at_hit(sc, tex, f2u(h.w), h.y, h.z) : ngi_constant_albedo(P, type);
     ngi_vertex(sc, wp, slot, false, wp.sample[slot], thr, (int)f2u(tp.w), nverts, type, g, -d /* :602 */, px, py, pz, primIdx, out);
 }
 
@@ -284,7 +301,7 @@ NGI_HD void ngi_logic_eye(const NgiDevScene& sc, const NgiWaveParams& wp, const 
     const NgiDevSensor& E = sc.sensor;
     out.shadow = false; out.extend = false;
     if (sample < wp.sample_end) {
-        NgiGeom g; g.sn = g.gn = g.dpdu = g.dpdv = mk3(0.0f);
+        NgiGeom g; g.sn = g.gn = g.dpdu = g.dpdv = g.albedo = mk3(0.0f);
         // EvaluatePosition / pdfPE / pdfE = 1 for the pinhole
         ngi_vertex(sc, wp, slot, true, sample, mk3(1.0f), -1, 1, NGI_E, g, mk3(0.0f), E.px, E.py, E.pz, E.prim, out);
     }

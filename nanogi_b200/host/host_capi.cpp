@@ -40,6 +40,18 @@ int ngi_host_save_image(const char* path, const float* film_rgb, int width, int 
     return 0;
 }
 
+int ngi_host_load_image(const char* path, int* width, int* height, float* rgb_out, uint64_t capacity_floats) {
+    if (!path || !width || !height) { g_err = "invalid argument"; return -1; }
+    std::vector<float> rgb;
+    std::string err;
+    if (!ngi::LoadImageRGB(path, *width, *height, rgb, err)) { g_err = err; return -1; }
+    if (rgb_out) {
+        if (capacity_floats < rgb.size()) { g_err = "buffer too small"; return -1; }
+        std::memcpy(rgb_out, rgb.data(), rgb.size() * sizeof(float));
+    }
+    return 0;
+}
+
 int ngi_host_parse_cli(int argc, const char* const* argv, NgiCliOptions* out) {
     if (!out) { g_err = "invalid argument"; return -1; }
     try {

@@ -10,7 +10,11 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cctype>
+#include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <iterator>
 #include <string>
 #include <vector>
 
@@ -181,6 +185,153 @@ inline bool SavePNG(const std::string& path, const float* film, int width, int h
 }
 
 // SaveImage, basic.hpp:506-672
+// ---- image readers for TexR textures ---------------------------------------------------------------------------
+// Host-side mirror of Texture::Load (reference include/nanogi/rt.hpp:168-258), which goes through FreeImage and keeps
+// float RGB with ROW 0 = TOP scanline (FreeImage's bottom-up bitmap flipped, :214-217); 8-bit channels become v / 255
+// with no gamma (:245-250). FreeImage is not available here, so the formats are read directly: PNG (8-bit RGB / RGBA /
+// grey, non-interlaced; zlib inflate + the five scanline filters), Radiance .hdr (RGBE, flat or new-style RLE), binary
+// PPM (P6) and PFM (PF / Pf). Anything else is an error, like an unsupported FreeImage type (:205-211).
+namespace detail {
+inline bool read_file(const std::string& path, std::vector<uint8_t>& out) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) return false;
+    out.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+    return true;
+}
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+inline bool decode_png(const std::vector<uint8_t>& f, int& w, int& h, std::vector<float>& rgb, std::string& err) {
+    size_t pos = 8;
+    int depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat;
+    w = h = 0;
+    while (pos + 12 <= f.size()) {
+        const uint32_t len = be32(&f[pos]);
+        const std::string type((const char*)&f[pos + 4], 4);
+        if (pos + 12 + len > f.size()) { err = "truncated PNG"; return false; }
+        const uint8_t* d = &f[pos + 8];
+        if (type == "IHDR") { w = (int)be32(d); h = (int)be32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+        else if (type == "IDAT") idat.insert(idat.end(), d, d + len);
+        else if (type == "IEND") break;
+        pos += 12 + len;
+    }
+    if (w <= 0 || h <= 0) { err = "PNG without IHDR"; return false; }
+    if (depth != 8 || interlace != 0 || !(ctype == 0 || ctype == 2 || ctype == 4 || ctype == 6)) { err = "unsupported PNG (need 8-bit, non-interlaced, grey/RGB/RGBA)"; return false; }
+    const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 4 ? 2 : 4;
+    const size_t stride = (size_t)w * ch;
+    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+    uLongf rawlen = (uLongf)raw.size();
+    if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) { err = "PNG inflate failed"; return false; }
+    std::vector<uint8_t> img(stride * (size_t)h);
+    for (int y = 0; y < h; y++) {
+        const uint8_t ft = raw[(stride + 1) * y];
+        const uint8_t* in = &raw[(stride + 1) * y + 1];
+        uint8_t* out = &img[stride * y];
+        const uint8_t* up = y ? &img[stride * (y - 1)] : nullptr;
+        for (size_t i = 0; i < stride; i++) {
+            const int a = i >= (size_t)ch ? out[i - ch] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)ch) ? up[i - ch] : 0;
+            int v = in[i];
+            switch (ft) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) / 2; break;
+                case 4: { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+                default: err = "bad PNG filter"; return false;
+            }
+            out[i] = (uint8_t)v;
+        }
+    }
+    rgb.resize((size_t)w * h * 3);
+    for (size_t i = 0; i < (size_t)w * h; i++)
+        for (int k = 0; k < 3; k++) rgb[3 * i + k] = (float)img[i * ch + (ch >= 3 ? k : 0)] / 255.0f;   // rt.hpp:245-250
+    return true;
+}
+
+inline bool decode_hdr(const std::vector<uint8_t>& f, int& w, int& h, std::vector<float>& rgb, std::string& err) {
+    size_t pos = 0;
+    auto line = [&]() { std::string s; while (pos < f.size() && f[pos] != '\n') s.push_back((char)f[pos++]); pos++; return s; };
+    std::string l = line();
+    while (pos < f.size() && !l.empty()) l = line();          // header ends with an empty line
+    l = line();
+    if (std::sscanf(l.c_str(), "-Y %d +X %d", &h, &w) != 2 || w <= 0 || h <= 0) { err = "unsupported .hdr orientation (need -Y h +X w)"; return false; }
+    std::vector<uint8_t> px((size_t)w * h * 4);
+    for (int y = 0; y < h; y++) {
+        uint8_t* row = &px[(size_t)y * w * 4];
+        if (pos + 4 <= f.size() && w >= 8 && w < 32768 && f[pos] == 2 && f[pos + 1] == 2 && ((f[pos + 2] << 8) | f[pos + 3]) == w) {
+            pos += 4;                                        // new-style RLE: the four channels separately
+            for (int c = 0; c < 4; c++) {
+                int x = 0;
+                while (x < w) {
+                    if (pos >= f.size()) { err = "truncated .hdr"; return false; }
+                    int n = f[pos++];
+                    if (n > 128) { n -= 128; if (pos >= f.size() || x + n > w) { err = "bad .hdr run"; return false; } const uint8_t v = f[pos++]; while (n--) row[4 * x++ + c] = v; }
+                    else { if (pos + n > f.size() || x + n > w) { err = "bad .hdr run"; return false; } while (n--) row[4 * x++ + c] = f[pos++]; }
+                }
+            }
+        } else {
+            if (pos + (size_t)w * 4 > f.size()) { err = "truncated .hdr"; return false; }
+            std::memcpy(row, &f[pos], (size_t)w * 4); pos += (size_t)w * 4;
+        }
+    }
+    rgb.resize((size_t)w * h * 3);
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        const int e = px[4 * i + 3];
+        const float s = e ? std::ldexp(1.0f, e - 136) : 0.0f;
+        for (int k = 0; k < 3; k++) rgb[3 * i + k] = e ? ((float)px[4 * i + k] + 0.5f) * s : 0.0f;
+    }
+    return true;
+}
+
+inline bool decode_pnm(const std::vector<uint8_t>& f, int& w, int& h, std::vector<float>& rgb, std::string& err) {
+    size_t pos = 0;
+    auto token = [&]() {
+        std::string s;
+        while (pos < f.size()) { if (f[pos] == '#') { while (pos < f.size() && f[pos] != '\n') pos++; } else if (std::isspace(f[pos])) pos++; else break; }
+        while (pos < f.size() && !std::isspace(f[pos])) s.push_back((char)f[pos++]);
+        return s;
+    };
+    const std::string magic = token();
+    w = std::atoi(token().c_str()); h = std::atoi(token().c_str());
+    const double third = std::atof(token().c_str());
+    pos++;                                                   // single whitespace before the raster
+    if (w <= 0 || h <= 0) { err = "bad PNM header"; return false; }
+    rgb.resize((size_t)w * h * 3);
+    if (magic == "P6") {
+        if (third != 255 || pos + (size_t)w * h * 3 > f.size()) { err = "unsupported PPM (need maxval 255)"; return false; }
+        for (size_t i = 0; i < (size_t)w * h * 3; i++) rgb[i] = (float)f[pos + i] / 255.0f;
+        return true;
+    }
+    if (magic == "PF" || magic == "Pf") {                    // PFM: little endian when the scale is negative, rows bottom-up
+        const int ch = magic == "PF" ? 3 : 1;
+        if (third >= 0 || pos + (size_t)w * h * ch * 4 > f.size()) { err = "unsupported PFM (need little endian)"; return false; }
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+                for (int k = 0; k < 3; k++) {
+                    float v; std::memcpy(&v, &f[pos + (((size_t)(h - 1 - y) * w + x) * ch + (ch == 3 ? k : 0)) * 4], 4);
+                    rgb[((size_t)y * w + x) * 3 + k] = v;
+                }
+        return true;
+    }
+    err = "unsupported PNM type " + magic;
+    return false;
+}
+}  // namespace detail
+
+// rgb: width * height * 3 floats, row 0 = top scanline
+inline bool LoadImageRGB(const std::string& path, int& width, int& height, std::vector<float>& rgb, std::string& err) {
+    std::vector<uint8_t> f;
+    if (!detail::read_file(path, f) || f.size() < 8) { err = "Failed to load an image " + path; return false; }
+    static const uint8_t png_sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    bool ok;
+    if (std::memcmp(f.data(), png_sig, 8) == 0) ok = detail::decode_png(f, width, height, rgb, err);
+    else if (f[0] == '#' && f[1] == '?') ok = detail::decode_hdr(f, width, height, rgb, err);
+    else if (f[0] == 'P' && (f[1] == '6' || f[1] == 'F' || f[1] == 'f')) ok = detail::decode_pnm(f, width, height, rgb, err);
+    else { err = "Unknown image format"; ok = false; }       // rt.hpp:176-183
+    if (!ok) err = path + ": " + err;
+    return ok;
+}
+
 inline bool SaveImage(const std::string& path, const float* film, int width, int height) {
     if (!detail::make_parent_dirs(path)) { NGI_LOG_WARN("Failed to create output directory : " + path); return false; }
     const std::string ext = detail::extension(path);

@@ -24,6 +24,10 @@ const int AppConfigVersionMax = 5;
 struct HostScene {
     std::vector<float> positions, normals, texcoords;
     std::vector<NgiPrimitive> prims;
+    // TexR textures (rt.hpp:1741-1765 LoadTexture: one Texture per distinct path)
+    struct HostTexture { std::string path; int width = 0, height = 0; std::vector<float> rgb; };
+    std::vector<HostTexture> textures;
+    mutable std::vector<NgiTexture> texture_descs;
     bool any_uv = false, all_uv = true;
     int sensor_prim = -1;
     std::vector<int> light_prims;
@@ -36,11 +40,23 @@ struct HostScene {
         d.num_tris = positions.size() / 9;
         d.positions = positions.data();
         d.normals = normals.data();
-        d.texcoords = (any_uv && all_uv && !texcoords.empty()) ? texcoords.data() : nullptr;
+        d.texcoords = (any_uv && !texcoords.empty()) ? texcoords.data() : nullptr;   // meshes without uv carry zeros
         d.prims = prims.data();
-        d.num_textures = 0;
-        d.textures = nullptr;
+        texture_descs.clear();
+        for (const HostTexture& t : textures) { NgiTexture nt; nt.width = t.width; nt.height = t.height; nt.rgb = t.rgb.data(); texture_descs.push_back(nt); }
+        d.num_textures = (uint32_t)texture_descs.size();
+        d.textures = texture_descs.empty() ? nullptr : texture_descs.data();
         return d;
+    }
+
+    // LoadTexture, rt.hpp:1741-1765 (textures are shared by path)
+    int LoadTexture(const std::string& path) {
+        for (size_t i = 0; i < textures.size(); i++) if (textures[i].path == path) return (int)i;
+        HostTexture t; t.path = path;
+        std::string err;
+        if (!LoadImageRGB(path, t.width, t.height, t.rgb, err)) { error = err; NGI_LOG_ERROR(error); return -1; }
+        textures.push_back(std::move(t));
+        return (int)textures.size() - 1;
     }
 
     static void ParseVec3(const yaml::Node& node, double out[3]) {  // rt.hpp:61-64
@@ -165,7 +181,7 @@ struct HostScene {
                 if ((prim.type & NGI_TYPE_D) > 0) {                                    // rt.hpp:1940-1957
                     const yaml::Node& DNode = paramsNode["D"];
                     if (DNode["R"]) ParseVec3(DNode["R"], prim.d_r);
-                    else if (DNode["TexR"]) { error = "D.TexR textures are not supported by this build yet"; NGI_LOG_ERROR(error); return false; }
+                    else if (DNode["TexR"]) { if ((prim.d_tex = LoadTexture(basePath + DNode["TexR"].as_string())) < 0) return false; }   // rt.hpp:1947-1951
                     else { error = "D requires R or TexR"; return false; }
                 }
                 if ((prim.type & NGI_TYPE_G) > 0) {                                    // rt.hpp:1965-1985
@@ -174,7 +190,7 @@ struct HostScene {
                     ParseVec3(GNode["K"], prim.g_k);
                     prim.g_roughness = GNode["Roughness"].as_double();
                     if (GNode["R"]) ParseVec3(GNode["R"], prim.g_r);
-                    else if (GNode["TexR"]) { error = "G.TexR textures are not supported by this build yet"; NGI_LOG_ERROR(error); return false; }
+                    else if (GNode["TexR"]) { if ((prim.g_tex = LoadTexture(basePath + GNode["TexR"].as_string())) < 0) return false; }   // rt.hpp:1975-1979
                     else { error = "G requires R or TexR"; return false; }
                 }
                 if ((prim.type & NGI_TYPE_S) > 0) {                                    // rt.hpp:1993-2040
@@ -197,7 +213,7 @@ struct HostScene {
                 }
                 prims.push_back(prim);
             }
-            if (any_uv && all_uv) texcoords.resize(positions.size() / 9 * 6, 0.f);
+            if (any_uv) texcoords.resize(positions.size() / 9 * 6, 0.f);
         } catch (const std::exception& e) {
             error = e.what();
             NGI_LOG_ERROR("YAML exception: " + error);                                 // rt.hpp:2147-2151

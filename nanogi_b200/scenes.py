@@ -88,11 +88,16 @@ def box_quads(lo, hi, inward: bool) -> np.ndarray:
     return q2
 
 
-def mesh_prim(types: List[str], tris: np.ndarray, normals: Optional[np.ndarray] = None, name: str = "mesh", **params) -> dict:
+def mesh_prim(types: List[str], tris: np.ndarray, normals: Optional[np.ndarray] = None, name: str = "mesh", uv: Optional[np.ndarray] = None,
+              **params) -> dict:
+    """`uv`: [nTri, 3, 2] texture coordinates; D / G params may carry "TexR": float array [H, W, 3] (row 0 = top) instead of "R"."""
     tris = np.asarray(tris, dtype=np.float64).reshape(-1, 3, 3)
     if normals is None:
         normals = flat_normals(tris)
-    return {"type": types, "mesh": {"name": name, "tris": tris, "normals": np.asarray(normals, dtype=np.float64)}, "params": params}
+    mesh = {"name": name, "tris": tris, "normals": np.asarray(normals, dtype=np.float64)}
+    if uv is not None:
+        mesh["uv"] = np.asarray(uv, dtype=np.float64).reshape(-1, 3, 2)
+    return {"type": types, "mesh": mesh, "params": params}
 
 
 def pinhole(eye, center, up, fov_deg: float) -> dict:
@@ -102,8 +107,17 @@ def pinhole(eye, center, up, fov_deg: float) -> dict:
 
 # ---- spec -> C ABI ----------------------------------------------------------------------------
 def to_scene_data(spec: Spec, aspect: float = 1.0, name: str = "scene") -> capi.SceneData:
-    pos, nrm, prims = [], [], []
+    pos, nrm, uvs, prims, textures = [], [], [], [], []
+    any_uv = any(pr.get("mesh") is not None and "uv" in pr["mesh"] for pr in spec)
     first = 0
+
+    def tex_index(img):
+        for i, t in enumerate(textures):
+            if t is img:
+                return i
+        textures.append(img)
+        return len(textures) - 1
+
     for pr in spec:
         tbits = 0
         for s in pr["type"]:
@@ -117,6 +131,8 @@ def to_scene_data(spec: Spec, aspect: float = 1.0, name: str = "scene") -> capi.
             first += int(t.shape[0])
             pos.append(t)
             nrm.append(n)
+            if any_uv:
+                uvs.append(np.asarray(pr["mesh"].get("uv", np.zeros((t.shape[0], 3, 2))), dtype=np.float32))
         P = pr["params"]
         if "L" in P:
             L = P["L"]
@@ -138,9 +154,16 @@ def to_scene_data(spec: Spec, aspect: float = 1.0, name: str = "scene") -> capi.
             kw.update(e_type=capi.E_PINHOLE, e_position=eye, e_vx=vx, e_vy=vy, e_vz=vz, e_fov=math.radians(E["fov"]),
                       e_aspect=float(aspect), e_we=E.get("We", [1, 1, 1]))
         if "D" in P:
-            kw["d_r"] = P["D"]["R"]
+            if "TexR" in P["D"]:
+                kw["d_tex"] = tex_index(P["D"]["TexR"])
+            else:
+                kw["d_r"] = P["D"]["R"]
         if "G" in P:
-            kw.update(g_r=P["G"]["R"], g_eta=P["G"]["Eta"], g_k=P["G"]["K"], g_roughness=float(P["G"]["Roughness"]))
+            kw.update(g_eta=P["G"]["Eta"], g_k=P["G"]["K"], g_roughness=float(P["G"]["Roughness"]))
+            if "TexR" in P["G"]:
+                kw["g_tex"] = tex_index(P["G"]["TexR"])
+            else:
+                kw["g_r"] = P["G"]["R"]
         if "S" in P:
             S = P["S"]
             kw["s_type"] = {"reflection": capi.S_REFLECTION, "refraction": capi.S_REFRACTION, "fresnel": capi.S_FRESNEL}[S["type"]]
@@ -151,11 +174,26 @@ def to_scene_data(spec: Spec, aspect: float = 1.0, name: str = "scene") -> capi.
         prims.append(capi.make_prim(**kw))
     positions = np.concatenate(pos, axis=0) if pos else np.zeros((0, 3, 3), np.float32)
     normals = np.concatenate(nrm, axis=0) if nrm else np.zeros((0, 3, 3), np.float32)
-    return capi.SceneData(positions, normals, prims, None, name=name)
+    texcoords = np.concatenate(uvs, axis=0) if (any_uv and uvs) else None
+    return capi.SceneData(positions, normals, prims, texcoords, name=name, textures=[np.asarray(t, dtype=np.float32) for t in textures])
+
+
+def write_pfm(path: str, img: np.ndarray) -> None:
+    """Little-endian colour PFM (rows bottom-up in the file); `img` is [H, W, 3] with row 0 = top."""
+    img = np.asarray(img, dtype="<f4")
+    with open(path, "wb") as f:
+        f.write(f"PF\n{img.shape[1]} {img.shape[0]}\n-1.0\n".encode())
+        f.write(img[::-1].tobytes())
+
+
+def write_texture(directory: str, index: int, lobe: str, img) -> str:
+    name = f"{index:03d}_{lobe}_tex.pfm"
+    write_pfm(os.path.join(directory, name), img)
+    return name
 
 
 def write_scene_files(spec: Spec, directory: str, version: int = 5) -> str:
-    """Writes scene.yml + one OBJ per mesh primitive (v / vn / f a//b). Returns the YAML path."""
+    """Writes scene.yml + one OBJ per mesh primitive (v / vn [/ vt] / f) + one PFM per TexR texture. Returns the YAML path."""
     os.makedirs(directory, exist_ok=True)
     lines = [f"version: {version}", "scene:", "  primitives:"]
 
@@ -173,7 +211,11 @@ def write_scene_files(spec: Spec, directory: str, version: int = 5) -> str:
                 np.savetxt(f, t, fmt="v %.9g %.9g %.9g")
                 np.savetxt(f, n, fmt="vn %.9g %.9g %.9g")
                 idx = np.arange(1, t.shape[0] + 1).reshape(-1, 3)
-                np.savetxt(f, np.repeat(idx, 2, axis=1), fmt="f %d//%d %d//%d %d//%d")
+                if "uv" in pr["mesh"]:
+                    np.savetxt(f, np.asarray(pr["mesh"]["uv"], dtype=np.float32).reshape(-1, 2), fmt="vt %.9g %.9g")
+                    np.savetxt(f, np.repeat(idx, 3, axis=1), fmt="f %d/%d/%d %d/%d/%d %d/%d/%d")
+                else:
+                    np.savetxt(f, np.repeat(idx, 2, axis=1), fmt="f %d//%d %d//%d %d//%d")
             lines += ["      mesh:", f"        path: '{fname}'"]
         lines.append("      params:")
         P = pr["params"]
@@ -190,11 +232,11 @@ def write_scene_files(spec: Spec, directory: str, version: int = 5) -> str:
                       "            view:", f"              eye: {vec(E['eye'])}", f"              center: {vec(E['center'])}",
                       f"              up: {vec(E['up'])}", "            perspective:", f"              fov: {float(E['fov'])!r}"]
         if "D" in P:
-            lines += ["        D:", f"          R: {vec(P['D']['R'])}"]
+            lines += ["        D:", f"          R: {vec(P['D']['R'])}" if "R" in P["D"] else f"          TexR: '{write_texture(directory, i, 'D', P['D']['TexR'])}'"]
         if "G" in P:
             G = P["G"]
-            lines += ["        G:", f"          R: {vec(G['R'])}", f"          Eta: {vec(G['Eta'])}", f"          K: {vec(G['K'])}",
-                      f"          Roughness: {float(G['Roughness'])!r}"]
+            lines += ["        G:", f"          R: {vec(G['R'])}" if "R" in G else f"          TexR: '{write_texture(directory, i, 'G', G['TexR'])}'",
+                      f"          Eta: {vec(G['Eta'])}", f"          K: {vec(G['K'])}", f"          Roughness: {float(G['Roughness'])!r}"]
         if "S" in P:
             S = P["S"]
             lines += ["        S:", f"          type: {S['type']}", f"          {S['type']}:", f"            R: {vec(S['R'])}"]
@@ -261,6 +303,39 @@ def cornell_spheres() -> Spec:
     spec.append(mesh_prim(["S"], tris * s_r + s_c, nrm, name="glass",
                           S={"type": "fresnel", "R": [0.60784313725, 0.80392156862, 1], "eta1": 1.0, "eta2": 2.0}))
     spec.append(pinhole(**CORNELL_CAMERA))
+    return spec
+
+
+def checker_texture(n: int = 8, res: int = 64, a=(0.9, 0.2, 0.2), b=(0.2, 0.3, 0.9)) -> np.ndarray:
+    y, x = np.mgrid[0:res, 0:res]
+    m = ((x * n // res) + (y * n // res)) % 2
+    return np.where(m[..., None] == 0, np.array(a, np.float32), np.array(b, np.float32)).astype(np.float32)
+
+
+def cornell_textured() -> Spec:
+    """the Cornell box with a TexR checker on the floor (D) and on the glossy sphere (G); uv of the floor
+    span [0, 2]^2 (exercises the fract wrap), of the sphere a lat-long map."""
+    spec = cornell_spheres()
+    tex_d, tex_g = checker_texture(8, 64), checker_texture(6, 32, (1.0, 0.8, 0.5), (0.6, 0.6, 0.7))
+    for pr in spec:
+        m = pr.get("mesh")
+        if m is None:
+            continue
+        if m["name"] == "floor":
+            t = m["tris"]
+            lo, hi = t.reshape(-1, 3).min(0), t.reshape(-1, 3).max(0)
+            m["uv"] = np.stack([(t[..., 0] - lo[0]) / (hi[0] - lo[0]) * 2, (t[..., 2] - lo[2]) / (hi[2] - lo[2]) * 2], axis=-1)
+            pr["params"]["D"] = {"TexR": tex_d}
+        if m["name"] == "glossy":
+            t = m["tris"]
+            c = t.reshape(-1, 3).mean(0)
+            d = t - c
+            d /= np.linalg.norm(d, axis=-1, keepdims=True)
+            m["uv"] = np.stack([np.arctan2(d[..., 2], d[..., 0]) / (2 * math.pi) + 0.5, np.arccos(np.clip(d[..., 1], -1, 1)) / math.pi], axis=-1)
+            G = dict(pr["params"]["G"])
+            G.pop("R")
+            G["TexR"] = tex_g
+            pr["params"]["G"] = G
     return spec
 
 

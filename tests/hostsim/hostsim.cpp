@@ -125,6 +125,8 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
     NgiDevScene& d = s->dev;
     d.nodes8 = s->nodes8.data(); d.tris8 = s->tris8.data(); d.nodes2 = s->nodes2.data(); d.tris2 = s->tris2.data();
     d.shade_tris = s->ha.shade_tris.data(); d.prims = s->ha.prims.data(); d.light_prims = s->ha.light_prims.data();
+    d.shade_uv = s->ha.shade_uv.empty() ? nullptr : s->ha.shade_uv.data();
+    d.textures = s->ha.textures.data(); d.tex_data = s->ha.tex_data.data();
     d.cdf = s->ha.cdf.data(); d.n_tris = n; d.n_lights = (unsigned)s->ha.light_prims.size(); d.sensor = s->ha.sensor;
     return s;
 }
@@ -199,6 +201,7 @@ __attribute__((visibility("default"))) int sim_eval_bsdf(void* h, const float* q
         const int type = (int)a[1];
         NgiGeom g; g.sn = mk3(a[2], a[3], a[4]); g.gn = mk3(a[5], a[6], a[7]);
         ngi_tangent_space(g);
+        g.albedo = ngi_constant_albedo(P, type);
         const f3 wi = mk3(a[8], a[9], a[10]);
         f3 wo = mk3(0.0f); bool valid = true;
         if (a[14] != 0.0f) wo = mk3(wo_in[3 * i], wo_in[3 * i + 1], wo_in[3 * i + 2]);

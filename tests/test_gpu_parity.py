@@ -87,6 +87,21 @@ def test_replay_small_scale(renderer, m):
     g.close()
 
 
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect"])
+def test_replay_textured(renderer):
+    """SURVEY 8(f) row 1: D.TexR / G.TexR on the device against the oracle's Texture::Evaluate, sample for sample."""
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_textured(), 0.01), 1.0)
+    g = capi.GpuScene(sd, 0)
+    pc.check_replay(g, sd, renderer, n=200000, w=96, h=96, m=-1, max_bad_pixels=0.01)
+    # the texture is really sampled: the floor is not uniformly coloured any more
+    flat = scenes.to_scene_data(scaled_spec(scenes.cornell_spheres(), 0.01), 1.0)
+    gf = capi.GpuScene(flat, 0)
+    a, _ = g.render(renderer, 400000, 48, 48, seed=3)
+    b, _ = gf.render(renderer, 400000, 48, 48, seed=3)
+    assert np.abs(a - b).mean() > 0.02 * b.mean()
+    g.close(); gf.close()
+
+
 def test_gpu_equals_simulator_sample_for_sample(cornell):
     """The CUDA kernels and the CPU-stepped device code are the same program. The triangle test is bit-identical
     (explicit roundings); the shading arithmetic is not (nvcc contracts a*b+c into FMAs, the host build of the

@@ -160,3 +160,76 @@ def test_png_writer(tmp_path):
     assert np.array_equal(img[::-1, :, ::-1], expect)
     with pytest.raises(capi.NgiError):
         capi.save_image(str(tmp_path / "a.bmp"), f)
+
+
+# ---- TexR textures: image readers + loader ---------------------------------------------------------
+def _png_bytes(img8, filters):
+    """Minimal PNG encoder applying the given scanline filter type per row (exercises all five unfilter paths)."""
+    import struct
+    import zlib
+    h, w, ch = img8.shape
+    raw = bytearray()
+    prev = np.zeros(w * ch, np.int32)
+    for y in range(h):
+        cur = img8[y].reshape(-1).astype(np.int32)
+        ft = filters[y % len(filters)]
+        left = np.concatenate([np.zeros(ch, np.int32), cur[:-ch]])
+        ul = np.concatenate([np.zeros(ch, np.int32), prev[:-ch]])
+        if ft == 0:
+            f = cur
+        elif ft == 1:
+            f = cur - left
+        elif ft == 2:
+            f = cur - prev
+        elif ft == 3:
+            f = cur - (left + prev) // 2
+        else:
+            p = left + prev - ul
+            pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - ul)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, ul))
+            f = cur - pred
+        raw.append(ft)
+        raw += bytes((f % 256).astype(np.uint8))
+        prev = cur
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    ctype = {1: 0, 2: 4, 3: 2, 4: 6}[ch]
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(bytes(raw))) + chunk(b"IEND", b"")
+
+
+@pytest.mark.parametrize("ch", [1, 3, 4])
+def test_png_reader_all_filters(tmp_path, ch):
+    rng = np.random.default_rng(ch)
+    img = rng.integers(0, 256, (13, 17, ch), dtype=np.uint8)
+    p = tmp_path / "t.png"
+    p.write_bytes(_png_bytes(img, [0, 1, 2, 3, 4]))
+    got = capi.load_image(str(p))
+    want = (img[..., :3] if ch >= 3 else np.repeat(img[..., :1], 3, axis=2)).astype(np.float32) / 255.0   # rt.hpp:245-250
+    assert got.shape == (13, 17, 3) and np.array_equal(got, want)
+
+
+def test_hdr_and_pfm_readers_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    film = (rng.random((9, 40, 3)) * 4).astype(np.float32)          # row 0 = bottom (film convention)
+    capi.save_image(str(tmp_path / "f.hdr"), film)
+    got = capi.load_image(str(tmp_path / "f.hdr"))                   # row 0 = top (texture convention)
+    assert got.shape == film.shape
+    assert np.abs(got - film[::-1]).max() <= 4.0 / 256   # RGBE: 8-bit mantissas under the pixel's largest exponent
+    from nanogi_b200 import scenes
+    scenes.write_pfm(str(tmp_path / "f.pfm"), film)
+    assert np.array_equal(capi.load_image(str(tmp_path / "f.pfm")), film)
+    with pytest.raises(capi.NgiError):
+        (tmp_path / "x.bin").write_bytes(b"not an image at all")
+        capi.load_image(str(tmp_path / "x.bin"))
+
+
+def test_scene_with_texr_loads_through_the_front_end(tmp_path):
+    from nanogi_b200 import scenes
+    spec = scenes.cornell_textured()
+    path = scenes.write_scene_files(spec, str(tmp_path))
+    sd, ref = capi.load_scene_file(path, 1.0), scenes.to_scene_data(spec, 1.0)
+    assert len(sd.textures) == 2 and all(np.array_equal(a, b) for a, b in zip(sd.textures, ref.textures))
+    assert np.array_equal(sd.texcoords, ref.texcoords) and np.array_equal(sd.positions, ref.positions)
+    assert [(p.d_tex, p.g_tex) for p in sd.prims] == [(p.d_tex, p.g_tex) for p in ref.prims]
+    assert sum(p.d_tex >= 0 for p in sd.prims) == 1 and sum(p.g_tex >= 0 for p in sd.prims) == 1

@@ -85,6 +85,13 @@ def test_replay_small_scale(renderer, m):
     pc.check_replay(pysim.SimScene(sd), sd, renderer, n=20000, m=m, wave_capacity=2048)
 
 
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect"])
+def test_replay_textured(renderer):
+    """D.TexR / G.TexR (nearest texel, fract wrap, uv interpolated at the hit) against the oracle's Texture."""
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_textured(), 0.01), 1.0)
+    pc.check_replay(pysim.SimScene(sd), sd, renderer, n=20000, m=-1, wave_capacity=2048)
+
+
 def test_replay_furnace_exact(furnace):
     sim = pysim.SimScene(furnace)
     orc = pyoracle.OracleScene(furnace)
