@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Image-level acceptance test of BASELINE.json's north_star ("Images"), run on the GPU box:
+
+    relative RMSE against a high-spp reference image within 1 % of the reference path's own RMSE at equal spp, and
+    no per-pixel-block mean bias beyond 3 sigma.
+
+    python tools/image_parity.py [--scene cornell_box|cornell_spheres] [--renderer pt|ptdirect] [--size 128] [--spp 64]
+                                 [--ref-spp 65536] [--oracle-ref-spp 4096] [--seeds 8] [-m 8]
+
+R_gpu    = GPU render at --ref-spp (the 64k-spp reference; the CPU path cannot reach that in minutes)
+R_oracle = CPU oracle render at --oracle-ref-spp (cross-check of R_gpu: its difference to R_gpu must be pure noise)
+K seeds per side at --spp: relRMSE_k = sqrt(mean (I_k - R_gpu)^2) / mean(R_gpu); blocks of 16 x 16 pixels: z = mean_k(block mean of
+I_gpu - I_oracle) / standard error. Prints one JSON line (committed under profiles/).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from nanogi_b200 import capi, scenes  # noqa: E402
+from oracle import pyoracle  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default="cornell_box")
+    ap.add_argument("--renderer", default="pt")
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--ref-spp", type=int, default=65536)
+    ap.add_argument("--oracle-ref-spp", type=int, default=4096)
+    ap.add_argument("--seeds", type=int, default=8)
+    ap.add_argument("-m", type=int, default=8)
+    ap.add_argument("--block", type=int, default=16)
+    a = ap.parse_args()
+    W = H = a.size
+    sd = scenes.to_scene_data(getattr(scenes, a.scene)(), 1.0)
+    gpu, orc = capi.GpuScene(sd, 0), pyoracle.OracleScene(sd)
+    npx = W * H
+    t0 = time.perf_counter()
+    # the reference in 8 independent parts (also gives its own standard error)
+    parts = [gpu.render(a.renderer, npx * a.ref_spp // 8, W, H, max_num_vertices=a.m, seed=9000 + i)[0].astype(np.float64) for i in range(8)]
+    R = np.mean(parts, axis=0)
+    t_ref = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Ro, _ = orc.render(a.renderer, npx * a.oracle_ref_spp, W, H, max_num_vertices=a.m, seed=77, rng_mode=0)
+    t_oref = time.perf_counter() - t0
+    n = npx * a.spp
+    Ig = np.stack([gpu.render(a.renderer, n, W, H, max_num_vertices=a.m, seed=100 + k)[0].astype(np.float64) for k in range(a.seeds)])
+    Io = np.stack([orc.render(a.renderer, n, W, H, max_num_vertices=a.m, seed=500 + k, rng_mode=0)[0] for k in range(a.seeds)])
+
+    def rel_rmse(I, ref):
+        return math.sqrt(((I - ref) ** 2).mean()) / ref.mean()
+    rg = np.array([rel_rmse(I, R) for I in Ig]); ro = np.array([rel_rmse(I, R) for I in Io])
+    # noise floor of the comparison: standard error of the mean relRMSE over the seeds
+    se = math.sqrt(rg.var(ddof=1) / a.seeds + ro.var(ddof=1) / a.seeds)
+    b = a.block
+
+    def blocks(F):
+        k = F.shape[0]
+        return F.reshape(k, H // b, b, W // b, b, 3).mean(axis=(2, 4, 5))
+    bg, bo = blocks(Ig), blocks(Io)
+    z = (bg.mean(0) - bo.mean(0)) / (np.sqrt(bg.var(0, ddof=1) / a.seeds + bo.var(0, ddof=1) / a.seeds) + 1e-300)
+    # reference cross-check: oracle reference vs GPU reference, per block, in units of the oracle reference's own noise
+    # (estimated from the equal-spp oracle renders: var scales with 1/spp)
+    bR, bRo = blocks(R[None])[0], blocks(Ro[None])[0]
+    sig_ref = np.sqrt(bo.var(0, ddof=1) * a.spp / a.oracle_ref_spp + np.stack([blocks(p[None])[0] for p in parts]).var(0, ddof=1) / 8)
+    zr = (bR - bRo) / (sig_ref + 1e-300)
+    out = {
+        "scene": a.scene, "renderer": a.renderer, "width": W, "height": H, "spp": a.spp, "max_num_vertices": a.m, "seeds": a.seeds,
+        "reference": {"kind": "gpu", "spp": a.ref_spp, "seconds": t_ref, "mean": float(R.mean())},
+        "oracle_reference": {"spp": a.oracle_ref_spp, "seconds": t_oref, "mean": float(Ro.mean()),
+                             "block_z_vs_gpu_reference_max": float(np.abs(zr).max()), "block_z_vs_gpu_reference_frac_gt3": float((np.abs(zr) > 3).mean()),
+                             "mean_rel_diff": float(abs(R.mean() - Ro.mean()) / Ro.mean())},
+        "rel_rmse_gpu": float(rg.mean()), "rel_rmse_oracle": float(ro.mean()), "rel_rmse_gpu_per_seed": rg.tolist(), "rel_rmse_oracle_per_seed": ro.tolist(),
+        "rel_rmse_diff_pct_of_oracle": float(abs(rg.mean() - ro.mean()) / ro.mean() * 100), "rel_rmse_diff_standard_error_pct": float(se / ro.mean() * 100),
+        "block": b, "blocks": int(z.size), "block_z_max": float(np.abs(z).max()), "block_z_frac_gt3": float((np.abs(z) > 3).mean()),
+        "expected_frac_gt3_student_t": "about 0.01 for 2K-2 = %d degrees of freedom (0.0027 for a normal)" % (2 * a.seeds - 2),
+        "pass_rmse_1pct": bool(abs(rg.mean() - ro.mean()) <= max(0.01 * ro.mean(), 2 * se)),
+    }
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
