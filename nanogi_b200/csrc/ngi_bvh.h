@@ -132,6 +132,10 @@ NGI_HD bool ngi_trace_bvh2(const float4* __restrict__ nodes, const float4* __res
 // (slot ^ octant) approximates front-to-back order (slot bit0/1/2 = child lies towards +x/+y/+z).
 // ------------------------------------------------------------------------------------------------
 #define NGI_BVH8_STACK 40
+// test-only instrumentation hook (tests/hostsim counts node steps / triangle tests per ray with it); empty in the product
+#ifndef NGI_TRACE_COUNT
+#define NGI_TRACE_COUNT(what)
+#endif
 #define NGI_BVH8_MAX_DEPTH 32     /* enforced by the build; traversal stacks are sized from it */
 
 NGI_HD unsigned ngi_byte(unsigned w, int i) { return (w >> (8 * i)) & 0xFFu; }
@@ -260,6 +264,7 @@ NGI_HD bool ngi_trace_bvh8(const uint4* __restrict__ nodes, const float4* __rest
             if (ngroup.y > 0x00FFFFFFu) {
                 if (sp < NGI_BVH8_STACK) stack[sp++] = ngroup;
             }
+            NGI_TRACE_COUNT(0);
             ngi_bvh8_node_step(nodes, ni, r, best.t, ngroup, tgroup);   // best.t == tmax until a hit is found
         } else {
             tgroup = ngroup;
@@ -272,6 +277,7 @@ NGI_HD bool ngi_trace_bvh8(const uint4* __restrict__ nodes, const float4* __rest
             const size_t ti = (size_t)tgroup.x + (unsigned)bit;
             const float4 a = ngi_ldg(tris + 3 * ti), b = ngi_ldg(tris + 3 * ti + 1), c = ngi_ldg(tris + 3 * ti + 2);
             float t, u, v;
+            NGI_TRACE_COUNT(1);
             if (ngi_tri_test(a, b, c, o, d, tmin, tmax, t, u, v)) {
                 if (ANY_HIT) { out.t = t; out.u = u; out.v = v; out.tri = 0; return true; }
                 ngi_accept(best, t, u, v, f2u(a.w));

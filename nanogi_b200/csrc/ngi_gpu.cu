@@ -397,6 +397,38 @@ __global__ void __launch_bounds__(kBlock) k_eval_bsdf(NgiDevScene sc, const floa
 // The path-state buffer (176 B + queues per slot, 369 MB at the default 2 Mi slots) is scene independent, and
 // cudaMalloc / cudaFree of that size cost 0.1-0.3 s: a released buffer is parked per device and handed to the
 // next scene handle that asks for the same capacity (the e2e path creates one handle per render).
+// Scene arrays and build temporaries come from the device's stream-ordered memory pool (cudaMallocAsync) with the
+// release threshold lifted, so that a host application that creates and destroys a scene per render (the e2e path:
+// ~45 allocations and ~30 frees per scene) re-uses the pool's memory instead of paying cudaMalloc / cudaFree (each
+// cudaFree synchronises the device). NGI_POOL_ALLOC=0 restores plain cudaMalloc / cudaFree.
+bool pool_alloc_enabled() {
+    static const bool on = [] { const char* e = getenv("NGI_POOL_ALLOC"); return e ? atoi(e) != 0 : true; }();
+    return on;
+}
+cudaError_t ngi_dmalloc(void** p, size_t bytes, cudaStream_t st) {
+    if (!pool_alloc_enabled()) return cudaMalloc(p, bytes);
+    static std::mutex m;
+    static bool tuned[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(m);
+        if (dev >= 0 && dev < 64 && !tuned[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            tuned[dev] = true;
+        }
+    }
+    return cudaMallocAsync(p, bytes, st);
+}
+void ngi_dfree(void* p, cudaStream_t st) {
+    if (!p) return;
+    if (pool_alloc_enabled()) cudaFreeAsync(p, st); else cudaFree(p);
+}
+
 struct WaveCacheEntry { void* mem = nullptr; unsigned capacity = 0; };
 constexpr int kWaveCacheSlots = 4;
 std::mutex g_wave_mutex;
@@ -466,16 +498,16 @@ struct Scene {
             if (l.stream2) cudaStreamDestroy(l.stream2);
             if (l.stream) cudaStreamDestroy(l.stream);
         }
-        for (void* p : allocs) cudaFree(p);
-        if (trace_cursor) cudaFree(trace_cursor);
-        if (stream) cudaStreamDestroy(stream);
+        for (void* p : allocs) ngi_dfree(p, stream);
+        if (trace_cursor) ngi_dfree(trace_cursor, stream);
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
     }
 };
 
 template <class T>
 int dev_alloc(Scene* s, T** out, size_t count, bool keep) {
     void* p = nullptr;
-    NGI_CUDA(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    NGI_CUDA(ngi_dmalloc(&p, std::max<size_t>(count * sizeof(T), 16), s->stream));
     if (keep) { s->allocs.push_back(p); s->info.device_bytes += count * sizeof(T); }
     *out = (T*)p;
     return NGI_OK;
@@ -497,7 +529,8 @@ int init_trace_launch(Scene* s) {
     if ((rc = persistent_grid(k_shadow, &s->grid_shadow))) return rc;
     if ((rc = persistent_grid(k_trace8<false>, &s->grid_trace[0]))) return rc;
     if ((rc = persistent_grid(k_trace8<true>, &s->grid_trace[1]))) return rc;
-    NGI_CUDA(cudaMalloc((void**)&s->trace_cursor, sizeof(unsigned)));
+    NGI_CUDA(ngi_dmalloc((void**)&s->trace_cursor, sizeof(unsigned), s->stream));
+    NGI_CUDA(cudaStreamSynchronize(s->stream));
     if (const char* e = getenv("NGI_TRACE_REFILL_MIN")) s->tune.refill_min = atoi(e);
     if (const char* e = getenv("NGI_TRACE_TRI_MIN")) s->tune.tri_min = atoi(e);
     if (const char* e = getenv("NGI_TRACE_OVERLAP")) s->overlap_trace = atoi(e) != 0;
@@ -684,7 +717,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
                     (void*)d_tmp, (void*)d_lo, (void*)d_hi, (void*)d_left, (void*)d_right, (void*)d_ncnt, (void*)d_cid[0], (void*)d_cid[1],
                     (void*)d_clo[0], (void*)d_clo[1], (void*)d_chi[0], (void*)d_chi[1], (void*)d_nn, (void*)d_keep, (void*)d_spos, (void*)d_newc, (void*)d_scan_tmp,
                     (void*)d_nodes8_tmp, (void*)d_cnt, (void*)d_q0, (void*)d_q1})
-        cudaFree(p);
+        ngi_dfree(p, st);
 
     NgiDevScene& d = s->dev;
     d.nodes8 = d_nodes8; d.tris8 = d_tris8; d.nodes2 = d_nodes2; d.tris2 = d_tris2;
@@ -1009,7 +1042,7 @@ int ngi_gpu_render(void* scene, const NgiRenderParams* params, float* film_rgb_h
     if (params->width <= 0 || params->height <= 0) return set_err(NGI_ERR_INVALID_ARGUMENT, "invalid width/height");
     const size_t bytes = (size_t)params->width * params->height * 3 * sizeof(float);
     float* d_film = nullptr;
-    NGI_CUDA(cudaMalloc((void**)&d_film, bytes));
+    NGI_CUDA(ngi_dmalloc((void**)&d_film, bytes, s->stream));
     NgiRenderParams p = *params;
     p.accumulate = 0;
     int rc = render_impl(s, &p, d_film, s->stream, out_stats);
@@ -1018,7 +1051,7 @@ int ngi_gpu_render(void* scene, const NgiRenderParams* params, float* film_rgb_h
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e != cudaSuccess) rc = set_err(NGI_ERR_CUDA, cudaGetErrorString(e));
     }
-    cudaFree(d_film);
+    ngi_dfree(d_film, s->stream);
     return rc;
 }
 

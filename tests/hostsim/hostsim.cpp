@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+static unsigned long long g_trace_count[2] = {0, 0};     // [0] BVH8 node steps, [1] triangle tests (sim_trace_stats)
+#define NGI_TRACE_COUNT(what) (g_trace_count[what]++)
 #include "../../nanogi_b200/csrc/ngi_build.h"
 #include "../../nanogi_b200/csrc/ngi_bvh.h"
 #include "../../nanogi_b200/csrc/ngi_scene_host.h"
@@ -152,6 +154,21 @@ __attribute__((visibility("default"))) int sim_trace(void* h, const NgiRay* rays
         out.tri = hit ? (any_hit ? 0u : hr.tri) : NGI_NO_HIT;
         hits[i] = out;
     }
+    return 0;
+}
+
+// traversal cost of the BVH8 on a ray batch (build-quality metric): out = {node steps, triangle tests}
+__attribute__((visibility("default"))) int sim_trace_stats(void* h, const NgiRay* rays, uint64_t n, int any_hit, double* out) {
+    SimScene* s = (SimScene*)h;
+    g_trace_count[0] = g_trace_count[1] = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const NgiRay& r = rays[i];
+        const f3 o = mk3(r.o[0], r.o[1], r.o[2]), d = mk3(r.d[0], r.d[1], r.d[2]);
+        NgiHitRec hr;
+        if (any_hit) ngi_trace_bvh8<true>(s->dev.nodes8, s->dev.tris8, o, d, r.tmin, r.tmax, hr);
+        else ngi_trace_bvh8<false>(s->dev.nodes8, s->dev.tris8, o, d, r.tmin, r.tmax, hr);
+    }
+    out[0] = (double)g_trace_count[0]; out[1] = (double)g_trace_count[1];
     return 0;
 }
 

@@ -27,6 +27,7 @@ def lib():
         L.sim_scene_info.argtypes = [C.c_void_p, C.c_void_p]
         L.sim_scene_info.restype = None
         L.sim_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]
+        L.sim_trace_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.sim_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sim_eval_bsdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.sim_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -65,6 +66,13 @@ class SimScene:
         hits = np.empty(rays.shape[0], capi.HIT_DTYPE)
         self.L.sim_trace(self.h, rays.ctypes.data, rays.shape[0], hits.ctypes.data, int(any_hit), accel)
         return hits
+
+    def trace_stats(self, rays, any_hit=False):
+        """BVH8 traversal cost of a ray batch: (node steps per ray, triangle tests per ray)."""
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(2, np.float64)
+        self.L.sim_trace_stats(self.h, rays.ctypes.data, rays.shape[0], int(any_hit), out.ctypes.data)
+        return out[0] / max(rays.shape[0], 1), out[1] / max(rays.shape[0], 1)
 
     def render(self, renderer, num_samples, width, height, max_num_vertices=-1, seed=1, sample_offset=0, film_norm_samples=None,
                wave_capacity=4096):
