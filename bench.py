@@ -63,6 +63,18 @@ def b_ray(n_tris: int) -> int:
     return max(d, 1) * 80 + 4 * 48 + 96
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE steady-state launch of the dominant trace kernel, from the committed
+# `ncu --set full` captures (profiles/r01_ncu_c2_final.txt, profiles/r01_ncu_c3_final.txt). Those runs used 2 Mi-slot waves,
+# where a steady-state launch traces one ray per slot (ended paths are regenerated in the same iteration), so the figure is
+# kept per ray and scaled to this run's rays per launch.
+NCU_DRAM_BYTES_PER_LAUNCH = {
+    "c2": {"k_extend": (176.288512e6 + 30.705664e6, 1 << 21, "profiles/r01_ncu_c2_final.txt"),
+           "k_shadow": (93.781760e6 + 3.983104e6, 1 << 21, "profiles/r01_ncu_c2_final.txt")},
+    "c3": {"k_extend": (350.019840e6 + 48.704768e6, 1 << 21, "profiles/r01_ncu_c3_final.txt"),
+           "k_shadow": (114.695168e6 + 7.332608e6, 1 << 21, "profiles/r01_ncu_c3_final.txt")},
+}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -284,8 +296,13 @@ def run_own(args, rank: int, local_rank: int, world: int):
         dom = "k_extend" if stt.extend_kernel_seconds >= stt.shadow_kernel_seconds else "k_shadow"
         sec, nl, rays = per[dom]
         achieved = rays * br / sec / 1e9 if sec > 0 else 0.0
+        traffic, traffic_src = None, None
+        ncu = NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload if args.workload in NCU_DRAM_BYTES_PER_LAUNCH else "", {}).get(dom)
+        if ncu:
+            traffic = ncu[0] / ncu[1] * (rays / max(nl, 1))          # bytes per launch of THIS run's size
+            traffic_src = "%s: %.0f B/ray of DRAM traffic (x %.0f rays per launch here) vs %d algorithmic B/ray" % (ncu[2], ncu[0] / ncu[1], rays / max(nl, 1), br)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "bytes_per_ray": br, "rays_per_launch": rays / max(nl, 1),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_ray": br, "rays_per_launch": rays / max(nl, 1),
                 "avg_launch_ms": sec / max(nl, 1) * 1e3, "grays_per_s": rays / sec / 1e9 if sec > 0 else 0.0,
                 "note": "algorithmic bytes (SURVEY 8d) / CUDA-event launch time; the scene (%.1f MB incl. BVH) is L2-resident, so "
                         "HBM is not the physical limiter of this workload — see profiles/ for L2/issue counters" % (info.device_bytes / 1e6)}

@@ -37,6 +37,8 @@ typedef struct NgiCliOptions {
     uint32_t wave_capacity;
     uint64_t seed;
     char device[16];
+    int64_t sample_offset;        /* [b200] --sample-offset */
+    char resume_from[1024];       /* [b200] --resume-from   */
 } NgiCliOptions;
 
 /* Loads a schema.yml scene (YAML + OBJ meshes). aspect = width/height (src/nanogi.cpp:2069).
@@ -49,7 +51,7 @@ NGI_API int ngi_host_scene_sensor(void* scene);
 NGI_API int ngi_host_scene_num_lights(void* scene);
 NGI_API void ngi_host_scene_free(void* scene);
 
-/* film: float RGB [height][width][3], row 0 = bottom. Format from the extension (.hdr/.exr/.png). */
+/* film: float RGB [height][width][3], row 0 = bottom. Format from the extension (.hdr/.exr/.png, and .pfm: lossless float, additive). */
 NGI_API int ngi_host_save_image(const char* path, const float* film_rgb, int width, int height);
 
 /* Reads a TexR texture image like Texture::Load (reference include/nanogi/rt.hpp:168-258): float RGB, row 0 = TOP.

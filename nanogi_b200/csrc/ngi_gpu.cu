@@ -238,12 +238,15 @@ constexpr unsigned kStageGrid = 148u * 8u;
 // reserves queue space with one atomic per queue: the queues are sequences of slot-ordered chunks, so the surface / eye
 // kernels read and write the path state almost as coalesced as a slot-indexed kernel would (pushing slot ids in atomic
 // order instead made those kernels 2.3x slower: every state access became a scattered 16-byte touch).
+// GEN = false: the hot path (pt / ptdirect with a pinhole sensor); GEN = true: the generic flavour (lt / ltdirect, E.area
+// sensors) — separate instantiations keep the code and the register budget of the hot-path kernels unchanged
+template <bool GEN>
 __global__ void __launch_bounds__(kBlock) k_classify(NgiDevScene sc, NgiWaveParams wp) {
     __shared__ unsigned s_warp[2][kBlock / 32];
     __shared__ unsigned s_base[2];
     const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int cls = slot < wp.capacity ? ngi_logic_classify(sc, wp, slot) : -1;
+    const int cls = slot < wp.capacity ? ngi_logic_classify<GEN>(sc, wp, slot) : -1;
     const unsigned ms = __ballot_sync(0xFFFFFFFFu, cls == NGI_CLASS_SURFACE), mr = __ballot_sync(0xFFFFFFFFu, cls == NGI_CLASS_REGENERATE);
     if (lane == 0) { s_warp[0][warp] = (unsigned)__popc(ms); s_warp[1][warp] = (unsigned)__popc(mr); }
     __syncthreads();
@@ -282,6 +285,7 @@ __device__ __forceinline__ void block_reserve(unsigned* const (&counters)[NQ], c
     __syncthreads();   // s_warp / s_base are reused by the next trip
 }
 
+template <bool GEN>
 __global__ void __launch_bounds__(kBlock, NGI_SURFACE_MIN_BLOCKS) k_surface(NgiDevScene sc, NgiWaveParams wp) {
     __shared__ unsigned s_warp[3][kBlock / 32];
     __shared__ unsigned s_base[3];
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(kBlock, NGI_SURFACE_MIN_BLOCKS) k_surface(NgiD
         const unsigned e = base + threadIdx.x;
         NgiVertexOut out; out.shadow = false; out.extend = false;
         unsigned slot = 0;
-        if (e < n) { slot = wp.surface_q[e]; ngi_logic_surface(sc, wp, slot, out); }
+        if (e < n) { slot = wp.surface_q[e]; ngi_logic_surface<GEN>(sc, wp, slot, out); }
         const bool need[3] = {out.shadow, out.extend, e < n && !out.extend};                      // a path that ended here is regenerated
         unsigned idx[3];
         block_reserve<3>(counters, need, idx, s_warp, s_base);
@@ -300,6 +304,7 @@ __global__ void __launch_bounds__(kBlock, NGI_SURFACE_MIN_BLOCKS) k_surface(NgiD
         if (need[2]) wp.regen_q[idx[2]] = slot;
     }
 }
+template <bool GEN>
 __global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_eye(NgiDevScene sc, NgiWaveParams wp) {
     __shared__ unsigned s_warp[2][kBlock / 32];
     __shared__ unsigned s_base[2];
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_eye(NgiDevScen
         const unsigned e = base + threadIdx.x;
         NgiVertexOut out; out.shadow = false; out.extend = false;
         unsigned slot = 0;
-        if (e < n) { slot = wp.regen_q[e]; ngi_logic_eye(sc, wp, slot, first + e, out); }
+        if (e < n) { slot = wp.regen_q[e]; ngi_logic_eye<GEN>(sc, wp, slot, first + e, out); }
         const bool need[2] = {out.shadow, out.extend};
         unsigned idx[2];
         block_reserve<2>(counters, need, idx, s_warp, s_base);
@@ -780,16 +785,23 @@ int launch_iteration(Scene* s, Lane& l, bool timed, size_t& ev_used, bool per_ra
     const NgiWaveParams& wp = l.wp;
     cudaStream_t st = l.stream;
     const unsigned P = wp.capacity;
-    const bool direct = wp.renderer == NGI_RENDERER_PTDIRECT;
+    const bool direct = wp.renderer == NGI_RENDERER_PTDIRECT || wp.renderer == NGI_RENDERER_LTDIRECT;   // renderers with a shadow queue
+    const bool lt = wp.renderer >= NGI_RENDERER_LT || s->dev.sensor.kind == NGI_ET_AREA;   // generic kernels
     k_iter_begin<<<1, 1, 0, st>>>(l.counters, wp.sample_end);
     if (timed) {
         while (l.events.size() < ev_used + 4) { cudaEvent_t e; NGI_CUDA(cudaEventCreate(&e)); l.events.push_back(e); }
         NGI_CUDA(cudaEventRecord(l.events[ev_used], st));
     }
     const unsigned sg = std::min(grid_for(P), kStageGrid);
-    k_classify<<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
-    k_surface<<<sg, kBlock, 0, st>>>(s->dev, wp);
-    k_eye<<<sg, kBlock, 0, st>>>(s->dev, wp);
+    if (lt) {
+        k_classify<true><<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
+        k_surface<true><<<sg, kBlock, 0, st>>>(s->dev, wp);
+        k_eye<true><<<sg, kBlock, 0, st>>>(s->dev, wp);
+    } else {
+        k_classify<false><<<grid_for(P), kBlock, 0, st>>>(s->dev, wp);
+        k_surface<false><<<sg, kBlock, 0, st>>>(s->dev, wp);
+        k_eye<false><<<sg, kBlock, 0, st>>>(s->dev, wp);
+    }
     if (timed) NGI_CUDA(cudaEventRecord(l.events[ev_used + 1], st));
     if (!timed && direct && s->overlap_trace) {
         // fork: shadow on stream2, extend on the lane's main stream, join
@@ -812,8 +824,9 @@ int launch_iteration(Scene* s, Lane& l, bool timed, size_t& ev_used, bool per_ra
 
 int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream_t st, NgiRenderStats* stats) {
     if (rp->struct_size != sizeof(NgiRenderParams)) return set_err(NGI_ERR_INVALID_ARGUMENT, "NgiRenderParams.struct_size mismatch (ABI)");
-    if (rp->renderer != NGI_RENDERER_PT && rp->renderer != NGI_RENDERER_PTDIRECT)
-        return set_err(NGI_ERR_UNSUPPORTED, "renderer not supported by this build (only pt and ptdirect are on the GPU path)");
+    if (rp->renderer < NGI_RENDERER_PT || rp->renderer > NGI_RENDERER_LTDIRECT)
+        return set_err(NGI_ERR_UNSUPPORTED, "renderer not supported by this build (pt, ptdirect, lt and ltdirect are on the GPU path)");
+    const bool has_shadow = rp->renderer == NGI_RENDERER_PTDIRECT || rp->renderer == NGI_RENDERER_LTDIRECT;
     if (rp->width <= 0 || rp->height <= 0 || rp->num_samples < 0 || rp->sample_offset < 0) return set_err(NGI_ERR_INVALID_ARGUMENT, "invalid width/height/num_samples");
     const size_t npx = (size_t)rp->width * rp->height;
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -843,7 +856,7 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     NGI_CUDA(cudaEventRecord(ev0, st));          // also the fork point: the film memset above precedes every lane
 
     const int kItersPerBatch = 8;
-    const int kernels_per_iter = rp->renderer == NGI_RENDERER_PTDIRECT ? 6 : 5;   // iter_begin, classify, surface, eye, extend (, shadow)
+    const int kernels_per_iter = has_shadow ? 6 : 5;   // iter_begin, classify, surface, eye, extend (, shadow)
     for (int k = 0; k < K; k++) {
         Lane& l = s->lanes[k];
         if ((rc = ensure_lane(s, l, P))) return rc;
@@ -938,10 +951,10 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         stats->trace_kernel_seconds = (extend_ms + shadow_ms) * 1e-3;
         stats->logic_kernel_seconds = logic_ms * 1e-3;
         stats->extend_kernel_seconds = extend_ms * 1e-3;
-        stats->shadow_kernel_seconds = rp->renderer == NGI_RENDERER_PTDIRECT ? shadow_ms * 1e-3 : 0.0;
+        stats->shadow_kernel_seconds = has_shadow ? shadow_ms * 1e-3 : 0.0;
         stats->logic_launches = timed_iters;
         stats->extend_launches = timed_iters;
-        stats->shadow_launches = rp->renderer == NGI_RENDERER_PTDIRECT ? timed_iters : 0;
+        stats->shadow_launches = has_shadow ? timed_iters : 0;
     }
     return NGI_OK;
 }

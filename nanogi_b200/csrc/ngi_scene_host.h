@@ -30,6 +30,26 @@ struct NgiHostArrays {
 
 inline f3 ngi_f3_from(const double* v) { return mk3((float)v[0], (float)v[1], (float)v[2]); }
 
+// CreateTriangleAreaDist, rt.hpp:1747-1765 (fp64), Distribution1D::Normalize basic.hpp:453-461: appends the normalised
+// area CDF (leading 0) of the triangle range to `cdf_out`, returns InvArea
+inline float ngi_area_cdf(const NgiSceneDesc* d, const int first_tri, const int num_tris, std::vector<float>& cdf_out, int& cdf_offset) {
+    std::vector<double> cdf(1, 0.0);
+    double sumArea = 0;
+    for (int t = 0; t < num_tris; t++) {
+        const float* q = d->positions + ((size_t)first_tri + t) * 9;
+        const double e1[3] = {(double)q[3] - q[0], (double)q[4] - q[1], (double)q[5] - q[2]};
+        const double e2[3] = {(double)q[6] - q[0], (double)q[7] - q[1], (double)q[8] - q[2]};
+        const double cx = e1[1] * e2[2] - e2[1] * e1[2], cy = e1[2] * e2[0] - e2[2] * e1[0], cz = e1[0] * e2[1] - e2[0] * e1[1];
+        const double area = std::sqrt(cx * cx + cy * cy + cz * cz) * 0.5;
+        cdf.push_back(cdf.back() + area);
+        sumArea += area;
+    }
+    const double invSum = 1.0 / cdf.back();
+    cdf_offset = (int)cdf_out.size();
+    for (double v : cdf) cdf_out.push_back((float)(v * invSum));
+    return (float)(1.0 / sumArea);
+}
+
 inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out) {
     if (!d || d->struct_size != sizeof(NgiSceneDesc)) { out.error = "NgiSceneDesc.struct_size mismatch (ABI)"; return false; }
     if (d->num_tris > 0 && (!d->positions || !d->normals)) { out.error = "positions / normals are NULL"; return false; }
@@ -67,29 +87,17 @@ inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out) {
         p.l_le = ngi_f3_from(s.l_le); p.l_vec = ngi_f3_from(s.l_vec);
         for (int t = 0; t < p.num_tris; t++) triPrim[(size_t)p.first_tri + t] = (int)i;
         if (s.type & NGI_TYPE_E) {
-            if (s.e_type != NGI_E_PINHOLE) { out.error = "E.area sensors are not supported yet (SURVEY 8f)"; return false; }
+            if (s.e_type != NGI_E_PINHOLE && s.e_type != NGI_E_AREA) { out.error = "unknown sensor type"; return false; }
+            if (s.e_type == NGI_E_AREA && (p.num_tris <= 0 || !d->texcoords)) {        // rt.hpp:1919-1924
+                out.error = "Raw sensor must be associated with mesh with UV coordinates"; return false;
+            }
             sensor = (int)i;                                                           // rt.hpp:1606-1610 (last one wins)
         }
         if (s.type & NGI_TYPE_L) {
             out.light_prims.push_back(i);                                              // rt.hpp:1612-1615
             if (s.l_type == NGI_L_AREA) {
                 if (p.num_tris <= 0) { out.error = "Area light must be associated with mesh"; return false; }   // rt.hpp:1826-1830
-                // CreateTriangleAreaDist, rt.hpp:1747-1765 (fp64), Distribution1D::Normalize basic.hpp:453-461
-                std::vector<double> cdf(1, 0.0);
-                double sumArea = 0;
-                for (int t = 0; t < p.num_tris; t++) {
-                    const float* q = d->positions + ((size_t)p.first_tri + t) * 9;
-                    const double e1[3] = {(double)q[3] - q[0], (double)q[4] - q[1], (double)q[5] - q[2]};
-                    const double e2[3] = {(double)q[6] - q[0], (double)q[7] - q[1], (double)q[8] - q[2]};
-                    const double cx = e1[1] * e2[2] - e2[1] * e1[2], cy = e1[2] * e2[0] - e2[2] * e1[0], cz = e1[0] * e2[1] - e2[0] * e1[1];
-                    const double area = std::sqrt(cx * cx + cy * cy + cz * cz) * 0.5;
-                    cdf.push_back(cdf.back() + area);
-                    sumArea += area;
-                }
-                const double invSum = 1.0 / cdf.back();
-                p.cdf_offset = (int)out.cdf.size();
-                for (double v : cdf) out.cdf.push_back((float)(v * invSum));
-                p.l_inv_area = (float)(1.0 / sumArea);
+                p.l_inv_area = ngi_area_cdf(d, p.first_tri, p.num_tris, out.cdf, p.cdf_offset);
             } else if (s.l_type == NGI_L_DIRECTIONAL) {                                // rt.hpp:2067-2073
                 double c[3], r2 = 0;
                 for (int k = 0; k < 3; k++) { c[k] = (bmax[k] + bmin[k]) * 0.5; r2 += (c[k] - bmax[k]) * (c[k] - bmax[k]); }
@@ -108,11 +116,20 @@ inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out) {
         out.textures.push_back(T);
         out.tex_data.insert(out.tex_data.end(), t.rgb, t.rgb + (size_t)t.width * t.height * 3);
     }
-    if (d->texcoords && d->num_textures > 0) out.shade_uv.assign(d->texcoords, d->texcoords + n * 6);
     if (sensor < 0) { out.error = "scene has no sensor (E) primitive"; return false; }
+    const bool area_sensor = d->prims[sensor].e_type == NGI_E_AREA;
+    if (d->texcoords && (d->num_textures > 0 || area_sensor)) out.shade_uv.assign(d->texcoords, d->texcoords + n * 6);
     {
         const NgiPrimitive& s = d->prims[sensor];
         NgiDevSensor& E = out.sensor;
+        std::memset(&E, 0, sizeof(E));
+        E.kind = area_sensor ? NGI_ET_AREA : NGI_ET_PINHOLE;
+        E.cdf_offset = -1;
+        if (area_sensor) {
+            E.first_tri = out.prims[sensor].first_tri; E.num_tris = out.prims[sensor].num_tris;
+            E.inv_area = ngi_area_cdf(d, E.first_tri, E.num_tris, out.cdf, E.cdf_offset);
+            E.we = ngi_f3_from(s.e_we);
+        }
         E.px = s.e_position[0]; E.py = s.e_position[1]; E.pz = s.e_position[2];
         E.vx = ngi_f3_from(s.e_vx); E.vy = ngi_f3_from(s.e_vy); E.vz = ngi_f3_from(s.e_vz);
         const double tanFov = std::tan(s.e_fov * 0.5);

@@ -1,6 +1,6 @@
 // ngi_shade.h — fp32 device restatement of nanogi's Primitive / emitter / BSDF functions.
 //
-// Replaces, for the pt / ptdirect path, the sampling and evaluation code of `struct Primitive`
+// Replaces, for the pt / ptdirect path (and lt / ltdirect), the sampling and evaluation code of `struct Primitive`
 // (reference include/nanogi/rt.hpp:379-1470) and the helpers at rt.hpp:55-140, :282-302, :2321-2374.
 // Each function cites the lines it restates. Arithmetic is fp32 (the reference is fp64) except the path
 // vertex position, which stays fp64 exactly like the reference's `geom.p` (see ngi_wave.h). All the
@@ -28,13 +28,18 @@ struct NgiDevPrim {           // 144 bytes, 16-byte aligned rows
     f3 l_center; float pad4;
 };
 
-struct NgiDevSensor {         // E.Pinhole, rt.hpp:422-429
+enum { NGI_ET_AREA = 0, NGI_ET_PINHOLE = 1 };
+struct NgiDevSensor {         // E.Pinhole, rt.hpp:422-429 / E.Area, rt.hpp:412-420
     double px, py, pz;
     f3 vx, vy, vz;
     float tan_fov;            // tan(Fov/2)
     float aspect;
     float inv_a;              // 1 / (tan^2 * aspect * 4), rt.hpp:974
     int prim;
+    int kind;                 // NGI_ET_*
+    int first_tri, num_tris, cdf_offset;   // E.Area: the sensor mesh and its area CDF (rt.hpp:1926-1927)
+    float inv_area;           // E.Area.InvArea
+    f3 we;                    // E.Area.We (rt.hpp:947-953); the pinhole's We is parsed but unused (rt.hpp:955-978)
 };
 
 // per-triangle shading record, indexed by GLOBAL triangle id: 5 x float4 = 80 B
@@ -224,16 +229,18 @@ NGI_HD bool ngi_sample_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& 
     return false;  // type 0 (a pure [L] primitive after `& ~Emitter`): assert(0) in the reference, rt.hpp:909
 }
 
-// ---- Primitive::EvaluateDirection (BSDF types, TransportDirection::EL) + EvaluateDirectionPDF ----
-// rt.hpp:990-1140 and :1219-1328. `pdf` is only meaningful when want_pdf.
+// ---- Primitive::EvaluateDirection (BSDF types) + EvaluateDirectionPDF ----
+// rt.hpp:990-1140 and :1219-1328. `transLE` = TransportDirection::LE (light paths: lt / ltdirect), a literal at every
+// call site; the eye-path renderers pass false (EL).
 NGI_HD f3 ngi_eval_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& g, const f3 wi, const f3 wo, const bool forceDegenerated,
-                        float& pdf) {
+                        float& pdf, const bool transLE = false) {
     pdf = 0.0f;
     if (!(type & NGI_BSDF)) return mk3(0.0f);
     const f3 localWi = ngi_to_local(g, wi), localWo = ngi_to_local(g, wo);
-    // shadingNormalCorrection, :994-1005 (EL => 1 unless the sides disagree)
+    // shadingNormalCorrection, :994-1005 (EL => 1 unless the sides disagree; LE => wiDotNs * woDotNg / (woDotNs * wiDotNg))
     const float wiDotNg = dot(wi, g.gn), woDotNg = dot(wo, g.gn);
-    const float snc = (wiDotNg * localWi.z <= 0.0f || woDotNg * localWo.z <= 0.0f) ? 0.0f : 1.0f;
+    float snc = (wiDotNg * localWi.z <= 0.0f || woDotNg * localWo.z <= 0.0f) ? 0.0f : 1.0f;
+    if (transLE && snc != 0.0f) snc = localWi.z * woDotNg / (localWo.z * wiDotNg);
     if (type & NGI_D) {                                                                       // :1013-1024, :1221-1231
         if (localWi.z <= 0.0f || localWo.z <= 0.0f) return mk3(0.0f);
         pdf = NGI_INV_PI_F;
@@ -258,15 +265,16 @@ NGI_HD f3 ngi_eval_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& g, c
         float etaI = P.s_eta1, etaT = P.s_eta2;
         if (localWi.z < 0.0f) { const float t = etaI; etaI = etaT; etaT = t; }
         const float eta = etaI / etaT;
+        const float refr = transLE ? 1.0f : eta;                                              // refrCorrection, :1095 / :1130
         if (P.s_type == NGI_ST_REFRACTION) {                                                  // :1084-1098, :1288-1291
             pdf = 1.0f;
-            return P.s_r * (snc * eta * eta);
+            return P.s_r * (snc * refr * refr);
         }
         if (P.s_type == NGI_ST_FRESNEL) {                                                     // :1106-1134, :1299-1325
             const float Fr = ngi_fresnel(localWi.z, etaI, etaT);
             if (localWi.z * localWo.z >= 0.0f) { pdf = Fr; return P.s_r * (Fr * snc); }
             pdf = 1.0f - Fr;
-            return P.s_r * ((1.0f - Fr) * snc * eta * eta);
+            return P.s_r * ((1.0f - Fr) * snc * refr * refr);
         }
     }
     return mk3(0.0f);
@@ -293,32 +301,85 @@ struct NgiLightSample {
     float pdf;   // pdfL * pdfPL
     int degenerate;   // point light
     int valid;        // 0 for lights that contribute nothing on this path (directional, rt.hpp:934-937)
+    int prim;         // index of the light primitive
+    int l_type;
 };
 
-// Scene::SampleEmitter (rt.hpp:2321-2336) + Primitive::SamplePosition for L (rt.hpp:483-563) + the pdfs
-NGI_HD NgiLightSample ngi_sample_light(const NgiDevScene& sc, const float uPick, const float u0, const float u1) {
+// SampleTriangleMesh (rt.hpp:488-525): triangle by area CDF with sample reuse, uniform point on it, face normal.
+// `tri` returns the global triangle id (for the uv of an E.area sensor point). `pd` (optional) receives the position
+// interpolated in fp64 like the reference (rt.hpp:508): a point that becomes a ray ORIGIN (first vertex of a light path,
+// E.area sensor point) must lie on its triangle to well below the 1e-4 ray epsilon — the fp32 interpolation is off the
+// plane by 1-2 ulp (1.2e-4 at Cornell coordinates), enough for the first ray to hit its own light.
+NGI_HD void ngi_sample_triangle_mesh(const NgiDevScene& sc, const int first_tri, const int num_tris, const int cdf_offset,
+                                     const float u0, const float u1, f3& p, f3& n, int& tri, float& bx, float& by, double* pd = nullptr) {
+    float u2;
+    const int i = ngi_cdf_sample_reuse(sc.cdf + cdf_offset, num_tris + 1, u0, u2);
+    const float s = sqrtf(fmaxf(0.0f, u2));                                                   // UniformSampleTriangle, rt.hpp:129-133
+    bx = 1.0f - s; by = u1 * s;
+    tri = first_tri + i;
+    const float4* r = sc.shade_tris + 5 * (size_t)tri;
+    const float4 r0 = ngi_ldg(r), r1 = ngi_ldg(r + 1), r2 = ngi_ldg(r + 2);
+    const f3 p1 = mk3(r0.x, r0.y, r0.z), p2 = mk3(r0.w, r1.x, r1.y), p3 = mk3(r1.z, r1.w, r2.x);
+    p = p1 * (1.0f - bx - by) + p2 * bx + p3 * by;                                            // rt.hpp:508
+    n = normalize(cross(p2 - p1, p3 - p1));                                                   // rt.hpp:521-522
+    if (pd) {
+        const double b1 = (double)bx, b2 = (double)by, b0 = 1.0 - b1 - b2;
+        pd[0] = (double)p1.x * b0 + (double)p2.x * b1 + (double)p3.x * b2;
+        pd[1] = (double)p1.y * b0 + (double)p2.y * b1 + (double)p3.y * b2;
+        pd[2] = (double)p1.z * b0 + (double)p2.z * b1 + (double)p3.z * b2;
+    }
+}
+
+// Scene::SampleEmitter (rt.hpp:2321-2336) + Primitive::SamplePosition for L (rt.hpp:483-563) + the pdfs.
+// `emission` = the sample starts a light path (lt / ltdirect): directional lights then get their disk position
+// (rt.hpp:549-562); as an NEE sample they contribute nothing (rt.hpp:934-937) and stay invalid.
+NGI_HD NgiLightSample ngi_sample_light(const NgiDevScene& sc, const float uPick, const float u0, const float u1, const bool emission = false,
+                                       double* pd = nullptr) {
     NgiLightSample ls;
     ls.valid = 0; ls.degenerate = 0; ls.pdf = 1.0f; ls.p = mk3(0.0f); ls.n = mk3(0.0f); ls.le = mk3(0.0f);
     const int n = (int)sc.n_lights;
     const int li = clampi((int)(uPick * (float)n), 0, n - 1);
-    const NgiDevPrim& L = sc.prims[ngi_ldg(sc.light_prims + li)];
+    ls.prim = (int)ngi_ldg(sc.light_prims + li);
+    const NgiDevPrim& L = sc.prims[ls.prim];
     const float pdfL = 1.0f / (float)n;                                                       // rt.hpp:2338-2344
     ls.le = L.l_le;
+    ls.l_type = L.l_type;
     if (L.l_type == NGI_LT_AREA) {
-        float u2;
-        const int i = ngi_cdf_sample_reuse(sc.cdf + L.cdf_offset, L.num_tris + 1, u0, u2);
-        const float s = sqrtf(fmaxf(0.0f, u2));                                               // UniformSampleTriangle, rt.hpp:129-133
-        const float bx = 1.0f - s, by = u1 * s;
-        const float4* r = sc.shade_tris + 5 * (size_t)(L.first_tri + i);
-        const float4 r0 = ngi_ldg(r), r1 = ngi_ldg(r + 1), r2 = ngi_ldg(r + 2);
-        const f3 p1 = mk3(r0.x, r0.y, r0.z), p2 = mk3(r0.w, r1.x, r1.y), p3 = mk3(r1.z, r1.w, r2.x);
-        ls.p = p1 * (1.0f - bx - by) + p2 * bx + p3 * by;                                     // rt.hpp:508
-        ls.n = normalize(cross(p2 - p1, p3 - p1));                                            // rt.hpp:521-522
+        int tri; float bx, by;
+        ngi_sample_triangle_mesh(sc, L.first_tri, L.num_tris, L.cdf_offset, u0, u1, ls.p, ls.n, tri, bx, by, pd);
         ls.pdf = pdfL * L.l_inv_area;
         ls.valid = 1;
+        return ls;
     } else if (L.l_type == NGI_LT_POINT) {
         ls.p = L.l_vec; ls.degenerate = 1; ls.pdf = pdfL; ls.valid = 1;                       // rt.hpp:542-547, :654-657
+    } else if (emission) {                                                                    // rt.hpp:549-562
+        float dx, dy;
+        ngi_concentric_disk(u0, u1, dx, dy);
+        f3 b, c;
+        ngi_orthonormal_basis(L.l_vec, b, c);
+        ls.n = L.l_vec;
+        ls.p = L.l_center - L.l_vec * L.l_radius + b * (dx * L.l_radius) + c * (dy * L.l_radius);
+        ls.pdf = pdfL * L.l_inv_area;
+        ls.valid = 1;
     }
-    // directional: EvaluateDirection(..., forceDegenerated=false) = 0 (rt.hpp:934-937) => contributes nothing
+    // directional as an NEE sample: EvaluateDirection(..., forceDegenerated=false) = 0 (rt.hpp:934-937) => contributes nothing
+    if (pd) { pd[0] = (double)ls.p.x; pd[1] = (double)ls.p.y; pd[2] = (double)ls.p.z; }
     return ls;
+}
+
+// ---- E.area sensor (rt.hpp:573-577, :947-953, :1179-1187, :1386-1391) ---------------------------
+// geom.uv of a point on triangle `tri` with barycentrics (bx -> 2nd vertex, by -> 3rd), rt.hpp:512-517 / :2221-2227
+NGI_HD void ngi_uv_at(const NgiDevScene& sc, const unsigned tri, const float bx, const float by, double& tu, double& tv) {
+    const float* t = sc.shade_uv + 6 * (size_t)tri;
+    const double w = (double)(1.0f - bx - by);
+    tu = (double)ngi_ldg(t + 0) * w + (double)ngi_ldg(t + 2) * (double)bx + (double)ngi_ldg(t + 4) * (double)by;
+    tv = (double)ngi_ldg(t + 1) * w + (double)ngi_ldg(t + 3) * (double)bx + (double)ngi_ldg(t + 5) * (double)by;
+}
+// RasterPosition(E.area) = geom.uv (rt.hpp:1386-1391) -> PixelIndex (rt.hpp:135-140)
+NGI_HD int ngi_area_sensor_pixel(const NgiDevScene& sc, const unsigned tri, const float bx, const float by, const int w, const int h) {
+    double tu, tv;
+    ngi_uv_at(sc, tri, bx, by, tu, tv);
+    const int pX = clampi((int)(tu * (double)w), 0, w - 1);
+    const int pY = clampi((int)(tv * (double)h), 0, h - 1);
+    return pY * w + pX;
 }

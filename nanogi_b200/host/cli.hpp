@@ -35,6 +35,8 @@ struct CliOptions {
     int gpus = 1;
     unsigned long long seed = 0; bool has_seed = false;
     unsigned wave_capacity = 0;
+    long long sample_offset = 0;
+    std::string resume_from;
     std::string device = "gpu";
     bool quiet = false;
 };
@@ -68,6 +70,9 @@ inline std::string CliUsage() {
       << "  --gpus arg (=1)                       [b200] number of GPUs (samples sharded by index)\n"
       << "  --seed arg                            [b200] Philox seed (default: time)\n"
       << "  --wave-capacity arg (=0)              [b200] path slots in flight (0 = default)\n"
+      << "  --sample-offset arg (=0)              [b200] first sample index (continue an earlier run's sample sequence)\n"
+      << "  --resume-from arg                     [b200] .pfm film of an earlier run with --sample-offset samples; the new\n"
+      << "                                        samples are added to it\n"
       << "  --device arg (=gpu)                   [b200] only 'gpu' is built in; there is no CPU fallback\n";
     return o.str();
 }
@@ -80,7 +85,7 @@ inline CliOptions ParseCli(int argc, const char* const* argv) {
         {"num-samples", 'n', true}, {"max-num-vertices", 'm', true}, {"width", 'w', true}, {"height", 'h', true},
         {"num-threads", 'j', true}, {"grain-size", 0, true}, {"progress-update-interval", 0, true},
         {"render-time", 't', true}, {"progress-image-update-interval", 0, true}, {"progress-image-update-format", 0, true},
-        {"gpus", 0, true}, {"seed", 0, true}, {"wave-capacity", 0, true}, {"device", 0, true}, {"quiet", 0, false},
+        {"gpus", 0, true}, {"seed", 0, true}, {"wave-capacity", 0, true}, {"sample-offset", 0, true}, {"resume-from", 0, true}, {"device", 0, true}, {"quiet", 0, false},
     };
     std::map<std::string, std::string> vm;
     std::vector<std::string> positional;
@@ -136,6 +141,8 @@ inline CliOptions ParseCli(int argc, const char* const* argv) {
     if (vm.count("gpus")) o.gpus = (int)to_ll("gpus", vm["gpus"]);
     if (vm.count("seed")) { o.seed = (unsigned long long)to_ll("seed", vm["seed"]); o.has_seed = true; }
     if (vm.count("wave-capacity")) o.wave_capacity = (unsigned)to_ll("wave-capacity", vm["wave-capacity"]);
+    if (vm.count("sample-offset")) o.sample_offset = to_ll("sample-offset", vm["sample-offset"]);
+    if (vm.count("resume-from")) o.resume_from = vm["resume-from"];
     if (vm.count("device")) o.device = vm["device"];
     o.quiet = vm.count("quiet") > 0;
     if (!o.help && !o.has_renderer) throw CliError("the option '--renderer' is required but missing");  // :2039

@@ -69,6 +69,8 @@ int ngi_host_parse_cli(int argc, const char* const* argv, NgiCliOptions* out) {
         copy_str(out->progress_image_update_format, sizeof(out->progress_image_update_format), o.progress_image_update_format);
         out->gpus = o.gpus; out->wave_capacity = o.wave_capacity; out->seed = o.seed;
         copy_str(out->device, sizeof(out->device), o.device);
+        out->sample_offset = o.sample_offset;
+        copy_str(out->resume_from, sizeof(out->resume_from), o.resume_from);
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }

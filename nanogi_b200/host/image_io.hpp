@@ -332,11 +332,24 @@ inline bool LoadImageRGB(const std::string& path, int& width, int& height, std::
     return ok;
 }
 
+// [b200, additive] lossless float film: PFM "PF", little endian, rows bottom-up = the film's own row order. Used by
+// --resume-from (a resumable film needs the exact float values; .hdr is RGBE and .png 8-bit).
+inline bool SavePFM(const std::string& path, const float* film, int width, int height) {
+    FILE* fp = std::fopen(path.c_str(), "wb");
+    if (!fp) return false;
+    std::fprintf(fp, "PF\n%d %d\n-1.0\n", width, height);
+    const size_t n = (size_t)width * height * 3;
+    const bool ok = std::fwrite(film, sizeof(float), n, fp) == n;
+    std::fclose(fp);
+    return ok;
+}
+
 inline bool SaveImage(const std::string& path, const float* film, int width, int height) {
     if (!detail::make_parent_dirs(path)) { NGI_LOG_WARN("Failed to create output directory : " + path); return false; }
     const std::string ext = detail::extension(path);
     bool ok;
     if (ext == ".hdr") ok = SaveHDR(path, film, width, height);
+    else if (ext == ".pfm") ok = SavePFM(path, film, width, height);
     else if (ext == ".exr") ok = SaveEXR(path, film, width, height);
     else if (ext == ".png") ok = SavePNG(path, film, width, height);
     else { NGI_LOG_ERROR("Invalid extension: " + ext); return false; }

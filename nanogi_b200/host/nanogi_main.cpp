@@ -4,9 +4,11 @@
 // (:117-180) and Renderer::Render (:182-221). The CLI, scene YAML, renderer names and film outputs are
 // the reference's; the per-sample loop is replaced by ONE call across the C ABI (include/nanogi_gpu.h):
 //     Renderer::Render(scene, film)   ->   ngi_gpu_scene_create + ngi_gpu_render
-// Only `pt` and `ptdirect` are on the GPU path; the other reference renderers (lt, ltdirect, bdpt, ptmnee)
-// are reported as unsupported instead of silently differing. There is no CPU fallback.
+// `pt` and `ptdirect` (the hot path) and `lt` / `ltdirect` are on the GPU path; bdpt and ptmnee are reported
+// as unsupported instead of silently differing. --render-time and progress images follow RenderProcess's pass loop.
+// There is no CPU fallback.
 #include <chrono>
+#include <functional>
 #include <cstdio>
 #include <ctime>
 #include <iostream>
@@ -30,23 +32,28 @@ const char* const RendererType_String[] = {"pt", "ptdirect", "lt", "ltdirect", "
 struct Renderer {
     int Type = -1;
     struct { long long NumSamples; double RenderTime; int MaxNumVertices; int Width; int Height; } Params;
+    double ProgressImageUpdateInterval = -1;
+    std::string ProgressImageUpdateFormat;
     int NumGpus = 1;
     unsigned long long Seed = 0;
     unsigned WaveCapacity = 0;
+    long long SampleOffset = 0;          // [b200] first sample index (resume: continue the Philox sample sequence)
+    std::string ResumeFrom;              // [b200] film of an earlier run (.pfm) rendered with SampleOffset samples
 
     // Renderer::Load, src/nanogi.cpp:117-180
     bool Load(const CliOptions& vm) {
         Type = -1;
         for (int i = 0; i < 6; i++) if (vm.renderer == RendererType_String[i]) Type = i;
         if (Type < 0) { NGI_LOG_ERROR("Invalid renderer type: " + vm.renderer); return false; }
-        if (Type > 1) { NGI_LOG_ERROR("Renderer '" + vm.renderer + "' is not supported by this build (GPU path: pt, ptdirect)"); return false; }
+        if (Type > NGI_RENDERER_LTDIRECT) { NGI_LOG_ERROR("Renderer '" + vm.renderer + "' is not supported by this build (GPU path: pt, ptdirect, lt, ltdirect)"); return false; }
         Params.NumSamples = vm.num_samples;
         Params.RenderTime = vm.render_time;
         Params.MaxNumVertices = vm.max_num_vertices;
         Params.Width = vm.width;
         Params.Height = vm.height;
+        ProgressImageUpdateInterval = vm.progress_image_update_interval;       // :163-167
+        ProgressImageUpdateFormat = vm.progress_image_update_format;
         if (vm.device != "gpu") { NGI_LOG_ERROR("--device " + vm.device + ": only 'gpu' is built in (no CPU fallback)"); return false; }
-        if (Params.RenderTime > 0) { NGI_LOG_ERROR("--render-time mode is not supported by this build; use --num-samples"); return false; }
         const int nd = ngi_gpu_device_count();
         if (nd <= 0) { NGI_LOG_ERROR(std::string("No CUDA device: ") + ngi_gpu_last_error()); return false; }
         NumGpus = vm.gpus;
@@ -55,48 +62,129 @@ struct Renderer {
         // src/nanogi.cpp:186-191: release builds seed from the clock
         Seed = vm.has_seed ? vm.seed : (unsigned long long)std::time(nullptr);
         WaveCapacity = vm.wave_capacity;
+        SampleOffset = vm.sample_offset;
+        ResumeFrom = vm.resume_from;
+        if (!ResumeFrom.empty() && SampleOffset <= 0) { NGI_LOG_ERROR("--resume-from needs --sample-offset = the number of samples in that film"); return false; }
         return true;
     }
 
-    // Renderer::Render, src/nanogi.cpp:182-221
+    // {{count}} expansion of the progress image path, src/nanogi.cpp:374-393 (ctemplate there)
+    static std::string ProgressPath(const std::string& format, long long count) {
+        char num[32];
+        std::snprintf(num, sizeof(num), "%010lld", count);
+        std::string out = format;
+        const std::string key = "{{count}}";
+        for (size_t pos = out.find(key); pos != std::string::npos; pos = out.find(key, pos + 10)) out.replace(pos, key.size(), num);
+        return out;
+    }
+
+    // Renderer::Render + RenderProcess, src/nanogi.cpp:182-221, :225-440. The reference's outer `while (true)` of
+    // parallel_for passes (:243-414) is kept: a pass is ONE call across the C ABI per GPU over a contiguous range of
+    // sample indices (counter-based RNG: the sample set does not depend on pass sizes or GPU count). --num-samples
+    // mode is a single pass unless progress images are requested; --render-time mode runs passes until the time is up
+    // (:336-346), sized to ~0.25 s of GPU work. Raw (unscaled) pass films are accumulated in fp64 and normalised by
+    // W*H / processedSamples like :429-437.
     bool Render(const HostScene& scene, std::vector<float>& film) const {
         const auto start = std::chrono::high_resolution_clock::now();
         const size_t npx = (size_t)Params.Width * Params.Height;
         const NgiSceneDesc desc = scene.desc();
+        std::vector<void*> handles(NumGpus, nullptr);
+        std::vector<std::string> errors(NumGpus);
+        auto for_each_gpu = [&](const std::function<void(int)>& fn) {
+            std::vector<std::thread> th;
+            for (int g = 1; g < NumGpus; g++) th.emplace_back(fn, g);
+            fn(0);
+            for (auto& t : th) t.join();
+            for (int g = 0; g < NumGpus; g++) if (!errors[g].empty()) { NGI_LOG_ERROR("GPU " + std::to_string(g) + ": " + errors[g]); return false; }
+            return true;
+        };
+        struct Cleanup { std::vector<void*>& h; ~Cleanup() { for (void* p : h) if (p) ngi_gpu_scene_destroy(p); } } cleanup{handles};
+        if (!for_each_gpu([&](int g) { if (ngi_gpu_scene_create(&desc, g, &handles[g]) != NGI_OK) errors[g] = ngi_gpu_last_error(); })) return false;
+
+        std::vector<double> acc(npx * 3, 0.0);                 // raw sum of sample contributions
+        long long processed = 0;                               // samples behind `acc` (incl. a resumed film's)
+        if (!ResumeFrom.empty()) {
+            int w = 0, h = 0; std::vector<float> rgb; std::string err;
+            if (!LoadImageRGB(ResumeFrom, w, h, rgb, err)) { NGI_LOG_ERROR(err); return false; }
+            if (w != Params.Width || h != Params.Height) { NGI_LOG_ERROR("--resume-from: image size differs from --width/--height"); return false; }
+            // the file holds film * W*H / N0 with row 0 = top; undo both
+            const double unscale = (double)SampleOffset / (double)npx;
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < w; x++)
+                    for (int k = 0; k < 3; k++) acc[((size_t)(h - 1 - y) * w + x) * 3 + k] = (double)rgb[((size_t)y * w + x) * 3 + k] * unscale;
+            processed = SampleOffset;
+        }
+        const long long first = SampleOffset;
         std::vector<std::vector<float>> films(NumGpus, std::vector<float>(npx * 3));
         std::vector<NgiRenderStats> stats(NumGpus);
-        std::vector<std::string> errors(NumGpus);
-        auto work = [&](int g) {
-            void* h = nullptr;
-            if (ngi_gpu_scene_create(&desc, g, &h) != NGI_OK) { errors[g] = ngi_gpu_last_error(); return; }
-            NgiRenderParams p{};
-            p.struct_size = sizeof(p);
-            p.renderer = Type;
-            // samples sharded by index: GPU g takes the contiguous range [g N/G, (g+1) N/G)
-            const long long lo = Params.NumSamples * g / NumGpus, hi = Params.NumSamples * (g + 1) / NumGpus;
-            p.num_samples = hi - lo; p.sample_offset = lo; p.film_norm_samples = Params.NumSamples;
-            p.max_num_vertices = Params.MaxNumVertices; p.width = Params.Width; p.height = Params.Height;
-            p.seed = Seed; p.wave_capacity = WaveCapacity;
-            if (ngi_gpu_render(h, &p, films[g].data(), &stats[g]) != NGI_OK) errors[g] = ngi_gpu_last_error();
-            ngi_gpu_scene_destroy(h);
+        unsigned long long ext = 0, sh = 0; double gpu_s = 0;
+        auto gather = [&](std::vector<float>& out) {
+            const double scale = processed > 0 ? (double)npx / (double)processed : 0.0;
+            out.resize(npx * 3);
+            for (size_t i = 0; i < npx * 3; i++) out[i] = (float)(acc[i] * scale);
         };
-        std::vector<std::thread> th;
-        for (int g = 1; g < NumGpus; g++) th.emplace_back(work, g);
-        work(0);
-        for (auto& t : th) t.join();
-        for (int g = 0; g < NumGpus; g++) if (!errors[g].empty()) { NGI_LOG_ERROR("GPU " + std::to_string(g) + ": " + errors[g]); return false; }
-        film = films[0];
-        for (int g = 1; g < NumGpus; g++) for (size_t i = 0; i < npx * 3; i++) film[i] += films[g][i];
-        const auto end = std::chrono::high_resolution_clock::now();
-        const double elapsed = (double)(std::chrono::duration_cast<std::chrono::milliseconds>(end - start).count()) / 1000.0;
-        unsigned long long ext = 0, sh = 0; double gs = 0;
-        for (auto& s : stats) { ext += s.extend_rays; sh += s.shadow_rays; gs = std::max(gs, s.gpu_seconds); }
+        const bool timed = Params.RenderTime > 0;
+        const bool passes = timed || ProgressImageUpdateInterval > 0;
+        long long pass_size = passes ? (1ll << 24) : Params.NumSamples;
+        long long done = 0, progressImageCount = 0;
+        auto prevImageUpdateTime = start;
+        auto seconds_since = [](std::chrono::high_resolution_clock::time_point t) {
+            return (double)(std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - t).count()) / 1000.0;
+        };
+        while (true) {
+            long long n = pass_size;
+            if (!timed) n = std::min(n, Params.NumSamples - done);
+            if (n > 0) {
+                const long long base = first + done;
+                const auto pass_start = std::chrono::high_resolution_clock::now();
+                if (!for_each_gpu([&](int g) {
+                        NgiRenderParams p{};
+                        p.struct_size = sizeof(p);
+                        p.renderer = Type;
+                        // samples sharded by index: GPU g takes the contiguous range [g n/G, (g+1) n/G) of this pass
+                        const long long lo = n * g / NumGpus, hi = n * (g + 1) / NumGpus;
+                        p.num_samples = hi - lo; p.sample_offset = base + lo; p.film_norm_samples = 0;   // raw sums
+                        p.max_num_vertices = Params.MaxNumVertices; p.width = Params.Width; p.height = Params.Height;
+                        p.seed = Seed; p.wave_capacity = WaveCapacity;
+                        if (ngi_gpu_render(handles[g], &p, films[g].data(), &stats[g]) != NGI_OK) errors[g] = ngi_gpu_last_error();
+                    })) return false;
+                double pass_gpu = 0;
+                for (int g = 0; g < NumGpus; g++) {
+                    for (size_t i = 0; i < npx * 3; i++) acc[i] += (double)films[g][i];
+                    ext += stats[g].extend_rays; sh += stats[g].shadow_rays; pass_gpu = std::max(pass_gpu, stats[g].gpu_seconds);
+                }
+                gpu_s += pass_gpu;
+                done += n; processed += n;
+                if (passes && seconds_since(pass_start) < 0.25 && pass_size < (1ll << 34)) pass_size *= 2;
+            }
+            const double elapsed = seconds_since(start);
+            if (!timed) {
+                char buf[64]; std::snprintf(buf, sizeof(buf), "Progress: %.1f%%", Params.NumSamples > 0 ? (double)done / Params.NumSamples * 100.0 : 100.0);
+                if (passes) NGI_LOG_INFO(buf);
+            } else {
+                char buf[96]; std::snprintf(buf, sizeof(buf), "Progress: %.1f%% (%.1fs / %.1fs)", elapsed / Params.RenderTime * 100.0, elapsed, Params.RenderTime);
+                NGI_LOG_INFO(buf);
+            }
+            const bool finished = timed ? elapsed > Params.RenderTime : done >= Params.NumSamples;
+            if (ProgressImageUpdateInterval > 0 && !finished && seconds_since(prevImageUpdateTime) > ProgressImageUpdateInterval) {   // :356-404
+                std::vector<float> snapshot;
+                gather(snapshot);
+                progressImageCount++;
+                NGI_LOG_INFO("Saving progress: ");
+                NGI_LOG_INDENTER();
+                SaveImage(ProgressPath(ProgressImageUpdateFormat, progressImageCount), snapshot.data(), Params.Width, Params.Height);
+                prevImageUpdateTime = std::chrono::high_resolution_clock::now();
+            }
+            if (finished) break;
+        }
+        gather(film);                                           // :429-437
+        const double elapsed = seconds_since(start);
         NGI_LOG_INFO("Progress: 100.0%");
-        NGI_LOG_INFO("# of samples: " + std::to_string(Params.NumSamples));
+        NGI_LOG_INFO("# of samples: " + std::to_string(done));
         NGI_LOG_INFO("Elapesed time: " + std::to_string(elapsed));
         char buf[256];
-        std::snprintf(buf, sizeof(buf), "GPU render: %.3f s, %.1f Mpaths/s, %.1f Mrays/s (extend %llu, shadow %llu)", gs,
-                      Params.NumSamples / gs / 1e6, (ext + sh) / gs / 1e6, ext, sh);
+        std::snprintf(buf, sizeof(buf), "GPU render: %.3f s, %.1f Mpaths/s, %.1f Mrays/s (extend %llu, shadow %llu)", gpu_s,
+                      gpu_s > 0 ? done / gpu_s / 1e6 : 0.0, gpu_s > 0 ? (ext + sh) / gpu_s / 1e6 : 0.0, ext, sh);
         NGI_LOG_INFO(buf);
         return true;
     }

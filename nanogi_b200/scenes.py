@@ -105,6 +105,16 @@ def pinhole(eye, center, up, fov_deg: float) -> dict:
                                                           "up": list(up), "fov": float(fov_deg)}}}
 
 
+def area_sensor(quad, we=(1.0, 1.0, 1.0), name: str = "sensor") -> dict:
+    """E.area ("raw") sensor, reference rt.hpp:412-420 / :1908-1928: a quad [4, 3] (corners in uv order (0,0) (1,0) (1,1) (0,1)) whose uv
+    coordinates ARE the raster position (rt.hpp:1386-1391); it looks along its geometric normal (p1-p0) x (p3-p0)."""
+    q = np.asarray(quad, dtype=np.float64).reshape(4, 3)
+    tris = np.array([[q[0], q[1], q[2]], [q[0], q[2], q[3]]])
+    uv = np.array([[[0, 0], [1, 0], [1, 1]], [[0, 0], [1, 1], [0, 1]]], dtype=np.float64)
+    pr = mesh_prim(["E"], tris, name=name, uv=uv, E={"type": "area", "We": list(we)})
+    return pr
+
+
 # ---- spec -> C ABI ----------------------------------------------------------------------------
 def to_scene_data(spec: Spec, aspect: float = 1.0, name: str = "scene") -> capi.SceneData:
     pos, nrm, uvs, prims, textures = [], [], [], [], []
@@ -144,7 +154,9 @@ def to_scene_data(spec: Spec, aspect: float = 1.0, name: str = "scene") -> capi.
                 kw["l_vec"] = L["direction"]
         if "E" in P:
             E = P["E"]
-            assert E["type"] == "pinhole"
+        if "E" in P and P["E"]["type"] == "area":
+            kw.update(e_type=capi.E_AREA, e_we=P["E"].get("We", [1, 1, 1]), e_aspect=float(aspect))
+        elif "E" in P:
             eye, center, up = (np.asarray(E[k], dtype=np.float64) for k in ("eye", "center", "up"))
             vz = eye - center
             vz /= np.linalg.norm(vz)
@@ -226,7 +238,9 @@ def write_scene_files(spec: Spec, directory: str, version: int = 5) -> str:
                 lines.append(f"            position: {vec(L['position'])}")
             if L["type"] == "directional":
                 lines.append(f"            direction: {vec(L['direction'])}")
-        if "E" in P:
+        if "E" in P and P["E"]["type"] == "area":
+            lines += ["        E:", "          type: area", "          area:", f"            We: {vec(P['E'].get('We', [1, 1, 1]))}"]
+        elif "E" in P:
             E = P["E"]
             lines += ["        E:", "          type: pinhole", "          pinhole:", f"            We: {vec(E.get('We', [1, 1, 1]))}",
                       "            view:", f"              eye: {vec(E['eye'])}", f"              center: {vec(E['center'])}",
@@ -303,6 +317,26 @@ def cornell_spheres() -> Spec:
     spec.append(mesh_prim(["S"], tris * s_r + s_c, nrm, name="glass",
                           S={"type": "fresnel", "R": [0.60784313725, 0.80392156862, 1], "eta1": 1.0, "eta2": 2.0}))
     spec.append(pinhole(**CORNELL_CAMERA))
+    return spec
+
+
+def cornell_raw_sensor(spheres: bool = False) -> Spec:
+    """Cornell box seen by an E.area ("raw") sensor instead of the pinhole: a 200 x 200 quad just inside the open front,
+    facing the back wall (the reference authors' verification device for lt / ltdirect / bdpt, rt.hpp:412-420)."""
+    spec = [p for p in (cornell_spheres() if spheres else cornell_box()) if "E" not in p["params"]]
+    z, lo, hi = 20.0, 178.0, 378.0
+    spec.append(area_sensor([[lo, lo, z], [hi, lo, z], [hi, hi, z], [lo, hi, z]]))
+    return spec
+
+
+def cornell_mixed_lights() -> Spec:
+    """C2's scene lit by all three light kinds: the area light, a point light and a directional light (inert in pt / ptdirect,
+    rt.hpp:934-937; a path origin in lt / ltdirect, rt.hpp:549-562)."""
+    spec = cornell_spheres()
+    cam = spec.pop()
+    spec.append({"type": ["L"], "mesh": None, "params": {"L": {"type": "point", "Le": [3.0e4, 2.0e4, 1.0e4], "position": [120.0, 400.0, 300.0]}}})
+    spec.append({"type": ["L"], "mesh": None, "params": {"L": {"type": "directional", "Le": [2.0, 2.0, 3.0], "direction": [0.3, -0.5, 0.81240384]}}})
+    spec.append(cam)
     return spec
 
 

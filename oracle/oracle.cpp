@@ -897,8 +897,8 @@ struct MtSampler {
     double Next() { return distDouble(engine); }
     unsigned int NextUInt() { return distUInt(engine); }
     void begin_sample(int64_t) {}
-    double sensor_pick() { return Next(); }
-    d2 sensor_pos() { d2 r; r.x = Next(); r.y = Next(); return r; }
+    double sensor_pick(int = 0) { return Next(); }
+    d2 sensor_pos(int = 0) { d2 r; r.x = Next(); r.y = Next(); return r; }
     double light_pick(int) { return Next(); }
     d2 light_pos(int) { d2 r; r.x = Next(); r.y = Next(); return r; }
     d2 dir(int) { d2 r; r.x = Next(); r.y = Next(); return r; }
@@ -923,9 +923,14 @@ inline double u01_24(uint32_t x) { return (double)((float)(x >> 8) * (1.0f / 167
 struct PhiloxSampler {
     uint32_t key[2] = {0, 0};
     int64_t sample = 0;
-    int cachedVertexA = -1, cachedVertexB = -1;
-    uint32_t a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-    void begin_sample(int64_t s) { sample = s; cachedVertexA = cachedVertexB = -1; }
+    int cachedVertexA = -1, cachedVertexB = -1, cachedVertexC = -1;
+    uint32_t a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c4[4] = {0, 0, 0, 0};
+    void begin_sample(int64_t s) { sample = s; cachedVertexA = cachedVertexB = cachedVertexC = -1; }
+    void blockC(int v) {
+        if (cachedVertexC == v) return;
+        uint32_t c[4] = {(uint32_t)sample, (uint32_t)((uint64_t)sample >> 32), (uint32_t)v, 2u};
+        philox4x32_10(c, key, c4); cachedVertexC = v;
+    }
     void blockA(int v) {
         if (cachedVertexA == v) return;
         uint32_t c[4] = {(uint32_t)sample, (uint32_t)((uint64_t)sample >> 32), (uint32_t)v, 0u};
@@ -936,8 +941,10 @@ struct PhiloxSampler {
         uint32_t c[4] = {(uint32_t)sample, (uint32_t)((uint64_t)sample >> 32), (uint32_t)v, 1u};
         philox4x32_10(c, key, b); cachedVertexB = v;
     }
-    double sensor_pick() { return 0.0; }                 // value unused by the pinhole path
-    d2 sensor_pos() { return d2(); }                     // value unused by the pinhole path
+    // block 2 = {sensor pick, sensor position u0, u1, -}: values only matter for an E.area sensor (rt.hpp:573-577);
+    // pt / ptdirect draw them once per sample (vertex 0), ltdirect once per path vertex
+    double sensor_pick(int v = 0) { blockC(v); return u01_24(c4[0]); }
+    d2 sensor_pos(int v = 0) { blockC(v); d2 r; r.x = u01_24(c4[1]); r.y = u01_24(c4[2]); return r; }
     double light_pick(int v) { blockB(v); return u01_24(b[0]); }
     d2 light_pos(int v) { blockB(v); d2 r; r.x = u01_24(b[1]); r.y = u01_24(b[2]); return r; }
     d2 dir(int v) { blockA(v); d2 r; r.x = u01_24(a[0]); r.y = u01_24(a[1]); return r; }
@@ -1074,6 +1081,124 @@ void ProcessSample_PTDirect(const Scene& scene, const RenderParams& Params, S& r
 }
 
 // ---------------------------------------------------------------------------------------------
+// ProcessSample_LT — src/nanogi.cpp:804-943. Light tracing: the film only receives paths that HIT a sensor
+// primitive, i.e. nothing with a pinhole (no mesh); meaningful with an E.area sensor.
+// ---------------------------------------------------------------------------------------------
+template <class S>
+void ProcessSample_LT(const Scene& scene, const RenderParams& Params, S& rng, std::vector<d3>& film, Counters& cnt) {
+    if (scene.LightPrimitiveIndices.empty()) return;
+    const Primitive* L = scene.SampleEmitter(NGI_TYPE_L, rng.light_pick(0));         // :808
+    const double pdfL = scene.EvaluateEmitterPDF(L);
+    SurfaceGeometry geomL;
+    L->SamplePosition(rng.light_pos(0), geomL);                                       // :819
+    const double pdfPL = L->EvaluatePositionPDF(geomL, true);
+    d3 throughput = L->EvaluatePosition(geomL, true) / pdfPL / pdfL;                  // :830
+    const Primitive* prim = L;
+    int type = NGI_TYPE_L;
+    SurfaceGeometry geom = geomL;
+    d3 wi;
+    int numVertices = 1;
+    while (true) {
+        if (Params.MaxNumVertices != -1 && numVertices >= Params.MaxNumVertices) break;      // :842
+        const int vtx = numVertices - 1;
+        d3 wo;
+        const d2 u = rng.dir(vtx); const double uc = rng.ucomp(vtx);
+        prim->SampleDirection(u, uc, type, geom, wi, wo);                                     // :852
+        const double pdfD = prim->EvaluateDirectionPDF(geom, type, wi, wo, true);             // :853
+        const d3 fs = prim->EvaluateDirection(geom, type, wi, wo, LE, true);                  // :861
+        if (is_zero(fs)) break;
+        throughput = throughput * (fs / pdfD);                                                // :874
+        Ray ray{geom.p, wo};                                                                  // :883
+        Intersection isect;
+        cnt.extend++;
+        if (!Intersect(scene, ray, isect)) break;                                             // :887
+        if ((isect.Prim->Type & NGI_TYPE_E) > 0) {                                            // :899-920
+            d2 rasterPos;
+            if (!isect.Prim->RasterPosition(-wo, isect.geom, rasterPos)) break;
+            const int pixelIndex = PixelIndex(rasterPos, Params.Width, Params.Height);
+            const d3 c = throughput
+                * isect.Prim->EvaluateDirection(isect.geom, NGI_TYPE_E, d3(), -ray.d, LE, false)
+                * isect.Prim->EvaluatePosition(isect.geom, false);
+            film[pixelIndex] = film[pixelIndex] + c;
+        }
+        const double rrProb = 0.5;                                                            // :929-937
+        if (rng.rr(vtx) > rrProb) break;
+        throughput = throughput / rrProb;
+        geom = isect.geom;                                                                    // :945-949
+        prim = isect.Prim;
+        type = isect.Prim->Type & ~NGI_TYPE_EMITTER;
+        wi = -ray.d;
+        numVertices++;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ProcessSample_LTDirect — src/nanogi.cpp:955-1131. Every light-path vertex (the light vertex included) is
+// connected to a sampled sensor position. NOTE `pdfPE = L->EvaluatePositionPDF(geomE, true)` (:1017): the
+// reference asks the LIGHT primitive, not E — i.e. InvArea of the light for an area light, 1 for a point
+// light. Replicated: it is part of the reference's output.
+// ---------------------------------------------------------------------------------------------
+template <class S>
+void ProcessSample_LTDirect(const Scene& scene, const RenderParams& Params, S& rng, std::vector<d3>& film, Counters& cnt) {
+    if (scene.LightPrimitiveIndices.empty()) return;
+    const Primitive* L = scene.SampleEmitter(NGI_TYPE_L, rng.light_pick(0));         // :959
+    const double pdfL = scene.EvaluateEmitterPDF(L);
+    SurfaceGeometry geomL;
+    L->SamplePosition(rng.light_pos(0), geomL);                                       // :970
+    const double pdfPL = L->EvaluatePositionPDF(geomL, true);
+    d3 throughput = L->EvaluatePosition(geomL, true) / pdfPL / pdfL;                  // :980
+    const Primitive* prim = L;
+    int type = NGI_TYPE_L;
+    SurfaceGeometry geom = geomL;
+    d3 wi;
+    int numVertices = 1;
+    while (true) {
+        if (Params.MaxNumVertices != -1 && numVertices >= Params.MaxNumVertices) break;      // :993
+        const int vtx = numVertices - 1;
+        {   // ---- direct sensor sampling, :1000-1052 ----
+            const Primitive* E = scene.SampleEmitter(NGI_TYPE_E, rng.sensor_pick(vtx));       // :1005
+            const double pdfE = scene.EvaluateEmitterPDF(E);
+            SurfaceGeometry geomE;
+            E->SamplePosition(rng.sensor_pos(vtx), geomE);                                    // :1016
+            const double pdfPE = L->EvaluatePositionPDF(geomE, true);                         // :1017 (sic: L)
+            const d3 ppE = normalize(geomE.p - geom.p);                                       // :1026
+            const d3 fsL = prim->EvaluateDirection(geom, type, wi, ppE, LE, false);           // :1027
+            const d3 fsE = E->EvaluateDirection(geomE, NGI_TYPE_E, d3(), -ppE, EL, false);    // :1028
+            const double G = GeometryTerm(geom, geomE);                                       // :1029
+            cnt.shadow++;
+            const double V = Visible(scene, geom.p, geomE.p) ? 1.0 : 0.0;                     // :1030
+            const d3 LeP = L->EvaluatePosition(geomE, true);                                  // :1031
+            const d3 C = throughput * fsL * G * V * fsE * LeP / pdfE / pdfPE;                 // :1032
+            if (!is_zero(C)) {                                                                // :1040-1049
+                d2 rasterPos;
+                E->RasterPosition(-ppE, geomE, rasterPos);
+                const int index = PixelIndex(rasterPos, Params.Width, Params.Height);
+                film[index] = film[index] + C;
+            }
+        }
+        d3 wo;
+        const d2 u = rng.dir(vtx); const double uc = rng.ucomp(vtx);
+        prim->SampleDirection(u, uc, type, geom, wi, wo);                                     // :1061
+        const double pdfD = prim->EvaluateDirectionPDF(geom, type, wi, wo, true);             // :1062
+        const d3 fs = prim->EvaluateDirection(geom, type, wi, wo, LE, true);                  // :1070
+        if (is_zero(fs)) break;
+        throughput = throughput * (fs / pdfD);                                                // :1083
+        Ray ray{geom.p, wo};                                                                  // :1092
+        Intersection isect;
+        cnt.extend++;
+        if (!Intersect(scene, ray, isect)) break;                                             // :1096
+        const double rrProb = 0.5;                                                            // :1107-1115
+        if (rng.rr(vtx) > rrProb) break;
+        throughput = throughput / rrProb;
+        geom = isect.geom;                                                                    // :1123-1127
+        prim = isect.Prim;
+        type = isect.Prim->Type & ~NGI_TYPE_EMITTER;
+        wi = -ray.d;
+        numVertices++;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Scene construction: the loader-side derivations of include/nanogi/rt.hpp:1606-1615 (sensor =
 // last E primitive, light list), :1747-1765 (area CDF), :2067-2073 (directional disk)
 // ---------------------------------------------------------------------------------------------
@@ -1169,7 +1294,9 @@ void RenderProcess(const Scene& scene, int renderer, const RenderParams& Params,
             for (int64_t sample = begin; sample != end; sample++) {               // :307-318
                 rng.begin_sample(sampleOffset + sample);
                 if (renderer == NGI_RENDERER_PT) ProcessSample_PT(scene, Params, rng, film, cnts[slot]);
-                else ProcessSample_PTDirect(scene, Params, rng, film, cnts[slot]);
+                else if (renderer == NGI_RENDERER_PTDIRECT) ProcessSample_PTDirect(scene, Params, rng, film, cnts[slot]);
+                else if (renderer == NGI_RENDERER_LT) ProcessSample_LT(scene, Params, rng, film, cnts[slot]);
+                else ProcessSample_LTDirect(scene, Params, rng, film, cnts[slot]);
             }
         }
     };
@@ -1210,7 +1337,7 @@ __attribute__((visibility("default"))) int oracle_render(void* s, int renderer, 
                                                           uint64_t seed, int rng_mode, int num_threads, double* film, double* stats) {
     Scene* sc = (Scene*)s;
     if (!sc || !film || width <= 0 || height <= 0 || num_samples < 0) { g_err = "invalid argument"; return -1; }
-    if (renderer != NGI_RENDERER_PT && renderer != NGI_RENDERER_PTDIRECT) { g_err = "renderer not on the pt/ptdirect path"; return -4; }
+    if (renderer < NGI_RENDERER_PT || renderer > NGI_RENDERER_LTDIRECT) { g_err = "renderer not supported (pt, ptdirect, lt, ltdirect)"; return -4; }
     if (sc->SensorPrimitiveIndex == (size_t)-1) { g_err = "scene has no sensor"; return -1; }
     if (num_threads <= 0) num_threads = std::max(1, (int)std::thread::hardware_concurrency() + num_threads);  // src/nanogi.cpp:149-152
     RenderParams P{width, height, max_num_vertices};

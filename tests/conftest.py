@@ -56,7 +56,7 @@ def scaled_spec(spec, scale, offset=0.0):
     for pr in out:
         if pr.get("mesh") is not None:
             pr["mesh"]["tris"] = pr["mesh"]["tris"] * scale + offset
-        if "E" in pr["params"]:
+        if "E" in pr["params"] and pr["params"]["E"]["type"] == "pinhole":
             E = pr["params"]["E"]
             E["eye"] = [x * scale + offset for x in E["eye"]]
             E["center"] = [x * scale + offset for x in E["center"]]

@@ -198,7 +198,8 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
     unsigned long long extend = 0, shadow = 0, iters = 0;
     while (true) {
         iter_counters[0] = iter_counters[1] = 0;
-        for (unsigned i = 0; i < P; i++) ngi_logic_step(s->dev, wp, i);
+        if (rp->renderer >= NGI_RENDERER_LT || s->dev.sensor.kind == NGI_ET_AREA) for (unsigned i = 0; i < P; i++) ngi_logic_step<true>(s->dev, wp, i);
+        else for (unsigned i = 0; i < P; i++) ngi_logic_step<false>(s->dev, wp, i);
         extend += iter_counters[1]; shadow += iter_counters[0];
         iters++;
         if (iter_counters[1] == 0 && iter_counters[0] == 0 && next_sample >= wp.sample_end) break;

@@ -1,0 +1,77 @@
+"""The drop-in `nanogi` command line (nanogi_b200/host/nanogi_main.cpp) end to end on the GPU box: reference CLI in,
+film file out — Run / Renderer::Load / Renderer::Render / RenderProcess's pass loop (reference src/nanogi.cpp:1993-2121,
+:117-221, :225-440)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from nanogi_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nanogi_b200", "nanogi")
+
+
+def run(*args):
+    r = subprocess.run([BIN, *[str(a) for a in args]], capture_output=True, text=True, timeout=600)
+    return r.returncode, r.stdout + r.stderr
+
+
+@pytest.fixture(scope="module")
+def scene_file(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cornell")
+    return scenes.write_scene_files(scenes.cornell_box(), str(d))
+
+
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect", "ltdirect"])
+def test_cli_renders_like_the_c_abi(scene_file, tmp_path, renderer):
+    out = tmp_path / f"{renderer}.pfm"
+    rc, log = run(renderer, scene_file, out, 64, 64, "-n", 64 * 64 * 64, "-m", 6, "--seed", 7)
+    assert rc == 0, log
+    img = capi.load_image(str(out))[::-1]                      # file is top-down, film is bottom-up
+    sd = capi.load_scene_file(scene_file, 1.0)
+    g = capi.GpuScene(sd, 0)
+    film, _ = g.render(renderer, 64 * 64 * 64, 64, 64, max_num_vertices=6, seed=7)
+    g.close()
+    assert np.allclose(img, film, rtol=1e-4, atol=1e-6 * film.max())
+
+
+def test_cli_unsupported_renderers_fail_loudly(scene_file, tmp_path):
+    for r in ("bdpt", "ptmnee"):
+        rc, log = run(r, scene_file, tmp_path / "x.hdr", 16, 16, "-n", 100)
+        assert rc != 0 and "not supported" in log
+    rc, log = run("nonsense", scene_file, tmp_path / "x.hdr", 16, 16)
+    assert rc != 0 and "Invalid renderer type" in log
+
+
+def test_cli_render_time_and_progress_images(scene_file, tmp_path):
+    """--render-time runs passes until the time is up (src/nanogi.cpp:336-346) and progress images are written between
+    passes with the {{count}} template (:356-404)."""
+    out = tmp_path / "t.hdr"
+    fmt = str(tmp_path / "progress" / "{{count}}.hdr")
+    rc, log = run("ptdirect", scene_file, out, 128, 128, "-t", 1.5, "--progress-image-update-interval", 0.3,
+                  "--progress-image-update-format", fmt, "--seed", 3)
+    assert rc == 0, log
+    assert out.exists()
+    shots = sorted(os.listdir(tmp_path / "progress"))
+    assert len(shots) >= 2 and shots[0] == "0000000001.hdr"
+    n = [int(line.split(":")[-1]) for line in log.splitlines() if "# of samples" in line][0]
+    assert n > 10_000_000                                       # far more than a CPU would do in 1.5 s
+    a = capi.load_image(str(tmp_path / "progress" / shots[0])); b = capi.load_image(str(out))
+    assert abs(a.mean() - b.mean()) < 0.1 * b.mean()            # progress images are normalised by the samples so far
+
+
+def test_cli_resume_continues_the_sample_sequence(scene_file, tmp_path):
+    """--sample-offset / --resume-from: two runs of N samples equal one run of 2N (counter-based RNG: the sample set is
+    the same; only the fp32 summation order differs)."""
+    n = 1 << 22
+    a, b, c = tmp_path / "a.pfm", tmp_path / "b.pfm", tmp_path / "c.pfm"
+    assert run("ptdirect", scene_file, a, 64, 64, "-n", n, "--seed", 9)[0] == 0
+    rc, log = run("ptdirect", scene_file, b, 64, 64, "-n", n, "--seed", 9, "--sample-offset", n, "--resume-from", a)
+    assert rc == 0, log
+    assert run("ptdirect", scene_file, c, 64, 64, "-n", 2 * n, "--seed", 9)[0] == 0
+    fb, fc = capi.load_image(str(b)), capi.load_image(str(c))
+    assert np.allclose(fb, fc, rtol=2e-3, atol=1e-5 * fc.max())
+    fa = capi.load_image(str(a))
+    assert not np.allclose(fa, fc, rtol=2e-3, atol=1e-5 * fc.max())

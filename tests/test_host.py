@@ -233,3 +233,34 @@ def test_scene_with_texr_loads_through_the_front_end(tmp_path):
     assert np.array_equal(sd.texcoords, ref.texcoords) and np.array_equal(sd.positions, ref.positions)
     assert [(p.d_tex, p.g_tex) for p in sd.prims] == [(p.d_tex, p.g_tex) for p in ref.prims]
     assert sum(p.d_tex >= 0 for p in sd.prims) == 1 and sum(p.g_tex >= 0 for p in sd.prims) == 1
+
+
+def test_cli_b200_additive_options_and_renderer_names():
+    o = capi.parse_cli(["nanogi", "ltdirect", "s.yml", "o.pfm", "64", "64", "-t", "2.5", "--progress-image-update-interval", "0.5",
+                        "--progress-image-update-format", "p/{{count}}.hdr", "--sample-offset", "4096", "--resume-from", "prev.pfm"])
+    assert o.renderer == b"ltdirect" and o.render_time == 2.5 and o.progress_image_update_interval == 0.5
+    assert o.progress_image_update_format == b"p/{{count}}.hdr" and o.sample_offset == 4096 and o.resume_from == b"prev.pfm"
+
+
+def test_pfm_film_round_trip(tmp_path):
+    """The additive lossless film format behind --resume-from: written bottom-up like the film, read back top-down."""
+    rng = np.random.default_rng(3)
+    film = rng.random((5, 7, 3), dtype=np.float32) * 100
+    path = str(tmp_path / "f.pfm")
+    capi.save_image(path, film)
+    img = capi.load_image(path)
+    assert np.array_equal(img[::-1], film)
+
+
+def test_area_sensor_scene_round_trips_through_yaml(tmp_path):
+    """E.area sensors: `type: area` + `We`, needs a mesh with uv (rt.hpp:1908-1928)."""
+    spec = scenes.cornell_raw_sensor()
+    path = scenes.write_scene_files(spec, str(tmp_path))
+    sd_file, sd_mem = capi.load_scene_file(path, 1.0), scenes.to_scene_data(spec, 1.0)
+    assert sd_file.texcoords is not None and np.allclose(sd_file.texcoords, sd_mem.texcoords)
+    a, b = sd_file.prims[sd_file.sensor_prim()], sd_mem.prims[sd_mem.sensor_prim()]
+    assert a.e_type == b.e_type == capi.E_AREA and list(a.e_we) == [1.0, 1.0, 1.0] and a.num_tris == 2
+    from oracle import pyoracle
+    fa, _ = pyoracle.OracleScene(sd_file).render("lt", 2000, 8, 8, max_num_vertices=4, seed=1, rng_mode=1)
+    fb, _ = pyoracle.OracleScene(sd_mem).render("lt", 2000, 8, 8, max_num_vertices=4, seed=1, rng_mode=1)
+    assert np.array_equal(fa, fb) and fa.max() > 0

@@ -245,3 +245,43 @@ def test_render_is_deterministic_in_philox_mode_and_shardable(cornell):
     a, _ = o.render("ptdirect", 12000, w, h, seed=5, rng_mode=1, sample_offset=0, film_norm_samples=n)
     b, _ = o.render("ptdirect", 8000, w, h, seed=5, rng_mode=1, sample_offset=12000, film_norm_samples=n)
     assert np.allclose(a + b, full, rtol=1e-12, atol=1e-15)
+
+
+# ---- lt / ltdirect and E.area sensors (row 4): known answers ----------------------------------
+def test_ltdirect_equals_ptdirect_times_light_area():
+    """ltdirect estimates the same image as ptdirect EXCEPT for the reference's own quirk at src/nanogi.cpp:1017
+    (`pdfPE = L->EvaluatePositionPDF(geomE)`: the LIGHT's 1/area instead of the pinhole's 1), which scales every
+    contribution by the light's area. With one area light of area A: mean(ltdirect) = A * mean(ptdirect)."""
+    from tests.conftest import scaled_spec
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_box(), 1.0 / 100.0), 1.0)
+    area = (343 - 213) * (332 - 227) / 100.0 ** 2
+    orc = pyoracle.OracleScene(sd)
+    n = 48 * 48 * 256
+    a, _ = orc.render("ptdirect", n, 48, 48, max_num_vertices=5, seed=1, rng_mode=1)
+    b, _ = orc.render("ltdirect", n, 48, 48, max_num_vertices=5, seed=2, rng_mode=1)
+    assert b.mean() / area == pytest.approx(a.mean(), rel=0.03)
+    # the images agree too, not just their means (8 x 8 blocks)
+    blk = lambda f: f.reshape(8, 6, 8, 6, 3).mean(axis=(1, 3, 4))
+    assert np.allclose(blk(b) / area, blk(a), rtol=0.25, atol=0.02 * a.mean())
+
+
+def test_light_tracing_hits_nothing_with_a_pinhole(cornell):
+    """`lt` adds to the film only when a light path HITS a sensor primitive (src/nanogi.cpp:899-920); a pinhole has no
+    mesh, so the reference's own `lt` image of a pinhole scene is black while all the rays are traced."""
+    orc = pyoracle.OracleScene(cornell)
+    f, st = orc.render("lt", 20000, 16, 16, max_num_vertices=6, seed=1, rng_mode=1)
+    assert f.max() == 0.0 and st["extend_rays"] >= 20000 and st["shadow_rays"] == 0
+
+
+def test_area_sensor_renderers_agree():
+    """With an E.area sensor all of pt, ptdirect and lt estimate the same measurement; ltdirect is off by the factor
+    InvArea(sensor) / InvArea(light) of the src/nanogi.cpp:1017 quirk."""
+    from tests.conftest import scaled_spec
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_raw_sensor(), 1.0 / 100.0), 1.0)
+    orc = pyoracle.OracleScene(sd)
+    n = 8 * 8 * 16384
+    means = {r: orc.render(r, n, 8, 8, max_num_vertices=5, seed=3 + i, rng_mode=1)[0].mean() for i, r in enumerate(["pt", "ptdirect", "lt", "ltdirect"])}
+    assert means["ptdirect"] == pytest.approx(means["pt"], rel=0.03)
+    assert means["lt"] == pytest.approx(means["pt"], rel=0.03)
+    light_area, sensor_area = (343 - 213) * (332 - 227) / 100.0 ** 2, (200.0 / 100.0) ** 2
+    assert means["ltdirect"] * sensor_area / light_area == pytest.approx(means["pt"], rel=0.04)

@@ -92,6 +92,36 @@ def test_replay_textured(renderer):
     pc.check_replay(pysim.SimScene(sd), sd, renderer, n=20000, m=-1, wave_capacity=2048)
 
 
+# ---- lt / ltdirect, E.area sensors, point + directional lights -------------------------
+@pytest.mark.parametrize("renderer", ["lt", "ltdirect"])
+@pytest.mark.parametrize("m", [-1, 3])
+def test_replay_light_tracing(renderer, m):
+    """Light paths (TransportDirection::LE: shading-normal correction ratio, no (eta_i/eta_t)^2) through D, G and S-fresnel
+    lobes; ltdirect connects every vertex to the pinhole. `lt` alone can only hit a sensor that has a mesh: with the
+    pinhole its film is exactly zero on both sides while the rays are still traced."""
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_spheres(), 0.01), 1.0)
+    pc.check_replay(pysim.SimScene(sd), sd, renderer, n=20000, m=m, wave_capacity=2048)
+
+
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect", "lt", "ltdirect"])
+def test_replay_area_sensor(renderer):
+    """E.area ("raw") sensor: position sampled on the sensor mesh, raster position = uv, We iff cos > 0; `lt` splats
+    on hits of the sensor mesh; ltdirect keeps the reference's `L->EvaluatePositionPDF(geomE)` quirk."""
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_raw_sensor(spheres=True), 0.01), 1.0)
+    pc.check_replay(pysim.SimScene(sd), sd, renderer, n=20000, w=16, h=16, m=6, wave_capacity=2048)
+
+
+@pytest.mark.parametrize("renderer", ["ptdirect", "lt", "ltdirect"])
+def test_replay_point_and_directional_lights(renderer):
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_mixed_lights(), 0.01), 1.0)
+    pc.check_replay(pysim.SimScene(sd), sd, renderer, n=20000, m=5, wave_capacity=2048)
+
+
+def test_light_tracing_statistics_cornell_scale(cornell):
+    """ltdirect at Cornell scale (fp32 self-intersection regime): statistical agreement with the oracle."""
+    pc.check_image_statistics(pysim.SimScene(cornell), cornell, "ltdirect", w=16, h=16, spp=256, seeds=6, m=6, block=4, wave_capacity=4096)
+
+
 def test_replay_furnace_exact(furnace):
     sim = pysim.SimScene(furnace)
     orc = pyoracle.OracleScene(furnace)

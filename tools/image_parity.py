@@ -17,8 +17,8 @@ Two additions make the verdict robust and sharp:
            (identical treatment of both sides) and its median over the seeds is reported next to the mean.
   paired   the oracle's counter-based mode (rng_mode=1) consumes the SAME Philox uniforms per (sample, vertex, slot) as the device, so
            I_gpu(seed) - I_oracle(seed) cancels the Monte-Carlo noise of all paths that do not diverge (fp32 vs fp64 shading): a bias
-           test several times more sensitive than independent seeds. Reported: paired block z, the relative block bias and that bias
-           in units of the block noise of ONE render at --headline-spp (the "3 sigma" of the north star).
+           test several times more sensitive than independent seeds. Reported: paired block z, the relative block bias and the
+           test's own standard error in units of the block noise of ONE render at --headline-spp (the "3 sigma" of the north star).
 Prints one JSON line (committed under profiles/).
 """
 import argparse
@@ -104,7 +104,9 @@ def main():
         "spp": a.paired_spp, "seeds": a.seeds, "block_z_max": float(np.abs(zp).max()), "block_z_frac_gt3": float((np.abs(zp) > 3).mean()),
         "rel_block_bias_max": float(np.abs(D.mean(0) / mo).max()), "rel_block_bias_rms": float(np.sqrt(((D.mean(0) / mo) ** 2).mean())),
         "rel_image_mean_diff": float((Pg.mean() - Po.mean()) / Po.mean()),
-        "block_bias_in_sigma_of_one_render_at_headline_spp_max": float(np.abs(D.mean(0) / (sig_headline + 1e-300)).max()),
+        # sensitivity: the paired test's own standard error per block, in units of the block noise of ONE render at the headline spp
+        # (a bias of 3 of those sigmas would show up here as z = 3 / this number)
+        "paired_se_in_sigma_of_one_render_at_headline_spp_median": float(np.median((D.std(0, ddof=1) / math.sqrt(a.seeds)) / (sig_headline + 1e-300))),
         "headline_spp": a.headline_spp,
         "pixels_differing_gt_1pct_frac": float((np.abs(Pg - Po).max(axis=3) > 0.01 * np.maximum(Po.max(axis=3), 1e-2 * Po.mean())).mean()),
     }
