@@ -168,7 +168,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -340,16 +340,31 @@ def run_own(args, rank: int, local_rank: int, world: int):
             "gpu_launches": int(cnt[0].item()), "wave_iterations": int(iters), "film_mean": film_mean,
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clk,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     scene.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """rank 0 prints ONE JSON line on the process's ORIGINAL stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
-    # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) out of it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints ONE JSON line on stdout. NCCL writes its version banner ("NCCL version 2.28.9+cuda12.9") to the C stdout
+    # of rank 0 at init whenever NCCL_DEBUG >= VERSION: keep fd 1 for the JSON line only and send everything else to stderr.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -376,7 +391,7 @@ def main():
             # convenience: re-launch under torchrun
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                    "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
-            sys.exit(subprocess.call(cmd))
+            sys.exit(subprocess.call(cmd, stdout=_JSON_FD))     # the ranks inherit the ORIGINAL stdout
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     run_own(args, rank, local_rank, world)
 

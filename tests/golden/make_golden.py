@@ -43,6 +43,18 @@ def main():
                 films[f"rays_{renderer}_{m}"] = np.array([st["extend_rays"], st["shadow_rays"]])
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), rays=rays, hits=hits, occ=occ, occ_tri=occ_hits["tri"], **films)
         print(name, "hit rate", float((hits["tri"] != capi.NO_HIT).mean()), "occluded", float((occ_hits["tri"] == 0).mean()))
+    # light tracing / raw sensor / mixed lights: unit-scale films of all four renderers
+    from tests.conftest import scaled_spec
+    films = {}
+    for scene in ("cornell_raw_sensor", "cornell_mixed_lights"):
+        spec = scenes.cornell_raw_sensor(spheres=True) if scene == "cornell_raw_sensor" else scenes.cornell_mixed_lights()
+        orc_s = pyoracle.OracleScene(scenes.to_scene_data(scaled_spec(spec, 0.01), 1.0))
+        for renderer in ("pt", "ptdirect", "lt", "ltdirect"):
+            f, st = orc_s.render(renderer, 4096, 16, 16, max_num_vertices=5, seed=3, rng_mode=1, num_threads=1)
+            films[f"film_{scene}_{renderer}"] = f
+            films[f"rays_{scene}_{renderer}"] = np.array([st["extend_rays"], st["shadow_rays"]])
+            print(scene, renderer, "mean", float(f.mean()))
+    np.savez_compressed(os.path.join(OUT, "light_tracing.npz"), **films)
     # BSDF tables on the C2 scene: D wall, G conductor sphere, S fresnel sphere
     sd = scenes.to_scene_data(scenes.cornell_spheres(), 1.0)
     orc = pyoracle.OracleScene(sd)

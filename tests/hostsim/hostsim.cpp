@@ -81,6 +81,76 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
         for (int j = 0; j < 3; j++) s->tris2[(size_t)k * 3 + j] = s->rec_in[(size_t)i * 3 + j];
         s->lo[n - 1 + k] = tlo[i]; s->hi[n - 1 + k] = thi[i];
     }
+    if (getenv("NGI_SIM_SAH")) {
+        // EXPERIMENT (build-quality yardstick, not a product path): top-down binned-SAH binary tree over the same leaves,
+        // collapsed by the same ngi_collapse_node — how much traversal cost is left in the PLOC topology?
+        s->left.assign(n - 1, 0); s->right.assign(n - 1, 0); s->cnt.assign(n - 1, 0u);
+        std::vector<unsigned> idx(n);
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::vector<float4>& lo = s->lo; std::vector<float4>& hi = s->hi;
+        int next_inner = 1;
+        struct Task { int node; unsigned b, e; };
+        std::vector<Task> st{{0, 0u, n}};
+        auto area = [](const float* mn, const float* mx) { const float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2]; return dx * dy + dy * dz + dz * dx; };
+        while (!st.empty()) {
+            const Task t = st.back(); st.pop_back();
+            float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f}, cmn[3] = {3e38f, 3e38f, 3e38f}, cmx[3] = {-3e38f, -3e38f, -3e38f};
+            for (unsigned i = t.b; i < t.e; i++) {
+                const float4 a = lo[n - 1 + idx[i]], b = hi[n - 1 + idx[i]];
+                const float l3[3] = {a.x, a.y, a.z}, h3[3] = {b.x, b.y, b.z};
+                for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], l3[k]); mx[k] = fmaxf(mx[k], h3[k]); const float c = 0.5f * (l3[k] + h3[k]); cmn[k] = fminf(cmn[k], c); cmx[k] = fmaxf(cmx[k], c); }
+            }
+            lo[t.node] = make_float4(mn[0], mn[1], mn[2], 0); hi[t.node] = make_float4(mx[0], mx[1], mx[2], 0);
+            s->cnt[t.node] = t.e - t.b;
+            const int NB = 32;
+            int bestAxis = -1, bestBin = -1; float bestCost = 3e38f;
+            for (int ax = 0; ax < 3; ax++) {
+                const float ext = cmx[ax] - cmn[ax];
+                if (!(ext > 0)) continue;
+                float bmn[NB][3], bmx[NB][3]; int bc[NB];
+                for (int b = 0; b < NB; b++) { bc[b] = 0; for (int k = 0; k < 3; k++) { bmn[b][k] = 3e38f; bmx[b][k] = -3e38f; } }
+                const float sc = NB / ext;
+                for (unsigned i = t.b; i < t.e; i++) {
+                    const float4 a = lo[n - 1 + idx[i]], b4 = hi[n - 1 + idx[i]];
+                    const float l3[3] = {a.x, a.y, a.z}, h3[3] = {b4.x, b4.y, b4.z};
+                    const int b = std::min(NB - 1, (int)((0.5f * (l3[ax] + h3[ax]) - cmn[ax]) * sc));
+                    bc[b]++;
+                    for (int k = 0; k < 3; k++) { bmn[b][k] = fminf(bmn[b][k], l3[k]); bmx[b][k] = fmaxf(bmx[b][k], h3[k]); }
+                }
+                float rA[NB]; int rC[NB];
+                float amn[3] = {3e38f, 3e38f, 3e38f}, amx[3] = {-3e38f, -3e38f, -3e38f}; int c = 0;
+                for (int b = NB - 1; b > 0; b--) { for (int k = 0; k < 3; k++) { amn[k] = fminf(amn[k], bmn[b][k]); amx[k] = fmaxf(amx[k], bmx[b][k]); } c += bc[b]; rA[b] = c ? area(amn, amx) : 0; rC[b] = c; }
+                for (int k = 0; k < 3; k++) { amn[k] = 3e38f; amx[k] = -3e38f; }
+                c = 0;
+                for (int b = 0; b < NB - 1; b++) {
+                    for (int k = 0; k < 3; k++) { amn[k] = fminf(amn[k], bmn[b][k]); amx[k] = fmaxf(amx[k], bmx[b][k]); }
+                    c += bc[b];
+                    if (c == 0 || rC[b + 1] == 0) continue;
+                    const float cost = area(amn, amx) * c + rA[b + 1] * rC[b + 1];
+                    if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestBin = b; }
+                }
+            }
+            unsigned mid;
+            if (bestAxis < 0) mid = (t.b + t.e) / 2;
+            else {
+                const float sc = NB / (cmx[bestAxis] - cmn[bestAxis]);
+                auto it = std::partition(idx.begin() + t.b, idx.begin() + t.e, [&](unsigned id) {
+                    const float4 a = lo[n - 1 + id], b4 = hi[n - 1 + id];
+                    const float c = bestAxis == 0 ? 0.5f * (a.x + b4.x) : bestAxis == 1 ? 0.5f * (a.y + b4.y) : 0.5f * (a.z + b4.z);
+                    return std::min(NB - 1, (int)((c - cmn[bestAxis]) * sc)) <= bestBin; });
+                mid = (unsigned)(it - idx.begin());
+                if (mid == t.b || mid == t.e) mid = (t.b + t.e) / 2;
+            }
+            auto child = [&](unsigned b, unsigned e) -> int {
+                if (e - b == 1) return (int)(n - 1 + idx[b]);
+                const int id = next_inner++;
+                st.push_back({id, b, e});
+                return id;
+            };
+            s->left[t.node] = child(t.b, mid);
+            s->right[t.node] = child(mid, t.e);
+        }
+    } else {
     // PLOC rounds, same per-item functions as the CUDA kernels (k_ploc_*)
     s->left.assign(n - 1, 0); s->right.assign(n - 1, 0); s->cnt.assign(n - 1, 0u);
     {
@@ -102,6 +172,7 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
             for (unsigned i = 0; i < C; i++) ngi_ploc_merge(pc, (int)i);
             merges += C - acc; C = acc; cur ^= 1;
         }
+    }
     }
     s->nodes2.resize((size_t)(n - 1) * 4);
     for (int i = 0; i < (int)n - 1; i++) ngi_pack2(s->lo.data(), s->hi.data(), s->left.data(), s->right.data(), (int)n, i, s->nodes2.data());
