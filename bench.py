@@ -16,9 +16,10 @@ Own arm (default)
             host memory -> ngi_gpu_scene_destroy; wall clock around the calls (they synchronise), max over ranks.
   roofline  dominant kernel (named in the JSON) timed live with CUDA events around every launch
             (NGI_RENDER_TIME_KERNELS pass on the same stream), algorithmic bytes per ray from SURVEY.md §8(d).
-  cpu_baseline  the CPU oracle (restated nanogi path; the real Embree+TBB binary cannot be built) on all
-            host cores, bounded sample of the same workload; rank 0, N = 1 only.
-Reference arm (`--impl reference`): the oracle on all host threads, same workload/metric, each step a bounded sample.
+  cpu_baseline  nanogi's own CPU code on all host cores (oracle/_ref: the reference's sources on stand-in third-party
+            headers, Embree replaced by a scalar BVH; the oracle port when oracle/_ref is absent), bounded sample of the
+            same workload; rank 0, N = 1 only.
+Reference arm (`--impl reference`): the same CPU code on all host threads, same workload/metric, each step a bounded sample.
 
 PyTorch is used for device memory, streams, events and torch.distributed only.
 """
@@ -134,28 +135,57 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+class CpuReference:
+    """The reference's CPU implementation of the path on the host cores. kind "reference": the reference's OWN sources
+    (src/nanogi.cpp + include/nanogi/*.hpp) built by oracle/build_ref.sh against the stand-in libraries of oracle/refshim —
+    its TBB-style sample loop, Primitive functions and film handling, with Embree's kernels replaced by a scalar BVH (so its
+    ray queries are slower than real Embree's SIMD ones). kind "port": the oracle restatement, when oracle/_ref is not there."""
+
+    def __init__(self, workload: str, sd, aspect: float):
+        from nanogi_b200 import scenes
+        from oracle import pyoracle, pyref
+        self.cores = os.cpu_count() or 1
+        self.orc = pyoracle.OracleScene(sd)
+        self.ref = None
+        if pyref.available() and sd.num_tris <= 200000 and not os.environ.get("NGI_BENCH_CPU_PORT"):
+            # the reference loads scene FILES: write the workload as schema.yml + OBJ (not part of any timed region)
+            self.ref = pyref.RefScene(getattr(scenes, WORKLOADS[workload][0])(), aspect)
+        self.kind = "reference" if self.ref is not None else "port"
+        self.note = ("nanogi's own sources (oracle/_ref: src/nanogi.cpp + include/nanogi/*.hpp on stand-in third-party headers; Embree's "
+                     "kernels replaced by a scalar BVH)" if self.ref is not None else
+                     "restated nanogi CPU path (oracle port, own BVH, no Embree)")
+
+    def render(self, renderer, n, W, H, m, seed):
+        """returns seconds"""
+        t0 = time.perf_counter()
+        if self.ref is not None:
+            self.ref.render(renderer, n, W, H, max_num_vertices=m, seed=seed, num_threads=self.cores)
+        else:
+            self.orc.render(renderer, n, W, H, max_num_vertices=m, seed=seed)
+        return time.perf_counter() - t0
+
+    def rays_per_path(self, renderer, W, H, m):
+        _, st = self.orc.render(renderer, 1 << 18, W, H, max_num_vertices=m, seed=3)
+        return (st["extend_rays"] + st["shadow_rays"]) / float(1 << 18)
+
+
 def run_reference(args, rank: int):
-    """The reference's CPU implementation of the path = the oracle restatement on all host threads (kind 'port')."""
+    """The reference arm: nanogi's own CPU implementation of the path on all host threads (see CpuReference)."""
     if rank != 0:
         return
-    from oracle import pyoracle
     gen, renderer, W, H, spp, m, desc = WORKLOADS[args.workload]
     sd = build_scene(args.workload, W / H)
-    orc = pyoracle.OracleScene(sd)
-    cores = os.cpu_count() or 1
-    # bounded sample: calibrate on 2^18 samples, then size a step to ~ args.cpu_seconds of wall time
-    t0 = time.perf_counter()
-    orc.render(renderer, 1 << 18, W, H, max_num_vertices=m, seed=11)
-    rate = (1 << 18) / (time.perf_counter() - t0)
+    cpu = CpuReference(args.workload, sd, W / H)
+    cores = cpu.cores
+    # bounded sample: calibrate on 2^18 samples, then size a step to ~ args.cpu_step_seconds of wall time
+    rate = (1 << 18) / cpu.render(renderer, 1 << 18, W, H, m, 11)
     n_step = int(max(1 << 18, min(rate * args.cpu_step_seconds, W * H * spp)))
     for i in range(args.warmup):
-        orc.render(renderer, n_step, W, H, max_num_vertices=m, seed=100 + i)
-    rays = 0.0
-    t0 = time.perf_counter()
+        cpu.render(renderer, n_step, W, H, m, 100 + i)
+    dt = 0.0
     for i in range(args.steps):
-        _, st = orc.render(renderer, n_step, W, H, max_num_vertices=m, seed=200 + i)
-        rays += st["extend_rays"] + st["shadow_rays"]
-    dt = time.perf_counter() - t0
+        dt += cpu.render(renderer, n_step, W, H, m, 200 + i)
+    rays = cpu.rays_per_path(renderer, W, H, m) * n_step * args.steps
     v = n_step * args.steps / dt / 1e6
     sample = f"{n_step} samples/step ({n_step / (W * H):.2f} spp of {spp}) x {args.steps} steps, same scene/resolution/renderer"
     line = {
@@ -163,8 +193,8 @@ def run_reference(args, rank: int):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "mrays_per_s": rays / dt / 1e6,
         "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp": spp, "max_num_vertices": m,
-                   "note": "restated nanogi CPU path (own BVH, no Embree; the real Embree+TBB binary cannot be built offline)"},
-        "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
+                   "note": cpu.note},
+        "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -310,18 +340,17 @@ def run_own(args, rank: int, local_rank: int, world: int):
     # ---- CPU baseline (oracle port) on the host cores: rank 0, N = 1 only -----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import pyoracle
-        orc = pyoracle.OracleScene(sd)
-        t0 = time.perf_counter()
-        orc.render(renderer, 1 << 18, W, H, max_num_vertices=m, seed=11)
-        rate = (1 << 18) / (time.perf_counter() - t0)
+        ref = CpuReference(args.workload, sd, W / H)
+        rate = (1 << 18) / ref.render(renderer, 1 << 18, W, H, m, 11)
         n_cpu = int(max(1 << 18, min(rate * args.cpu_seconds, n_rank)))
-        t0 = time.perf_counter()
-        fo, so = orc.render(renderer, n_cpu, W, H, max_num_vertices=m, seed=12)
-        dtc = time.perf_counter() - t0
-        cpu = {"value": n_cpu / dtc / 1e6, "unit": "Mpaths/s", "cores": os.cpu_count() or 1, "kind": "port",
+        dtc = ref.render(renderer, n_cpu, W, H, m, 12)
+        cpu = {"value": n_cpu / dtc / 1e6, "unit": "Mpaths/s", "cores": ref.cores, "kind": ref.kind,
                "sample": f"{n_cpu} samples ({n_cpu / (W * H):.2f} spp of {spp}) of the same scene/resolution/renderer, {dtc:.1f} s",
-               "mrays_per_s": (so["extend_rays"] + so["shadow_rays"]) / dtc / 1e6, "film_mean": float(fo.mean())}
+               "mrays_per_s": ref.rays_per_path(renderer, W, H, m) * n_cpu / dtc / 1e6, "note": ref.note}
+        if ref.kind == "reference":          # the oracle port next to it, for scale (its ray queries use a SAH BVH)
+            t0 = time.perf_counter()
+            ref.orc.render(renderer, n_cpu, W, H, max_num_vertices=m, seed=12)
+            cpu["oracle_port_value"] = n_cpu / (time.perf_counter() - t0) / 1e6
 
     if rank == 0:
         line = {
