@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Generates the golden fixtures of tests/golden/ from the CPU oracle (oracle/oracle.cpp).
 
-The reference ships no tests, golden vectors or numeric images and cannot be built or imported here
-(SURVEY.md §8c), so these fixtures are NOT reference outputs: they pin the oracle restatement itself (a change of the
-oracle's behaviour shows up as a diff here) and give the GPU tests fixed, machine-independent vectors.
+These fixtures are generated from the oracle (which is itself pinned against the reference's own code: see
+make_reference_golden.py / reference_films.npz and DESIGN.md §2): a change of the oracle's behaviour shows up as a diff here, and
+the GPU tests get fixed, machine-independent vectors (ray batches, Philox-replay films, BSDF tables).
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import os

@@ -75,3 +75,25 @@ def test_cli_resume_continues_the_sample_sequence(scene_file, tmp_path):
     assert np.allclose(fb, fc, rtol=2e-3, atol=1e-5 * fc.max())
     fa = capi.load_image(str(a))
     assert not np.allclose(fa, fc, rtol=2e-3, atol=1e-5 * fc.max())
+
+
+def test_cli_matches_the_reference_binary(scene_file, tmp_path):
+    """Same command line into the reference application itself (oracle/_ref/nanogi_ref: src/nanogi.cpp's own main on stand-in
+    libraries, CPU) and into the drop-in (GPU): the two images agree within Monte-Carlo noise, block by block."""
+    from oracle import pyref
+    if not os.path.exists(pyref.BIN_PATH):
+        pytest.skip("oracle/_ref/nanogi_ref not built")
+    n, w = 64 * 64 * 256, 64
+    ref_img, gpu_img = tmp_path / "ref.exr", tmp_path / "gpu.pfm"
+    r = subprocess.run([pyref.BIN_PATH, "ptdirect", scene_file, str(ref_img), str(w), str(w), "-n", str(n), "-m", "6"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and ref_img.exists(), r.stdout[-2000:]
+    rc, log = run("ptdirect", scene_file, gpu_img, w, w, "-n", n, "-m", 6, "--seed", 11)
+    assert rc == 0, log
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    a = cv2.imread(str(ref_img), cv2.IMREAD_UNCHANGED)[:, :, ::-1].astype(np.float64)     # BGR -> RGB, top-down
+    b = capi.load_image(str(gpu_img)).astype(np.float64)
+    assert a.shape == b.shape == (w, w, 3)
+    assert abs(a.mean() - b.mean()) < 0.02 * a.mean()
+    blk = lambda f: f.reshape(8, 8, 8, 8, 3).mean(axis=(1, 3, 4))
+    assert np.allclose(blk(a), blk(b), rtol=0.15, atol=0.02 * a.mean())

@@ -1,6 +1,6 @@
-"""The oracle pinned against known answers we derived analytically (the reference ships no
-tests or golden vectors, so these are the anchors; golden fixtures generated from the oracle live in
-tests/golden and are checked by tests/test_golden.py)."""
+"""The oracle against known answers we derived analytically — the second, independent anchor next to the pin against the
+reference's own code (tests/test_reference_pin.py, tests/golden/reference_films.npz). The reference ships no
+tests or golden vectors of its own."""
 import math
 
 import numpy as np

@@ -49,7 +49,13 @@ def main():
     ap.add_argument("--headline-spp", type=int, default=1024)
     ap.add_argument("-m", type=int, default=8)
     ap.add_argument("--block", type=int, default=16)
+    ap.add_argument("--cpu-side", default="auto", choices=["auto", "reference", "oracle"],
+                    help="who renders the independent-seed CPU images: nanogi's own code (oracle/_ref) or the oracle port")
     a = ap.parse_args()
+    # the reference's logger writes to the C stdout: keep fd 1 for the JSON line only
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     W = H = a.size
     sd = scenes.to_scene_data(getattr(scenes, a.scene)(), 1.0)
     if os.environ.get("NGI_IMAGE_PARITY_BACKEND") == "sim":      # CPU dry run of this script (test-only simulator of the device code)
@@ -58,6 +64,15 @@ def main():
     else:
         gpu = capi.GpuScene(sd, 0)
     orc = pyoracle.OracleScene(sd)
+    from oracle import pyref
+    use_ref = a.cpu_side == "reference" or (a.cpu_side == "auto" and pyref.available())
+    ref = pyref.RefScene(getattr(scenes, a.scene)(), 1.0) if use_ref else None
+
+    def cpu_render(n, seed):
+        """an independent-seed CPU image: the reference's own multi-threaded Renderer::Render when oracle/_ref is there"""
+        if ref is not None:
+            return ref.render(a.renderer, n, W, H, max_num_vertices=a.m, seed=seed, num_threads=os.cpu_count() or 1)
+        return orc.render(a.renderer, n, W, H, max_num_vertices=a.m, seed=seed, rng_mode=0)[0]
     npx = W * H
     t0 = time.perf_counter()
     # the reference in 8 independent parts (also gives its own standard error)
@@ -65,11 +80,11 @@ def main():
     R = np.mean(parts, axis=0)
     t_ref = time.perf_counter() - t0
     t0 = time.perf_counter()
-    Ro, _ = orc.render(a.renderer, npx * a.oracle_ref_spp, W, H, max_num_vertices=a.m, seed=77, rng_mode=0)
+    Ro = cpu_render(npx * a.oracle_ref_spp, 77)
     t_oref = time.perf_counter() - t0
     n = npx * a.spp
     Ig = np.stack([gpu.render(a.renderer, n, W, H, max_num_vertices=a.m, seed=100 + k)[0].astype(np.float64) for k in range(a.seeds)])
-    Io = np.stack([orc.render(a.renderer, n, W, H, max_num_vertices=a.m, seed=500 + k, rng_mode=0)[0] for k in range(a.seeds)])
+    Io = np.stack([cpu_render(n, 500 + k) for k in range(a.seeds)])
 
     def rel_rmse(I, ref):
         return math.sqrt(((I - ref) ** 2).mean()) / ref.mean()
@@ -111,6 +126,7 @@ def main():
         "pixels_differing_gt_1pct_frac": float((np.abs(Pg - Po).max(axis=3) > 0.01 * np.maximum(Po.max(axis=3), 1e-2 * Po.mean())).mean()),
     }
     out = {
+        "cpu_side": "nanogi's own code (oracle/_ref, all host threads)" if ref is not None else "oracle port",
         "scene": a.scene, "renderer": a.renderer, "width": W, "height": H, "spp": a.spp, "max_num_vertices": a.m, "seeds": a.seeds,
         "reference": {"kind": "gpu", "spp": a.ref_spp, "seconds": t_ref, "mean": float(R.mean())},
         "oracle_reference": {"spp": a.oracle_ref_spp, "seconds": t_oref, "mean": float(Ro.mean()),
@@ -128,7 +144,7 @@ def main():
         "expected_frac_gt3_student_t": "about 0.01 for 2K-2 = %d degrees of freedom (0.0027 for a normal)" % (2 * a.seeds - 2),
         "pass_rmse_1pct": bool(abs(rg.mean() - ro.mean()) <= max(0.01 * ro.mean(), 2 * se)),
     }
-    print(json.dumps(out), flush=True)
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":
