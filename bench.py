@@ -73,6 +73,8 @@ NCU_DRAM_BYTES_PER_LAUNCH = {
            "k_shadow": (93.781760e6 + 3.983104e6, 1 << 21, "profiles/r01_ncu_c2_final.txt")},
     "c3": {"k_extend": (350.019840e6 + 48.704768e6, 1 << 21, "profiles/r01_ncu_c3_final.txt"),
            "k_shadow": (114.695168e6 + 7.332608e6, 1 << 21, "profiles/r01_ncu_c3_final.txt")},
+    "c4": {"k_extend": (1.420079e9 + 60.782080e6, 1 << 21, "profiles/r01_ncu_c4.txt"),
+           "k_shadow": (0.439095e9 + 21.539584e6, 1 << 21, "profiles/r01_ncu_c4.txt")},
 }
 
 

@@ -50,6 +50,9 @@ constexpr int kBlock = 256;
 #define NGI_TRACE_BLOCK 64   /* persistent trace kernels: small CTAs hand their SM slot back as soon as their 2 warps run dry */
 #endif
 constexpr int kTraceBlock = NGI_TRACE_BLOCK;
+#ifndef NGI_TRACE_MIN_BLOCKS
+#define NGI_TRACE_MIN_BLOCKS (1152 / NGI_TRACE_BLOCK)   /* 36 resident warps per SM = 56 registers per thread (the measured configuration) */
+#endif
 #ifndef NGI_SURFACE_MIN_BLOCKS
 #define NGI_SURFACE_MIN_BLOCKS 4
 #endif
@@ -331,8 +334,9 @@ struct ExtendSource {
     __device__ __forceinline__ unsigned* cursor() const { return wp.fetch_cursors + 1; }
     __device__ __forceinline__ unsigned load(unsigned i, f3& o, f3& d, float& tmin, float& tmax) const {
         const unsigned slot = wp.extend_q[i];
-        const float4 di = wp.dir_info[slot];
-        o = mk3((float)wp.px[slot], (float)wp.py[slot], (float)wp.pz[slot]);                 // rt.hpp:2166-2168
+        const float4 di = wp.sb[slot].dir_info;
+        const NgiSlotA* sa = wp.sa + slot;
+        o = mk3((float)sa->px, (float)sa->py, (float)sa->pz);                                // rt.hpp:2166-2168
         d = mk3(di.x, di.y, di.z); tmin = NGI_EPS_F; tmax = NGI_INF_F;                        // rt.hpp:2246-2249
         return slot;
     }
@@ -367,11 +371,11 @@ __global__ void __launch_bounds__(kBlock) k_shadow_per_ray(NgiDevScene sc, NgiWa
     const unsigned n = wp.iter_counters[0];
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_shadow_step(sc, wp, e);
 }
-__global__ void __launch_bounds__(kTraceBlock) k_extend(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
+__global__ void __launch_bounds__(kTraceBlock, NGI_TRACE_MIN_BLOCKS) k_extend(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
     ExtendSource src; src.wp = wp;
     ngi_trace_warp<false>(sc.nodes8, sc.tris8, src, tune);
 }
-__global__ void __launch_bounds__(kTraceBlock) k_shadow(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
+__global__ void __launch_bounds__(kTraceBlock, NGI_TRACE_MIN_BLOCKS) k_shadow(NgiDevScene sc, NgiWaveParams wp, NgiTraceTuning tune) {
     ShadowSource src; src.wp = wp;
     ngi_trace_warp<true>(sc.nodes8, sc.tris8, src, tune);
 }
@@ -750,7 +754,7 @@ int ensure_lane(Scene* s, Lane& l, unsigned P) {
     if (l.wave_capacity == P && l.wave_mem) return NGI_OK;
     if (l.graph_exec) { cudaGraphExecDestroy(l.graph_exec); l.graph_exec = nullptr; }
     if (l.wave_mem) { wave_cache_put(s->device, l.wave_mem, l.wave_capacity); l.wave_mem = nullptr; }
-    // per slot: sample 8 + thr_pix 16 + p 24 + dir_info 16 + hit 16 = 80 B; shadow queue 2 entries x 48 B; 3 slot queues
+    // per slot: record A 32 (sample, p) + record B 32 (thr_pix, dir_info) + hit 16 = 80 B; shadow queue 2 entries x 48 B; 3 slot queues
     const size_t bytes = (size_t)P * (8 + 16 + 24 + 16 + 16 + 96 + 4 + 4 + 4);
     l.wave_mem = wave_cache_take(s->device, P);
     if (!l.wave_mem) NGI_CUDA(cudaMalloc(&l.wave_mem, bytes));
@@ -761,14 +765,10 @@ int ensure_lane(Scene* s, Lane& l, unsigned P) {
 void carve_wave(Lane& l, NgiWaveParams& wp) {
     const size_t P = l.wave_capacity;
     unsigned char* p = (unsigned char*)l.wave_mem;
-    wp.thr_pix = (float4*)p; p += P * 16;
-    wp.dir_info = (float4*)p; p += P * 16;
+    wp.sa = (NgiSlotA*)p; p += P * 32;          // cudaMalloc'ed memory is 256-byte aligned: every record starts on a sector
+    wp.sb = (NgiSlotB*)p; p += P * 32;
     wp.hit = (float4*)p; p += P * 16;
     wp.shadow_q = (float4*)p; p += P * 96;
-    wp.sample = (unsigned long long*)p; p += P * 8;
-    wp.px = (double*)p; p += P * 8;
-    wp.py = (double*)p; p += P * 8;
-    wp.pz = (double*)p; p += P * 8;
     wp.extend_q = (unsigned*)p; p += P * 4;
     wp.surface_q = (unsigned*)p; p += P * 4;
     wp.regen_q = (unsigned*)p; p += P * 4;
@@ -876,7 +876,7 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         *l.counters_host = init;
         NGI_CUDA(cudaStreamWaitEvent(l.stream, ev0, 0));
         NGI_CUDA(cudaMemcpyAsync(l.counters, l.counters_host, sizeof(init), cudaMemcpyHostToDevice, l.stream));
-        NGI_CUDA(cudaMemsetAsync(wp.dir_info, 0, (size_t)P * 16, l.stream));   // every slot starts idle
+        NGI_CUDA(cudaMemsetAsync(wp.sb, 0, (size_t)P * 32, l.stream));         // every slot starts idle (dir_info.w = 0)
         if (!timed && (!l.graph_exec || !same_wp(l.graph_wp, wp) || l.graph_iters != kItersPerBatch)) {
             // the batch of kItersPerBatch iterations is captured once into a CUDA graph and replayed
             if (l.graph_exec) { cudaGraphExecDestroy(l.graph_exec); l.graph_exec = nullptr; }

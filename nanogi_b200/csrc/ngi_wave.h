@@ -27,12 +27,17 @@
 #define NGI_INFO_ALIVE 1u
 #define NGI_INFO_RR_SURVIVE 2u
 
+// Path state of one slot: two 32-byte records + the hit record. 32 bytes = one DRAM / L2 sector: the stage that (re)starts a
+// path writes whole sectors, so L2 never has to fetch a sector from HBM just to merge a partial write into it. (The first
+// layout was one array per field — sample, px, py, pz at 8 B, thr_pix and dir_info at 16 B. The eye stage writes only the
+// slots whose path ended, ~half of them in a random pattern, so nearly every sector it touched was written partially:
+// profiles/r01_ncu_c2_final.txt shows it READING 98 B from DRAM per entry — fills — and writing 155 B for 112 B of payload.)
+struct alignas(32) NgiSlotA { unsigned long long sample; double px, py, pz; };   // sample index (Philox counter), vertex position (fp64)
+struct alignas(32) NgiSlotB { float4 thr_pix; float4 dir_info; };                // throughput.xyz | pixel (or light prim) bits; extend-ray
+                                                                                 // direction.xyz | info bits (alive | rr_survive<<1 | numVertices<<8)
 struct NgiWaveParams {
-    // path state, SoA, one entry per slot
-    unsigned long long* sample;   // sample index (Philox counter)
-    float4* thr_pix;              // throughput.xyz, pixel index (int bits)
-    double* px; double* py; double* pz;   // current vertex position (fp64)
-    float4* dir_info;             // extend-ray direction.xyz, info bits (alive | rr_survive<<1 | numVertices<<8)
+    NgiSlotA* sa;
+    NgiSlotB* sb;
     float4* hit;                  // t, u, v, global triangle id (written by the extend kernel)
     // shadow queue: 3 x float4 per entry = (o.xyz, tmax) (d.xyz, pixel) (C.xyz, -)
     float4* shadow_q;
@@ -337,16 +342,18 @@ NGI_HD void ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const uns
     }
     if (!ok) return;
     const unsigned survive = (u01(ra[3]) > 0.5f) ? 0u : NGI_INFO_RR_SURVIVE;              // :583-587, decided up front
-    wp.sample[slot] = sample;
-    wp.thr_pix[slot] = make_float4(thr.x, thr.y, thr.z, u2f((unsigned)aux));
-    wp.px[slot] = px; wp.py[slot] = py; wp.pz[slot] = pz;
-    wp.dir_info[slot] = make_float4(wo.x, wo.y, wo.z, u2f(NGI_INFO_ALIVE | survive | ((unsigned)nverts << 8)));
+    NgiSlotA a; a.sample = sample; a.px = px; a.py = py; a.pz = pz;
+    NgiSlotB b;
+    b.thr_pix = make_float4(thr.x, thr.y, thr.z, u2f((unsigned)aux));
+    b.dir_info = make_float4(wo.x, wo.y, wo.z, u2f(NGI_INFO_ALIVE | survive | ((unsigned)nverts << 8)));
+    wp.sa[slot] = a;                                                                       // two whole sectors
+    wp.sb[slot] = b;
     out.extend = true;
 }
 
 template <bool GEN>
 NGI_HD int ngi_logic_classify(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
-    const float4 di = wp.dir_info[slot];
+    const float4 di = wp.sb[slot].dir_info;
     const unsigned info = f2u(di.w);
     if (!(info & NGI_INFO_ALIVE)) return NGI_CLASS_REGENERATE;
     const float4 h = wp.hit[slot];
@@ -361,7 +368,7 @@ NGI_HD int ngi_logic_classify(const NgiDevScene& sc, const NgiWaveParams& wp, co
             ngi_reconstruct(sc, tri, h.y, h.z, g);
             const f3 d = mk3(di.x, di.y, di.z);
             if (dot(g.sn, -d) > 0.0f) {
-                const float4 tp = wp.thr_pix[slot];
+                const float4 tp = wp.sb[slot].thr_pix;
                 ngi_film_add(wp.film, (int)f2u(tp.w), mk3(tp.x, tp.y, tp.z) * P.l_le * wp.film_scale);
             }
         }
@@ -375,7 +382,7 @@ NGI_HD int ngi_logic_classify(const NgiDevScene& sc, const NgiWaveParams& wp, co
             ngi_reconstruct(sc, tri, h.y, h.z, g);
             const f3 d = mk3(di.x, di.y, di.z);
             if (dot(g.sn, -d) > 0.0f) {
-                const float4 tp = wp.thr_pix[slot];
+                const float4 tp = wp.sb[slot].thr_pix;
                 ngi_film_add(wp.film, ngi_area_sensor_pixel(sc, tri, h.y, h.z, wp.width, wp.height),
                              mk3(tp.x, tp.y, tp.z) * sc.sensor.we * wp.film_scale);
             }
@@ -389,11 +396,11 @@ NGI_HD int ngi_logic_classify(const NgiDevScene& sc, const NgiWaveParams& wp, co
 
 template <bool GEN>
 NGI_HD void ngi_logic_surface(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot, NgiVertexOut& out) {
-    const float4 di = wp.dir_info[slot];
+    const float4 di = wp.sb[slot].dir_info;
     const unsigned info = f2u(di.w);
     const float4 h = wp.hit[slot];
     const f3 d = mk3(di.x, di.y, di.z);
-    const float4 tp = wp.thr_pix[slot];
+    const float4 tp = wp.sb[slot].thr_pix;
     // isect.geom.p = ray.o + ray.d * (double)tfar, rt.hpp:2197. In the reference ray.d is the fp64
     // direction whose fp32 ROUNDING was traced (rt.hpp:2169-2171): the reconstructed point is off the
     // traced ray by (d64 - d32) * t, which together with the absolute 1e-4 epsilon decides how often
@@ -402,9 +409,10 @@ NGI_HD void ngi_logic_surface(const NgiDevScene& sc, const NgiWaveParams& wp, co
     // is re-created as a uniform +-ulp/2 dither hashed from the hit record (tests/test_sim_parity.py).
     double ddx, ddy, ddz;
     ngi_dither_direction(d, h, ddx, ddy, ddz);
-    const double px = wp.px[slot] + ddx * (double)h.x;
-    const double py = wp.py[slot] + ddy * (double)h.x;
-    const double pz = wp.pz[slot] + ddz * (double)h.x;
+    const NgiSlotA sa = wp.sa[slot];
+    const double px = sa.px + ddx * (double)h.x;
+    const double py = sa.py + ddy * (double)h.x;
+    const double pz = sa.pz + ddz * (double)h.x;
     NgiGeom g;
     const int primIdx = ngi_reconstruct(sc, f2u(h.w), h.y, h.z, g);
     const int nverts = (int)(info >> 8) + 1;                                                  // :603
@@ -413,7 +421,7 @@ NGI_HD void ngi_logic_surface(const NgiDevScene& sc, const NgiWaveParams& wp, co
     const int type = P.type & ~NGI_EMITTER;                                                   // :601
     const int tex = (type & NGI_D) ? P.d_tex : P.g_tex;
     g.albedo = (tex >= 0 && sc.shade_uv) ? ngi_texture_at_hit(sc, tex, f2u(h.w), h.y, h.z) : ngi_constant_albedo(P, type);
-    ngi_vertex<NGI_VTX_SURFACE, GEN>(sc, wp, slot, wp.sample[slot], thr, (int)f2u(tp.w), nverts, type, g, -d /* :602 */, px, py, pz, primIdx,
+    ngi_vertex<NGI_VTX_SURFACE, GEN>(sc, wp, slot, sa.sample, thr, (int)f2u(tp.w), nverts, type, g, -d /* :602 */, px, py, pz, primIdx,
                                     mk3(0.0f), 0, 0, out);
 }
 
@@ -456,7 +464,7 @@ NGI_HD void ngi_logic_eye(const NgiDevScene& sc, const NgiWaveParams& wp, const 
                                             pd[0], pd[1], pd[2], ls.prim, ls.le, ls.l_type, ls.degenerate, out);
         }
     }
-    if (!out.extend) wp.dir_info[slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));           // idle slot
+    if (!out.extend) wp.sb[slot].dir_info = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));        // idle slot
 }
 
 // all three for one slot (the CPU simulator's order; the CUDA kernels regroup slots between the stages)
@@ -474,9 +482,10 @@ NGI_HD_NOINLINE void ngi_logic_step(const NgiDevScene& sc, const NgiWaveParams& 
 
 // ---- extend / shadow bodies (BVH8 = product path) -----------------------------------------------
 NGI_HD void ngi_extend_step(const NgiDevScene& sc, const NgiWaveParams& wp, const unsigned slot) {
-    const float4 di = wp.dir_info[slot];
+    const float4 di = wp.sb[slot].dir_info;
     if (!(f2u(di.w) & NGI_INFO_ALIVE)) return;
-    const f3 o = mk3((float)wp.px[slot], (float)wp.py[slot], (float)wp.pz[slot]);             // rt.hpp:2166-2168
+    const NgiSlotA sa = wp.sa[slot];
+    const f3 o = mk3((float)sa.px, (float)sa.py, (float)sa.pz);                               // rt.hpp:2166-2168
     NgiHitRec h;
     ngi_trace_bvh8<false>(sc.nodes8, sc.tris8, o, mk3(di.x, di.y, di.z), NGI_EPS_F, NGI_INF_F, h);   // rt.hpp:2246-2249
     wp.hit[slot] = make_float4(h.t, h.u, h.v, u2f(h.tri));

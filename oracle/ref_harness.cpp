@@ -42,7 +42,13 @@ namespace {
 thread_local std::string g_err;
 struct RefScene { nanogi::Scene scene; };
 bool g_logger_running = false;
-void ensure_logger() { if (!g_logger_running) { NGI_LOG_RUN(); g_logger_running = true; } }
+void ensure_logger() {
+    if (g_logger_running) return;
+    // the reference logs every loader step to std::cout; drop it unless NGI_REF_LOG is set (nothing else in a Python host uses cout)
+    if (!getenv("NGI_REF_LOG")) std::cout.rdbuf(nullptr);
+    NGI_LOG_RUN();
+    g_logger_running = true;
+}
 
 nanogi::SurfaceGeometry geom_from(const double* g, bool degenerated) {
     nanogi::SurfaceGeometry geom;

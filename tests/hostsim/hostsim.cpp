@@ -252,15 +252,15 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
     if (stats) std::fill(stats, stats + 4, 0.0);
     if (rp->max_num_vertices != -1 && rp->max_num_vertices < 2) return 0;
     const unsigned P = rp->wave_capacity ? rp->wave_capacity : 4096;
-    std::vector<unsigned long long> sample(P);
-    std::vector<float4> thr_pix(P), dir_info(P, make_float4(0, 0, 0, 0)), hit(P), shadow_q((size_t)P * 2 * 3);
-    std::vector<double> px(P), py(P), pz(P);
+    std::vector<float4> hit(P), shadow_q((size_t)P * 2 * 3);
+    std::vector<NgiSlotA> sa(P); std::vector<NgiSlotB> sb(P);
+    std::memset(sb.data(), 0, sizeof(NgiSlotB) * P);
     unsigned iter_counters[2] = {0, 0}, fetch_cursors[2] = {0, 0};
     std::vector<unsigned> extend_q(P);
     unsigned long long next_sample = (unsigned long long)rp->sample_offset;
     NgiWaveParams wp;
-    wp.sample = sample.data(); wp.thr_pix = thr_pix.data(); wp.px = px.data(); wp.py = py.data(); wp.pz = pz.data();
-    wp.dir_info = dir_info.data(); wp.hit = hit.data(); wp.shadow_q = shadow_q.data(); wp.iter_counters = iter_counters;
+    wp.sa = sa.data(); wp.sb = sb.data();
+    wp.hit = hit.data(); wp.shadow_q = shadow_q.data(); wp.iter_counters = iter_counters;
     wp.extend_q = extend_q.data(); wp.fetch_cursors = fetch_cursors;
     wp.next_sample = &next_sample; wp.film = film; wp.capacity = P; wp.renderer = rp->renderer; wp.max_verts = rp->max_num_vertices;
     wp.width = rp->width; wp.height = rp->height; wp.sample_end = (unsigned long long)(rp->sample_offset + rp->num_samples);

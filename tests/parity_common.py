@@ -156,7 +156,7 @@ def check_replay(backend, sd, renderer, n=20000, w=48, h=48, m=-1, seed=7, max_b
 
 
 # ---- statistical image parity (BASELINE north_star "Images") -------------------------------------------
-def check_image_statistics(backend, sd, renderer, w=32, h=32, spp=256, seeds=6, m=-1, block=8, z_max=5.5, **kw):
+def check_image_statistics(backend, sd, renderer, w=32, h=32, spp=256, seeds=6, m=-1, block=8, z_max=5.5, cpu_render=None, **kw):
     """K independent seeds per side; per-block means of (backend - oracle) within z_max sigma and the
     whole-image means within 4 sigma; relative RMSE against the pooled estimate agrees.
     The oracle runs in its counter-based mode (Philox keyed by seed and sample index, seeds disjoint from the
@@ -164,7 +164,10 @@ def check_image_statistics(backend, sd, renderer, w=32, h=32, spp=256, seeds=6, 
     z statistic (Student-t with ~2K-2 dof, heavy tailed for pt's light hits) crossed 4.5 about once in 10 runs."""
     orc = pyoracle.OracleScene(sd)
     n = w * h * spp
-    fo = np.stack([orc.render(renderer, n, w, h, max_num_vertices=m, seed=100 + s, rng_mode=1)[0] for s in range(seeds)])
+    if cpu_render is not None:      # e.g. the reference's own code (oracle/pyref.py) instead of the oracle port
+        fo = np.stack([cpu_render(n, 100 + s) for s in range(seeds)])
+    else:
+        fo = np.stack([orc.render(renderer, n, w, h, max_num_vertices=m, seed=100 + s, rng_mode=1)[0] for s in range(seeds)])
     fg = np.stack([film_and_stats(backend.render(renderer, n, w, h, max_num_vertices=m, seed=200 + s, **kw))[0] for s in range(seeds)])
     def blocks(f):
         k, hh, ww, c = f.shape

@@ -197,6 +197,19 @@ def test_image_statistics_c2(gpu_c2, cornell_spheres):
     pc.check_image_statistics(gpu_c2, cornell_spheres, "ptdirect", w=64, h=64, spp=128, seeds=8, m=-1, block=16)
 
 
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect", "ltdirect"])
+def test_image_statistics_against_the_reference_code(gpu_cornell, cornell, renderer):
+    """The GPU path against nanogi's OWN code (oracle/_ref: src/nanogi.cpp on stand-in libraries, one thread so that the run is
+    a deterministic function of the seed), not against the oracle port: block bias, image mean and clamped relRMSE."""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built")
+    ref = pyref.RefScene(scenes.cornell_box(), 1.0)
+    pc.check_image_statistics(gpu_cornell, cornell, renderer, w=32, h=32, spp=128, seeds=6, m=6, block=8,
+                              cpu_render=lambda n, seed: ref.render(renderer, n, 32, 32, max_num_vertices=6, seed=seed, num_threads=1))
+    ref.close()
+
+
 def test_sharding_and_wave_capacity(gpu_cornell):
     pc.check_sharding(gpu_cornell)
     a, sa = gpu_cornell.render("ptdirect", 100000, 32, 32, seed=4, wave_capacity=4096)

@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--scene", default="cornell_box")
     ap.add_argument("--renderer", default="pt")
     ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--width", type=int, default=0, help="with --height: a non-square image (both multiples of --block)")
+    ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--ref-spp", type=int, default=65536)
     ap.add_argument("--oracle-ref-spp", type=int, default=4096)
@@ -57,7 +59,9 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
     W = H = a.size
-    sd = scenes.to_scene_data(getattr(scenes, a.scene)(), 1.0)
+    if a.width and a.height:
+        W, H = a.width, a.height
+    sd = scenes.to_scene_data(getattr(scenes, a.scene)(), W / H)
     if os.environ.get("NGI_IMAGE_PARITY_BACKEND") == "sim":      # CPU dry run of this script (test-only simulator of the device code)
         from tests.hostsim import pysim
         gpu = pysim.SimScene(sd)
@@ -66,7 +70,7 @@ def main():
     orc = pyoracle.OracleScene(sd)
     from oracle import pyref
     use_ref = a.cpu_side == "reference" or (a.cpu_side == "auto" and pyref.available())
-    ref = pyref.RefScene(getattr(scenes, a.scene)(), 1.0) if use_ref else None
+    ref = pyref.RefScene(getattr(scenes, a.scene)(), W / H) if use_ref else None
 
     def cpu_render(n, seed):
         """an independent-seed CPU image: the reference's own multi-threaded Renderer::Render when oracle/_ref is there"""
