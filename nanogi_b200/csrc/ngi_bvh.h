@@ -168,6 +168,27 @@ NGI_HD unsigned ngi_sext_s8x4(unsigned x) {
 #endif
 }
 
+// Two plane distances with ONE instruction: sm_100's packed FFMA2 (PTX fma.rn.f32x2) computes (q0, q1) * s + b with the scale
+// and the offset as scalar operands; each half is an IEEE fma.rn, i.e. bit-identical to two fmaf(). The traversal kernels are
+// issue-bound (profiles/r01_ncu_c3_final.txt: 68 % issue slots, the node step is half of all issued instructions and 48 of its
+// ~260 instructions are these FMAs), so it removes 24 issue slots per node step — MEASURED AND REJECTED (default off): the
+// register pairs it needs push the 56-register kernel into spills (6 LDL + 6 STL per step) and k_extend got 2-3 % slower on C2 and
+// C3; at 64 registers (no spills, 32 instead of 36 warps per SM) 4 % slower (profiles/r01_sweep_ffma2.txt). The binding resource
+// is the ALU pipe (PRMT / FMNMX / mask assembly), which FFMA2 does not touch.
+#ifndef NGI_USE_FFMA2
+#define NGI_USE_FFMA2 0
+#endif
+NGI_HD void ngi_fma2(const float q0, const float q1, const float s, const float b, float& r0, float& r1) {
+#if defined(__CUDA_ARCH__) && NGI_USE_FFMA2
+    unsigned long long q, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(q0), "f"(q1));
+    asm("{\n\t.reg .b64 ss, bb;\n\tmov.b64 ss, {%2, %2};\n\tmov.b64 bb, {%3, %3};\n\tfma.rn.f32x2 %0, %1, ss, bb;\n\t}" : "=l"(r) : "l"(q), "f"(s), "f"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+#else
+    r0 = fmaf(q0, s, b); r1 = fmaf(q1, s, b);
+#endif
+}
+
 // per-ray constants of a BVH8 traversal
 struct NgiRayCtx {
     f3 o, d;
@@ -226,13 +247,21 @@ NGI_HD void ngi_bvh8_node_step(const uint4* __restrict__ nodes, const size_t ni,
         const unsigned ny = r.negy ? hiy : loy, fy = r.negy ? loy : hiy;
         const unsigned nz = r.negz ? hiz : loz, fz = r.negz ? loz : hiz;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float tnx = fmaf(ngi_q1(nx, i, one), sx, bx), tfx = fmaf(ngi_q1(fx, i, one), sx, bx);
-            const float tny = fmaf(ngi_q1(ny, i, one), sy, by), tfy = fmaf(ngi_q1(fy, i, one), sy, by);
-            const float tnz = fmaf(ngi_q1(nz, i, one), sz, bz), tfz = fmaf(ngi_q1(fz, i, one), sz, bz);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, limit));
-            if (tn <= tf) hitmask |= ngi_byte(child_bits4, i) << ngi_byte(bit_index4, i);   // empty slots have no bits
+        for (int i = 0; i < 4; i += 2) {
+            // children i and i + 1 together: six packed FMAs for the twelve plane distances
+            float tnx[2], tfx[2], tny[2], tfy[2], tnz[2], tfz[2];
+            ngi_fma2(ngi_q1(nx, i, one), ngi_q1(nx, i + 1, one), sx, bx, tnx[0], tnx[1]);
+            ngi_fma2(ngi_q1(fx, i, one), ngi_q1(fx, i + 1, one), sx, bx, tfx[0], tfx[1]);
+            ngi_fma2(ngi_q1(ny, i, one), ngi_q1(ny, i + 1, one), sy, by, tny[0], tny[1]);
+            ngi_fma2(ngi_q1(fy, i, one), ngi_q1(fy, i + 1, one), sy, by, tfy[0], tfy[1]);
+            ngi_fma2(ngi_q1(nz, i, one), ngi_q1(nz, i + 1, one), sz, bz, tnz[0], tnz[1]);
+            ngi_fma2(ngi_q1(fz, i, one), ngi_q1(fz, i + 1, one), sz, bz, tfz[0], tfz[1]);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const float tn = fmaxf(fmaxf(tnx[k], tny[k]), fmaxf(tnz[k], r.tmin));
+                const float tf = fminf(fminf(tfx[k], tfy[k]), fminf(tfz[k], limit));
+                if (tn <= tf) hitmask |= ngi_byte(child_bits4, i + k) << ngi_byte(bit_index4, i + k);   // empty slots have no bits
+            }
         }
     }
     ngroup.x = n1.x;
