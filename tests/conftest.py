@@ -26,6 +26,10 @@ def _built():
                                os.path.join(pkg, "host", "host_capi.cpp"), "-lz"])
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "liboracle.so"])
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "hostsim"), "-s", "libhostsim.so"])
+    # the reference's own sources on stand-in libraries (oracle/_ref): only where /root/reference exists; tests/test_reference_pin.py
+    # skips itself where it does not (the committed tests/golden/reference_films.npz still pins the oracle there)
+    if os.path.exists(os.path.join(REFERENCE, "src", "nanogi.cpp")) and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libnanogi_ref.so")):
+        subprocess.check_call(["bash", os.path.join(ROOT, "oracle", "build_ref.sh")], stdout=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")

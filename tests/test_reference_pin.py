@@ -18,7 +18,11 @@ from nanogi_b200 import capi, scenes
 from oracle import pyoracle, pyref
 from tests import parity_common as pc
 
-pytestmark = pytest.mark.skipif(not pyref.available(), reason="oracle/_ref not built (needs /root/reference at build time)")
+@pytest.fixture(autouse=True)
+def _need_ref(_built):
+    """checked at run time, after tests/conftest.py has had the chance to build oracle/_ref"""
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
 
 SCENES = {
     "cornell_box": (scenes.cornell_box, 8),                       # C1's scene and vertex cap
