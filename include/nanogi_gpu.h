@@ -1,5 +1,6 @@
 /*
- * nanogi_gpu.h — C ABI of the B200 (sm_100a) render module for nanogi's `pt` / `ptdirect` path.
+ * nanogi_gpu.h — C ABI of the B200 (sm_100a) render module for nanogi's `pt` / `ptdirect` path
+ * (widened to `lt` / `ltdirect`, E.area sensors and TexR textures: SURVEY.md §8f).
  *
  * This is the drop-in boundary. The reference has no formal plugin API; the
  * operator slot a GPU path can live behind is
@@ -38,7 +39,7 @@ typedef enum NgiStatus {
     NGI_ERR_INVALID_ARGUMENT = -1,
     NGI_ERR_NO_DEVICE = -2,       /* no CUDA device: the GPU path never falls back to the CPU   */
     NGI_ERR_CUDA = -3,
-    NGI_ERR_UNSUPPORTED = -4,     /* renderer / primitive kind outside the pt / ptdirect scope  */
+    NGI_ERR_UNSUPPORTED = -4,     /* renderer outside pt / ptdirect / lt / ltdirect (bdpt, ptmnee) */
     NGI_ERR_OUT_OF_MEMORY = -5
 } NgiStatus;
 
@@ -87,7 +88,8 @@ typedef struct NgiPrimitive {
     double e_vx[3], e_vy[3], e_vz[3]; /* E.Pinhole.Vx/Vy/Vz (rt.hpp:1898-1900)               */
     double e_fov;            /* vertical fov in RADIANS (rt.hpp:1897)                        */
     double e_aspect;         /* W/H from the CLI (src/nanogi.cpp:2069)                       */
-    double e_we[3];          /* parsed but unused by evaluation (rt.hpp:1895 vs :955-978)    */
+    double e_we[3];          /* E.Area.We (rt.hpp:947-953); the pinhole's We is parsed but unused
+                                by evaluation (rt.hpp:1895 vs :955-978)                        */
 } NgiPrimitive;
 
 /* Nearest-neighbour RGB texture, reference include/nanogi/rt.hpp:157-270 (row 0 = top after flip) */
@@ -119,7 +121,7 @@ typedef struct NgiSceneDesc {
 /* Renderer::Params, reference src/nanogi.cpp:85-97, plus the counter-based-RNG / shard fields */
 typedef struct NgiRenderParams {
     uint32_t struct_size;        /* = sizeof(NgiRenderParams)                                */
-    int32_t renderer;            /* NGI_RENDERER_PT | NGI_RENDERER_PTDIRECT                   */
+    int32_t renderer;            /* NGI_RENDERER_PT | _PTDIRECT | _LT | _LTDIRECT             */
     int64_t num_samples;         /* samples THIS call traces (the shard)                      */
     int64_t sample_offset;       /* first sample index of the shard                           */
     int64_t film_norm_samples;   /* N in film *= W*H/N (src/nanogi.cpp:436); 0 = no scaling   */
@@ -183,9 +185,11 @@ NGI_API int ngi_gpu_scene_create(const NgiSceneDesc* desc, int device, void** ou
 NGI_API int ngi_gpu_scene_info(void* scene, NgiSceneInfo* out);
 NGI_API void ngi_gpu_scene_destroy(void* scene);
 
-/* Replaces Renderer::Render + RenderProcess + ProcessSample_PT / ProcessSample_PTDirect,
- * reference src/nanogi.cpp:182-221, :225-440, :446-607, :609-802. Writes the film (scaled by
- * W*H/film_norm_samples) into caller HOST memory: float[W*H*3], row 0 = bottom. */
+/* Replaces Renderer::Render + RenderProcess + ProcessSample_PT / ProcessSample_PTDirect (and, on the same
+ * kernels, ProcessSample_LT / ProcessSample_LTDirect), reference src/nanogi.cpp:182-221, :225-440, :446-607,
+ * :609-802, :804-1131. Writes the film (scaled by W*H/film_norm_samples; 0 = raw sums, which is how a host
+ * accumulates several passes: --render-time, progress images, resume) into caller HOST memory:
+ * float[W*H*3], row 0 = bottom. */
 NGI_API int ngi_gpu_render(void* scene, const NgiRenderParams* params, float* film_rgb_host,
                            NgiRenderStats* out_stats);
 

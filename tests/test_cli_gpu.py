@@ -37,6 +37,19 @@ def test_cli_renders_like_the_c_abi(scene_file, tmp_path, renderer):
     assert np.allclose(img, film, rtol=1e-4, atol=1e-6 * film.max())
 
 
+def test_cli_multi_gpu_shards_sum_to_the_single_gpu_film(scene_file, tmp_path):
+    """--gpus 2 (one host thread per device, samples sharded by index, films added on the host): the same sample set as one GPU."""
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    n = 1 << 24
+    one, two = tmp_path / "one.pfm", tmp_path / "two.pfm"
+    assert run("ptdirect", scene_file, one, 64, 64, "-n", n, "-m", 8, "--seed", 13)[0] == 0
+    rc, log = run("ptdirect", scene_file, two, 64, 64, "-n", n, "-m", 8, "--seed", 13, "--gpus", 2)
+    assert rc == 0, log
+    a, b = capi.load_image(str(one)), capi.load_image(str(two))
+    assert np.allclose(a, b, rtol=2e-3, atol=1e-5 * a.max())
+
+
 def test_cli_unsupported_renderers_fail_loudly(scene_file, tmp_path):
     for r in ("bdpt", "ptmnee"):
         rc, log = run(r, scene_file, tmp_path / "x.hdr", 16, 16, "-n", 100)
