@@ -4,6 +4,7 @@
     python tools/ncu_summary.py launches gpurun_out/launches_<tag>.csv  > profiles/<round>_launches_<tag>.txt
     python tools/ncu_summary.py full     gpurun_out/prof_<tag>.ncu-rep  > profiles/<round>_ncu_<tag>.txt
     python tools/ncu_summary.py source   gpurun_out/prof_<tag>.ncu-rep <kernel-id> [top]   (hot SASS/source lines)
+    python tools/ncu_summary.py blocks   gpurun_out/prof_<tag>.ncu-rep <kernel name>        (issue share / active lanes per basic block)
 """
 import collections
 import csv
@@ -108,11 +109,63 @@ def source(path, kid, top=40):
         print(f"{int(r[s].replace(',', '')) / tot * 100:5.1f}%  {r[0][:14]:14s} {r[1][:110]}")
 
 
+def blocks(path, kernel, min_share=0.004):
+    """Basic-block profile of one kernel from the source page of an `--import-source on` capture: for every run of SASS
+    instructions with the same execution count, its share of all issued warp instructions, the average number of active
+    lanes, its share of the stall samples and its opcode mix. This is what tells which PHASE of the persistent traversal loop
+    (fetch / node step / triangle test / pop) the issue slots go to and how full its warps are."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-kernel-base", "function"], capture_output=True, text=True).stdout
+    tables, cur = [], None
+    for ln in out.splitlines():
+        if ln.startswith('"Kernel Name"'):
+            cur = {"name": ln, "rows": []}
+            tables.append(cur)
+        elif cur is not None:
+            cur["rows"].append(ln)
+    for t in tables:
+        if kernel not in t["name"]:
+            continue
+        rows = list(csv.reader(io.StringIO("\n".join(t["rows"]))))
+        hdr = rows[0]
+        ix = {h: i for i, h in enumerate(hdr)}
+        body = [r for r in rows[1:] if len(r) == len(hdr)]
+
+        def num(x):
+            try:
+                return float(x.replace(",", ""))
+            except ValueError:
+                return 0.0
+        tot_i = sum(num(r[ix["Instructions Executed"]]) for r in body)
+        tot_t = sum(num(r[ix["Thread Instructions Executed"]]) for r in body)
+        print(f"# {path}: {t['name']}  ({len(body)} SASS instructions)")
+        print(f"# warp instructions {tot_i:.4g}, thread instructions {tot_t:.4g}, average active lanes {tot_t / max(tot_i, 1):.2f}")
+        blks = []
+        for r in body:
+            ie, te, sm = num(r[ix["Instructions Executed"]]), num(r[ix["Thread Instructions Executed"]]), num(r[ix["# Samples"]])
+            op = r[1].split()[0] if r[1].split() else ""
+            if blks and blks[-1]["ie"] == ie and not r[1].strip().startswith(("BRA", "@")):
+                b = blks[-1]; b["n"] += 1; b["te"] += te; b["sm"] += sm; b["last"] = r[0]; b["ops"].append(op)
+            else:
+                blks.append({"first": r[0], "last": r[0], "ie": ie, "n": 1, "te": te, "sm": sm, "ops": [op]})
+        tot_s = sum(b["sm"] for b in blks) or 1
+        print(f"{'addresses':13s} {'instr':>5s} {'executed':>10s} {'issue share':>11s} {'lanes':>6s} {'samples':>8s}  opcode mix")
+        for b in blks:
+            w = b["ie"] * b["n"]
+            if w / max(tot_i, 1) < min_share:
+                continue
+            mix = collections.Counter(o.split(".")[0] for o in b["ops"]).most_common(6)
+            print(f"{b['first'][-5:]}-{b['last'][-5:]:7s} {b['n']:5d} {b['ie']:10.4g} {100 * w / tot_i:10.1f}% {b['te'] / max(w, 1):6.1f} {100 * b['sm'] / tot_s:7.1f}%  "
+                  + " ".join(f"{k}:{v}" for k, v in mix))
+        return
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "launches":
         launches(sys.argv[2])
     elif mode == "full":
         full(sys.argv[2])
+    elif mode == "blocks":
+        blocks(sys.argv[2], sys.argv[3])
     else:
         source(*sys.argv[2:])
