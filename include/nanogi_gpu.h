@@ -59,7 +59,7 @@ enum { NGI_E_AREA = 0, NGI_E_PINHOLE = 1 };
 enum { NGI_S_REFLECTION = 0, NGI_S_REFRACTION = 1, NGI_S_FRESNEL = 2 };
 /* reference src/nanogi.cpp:51-69. pt / ptdirect are the hot path; lt / ltdirect (src/nanogi.cpp:804-1131) run on the
  * same wavefront machinery. bdpt / ptmnee are not accepted. */
-enum { NGI_RENDERER_PT = 0, NGI_RENDERER_PTDIRECT = 1, NGI_RENDERER_LT = 2, NGI_RENDERER_LTDIRECT = 3 };
+enum { NGI_RENDERER_PT = 0, NGI_RENDERER_PTDIRECT = 1, NGI_RENDERER_LT = 2, NGI_RENDERER_LTDIRECT = 3, NGI_RENDERER_BDPT = 4 };
 
 /*
  * One scene primitive = mesh range + material + emitter parameters.

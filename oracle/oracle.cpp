@@ -919,6 +919,11 @@ struct MtSampler {
     d2 light_pos(int) { return Next2D(); }
     void dir_ucomp(int, d2& u, double& uc) { uc = Next(); u = Next2D(); }
     double rr(int) { return Next(); }
+    // bdpt subpaths (kind 0 = light subpath, 1 = eye subpath): plain sequential draws in the reference's call order
+    double bd_emitter_pick(int) { return Next(); }
+    d2 bd_emitter_pos(int) { return Next2D(); }
+    void bd_dir_ucomp(int, int, d2& u, double& uc) { uc = Next(); u = Next2D(); }
+    double bd_rr(int, int) { return Next(); }
 };
 
 // Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11)
@@ -963,6 +968,17 @@ struct PhiloxSampler {
     double light_pick(int v) { blockB(v); return u01_24(b[0]); }
     d2 light_pos(int v) { blockB(v); d2 r; r.x = u01_24(b[1]); r.y = u01_24(b[2]); return r; }
     void dir_ucomp(int v, d2& u, double& uc) { blockA(v); u.x = u01_24(a[0]); u.y = u01_24(a[1]); uc = u01_24(a[2]); }
+    // bdpt: the light subpath uses block 1 (emitter) and block 0 (directions, RR) like lt; the eye subpath block 2 (emitter)
+    // and block 3 (directions, RR) — the two subpaths of one sample index must not share uniforms
+    uint32_t d4[4] = {0, 0, 0, 0};
+    void blockD(int v) { uint32_t c[4] = {(uint32_t)sample, (uint32_t)((uint64_t)sample >> 32), (uint32_t)v, 3u}; philox4x32_10(c, key, d4); }
+    double bd_emitter_pick(int kind) { return kind == 0 ? light_pick(0) : sensor_pick(0); }
+    d2 bd_emitter_pos(int kind) { return kind == 0 ? light_pos(0) : sensor_pos(0); }
+    void bd_dir_ucomp(int kind, int v, d2& u, double& uc) {
+        if (kind == 0) { dir_ucomp(v, u, uc); return; }
+        blockD(v); u.x = u01_24(d4[0]); u.y = u01_24(d4[1]); uc = u01_24(d4[2]);
+    }
+    double bd_rr(int kind, int v) { if (kind == 0) return rr(v); blockD(v); return u01_24(d4[3]); }
     double rr(int v) { blockA(v); return u01_24(a[3]); }
 };
 
@@ -1213,6 +1229,211 @@ void ProcessSample_LTDirect(const Scene& scene, const RenderParams& Params, S& r
 }
 
 // ---------------------------------------------------------------------------------------------
+// bdpt — include/nanogi/bdpt.hpp:38-539 (PathVertex, Path) and ProcessSample_BDPT, src/nanogi.cpp:1133-1186.
+// SURVEY §8f row 4 ("then bdpt"). Restated function by function; the weight actually used by the reference is
+// EvaluatePowerHeuristicsMISWeightOpt (bdpt.hpp:184), the O(n) per-strategy EvaluatePDF products.
+// ---------------------------------------------------------------------------------------------
+struct PathVertex { int type = 0; SurfaceGeometry geom; const Primitive* primitive = nullptr; };   // bdpt.hpp:38-43
+
+struct Path {
+    std::vector<PathVertex> vertices;
+
+    // bdpt.hpp:54-123
+    template <class S>
+    void SampleSubpath(const Scene& scene, S& rng, int kind, TransportDirection transDir, int maxPathVertices, Counters& cnt) {
+        PathVertex v;
+        vertices.clear();
+        for (int step = 0; maxPathVertices == -1 || step < maxPathVertices; step++) {
+            if (step == 0) {
+                const int type = transDir == LE ? NGI_TYPE_L : NGI_TYPE_E;
+                const Primitive* emitter = scene.SampleEmitter(type, rng.bd_emitter_pick(kind));     // :63
+                v.primitive = emitter;
+                v.type = type;
+                emitter->SamplePosition(rng.bd_emitter_pos(kind), v.geom);                            // :66
+                vertices.push_back(v);
+            } else {
+                const PathVertex* pv = &vertices.back();
+                const PathVertex* ppv = vertices.size() > 1 ? &vertices[vertices.size() - 2] : nullptr;
+                d3 wo;
+                const d3 wi = ppv ? normalize(ppv->geom.p - pv->geom.p) : d3();                       // :77
+                d2 u; double uc; rng.bd_dir_ucomp(kind, step - 1, u, uc);
+                pv->primitive->SampleDirection(u, uc, pv->type, pv->geom, wi, wo);                    // :78
+                const d3 f = pv->primitive->EvaluateDirection(pv->geom, pv->type, wi, wo, transDir, true);   // :81
+                if (is_zero(f)) break;
+                Ray ray{pv->geom.p, wo};
+                Intersection isect;
+                cnt.extend++;
+                if (!Intersect(scene, ray, isect)) break;                                             // :92
+                v.geom = isect.geom;                                                                  // :100-102
+                v.primitive = isect.Prim;
+                v.type = isect.Prim->Type & ~NGI_TYPE_EMITTER;
+                const double rrProb = 0.5;                                                            // :108-113
+                if (rng.bd_rr(kind, step - 1) > rrProb) { vertices.push_back(v); break; }
+                vertices.push_back(v);
+            }
+        }
+    }
+
+    // bdpt.hpp:125-177
+    bool Connect(const Scene& scene, int s, int t, const Path& subpathL, const Path& subpathE, Counters& cnt) {
+        vertices.clear();
+        if (s == 0 && t > 0) {
+            if ((subpathE.vertices[t - 1].primitive->Type & NGI_TYPE_L) == 0) return false;
+            for (int i = t - 1; i >= 0; i--) vertices.push_back(subpathE.vertices[i]);
+            vertices.front().type = NGI_TYPE_L;
+        } else if (s > 0 && t == 0) {
+            if ((subpathL.vertices[s - 1].primitive->Type & NGI_TYPE_E) == 0) return false;
+            for (int i = 0; i < s; i++) vertices.push_back(subpathL.vertices[i]);
+            vertices.back().type = NGI_TYPE_E;
+        } else {
+            cnt.shadow++;
+            if (!Visible(scene, subpathL.vertices[s - 1].geom.p, subpathE.vertices[t - 1].geom.p)) return false;
+            for (int i = 0; i < s; i++) vertices.push_back(subpathL.vertices[i]);
+            for (int i = t - 1; i >= 0; i--) vertices.push_back(subpathE.vertices[i]);
+        }
+        return true;
+    }
+
+    d3 dirTo(int from, int to) const { return normalize(vertices[to].geom.p - vertices[from].geom.p); }
+
+    // bdpt.hpp:187-205
+    double SelectionProb(int s) const {
+        const double rrProb = 0.5;
+        const int n = (int)vertices.size();
+        const int t = n - s;
+        double selectionProb = 1;
+        for (int i = 1; i < s - 1; i++) selectionProb *= rrProb;
+        for (int i = t - 2; i >= 1; i--) selectionProb *= rrProb;
+        return selectionProb;
+    }
+    // bdpt.hpp:207-215
+    d2 RasterPosition() const {
+        const PathVertex& v = vertices[vertices.size() - 1];
+        d2 rasterPos;
+        v.primitive->RasterPosition(dirTo((int)vertices.size() - 1, (int)vertices.size() - 2), v.geom, rasterPos);
+        return rasterPos;
+    }
+    // bdpt.hpp:217-250
+    d3 EvaluateCst(int s) const {
+        const int n = (int)vertices.size();
+        const int t = n - s;
+        d3 cst;
+        if (s == 0 && t > 0) {
+            const PathVertex& v = vertices[0];
+            cst = v.primitive->EvaluatePosition(v.geom, false) * v.primitive->EvaluateDirection(v.geom, v.type, d3(), dirTo(0, 1), EL, false);
+        } else if (s > 0 && t == 0) {
+            const PathVertex& v = vertices[n - 1];
+            cst = v.primitive->EvaluatePosition(v.geom, false) * v.primitive->EvaluateDirection(v.geom, v.type, d3(), dirTo(n - 1, n - 2), LE, false);
+        } else if (s > 0 && t > 0) {
+            const PathVertex* vL = &vertices[s - 1];
+            const PathVertex* vE = &vertices[s];
+            const d3 fsL = vL->primitive->EvaluateDirection(vL->geom, vL->type, s - 2 >= 0 ? dirTo(s - 1, s - 2) : d3(), dirTo(s - 1, s), LE, false);
+            const d3 fsE = vE->primitive->EvaluateDirection(vE->geom, vE->type, s + 1 < n ? dirTo(s, s + 1) : d3(), dirTo(s, s - 1), EL, false);
+            const double G = GeometryTerm(vL->geom, vE->geom);
+            cst = fsL * G * fsE;
+        }
+        return cst;
+    }
+    static d3 LocalContrb(const d3& f, double p) { return is_zero(f) ? d3() : f / p; }   // bdpt.hpp:258-263
+    // bdpt.hpp:252-343
+    d3 EvaluateUnweightContribution(const Scene& scene, int s) const {
+        const int n = (int)vertices.size();
+        const int t = n - s;
+        d3 alphaL;
+        if (s == 0) alphaL = d3(1);
+        else {
+            const PathVertex& v0 = vertices[0];
+            alphaL = LocalContrb(v0.primitive->EvaluatePosition(v0.geom, true), v0.primitive->EvaluatePositionPDF(v0.geom, true) * scene.EvaluateEmitterPDF(v0.primitive));
+            for (int i = 0; i < s - 1; i++) {
+                const PathVertex* v = &vertices[i];
+                const d3 wi = i >= 1 ? dirTo(i, i - 1) : d3();
+                const d3 wo = dirTo(i, i + 1);
+                alphaL = alphaL * LocalContrb(v->primitive->EvaluateDirection(v->geom, v->type, wi, wo, LE, true), v->primitive->EvaluateDirectionPDF(v->geom, v->type, wi, wo, true));
+            }
+        }
+        if (is_zero(alphaL)) return d3();
+        d3 alphaE;
+        if (t == 0) alphaE = d3(1);
+        else {
+            const PathVertex& vn = vertices[n - 1];
+            alphaE = LocalContrb(vn.primitive->EvaluatePosition(vn.geom, true), vn.primitive->EvaluatePositionPDF(vn.geom, true) * scene.EvaluateEmitterPDF(vn.primitive));
+            for (int i = n - 1; i > s; i--) {
+                const PathVertex* v = &vertices[i];
+                const d3 wi = i < n - 1 ? dirTo(i, i + 1) : d3();
+                const d3 wo = dirTo(i, i - 1);
+                alphaE = alphaE * LocalContrb(v->primitive->EvaluateDirection(v->geom, v->type, wi, wo, EL, true), v->primitive->EvaluateDirectionPDF(v->geom, v->type, wi, wo, true));
+            }
+        }
+        if (is_zero(alphaE)) return d3();
+        const d3 cst = EvaluateCst(s);
+        if (is_zero(cst)) return d3();
+        return alphaL * cst * alphaE;
+    }
+    // bdpt.hpp:491-535
+    double EvaluatePDF(const Scene& scene, int s) const {
+        if (is_zero(EvaluateCst(s))) return 0;
+        double pdf = 1;
+        const int n = (int)vertices.size();
+        const int t = n - s;
+        if (s > 0) {
+            pdf *= vertices[0].primitive->EvaluatePositionPDF(vertices[0].geom, true) * scene.EvaluateEmitterPDF(vertices[0].primitive);
+            for (int i = 0; i < s - 1; i++) {
+                const PathVertex* vi = &vertices[i];
+                pdf *= vi->primitive->EvaluateDirectionPDF(vi->geom, vi->type, i - 1 >= 0 ? dirTo(i, i - 1) : d3(), dirTo(i, i + 1), true);
+                pdf *= GeometryTerm(vi->geom, vertices[i + 1].geom);
+            }
+        }
+        if (t > 0) {
+            pdf *= vertices[n - 1].primitive->EvaluatePositionPDF(vertices[n - 1].geom, true) * scene.EvaluateEmitterPDF(vertices[n - 1].primitive);
+            for (int i = n - 1; i >= s + 1; i--) {
+                const PathVertex* vi = &vertices[i];
+                pdf *= vi->primitive->EvaluateDirectionPDF(vi->geom, vi->type, i + 1 < n ? dirTo(i, i + 1) : d3(), dirTo(i, i - 1), true);
+                pdf *= GeometryTerm(vi->geom, vertices[i - 1].geom);
+            }
+        }
+        return pdf;
+    }
+    // bdpt.hpp:362-380
+    double EvaluatePowerHeuristicsMISWeightOpt(const Scene& scene, int s) const {
+        double invWeight = 0;
+        const int n = (int)vertices.size();
+        const double ps = EvaluatePDF(scene, s);
+        for (int i = 0; i <= n; i++) {
+            const double pi = EvaluatePDF(scene, i);
+            if (pi > 0) { const double r = pi / ps; invWeight += r * r; }
+        }
+        return 1.0 / invWeight;
+    }
+    // bdpt.hpp:181-185
+    d3 EvaluateContribution(const Scene& scene, int s) const {
+        const d3 Cstar = EvaluateUnweightContribution(scene, s);
+        return is_zero(Cstar) ? d3() : Cstar * EvaluatePowerHeuristicsMISWeightOpt(scene, s);
+    }
+};
+
+// ProcessSample_BDPT — src/nanogi.cpp:1133-1186
+template <class S>
+void ProcessSample_BDPT(const Scene& scene, const RenderParams& Params, S& rng, std::vector<d3>& film, Counters& cnt) {
+    if (scene.LightPrimitiveIndices.empty()) return;
+    Path subpathL, subpathE, path;
+    subpathL.SampleSubpath(scene, rng, 0, LE, Params.MaxNumVertices, cnt);                // :1137
+    subpathE.SampleSubpath(scene, rng, 1, EL, Params.MaxNumVertices, cnt);                // :1138
+    const int nL = (int)subpathL.vertices.size(), nE = (int)subpathE.vertices.size();
+    for (int n = 2; n <= nE + nL; n++) {                                                   // :1148
+        if (Params.MaxNumVertices != -1 && n > Params.MaxNumVertices) continue;
+        const int minS = std::max(0, n - nE), maxS = std::min(nL, n);
+        for (int s = minS; s <= maxS; s++) {
+            const int t = n - s;
+            if (!path.Connect(scene, s, t, subpathL, subpathE, cnt)) continue;             // :1164
+            const d3 C = path.EvaluateContribution(scene, s) / path.SelectionProb(s);      // :1172
+            if (is_zero(C)) continue;
+            const int px = PixelIndex(path.RasterPosition(), Params.Width, Params.Height); // :1180
+            film[px] = film[px] + C;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Scene construction: the loader-side derivations of include/nanogi/rt.hpp:1606-1615 (sensor =
 // last E primitive, light list), :1747-1765 (area CDF), :2067-2073 (directional disk)
 // ---------------------------------------------------------------------------------------------
@@ -1310,7 +1531,8 @@ void RenderProcess(const Scene& scene, int renderer, const RenderParams& Params,
                 if (renderer == NGI_RENDERER_PT) ProcessSample_PT(scene, Params, rng, film, cnts[slot]);
                 else if (renderer == NGI_RENDERER_PTDIRECT) ProcessSample_PTDirect(scene, Params, rng, film, cnts[slot]);
                 else if (renderer == NGI_RENDERER_LT) ProcessSample_LT(scene, Params, rng, film, cnts[slot]);
-                else ProcessSample_LTDirect(scene, Params, rng, film, cnts[slot]);
+                else if (renderer == NGI_RENDERER_LTDIRECT) ProcessSample_LTDirect(scene, Params, rng, film, cnts[slot]);
+                else ProcessSample_BDPT(scene, Params, rng, film, cnts[slot]);
             }
         }
     };
@@ -1351,7 +1573,7 @@ __attribute__((visibility("default"))) int oracle_render(void* s, int renderer, 
                                                           uint64_t seed, int rng_mode, int num_threads, double* film, double* stats) {
     Scene* sc = (Scene*)s;
     if (!sc || !film || width <= 0 || height <= 0 || num_samples < 0) { g_err = "invalid argument"; return -1; }
-    if (renderer < NGI_RENDERER_PT || renderer > NGI_RENDERER_LTDIRECT) { g_err = "renderer not supported (pt, ptdirect, lt, ltdirect)"; return -4; }
+    if (renderer < NGI_RENDERER_PT || renderer > NGI_RENDERER_BDPT) { g_err = "renderer not supported (pt, ptdirect, lt, ltdirect, bdpt)"; return -4; }
     if (sc->SensorPrimitiveIndex == (size_t)-1) { g_err = "scene has no sensor"; return -1; }
     if (num_threads <= 0) num_threads = std::max(1, (int)std::thread::hardware_concurrency() + num_threads);  // src/nanogi.cpp:149-152
     RenderParams P{width, height, max_num_vertices};

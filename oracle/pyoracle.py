@@ -89,7 +89,7 @@ class OracleScene:
     def render(self, renderer, num_samples, width, height, max_num_vertices=-1, seed=1, rng_mode=0, num_threads=0,
                sample_offset=0, film_norm_samples=None):
         """Returns (film float64 [H, W, 3] row 0 = bottom, stats dict)."""
-        r = {"pt": 0, "ptdirect": 1, "lt": 2, "ltdirect": 3}[renderer] if isinstance(renderer, str) else int(renderer)
+        r = {"pt": 0, "ptdirect": 1, "lt": 2, "ltdirect": 3, "bdpt": 4}[renderer] if isinstance(renderer, str) else int(renderer)
         film = np.zeros((height, width, 3), np.float64)
         stats = np.zeros(4, np.float64)
         norm = num_samples if film_norm_samples is None else film_norm_samples

@@ -89,7 +89,7 @@ class RefScene:
     def render(self, renderer, num_samples, width, height, max_num_vertices=-1, seed=1, num_threads=1):
         """Renderer::Render. `seed` is what std::time(nullptr) returns to the reference's master RNG (src/nanogi.cpp:190).
         Returns the film float64 [H, W, 3], row 0 = bottom."""
-        r = {"pt": 0, "ptdirect": 1, "lt": 2, "ltdirect": 3}[renderer] if isinstance(renderer, str) else int(renderer)
+        r = {"pt": 0, "ptdirect": 1, "lt": 2, "ltdirect": 3, "bdpt": 4}[renderer] if isinstance(renderer, str) else int(renderer)
         film = np.zeros((height, width, 3), np.float64)
         if self.L.ref_render(self.h, r, int(num_samples), int(max_num_vertices), int(width), int(height), int(num_threads), int(seed), film.ctypes.data) != 0:
             raise RuntimeError("ref_render: " + self.L.ref_last_error().decode())

@@ -91,7 +91,7 @@ REF_API int ref_render(void* h, int renderer, long long num_samples, int max_num
                        long long seed, double* film_out) {
     ensure_logger();
     const nanogi::Scene& sc = ((RefScene*)h)->scene;
-    if (renderer < 0 || renderer > 3) { g_err = "renderer must be pt / ptdirect / lt / ltdirect"; return -1; }
+    if (renderer < 0 || renderer > 4) { g_err = "renderer must be pt / ptdirect / lt / ltdirect / bdpt"; return -1; }
     Renderer r;
     r.Type = (RendererType)renderer;
     r.NumThreads = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();

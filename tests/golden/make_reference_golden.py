@@ -35,7 +35,7 @@ def main():
     out = {"meta": np.array([N, W, H, SEED])}
     for name, (make, m) in SCENES.items():
         ref = pyref.RefScene(make(), W / H)
-        for renderer in ("pt", "ptdirect", "lt", "ltdirect"):
+        for renderer in ("pt", "ptdirect", "lt", "ltdirect", "bdpt"):
             f = ref.render(renderer, N, W, H, max_num_vertices=m, seed=SEED, num_threads=1)
             out[f"film_{name}_{renderer}"] = f
             print(name, renderer, "mean", float(f.mean()))

@@ -32,7 +32,7 @@ SCENES = {
     "cornell_textured": (scenes.cornell_textured, -1),            # D.TexR / G.TexR through the reference's Texture::Load / Evaluate
     "furnace": (lambda: scenes.furnace(0.5, 1.0), 5),             # six [L, D] walls: uniform light pick over 6 lights
 }
-RENDERERS = ["pt", "ptdirect", "lt", "ltdirect"]
+RENDERERS = ["pt", "ptdirect", "lt", "ltdirect", "bdpt"]
 
 
 @pytest.fixture(scope="module", params=sorted(SCENES))
