@@ -24,8 +24,8 @@ TYPE_D, TYPE_G, TYPE_S, TYPE_L, TYPE_E = 1, 2, 4, 8, 16
 L_AREA, L_POINT, L_DIRECTIONAL = 0, 1, 2
 E_AREA, E_PINHOLE = 0, 1
 S_REFLECTION, S_REFRACTION, S_FRESNEL = 0, 1, 2
-RENDERER_PT, RENDERER_PTDIRECT, RENDERER_LT, RENDERER_LTDIRECT = 0, 1, 2, 3
-RENDERERS = {"pt": RENDERER_PT, "ptdirect": RENDERER_PTDIRECT, "lt": RENDERER_LT, "ltdirect": RENDERER_LTDIRECT}
+RENDERER_PT, RENDERER_PTDIRECT, RENDERER_LT, RENDERER_LTDIRECT, RENDERER_BDPT = 0, 1, 2, 3, 4
+RENDERERS = {"pt": RENDERER_PT, "ptdirect": RENDERER_PTDIRECT, "lt": RENDERER_LT, "ltdirect": RENDERER_LTDIRECT, "bdpt": RENDERER_BDPT}
 RENDER_TIME_KERNELS = 1  # NGI_RENDER_TIME_KERNELS
 RENDER_PER_RAY_TRACE = 2  # NGI_RENDER_PER_RAY_TRACE
 NO_HIT = 0xFFFFFFFF

@@ -28,6 +28,7 @@
 #include "ngi_bvh.h"
 #include "ngi_scene_host.h"
 #include "ngi_wave.h"
+#include "ngi_bdpt.h"
 #include "ngi_trace_warp.cuh"
 
 namespace {
@@ -325,6 +326,20 @@ __global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_eye(NgiDevScen
         if (need[0]) ngi_write_shadow(wp, idx[0], out);
         if (need[1]) wp.extend_q[idx[1]] = slot;
     }
+}
+
+// bdpt (ngi_bdpt.h): one sample per thread, subpaths in local memory; rays counted per block
+__global__ void __launch_bounds__(128) k_bdpt(NgiDevScene sc, NgiBdParams bp, unsigned long long first, unsigned long long count,
+                                              unsigned long long* __restrict__ ray_counters /* [0] extend, [1] shadow */) {
+    NgiBdVertex VL[NGI_BD_MAX_VERTS], VE[NGI_BD_MAX_VERTS];
+    NgiBdCounters cnt; cnt.extend = 0; cnt.shadow = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < count; i += (unsigned long long)gridDim.x * blockDim.x)
+        ngi_bdpt_sample(sc, bp, first + i, VL, VE, cnt);
+    for (int off = 16; off > 0; off >>= 1) {
+        cnt.extend += __shfl_xor_sync(0xFFFFFFFFu, cnt.extend, off);
+        cnt.shadow += __shfl_xor_sync(0xFFFFFFFFu, cnt.shadow, off);
+    }
+    if ((threadIdx.x & 31u) == 0u) { atomicAdd(ray_counters + 0, cnt.extend); atomicAdd(ray_counters + 1, cnt.shadow); }
 }
 
 // Scene::Intersect's ray query (rt.hpp:2162-2182) for the compacted extend queue of this iteration
@@ -824,8 +839,8 @@ int launch_iteration(Scene* s, Lane& l, bool timed, size_t& ev_used, bool per_ra
 
 int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream_t st, NgiRenderStats* stats) {
     if (rp->struct_size != sizeof(NgiRenderParams)) return set_err(NGI_ERR_INVALID_ARGUMENT, "NgiRenderParams.struct_size mismatch (ABI)");
-    if (rp->renderer < NGI_RENDERER_PT || rp->renderer > NGI_RENDERER_LTDIRECT)
-        return set_err(NGI_ERR_UNSUPPORTED, "renderer not supported by this build (pt, ptdirect, lt and ltdirect are on the GPU path)");
+    if (rp->renderer < NGI_RENDERER_PT || rp->renderer > NGI_RENDERER_BDPT)
+        return set_err(NGI_ERR_UNSUPPORTED, "renderer not supported by this build (pt, ptdirect, lt, ltdirect and bdpt are on the GPU path)");
     const bool has_shadow = rp->renderer == NGI_RENDERER_PTDIRECT || rp->renderer == NGI_RENDERER_LTDIRECT;
     if (rp->width <= 0 || rp->height <= 0 || rp->num_samples < 0 || rp->sample_offset < 0) return set_err(NGI_ERR_INVALID_ARGUMENT, "invalid width/height/num_samples");
     const size_t npx = (size_t)rp->width * rp->height;
@@ -835,6 +850,35 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         // MaxNumVertices <= 1: the loop exits before the first direction is sampled (src/nanogi.cpp:485)
         NGI_CUDA(cudaStreamSynchronize(st));
         if (stats) stats->paths = (uint64_t)rp->num_samples;
+        return NGI_OK;
+    }
+    if (rp->renderer == NGI_RENDERER_BDPT) {
+        // one thread per sample (ngi_bdpt.h): no wavefront state, a single launch over the shard
+        NgiBdParams bp;
+        bp.film = film_dev; bp.width = rp->width; bp.height = rp->height; bp.max_verts = rp->max_num_vertices;
+        bp.seed_lo = (unsigned)rp->seed; bp.seed_hi = (unsigned)(rp->seed >> 32);
+        bp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
+        unsigned long long* d_cnt = nullptr;
+        NGI_CUDA(ngi_dmalloc((void**)&d_cnt, 2 * sizeof(unsigned long long), st));
+        NGI_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+        cudaEvent_t e0, e1;
+        NGI_CUDA(cudaEventCreate(&e0)); NGI_CUDA(cudaEventCreate(&e1));
+        NGI_CUDA(cudaEventRecord(e0, st));
+        const unsigned grid = (unsigned)std::min<unsigned long long>(((unsigned long long)rp->num_samples + 127ull) / 128ull, 148ull * 64ull);
+        k_bdpt<<<grid, 128, 0, st>>>(s->dev, bp, (unsigned long long)rp->sample_offset, (unsigned long long)rp->num_samples, d_cnt);
+        NGI_CUDA(cudaEventRecord(e1, st));
+        unsigned long long h_cnt[2] = {0, 0};
+        NGI_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        NGI_CUDA(cudaStreamSynchronize(st));
+        NGI_CUDA(cudaGetLastError());
+        float ms = 0;
+        NGI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        ngi_dfree(d_cnt, st);
+        if (stats) {
+            stats->paths = (uint64_t)rp->num_samples; stats->extend_rays = h_cnt[0]; stats->shadow_rays = h_cnt[1];
+            stats->kernel_launches = 1; stats->wave_iterations = 1; stats->gpu_seconds = ms * 1e-3;
+        }
         return NGI_OK;
     }
     const bool per_ray = (rp->flags & NGI_RENDER_PER_RAY_TRACE) != 0;

@@ -4,7 +4,7 @@
 // (:117-180) and Renderer::Render (:182-221). The CLI, scene YAML, renderer names and film outputs are
 // the reference's; the per-sample loop is replaced by ONE call across the C ABI (include/nanogi_gpu.h):
 //     Renderer::Render(scene, film)   ->   ngi_gpu_scene_create + ngi_gpu_render
-// `pt` and `ptdirect` (the hot path) and `lt` / `ltdirect` are on the GPU path; bdpt and ptmnee are reported
+// `pt` and `ptdirect` (the hot path) and `lt` / `ltdirect` / `bdpt` are on the GPU path; ptmnee is reported
 // as unsupported instead of silently differing. --render-time and progress images follow RenderProcess's pass loop.
 // There is no CPU fallback.
 #include <chrono>
@@ -45,7 +45,7 @@ struct Renderer {
         Type = -1;
         for (int i = 0; i < 6; i++) if (vm.renderer == RendererType_String[i]) Type = i;
         if (Type < 0) { NGI_LOG_ERROR("Invalid renderer type: " + vm.renderer); return false; }
-        if (Type > NGI_RENDERER_LTDIRECT) { NGI_LOG_ERROR("Renderer '" + vm.renderer + "' is not supported by this build (GPU path: pt, ptdirect, lt, ltdirect)"); return false; }
+        if (Type > NGI_RENDERER_BDPT) { NGI_LOG_ERROR("Renderer '" + vm.renderer + "' is not supported by this build (GPU path: pt, ptdirect, lt, ltdirect, bdpt)"); return false; }
         Params.NumSamples = vm.num_samples;
         Params.RenderTime = vm.render_time;
         Params.MaxNumVertices = vm.max_num_vertices;

@@ -49,7 +49,7 @@ def main():
     for scene in ("cornell_raw_sensor", "cornell_mixed_lights"):
         spec = scenes.cornell_raw_sensor(spheres=True) if scene == "cornell_raw_sensor" else scenes.cornell_mixed_lights()
         orc_s = pyoracle.OracleScene(scenes.to_scene_data(scaled_spec(spec, 0.01), 1.0))
-        for renderer in ("pt", "ptdirect", "lt", "ltdirect"):
+        for renderer in ("pt", "ptdirect", "lt", "ltdirect", "bdpt"):
             f, st = orc_s.render(renderer, 4096, 16, 16, max_num_vertices=5, seed=3, rng_mode=1, num_threads=1)
             films[f"film_{scene}_{renderer}"] = f
             films[f"rays_{scene}_{renderer}"] = np.array([st["extend_rays"], st["shadow_rays"]])

@@ -19,6 +19,7 @@ static unsigned long long g_trace_count[2] = {0, 0};     // [0] BVH8 node steps,
 #include "../../nanogi_b200/csrc/ngi_bvh.h"
 #include "../../nanogi_b200/csrc/ngi_scene_host.h"
 #include "../../nanogi_b200/csrc/ngi_wave.h"
+#include "../../nanogi_b200/csrc/ngi_bdpt.h"
 
 namespace {
 
@@ -251,6 +252,17 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
     std::fill(film, film + npx * 3, 0.0f);
     if (stats) std::fill(stats, stats + 4, 0.0);
     if (rp->max_num_vertices != -1 && rp->max_num_vertices < 2) return 0;
+    if (rp->renderer == NGI_RENDERER_BDPT) {       // k_bdpt: one sample after the other
+        NgiBdParams bp;
+        bp.film = film; bp.width = rp->width; bp.height = rp->height; bp.max_verts = rp->max_num_vertices;
+        bp.seed_lo = (unsigned)rp->seed; bp.seed_hi = (unsigned)(rp->seed >> 32);
+        bp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
+        std::vector<NgiBdVertex> VL(NGI_BD_MAX_VERTS), VE(NGI_BD_MAX_VERTS);
+        NgiBdCounters cnt; cnt.extend = 0; cnt.shadow = 0;
+        for (long long i = 0; i < rp->num_samples; i++) ngi_bdpt_sample(s->dev, bp, (unsigned long long)(rp->sample_offset + i), VL.data(), VE.data(), cnt);
+        if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)cnt.extend; stats[2] = (double)cnt.shadow; stats[3] = 1; }
+        return 0;
+    }
     const unsigned P = rp->wave_capacity ? rp->wave_capacity : 4096;
     std::vector<float4> hit(P), shadow_q((size_t)P * 2 * 3);
     std::vector<NgiSlotA> sa(P); std::vector<NgiSlotB> sb(P);

@@ -136,6 +136,27 @@ def test_light_tracing_statistics_cornell_scale(gpu_cornell, cornell):
     pc.check_image_statistics(gpu_cornell, cornell, "ltdirect", w=32, h=32, spp=256, seeds=6, m=6, block=8)
 
 
+@pytest.mark.parametrize("scene,m", [("cornell_spheres", -1), ("cornell_mixed_lights", 5), ("cornell_raw_sensor", 6), ("cornell_textured", 4)])
+def test_replay_bdpt(scene, m):
+    """bdpt on the device against the oracle (bit-exact against the reference's bdpt.hpp), same Philox uniforms."""
+    spec = scenes.cornell_raw_sensor(spheres=True) if scene == "cornell_raw_sensor" else getattr(scenes, scene)()
+    sd = scenes.to_scene_data(scaled_spec(spec, 0.01), 1.0)
+    g = capi.GpuScene(sd, 0)
+    pc.check_replay(g, sd, "bdpt", n=200000, w=64, h=64, m=m, max_bad_pixels=0.02)
+    g.close()
+
+
+def test_bdpt_statistics_and_agreement_with_ptdirect(gpu_cornell, cornell):
+    """bdpt at Cornell scale against the oracle (independent seeds), and bdpt = ptdirect in expectation (the pinhole scene has
+    no directional light, so both estimate the same image)."""
+    pc.check_image_statistics(gpu_cornell, cornell, "bdpt", w=32, h=32, spp=128, seeds=6, m=6, block=8)
+    a, _ = gpu_cornell.render("bdpt", 1 << 22, 32, 32, max_num_vertices=6, seed=3)
+    b, _ = gpu_cornell.render("ptdirect", 1 << 24, 32, 32, max_num_vertices=6, seed=4)
+    assert abs(a.mean() - b.mean()) < 0.02 * b.mean()
+    blk = lambda f: f.reshape(4, 8, 4, 8, 3).mean(axis=(1, 3, 4))
+    assert np.allclose(blk(a), blk(b), rtol=0.1, atol=0.02 * b.mean())
+
+
 def test_gpu_equals_simulator_light_tracing(cornell):
     from tests.hostsim import pysim
     small = scenes.to_scene_data(scaled_spec(scenes.cornell_raw_sensor(), 0.01), 1.0)
@@ -254,7 +275,7 @@ def test_timed_and_graph_paths_agree(gpu_cornell):
 
 def test_error_paths(gpu_cornell):
     with pytest.raises(capi.NgiError, match="not supported"):
-        gpu_cornell.render(4, 10, 4, 4)           # bdpt is not on the GPU path
+        gpu_cornell.render(5, 10, 4, 4)           # ptmnee is not on the GPU path
     with pytest.raises(capi.NgiError):
         gpu_cornell.render("pt", 10, 0, 4)
     film, st = gpu_cornell.render("pt", 0, 4, 4)

@@ -122,6 +122,19 @@ def test_light_tracing_statistics_cornell_scale(cornell):
     pc.check_image_statistics(pysim.SimScene(cornell), cornell, "ltdirect", w=16, h=16, spp=256, seeds=6, m=6, block=4, wave_capacity=4096)
 
 
+@pytest.mark.parametrize("scene,m", [("cornell_spheres", -1), ("cornell_mixed_lights", 5), ("cornell_raw_sensor", 6), ("cornell_textured", 4)])
+def test_replay_bdpt(scene, m):
+    """bdpt (one sample per thread, ngi_bdpt.h) against the oracle's restatement of bdpt.hpp — itself bit-exact against the
+    reference's own code (tests/test_reference_pin.py): same Philox uniforms, sample-exact films and ray counts at unit scale."""
+    spec = scenes.cornell_raw_sensor(spheres=True) if scene == "cornell_raw_sensor" else getattr(scenes, scene)()
+    sd = scenes.to_scene_data(scaled_spec(spec, 0.01), 1.0)
+    pc.check_replay(pysim.SimScene(sd), sd, "bdpt", n=15000, w=24, h=24, m=m)
+
+
+def test_bdpt_statistics_cornell_scale(cornell):
+    pc.check_image_statistics(pysim.SimScene(cornell), cornell, "bdpt", w=16, h=16, spp=128, seeds=6, m=6, block=4)
+
+
 def test_replay_furnace_exact(furnace):
     sim = pysim.SimScene(furnace)
     orc = pyoracle.OracleScene(furnace)
