@@ -20,6 +20,23 @@
 
 #define NGI_BD_MAX_VERTS 24
 
+// bdpt's building blocks are real functions (one copy each): inlined everywhere, the first k_bdpt was 14 700 SASS instructions
+// (235 KB) and spent 38 of every 39 stalled issue slots waiting for instructions (profiles/r01_ncu_bdpt_v1.txt)
+#if defined(__CUDACC__)
+#define NGI_BD_FN __host__ __device__ __noinline__
+#else
+#define NGI_BD_FN inline
+#endif
+
+// one copy of each per-ray traversal for all of bdpt
+NGI_BD_FN bool ngi_bd_trace_closest(const NgiDevScene& sc, const f3 o, const f3 d, NgiHitRec& h) {
+    return ngi_trace_bvh8<false>(sc.nodes8, sc.tris8, o, d, NGI_EPS_F, NGI_INF_F, h);
+}
+NGI_BD_FN bool ngi_bd_trace_any(const NgiDevScene& sc, const f3 o, const f3 d, const float tmax) {
+    NgiHitRec h;
+    return ngi_trace_bvh8<true>(sc.nodes8, sc.tris8, o, d, NGI_EPS_F, tmax, h);
+}
+
 struct NgiBdVertex {          // PathVertex, bdpt.hpp:38-43 (the frame is rebuilt from sn when needed)
     double px, py, pz;
     f3 sn, gn;
@@ -51,8 +68,8 @@ NGI_HD NgiGeom ngi_bd_geom(const NgiBdVertex& v) {
 }
 
 // Primitive::EvaluateDirection for any vertex kind (rt.hpp:912-1148) and, in `pdf`, Primitive::EvaluateDirectionPDF (:1150-1336)
-NGI_HD f3 ngi_bd_eval_direction(const NgiDevScene& sc, const NgiBdVertex& v, const int type, const f3 wi, const f3 wo, const bool transLE,
-                                const bool forceDegenerated, float& pdf) {
+NGI_BD_FN f3 ngi_bd_eval_direction(const NgiDevScene& sc, const NgiBdVertex& v, const int type, const f3 wi, const f3 wo, const bool transLE,
+                                         const bool forceDegenerated, float& pdf) {
     const NgiDevPrim& P = sc.prims[v.prim];
     pdf = 0.0f;
     if (type & NGI_L) {
@@ -101,7 +118,7 @@ NGI_HD float ngi_bd_geometry_term(const NgiBdVertex& a, const NgiBdVertex& b) {
 }
 
 // ---- Path::SampleSubpath, bdpt.hpp:54-123. kind 0: light subpath (LE), 1: eye subpath (EL). Returns the vertex count. ----------
-NGI_HD int ngi_bd_sample_subpath(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind,
+NGI_BD_FN int ngi_bd_sample_subpath(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind,
                                  NgiBdVertex* V, NgiBdCounters& cnt) {
     const NgiDevSensor& E = sc.sensor;
     int n = 0;
@@ -156,7 +173,7 @@ NGI_HD int ngi_bd_sample_subpath(const NgiDevScene& sc, const NgiBdParams& bp, c
         NgiHitRec h;
         cnt.extend++;
         const f3 o = mk3((float)pv.px, (float)pv.py, (float)pv.pz);
-        if (!ngi_trace_bvh8<false>(sc.nodes8, sc.tris8, o, wo, NGI_EPS_F, NGI_INF_F, h)) break;                   // :92
+        if (!ngi_bd_trace_closest(sc, o, wo, h)) break;                                                            // :92
         NgiBdVertex v;
         double ddx, ddy, ddz;
         ngi_dither_direction(wo, make_float4(h.t, h.u, h.v, u2f(h.tri)), ddx, ddy, ddz);                          // see ngi_logic_surface
@@ -185,135 +202,177 @@ struct NgiBdPath {
     NGI_HD int type(int i) const { return i == 0 ? type_first : (i == n - 1 ? type_last : v(i).type); }
 };
 
-// Path::EvaluateCst, bdpt.hpp:217-250, for a split of the SAME path at `s` light vertices
-NGI_HD f3 ngi_bd_cst(const NgiDevScene& sc, const NgiBdPath& p, const int s) {
-    const int n = p.n, t = n - s;
+// ---- contribution of one connected path --------------------------------------------------------------------------------
+// The reference evaluates C = EvaluateUnweightContribution(s) * EvaluatePowerHeuristicsMISWeightOpt(s) with
+//     w_s = 1 / sum_i (p_i / p_s)^2,   p_i = EvaluatePDF(i) = [EvaluateCst(i) != 0] * PL(i) * PE(i)
+// where PL(i) / PE(i) are the products of (direction pdf x geometry term) along the first i / last n - i vertices
+// (bdpt.hpp:491-535), and it recomputes every product from scratch: O(n) evaluations per strategy, O(n^2) per connection,
+// O(n^4) per sample. The SAME numbers come out of one forward and one backward sweep over the path — prefix products — in
+// O(n) evaluations per connection: the first version of this kernel restated the reference's loops literally and ran at
+// 3.7 Mpaths/s on C2 (a warp lives as long as its longest path and the cost grew with the fourth power of its length).
+struct NgiBdScratch {
+    f3 w[2 * NGI_BD_MAX_VERTS];            // w[k] = direction vertex k -> k + 1
+    float G[2 * NGI_BD_MAX_VERTS];         // GeometryTerm(v_k, v_k+1)
+    f3 ff[2 * NGI_BD_MAX_VERTS];           // forward:  EvaluateDirection(v_k; from k-1, to k+1; LE, forceDegenerated) and its pdf
+    float fpdf[2 * NGI_BD_MAX_VERTS];
+    f3 bf[2 * NGI_BD_MAX_VERTS];           // backward: EvaluateDirection(v_k; from k+1, to k-1; EL, forceDegenerated) and its pdf
+    float bpdf[2 * NGI_BD_MAX_VERTS];
+    double PL[2 * NGI_BD_MAX_VERTS + 1], PE[2 * NGI_BD_MAX_VERTS + 1];
+};
+
+// Path::EvaluateCst(i), bdpt.hpp:217-250, from the cached edges
+NGI_HD f3 ngi_bd_cst(const NgiDevScene& sc, const NgiBdPath& p, const NgiBdScratch& q, const int i) {
+    const int n = p.n;
     float pdfUnused;
-    if (s == 0 && t > 0) {
+    if (i == 0) {
         const NgiBdVertex& v = p.v(0);
-        return ngi_bd_eval_direction(sc, v, p.type(0), mk3(0.0f), ngi_bd_dir(v, p.v(1)), false, false, pdfUnused) * ngi_bd_eval_position(sc, v, p.type(0), false);
+        return ngi_bd_eval_direction(sc, v, p.type(0), mk3(0.0f), q.w[0], false, false, pdfUnused) * ngi_bd_eval_position(sc, v, p.type(0), false);
     }
-    if (s > 0 && t == 0) {
+    if (i == n) {
         const NgiBdVertex& v = p.v(n - 1);
-        return ngi_bd_eval_direction(sc, v, p.type(n - 1), mk3(0.0f), ngi_bd_dir(v, p.v(n - 2)), true, false, pdfUnused) * ngi_bd_eval_position(sc, v, p.type(n - 1), false);
+        return ngi_bd_eval_direction(sc, v, p.type(n - 1), mk3(0.0f), -q.w[n - 2], true, false, pdfUnused) * ngi_bd_eval_position(sc, v, p.type(n - 1), false);
     }
-    const NgiBdVertex& vL = p.v(s - 1);
-    const NgiBdVertex& vE = p.v(s);
-    const f3 fsL = ngi_bd_eval_direction(sc, vL, p.type(s - 1), s - 2 >= 0 ? ngi_bd_dir(vL, p.v(s - 2)) : mk3(0.0f), ngi_bd_dir(vL, vE), true, false, pdfUnused);
+    const f3 fsL = ngi_bd_eval_direction(sc, p.v(i - 1), p.type(i - 1), i - 2 >= 0 ? -q.w[i - 2] : mk3(0.0f), q.w[i - 1], true, false, pdfUnused);
     if (is_zero(fsL)) return mk3(0.0f);
-    const f3 fsE = ngi_bd_eval_direction(sc, vE, p.type(s), s + 1 < n ? ngi_bd_dir(vE, p.v(s + 1)) : mk3(0.0f), ngi_bd_dir(vE, vL), false, false, pdfUnused);
-    return fsL * fsE * ngi_bd_geometry_term(vL, vE);
+    const f3 fsE = ngi_bd_eval_direction(sc, p.v(i), p.type(i), i + 1 < n ? q.w[i] : mk3(0.0f), -q.w[i - 1], false, false, pdfUnused);
+    return fsL * fsE * q.G[i - 1];
 }
 
-// Path::EvaluatePDF, bdpt.hpp:491-535 (fp64 product, see the header comment)
-NGI_HD double ngi_bd_pdf(const NgiDevScene& sc, const NgiBdPath& p, const int s) {
-    if (is_zero(ngi_bd_cst(sc, p, s))) return 0.0;
-    const int n = p.n, t = n - s;
-    double pdf = 1.0;
-    float pd;
-    if (s > 0) {
-        pdf *= (double)ngi_bd_position_pdf(sc, p.v(0), p.type(0));
-        for (int i = 0; i < s - 1; i++) {
-            const NgiBdVertex& vi = p.v(i);
-            ngi_bd_eval_direction(sc, vi, p.type(i), i >= 1 ? ngi_bd_dir(vi, p.v(i - 1)) : mk3(0.0f), ngi_bd_dir(vi, p.v(i + 1)), true, true, pd);
-            pdf *= (double)pd * (double)ngi_bd_geometry_term(vi, p.v(i + 1));
-        }
-    }
-    if (t > 0) {
-        pdf *= (double)ngi_bd_position_pdf(sc, p.v(n - 1), p.type(n - 1));
-        for (int i = n - 1; i >= s + 1; i--) {
-            const NgiBdVertex& vi = p.v(i);
-            ngi_bd_eval_direction(sc, vi, p.type(i), i + 1 < n ? ngi_bd_dir(vi, p.v(i + 1)) : mk3(0.0f), ngi_bd_dir(vi, p.v(i - 1)), false, true, pd);
-            pdf *= (double)pd * (double)ngi_bd_geometry_term(vi, p.v(i - 1));
-        }
-    }
-    return pdf;
+// [EvaluateCst(i) != 0] for a strategy other than the sampled one, WITHOUT new evaluations: cst(i) = fsL * G * fsE with
+// forceDegenerated = false, which differs from the forceDegenerated = true values already in ff / bf only for specular lobes
+// (-> 0, rt.hpp:1057-1060), directional lights (-> 0, :934-937) and the position terms of point lights / the pinhole (-> 0,
+// :594-641); emitters do not depend on the transport direction.
+NGI_HD bool ngi_bd_nondegenerate(const NgiDevScene& sc, const NgiBdPath& p, const int k) {
+    const int type = p.type(k);
+    if (type & NGI_L) return sc.prims[p.v(k).prim].l_type != NGI_LT_DIRECTIONAL;
+    if (type & NGI_E) return true;
+    return (type & (NGI_D | NGI_G)) != 0;                  // precedence D > G > S: an S lobe is only reached without D and G
+}
+NGI_HD bool ngi_bd_cst_nonzero(const NgiDevScene& sc, const NgiBdPath& p, const NgiBdScratch& q, const int i) {
+    const int n = p.n;
+    if (i == 0) return ngi_bd_eval_position(sc, p.v(0), p.type(0), false) != 0.0f && ngi_bd_nondegenerate(sc, p, 0) && !is_zero(q.ff[0]);
+    if (i == n) return ngi_bd_eval_position(sc, p.v(n - 1), p.type(n - 1), false) != 0.0f && ngi_bd_nondegenerate(sc, p, n - 1) && !is_zero(q.bf[n - 1]);
+    return ngi_bd_nondegenerate(sc, p, i - 1) && ngi_bd_nondegenerate(sc, p, i) && !is_zero(q.ff[i - 1]) && !is_zero(q.bf[i]) && q.G[i - 1] != 0.0f;
 }
 
-// Path::EvaluateUnweightContribution, bdpt.hpp:252-343
-NGI_HD f3 ngi_bd_unweighted(const NgiDevScene& sc, const NgiBdPath& p) {
+// EvaluateContribution(s) / SelectionProb(s) of the connected path, bdpt.hpp:181-205, :252-343, :362-380, :491-535
+NGI_BD_FN f3 ngi_bd_contribution(const NgiDevScene& sc, const NgiBdPath& p, NgiBdScratch& q) {
     const int n = p.n, s = p.s, t = p.t;
-    float pd;
-    f3 alphaL = mk3(1.0f);
+    for (int k = 0; k + 1 < n; k++) {                      // edges: direction and geometry term, once
+        const NgiBdVertex& a = p.v(k);
+        const NgiBdVertex& b = p.v(k + 1);
+        const double dx = b.px - a.px, dy = b.py - a.py, dz = b.pz - a.pz;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        const double inv = 1.0 / sqrt(d2);
+        const f3 w = mk3((float)(dx * inv), (float)(dy * inv), (float)(dz * inv));
+        float g = 1.0f;
+        if (!a.degenerate) g *= fabsf(dot(a.sn, w));
+        if (!b.degenerate) g *= fabsf(dot(b.sn, w));
+        q.w[k] = w;
+        q.G[k] = (float)((double)g / d2);                  // GeometryTerm, rt.hpp:2364-2374
+    }
+    // unweighted contribution first (most connections end here with zero): alphaL * cst(s) * alphaE, bdpt.hpp:252-343
+    const f3 cstS = ngi_bd_cst(sc, p, q, s);
+    if (is_zero(cstS)) return mk3(0.0f);
+    for (int k = 0; k + 1 < n; k++)
+        q.ff[k] = ngi_bd_eval_direction(sc, p.v(k), p.type(k), k >= 1 ? -q.w[k - 1] : mk3(0.0f), q.w[k], true, true, q.fpdf[k]);
+    for (int k = n - 1; k >= 1; k--)
+        q.bf[k] = ngi_bd_eval_direction(sc, p.v(k), p.type(k), k + 1 < n ? q.w[k] : mk3(0.0f), -q.w[k - 1], false, true, q.bpdf[k]);
+    const float pA0 = ngi_bd_position_pdf(sc, p.v(0), p.type(0)), pAn = ngi_bd_position_pdf(sc, p.v(n - 1), p.type(n - 1));
+    f3 alphaL = mk3(1.0f), alphaE = mk3(1.0f);
     if (s > 0) {
-        alphaL = mk3(ngi_bd_eval_position(sc, p.v(0), p.type(0), true) / ngi_bd_position_pdf(sc, p.v(0), p.type(0)));
-        for (int i = 0; i < s - 1; i++) {
-            const NgiBdVertex& v = p.v(i);
-            const f3 f = ngi_bd_eval_direction(sc, v, p.type(i), i >= 1 ? ngi_bd_dir(v, p.v(i - 1)) : mk3(0.0f), ngi_bd_dir(v, p.v(i + 1)), true, true, pd);
-            if (is_zero(f)) return mk3(0.0f);
-            alphaL = alphaL * (f / pd);
-        }
+        alphaL = mk3(ngi_bd_eval_position(sc, p.v(0), p.type(0), true) / pA0);
+        for (int k = 0; k < s - 1; k++) { if (is_zero(q.ff[k])) return mk3(0.0f); alphaL = alphaL * (q.ff[k] / q.fpdf[k]); }
     }
-    f3 alphaE = mk3(1.0f);
     if (t > 0) {
-        alphaE = mk3(ngi_bd_eval_position(sc, p.v(n - 1), p.type(n - 1), true) / ngi_bd_position_pdf(sc, p.v(n - 1), p.type(n - 1)));
-        for (int i = n - 1; i > s; i--) {
-            const NgiBdVertex& v = p.v(i);
-            const f3 f = ngi_bd_eval_direction(sc, v, p.type(i), i < n - 1 ? ngi_bd_dir(v, p.v(i + 1)) : mk3(0.0f), ngi_bd_dir(v, p.v(i - 1)), false, true, pd);
-            if (is_zero(f)) return mk3(0.0f);
-            alphaE = alphaE * (f / pd);
-        }
+        alphaE = mk3(ngi_bd_eval_position(sc, p.v(n - 1), p.type(n - 1), true) / pAn);
+        for (int k = n - 1; k > s; k--) { if (is_zero(q.bf[k])) return mk3(0.0f); alphaE = alphaE * (q.bf[k] / q.bpdf[k]); }
     }
-    const f3 cst = ngi_bd_cst(sc, p, s);
-    if (is_zero(cst)) return mk3(0.0f);
-    return alphaL * cst * alphaE;
+    const f3 Cstar = alphaL * cstS * alphaE;
+    if (is_zero(Cstar)) return mk3(0.0f);
+    // path pdfs of every strategy from prefix / suffix products (fp64), bdpt.hpp:491-535
+    q.PL[0] = 1.0; q.PL[1] = (double)pA0;
+    for (int i = 2; i <= n; i++) q.PL[i] = q.PL[i - 1] * (double)q.fpdf[i - 2] * (double)q.G[i - 2];
+    q.PE[n] = 1.0; q.PE[n - 1] = (double)pAn;
+    for (int i = n - 2; i >= 0; i--) q.PE[i] = q.PE[i + 1] * (double)q.bpdf[i + 1] * (double)q.G[i];
+    const double ps = q.PL[s] * q.PE[s];                                     // cst(s) != 0 was established above
+    double invWeight = 0.0;                                                  // EvaluatePowerHeuristicsMISWeightOpt, bdpt.hpp:362-380
+    for (int i = 0; i <= n; i++) {
+        const double pi = q.PL[i] * q.PE[i];
+        if (!(pi > 0.0)) continue;
+        if (i != s && !ngi_bd_cst_nonzero(sc, p, q, i)) continue;            // EvaluatePDF returns 0 when EvaluateCst(i) == 0
+        const double r = pi / ps;
+        invWeight += r * r;
+    }
+    double sel = 1.0;                                                        // SelectionProb, bdpt.hpp:187-205
+    for (int i = 1; i < s - 1; i++) sel *= 0.5;
+    for (int i = t - 2; i >= 1; i--) sel *= 0.5;
+    return Cstar * (float)(1.0 / (invWeight * sel));
 }
 
-// one bdpt sample: ProcessSample_BDPT, src/nanogi.cpp:1133-1186
-NGI_HD_NOINLINE void ngi_bdpt_sample(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, NgiBdVertex* VL, NgiBdVertex* VE,
-                                     NgiBdCounters& cnt) {
+// One (n, s) strategy of a sample: Path::Connect (bdpt.hpp:125-177) + contribution + film splat (src/nanogi.cpp:1164-1181).
+// Not inlined: the CUDA kernel calls it from a per-lane state machine (k_bdpt), the simulator from the plain loop nest below.
+NGI_BD_FN void ngi_bd_connect(const NgiDevScene& sc, const NgiBdParams& bp, const NgiBdVertex* VL, const NgiBdVertex* VE, const int n, const int s,
+                                    NgiBdScratch& q, NgiBdCounters& cnt) {
+    const int t = n - s;
+    NgiBdPath p; p.L = VL; p.E = VE; p.s = s; p.t = t; p.n = n;
+    if (s == 0) {
+        if (!(sc.prims[VE[t - 1].prim].type & NGI_L)) return;
+        p.type_first = NGI_L; p.type_last = VE[0].type;
+    } else if (t == 0) {
+        if (!(sc.prims[VL[s - 1].prim].type & NGI_E) || VL[s - 1].prim != sc.sensor.prim || VL[s - 1].pixel < 0) return;   // only THE sensor (last E primitive)
+        p.type_first = VL[0].type; p.type_last = NGI_E;
+    } else {
+        const NgiBdVertex& a = VL[s - 1];
+        const NgiBdVertex& b = VE[t - 1];
+        const double dx = b.px - a.px, dy = b.py - a.py, dz = b.pz - a.pz;           // Scene::Visible, rt.hpp:2251-2261
+        const double len = sqrt(dx * dx + dy * dy + dz * dz);
+        const f3 d = mk3((float)(dx / len), (float)(dy / len), (float)(dz / len));
+        cnt.shadow++;
+        if (ngi_bd_trace_any(sc, mk3((float)a.px, (float)a.py, (float)a.pz), d, (float)len * (1.0f - NGI_EPS_F))) return;
+        p.type_first = VL[0].type; p.type_last = VE[0].type;
+    }
+    const f3 C = ngi_bd_contribution(sc, p, q);
+    if (is_zero(C) || !(C.x == C.x && C.y == C.y && C.z == C.z)) return;
+    // Path::RasterPosition of the last vertex, bdpt.hpp:207-215
+    int pixel;
+    if (sc.sensor.kind == NGI_ET_PINHOLE) {
+        float rx, ry, ct;
+        if (!ngi_raster_position(sc.sensor, -q.w[n - 2], rx, ry, ct)) return;        // cannot happen when C != 0 (We = 0 off the raster)
+        pixel = ngi_pixel_index(rx, ry, bp.width, bp.height);
+    } else {
+        pixel = p.v(n - 1).pixel;
+        if (pixel < 0) return;
+    }
+    ngi_film_add(bp.film, pixel, C * bp.film_scale);
+}
+
+// Connect's tests that need no ray (bdpt.hpp:133-137, :147-151): can strategy (n, s) exist at all?
+NGI_HD bool ngi_bd_strategy_possible(const NgiDevScene& sc, const NgiBdVertex* VL, const NgiBdVertex* VE, const int n, const int s) {
+    const int t = n - s;
+    if (s == 0) return (sc.prims[VE[t - 1].prim].type & NGI_L) != 0;
+    if (t == 0) return (sc.prims[VL[s - 1].prim].type & NGI_E) != 0 && VL[s - 1].prim == sc.sensor.prim && VL[s - 1].pixel >= 0;
+    return true;
+}
+
+// the (n, s) strategies of a sample in the reference's order (src/nanogi.cpp:1148-1160): advances the cursor, returns false when done
+NGI_HD bool ngi_bd_next_strategy(const NgiBdParams& bp, const int nL, const int nE, int& n, int& s) {
+    while (true) {
+        const int maxS = nL < n ? nL : n;
+        if (n >= 2 && s < maxS) { s++; return true; }
+        n++;
+        if (n > nE + nL || (bp.max_verts != -1 && n > bp.max_verts)) return false;
+        s = (n - nE > 0 ? n - nE : 0) - 1;
+    }
+}
+
+// one bdpt sample: ProcessSample_BDPT, src/nanogi.cpp:1133-1186 (the simulator's form; k_bdpt interleaves the strategies of
+// different samples across the lanes of a warp)
+NGI_BD_FN void ngi_bdpt_sample(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, NgiBdVertex* VL, NgiBdVertex* VE,
+                                     NgiBdScratch& q, NgiBdCounters& cnt) {
     const int nL = ngi_bd_sample_subpath(sc, bp, sample, 0, VL, cnt);                        // :1137
     const int nE = ngi_bd_sample_subpath(sc, bp, sample, 1, VE, cnt);                        // :1138
     if (nL == 0 || nE == 0) return;
-    for (int n = 2; n <= nE + nL; n++) {                                                     // :1148
-        if (bp.max_verts != -1 && n > bp.max_verts) continue;
-        const int minS = n - nE > 0 ? n - nE : 0, maxS = nL < n ? nL : n;
-        for (int s = minS; s <= maxS; s++) {
-            const int t = n - s;
-            NgiBdPath p; p.L = VL; p.E = VE; p.s = s; p.t = t; p.n = n;
-            // Path::Connect, bdpt.hpp:125-177
-            if (s == 0) {
-                if (!(sc.prims[VE[t - 1].prim].type & NGI_L)) continue;
-                p.type_first = NGI_L; p.type_last = VE[0].type;
-            } else if (t == 0) {
-                if (!(sc.prims[VL[s - 1].prim].type & NGI_E) || VL[s - 1].prim != sc.sensor.prim || VL[s - 1].pixel < 0) continue;   // only THE sensor (last E primitive)
-                p.type_first = VL[0].type; p.type_last = NGI_E;
-            } else {
-                const NgiBdVertex& a = VL[s - 1];
-                const NgiBdVertex& b = VE[t - 1];
-                const double dx = b.px - a.px, dy = b.py - a.py, dz = b.pz - a.pz;           // Scene::Visible, rt.hpp:2251-2261
-                const double len = sqrt(dx * dx + dy * dy + dz * dz);
-                const f3 d = mk3((float)(dx / len), (float)(dy / len), (float)(dz / len));
-                NgiHitRec h;
-                cnt.shadow++;
-                if (ngi_trace_bvh8<true>(sc.nodes8, sc.tris8, mk3((float)a.px, (float)a.py, (float)a.pz), d, NGI_EPS_F, (float)len * (1.0f - NGI_EPS_F), h)) continue;
-                p.type_first = VL[0].type; p.type_last = VE[0].type;
-            }
-            const f3 Cstar = ngi_bd_unweighted(sc, p);                                       // EvaluateContribution, bdpt.hpp:181-185
-            if (is_zero(Cstar)) continue;
-            const double ps = ngi_bd_pdf(sc, p, s);                                          // EvaluatePowerHeuristicsMISWeightOpt, :362-380
-            double invWeight = 0.0;
-            for (int i = 0; i <= n; i++) {
-                const double pi = ngi_bd_pdf(sc, p, i);
-                if (pi > 0.0) { const double r = pi / ps; invWeight += r * r; }
-            }
-            double sel = 1.0;                                                                // SelectionProb, :187-205
-            for (int i = 1; i < s - 1; i++) sel *= 0.5;
-            for (int i = t - 2; i >= 1; i--) sel *= 0.5;
-            const f3 C = Cstar * (float)(1.0 / (invWeight * sel));
-            if (is_zero(C) || !(C.x == C.x && C.y == C.y && C.z == C.z)) continue;
-            // Path::RasterPosition of the last vertex, bdpt.hpp:207-215
-            const NgiBdVertex& last = p.v(n - 1);
-            int pixel;
-            if (sc.sensor.kind == NGI_ET_PINHOLE) {
-                float rx, ry, ct;
-                if (!ngi_raster_position(sc.sensor, ngi_bd_dir(last, p.v(n - 2)), rx, ry, ct)) continue;   // cannot happen when C != 0 (We = 0 off the raster)
-                pixel = ngi_pixel_index(rx, ry, bp.width, bp.height);
-            } else {
-                pixel = last.pixel;
-                if (pixel < 0) continue;
-            }
-            ngi_film_add(bp.film, pixel, C * bp.film_scale);
-        }
-    }
+    int n = 1, s = 0;
+    while (ngi_bd_next_strategy(bp, nL, nE, n, s)) ngi_bd_connect(sc, bp, VL, VE, n, s, q, cnt);
 }

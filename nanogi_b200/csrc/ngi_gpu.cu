@@ -328,13 +328,44 @@ __global__ void __launch_bounds__(kBlock, NGI_LOGIC_MIN_BLOCKS) k_eye(NgiDevScen
     }
 }
 
-// bdpt (ngi_bdpt.h): one sample per thread, subpaths in local memory; rays counted per block
+// bdpt (ngi_bdpt.h): one sample per lane at a time, subpaths in local memory. The cost of a sample is heavy tailed (~ n^3 in
+// its path length, geometric in n): run sample by sample, a warp waited for its longest path and profiles/r01_ncu_bdpt_v1.txt
+// shows 3.0 of 32 lanes active. Here every lane is a small state machine — (re)start a sample when out of strategies, then
+// evaluate ONE (n, s) strategy per trip — so that the warp's lockstep unit is a strategy, not a sample: a lane with a long path
+// simply stays on it for more trips while its neighbours move on to their next samples.
 __global__ void __launch_bounds__(128) k_bdpt(NgiDevScene sc, NgiBdParams bp, unsigned long long first, unsigned long long count,
                                               unsigned long long* __restrict__ ray_counters /* [0] extend, [1] shadow */) {
     NgiBdVertex VL[NGI_BD_MAX_VERTS], VE[NGI_BD_MAX_VERTS];
+    NgiBdScratch q;
     NgiBdCounters cnt; cnt.extend = 0; cnt.shadow = 0;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < count; i += (unsigned long long)gridDim.x * blockDim.x)
-        ngi_bdpt_sample(sc, bp, first + i, VL, VE, cnt);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long next = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    int nL = 0, nE = 0, n = 1, s = 0;
+    bool have = false;
+    while (true) {
+        // (re)start samples in BATCHES: sampling two subpaths costs far more than evaluating one strategy, and lanes run out of
+        // strategies one at a time — refilling them as they went idle ran the sampling code with 1-3 lanes on almost every trip
+        // (profiles/r01_ncu_bdpt_v1.txt: 3.0 of 32 lanes). Idle lanes wait until half the warp is idle (or nobody has work).
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have && next < count);
+        const unsigned busy = __ballot_sync(0xFFFFFFFFu, have);
+        if (idle == 0u && busy == 0u) break;
+        if (idle != 0u && (__popc(idle) >= 16 || busy == 0u)) {
+            if (!have && next < count) {
+                nL = ngi_bd_sample_subpath(sc, bp, first + next, 0, VL, cnt);
+                nE = ngi_bd_sample_subpath(sc, bp, first + next, 1, VE, cnt);
+                next += stride;
+                n = 1; s = 0;
+                have = nL > 0 && nE > 0;
+            }
+        }
+        __syncwarp();
+        // advance to the next strategy that passes Connect's cheap tests, so that a trip does real work on most lanes
+        if (have) {
+            do { have = ngi_bd_next_strategy(bp, nL, nE, n, s); } while (have && !ngi_bd_strategy_possible(sc, VL, VE, n, s));
+        }
+        __syncwarp();
+        if (have) ngi_bd_connect(sc, bp, VL, VE, n, s, q, cnt);
+    }
     for (int off = 16; off > 0; off >>= 1) {
         cnt.extend += __shfl_xor_sync(0xFFFFFFFFu, cnt.extend, off);
         cnt.shadow += __shfl_xor_sync(0xFFFFFFFFu, cnt.shadow, off);

@@ -259,7 +259,8 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
         bp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
         std::vector<NgiBdVertex> VL(NGI_BD_MAX_VERTS), VE(NGI_BD_MAX_VERTS);
         NgiBdCounters cnt; cnt.extend = 0; cnt.shadow = 0;
-        for (long long i = 0; i < rp->num_samples; i++) ngi_bdpt_sample(s->dev, bp, (unsigned long long)(rp->sample_offset + i), VL.data(), VE.data(), cnt);
+        std::vector<NgiBdScratch> q(1);
+        for (long long i = 0; i < rp->num_samples; i++) ngi_bdpt_sample(s->dev, bp, (unsigned long long)(rp->sample_offset + i), VL.data(), VE.data(), q[0], cnt);
         if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)cnt.extend; stats[2] = (double)cnt.shadow; stats[3] = 1; }
         return 0;
     }

@@ -146,7 +146,10 @@ def check_replay(backend, sd, renderer, n=20000, w=48, h=48, m=-1, seed=7, max_b
     fg, sg = film_and_stats(backend.render(renderer, n, w, h, max_num_vertices=m, seed=seed, **kw))
     assert np.isfinite(fg).all()
     assert abs(sg["extend_rays"] - so["extend_rays"]) <= max(3, 2e-4 * so["extend_rays"]), (sg["extend_rays"], so["extend_rays"])
-    assert sg["shadow_rays"] <= so["shadow_rays"]   # zero-contribution shadow rays are not traced on the device
+    if renderer == "bdpt":      # every connection is traced on both sides; a path that branches differently in fp32 moves the count either way
+        assert abs(sg["shadow_rays"] - so["shadow_rays"]) <= max(3, 2e-3 * so["shadow_rays"]), (sg["shadow_rays"], so["shadow_rays"])
+    else:
+        assert sg["shadow_rays"] <= so["shadow_rays"]   # zero-contribution shadow rays are not traced on the device
     diff = np.abs(fg - fo).max(axis=2)
     tol = 2e-3 * np.maximum(np.abs(fo).max(axis=2), 1e-2 * max(fo.mean(), 1e-9))
     bad = (diff > tol).mean()

@@ -147,14 +147,15 @@ def test_replay_bdpt(scene, m):
 
 
 def test_bdpt_statistics_and_agreement_with_ptdirect(gpu_cornell, cornell):
-    """bdpt at Cornell scale against the oracle (independent seeds), and bdpt = ptdirect in expectation (the pinhole scene has
-    no directional light, so both estimate the same image)."""
+    """bdpt at Cornell scale against the oracle (independent seeds). The reference's own bdpt is 2-3 % darker than its pt / ptdirect
+    on this scene (oracle, 4 M samples, -m 6: 0.13141 vs 0.13489 — the oracle is bit-exact against the reference's code, so that
+    is the reference's estimator, not ours): the device must reproduce THAT mean, and only roughly ptdirect's."""
     pc.check_image_statistics(gpu_cornell, cornell, "bdpt", w=32, h=32, spp=128, seeds=6, m=6, block=8)
     a, _ = gpu_cornell.render("bdpt", 1 << 22, 32, 32, max_num_vertices=6, seed=3)
+    fo, _ = pyoracle.OracleScene(cornell).render("bdpt", 1 << 21, 32, 32, max_num_vertices=6, seed=9, rng_mode=1)
+    assert abs(a.mean() - fo.mean()) < 0.01 * fo.mean(), (float(a.mean()), float(fo.mean()))
     b, _ = gpu_cornell.render("ptdirect", 1 << 24, 32, 32, max_num_vertices=6, seed=4)
-    assert abs(a.mean() - b.mean()) < 0.02 * b.mean()
-    blk = lambda f: f.reshape(4, 8, 4, 8, 3).mean(axis=(1, 3, 4))
-    assert np.allclose(blk(a), blk(b), rtol=0.1, atol=0.02 * b.mean())
+    assert abs(a.mean() - b.mean()) < 0.05 * b.mean()
 
 
 def test_gpu_equals_simulator_light_tracing(cornell):
