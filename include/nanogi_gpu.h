@@ -39,7 +39,7 @@ typedef enum NgiStatus {
     NGI_ERR_INVALID_ARGUMENT = -1,
     NGI_ERR_NO_DEVICE = -2,       /* no CUDA device: the GPU path never falls back to the CPU   */
     NGI_ERR_CUDA = -3,
-    NGI_ERR_UNSUPPORTED = -4,     /* renderer outside pt / ptdirect / lt / ltdirect (bdpt, ptmnee) */
+    NGI_ERR_UNSUPPORTED = -4,     /* renderer outside pt / ptdirect / lt / ltdirect / bdpt (ptmnee) */
     NGI_ERR_OUT_OF_MEMORY = -5
 } NgiStatus;
 
@@ -58,7 +58,8 @@ enum { NGI_L_AREA = 0, NGI_L_POINT = 1, NGI_L_DIRECTIONAL = 2 };
 enum { NGI_E_AREA = 0, NGI_E_PINHOLE = 1 };
 enum { NGI_S_REFLECTION = 0, NGI_S_REFRACTION = 1, NGI_S_FRESNEL = 2 };
 /* reference src/nanogi.cpp:51-69. pt / ptdirect are the hot path; lt / ltdirect (src/nanogi.cpp:804-1131) run on the
- * same wavefront machinery. bdpt / ptmnee are not accepted. */
+ * same wavefront machinery; bdpt (src/nanogi.cpp:1133-1186, bdpt.hpp) as one sample per thread
+ * (SURVEY 8f row 4). ptmnee is not accepted. */
 enum { NGI_RENDERER_PT = 0, NGI_RENDERER_PTDIRECT = 1, NGI_RENDERER_LT = 2, NGI_RENDERER_LTDIRECT = 3, NGI_RENDERER_BDPT = 4 };
 
 /*
@@ -121,7 +122,7 @@ typedef struct NgiSceneDesc {
 /* Renderer::Params, reference src/nanogi.cpp:85-97, plus the counter-based-RNG / shard fields */
 typedef struct NgiRenderParams {
     uint32_t struct_size;        /* = sizeof(NgiRenderParams)                                */
-    int32_t renderer;            /* NGI_RENDERER_PT | _PTDIRECT | _LT | _LTDIRECT             */
+    int32_t renderer;            /* NGI_RENDERER_PT | _PTDIRECT | _LT | _LTDIRECT | _BDPT     */
     int64_t num_samples;         /* samples THIS call traces (the shard)                      */
     int64_t sample_offset;       /* first sample index of the shard                           */
     int64_t film_norm_samples;   /* N in film *= W*H/N (src/nanogi.cpp:436); 0 = no scaling   */
