@@ -49,7 +49,10 @@ def launches(path):
         if len(r) <= vi:
             continue
         name = re.sub(r"\(.*", "", r[ki])
-        name = re.sub(r"<.*", "", name) if name.startswith("void ") else name
+        if name.startswith("void "):          # templated kernels: "void <unnamed>::k_surface<(bool)0>" -> "<unnamed>::k_surface<0>", "void cub::X<...>" -> "void cub::X"
+            body = name[5:]
+            m = re.match(r"(<unnamed>::\w+)<\(?(?:bool\)?)?(\w+)>$", body)
+            name = f"{m.group(1)}<{m.group(2)}>" if m else "void " + re.sub(r"<.*", "", body)
         v = float(r[vi].replace(",", ""))
         v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[ui], 1.0)
         agg[name][0] += 1
