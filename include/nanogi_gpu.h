@@ -140,6 +140,9 @@ typedef struct NgiRenderParams {
 /* cross-check: run the two trace stages as one-thread-per-ray kernels instead of the warp-cooperative
  * persistent kernels (same building blocks, results identical up to the film's summation order) */
 #define NGI_RENDER_PER_RAY_TRACE 2u
+/* bdpt cross-check: run the one-sample-per-thread megakernel (ngi_bdpt.h) instead of the wavefront
+ * stages (ngi_bdpt_wave.h); same Philox counters, results identical up to the film's summation order */
+#define NGI_RENDER_BDPT_PER_THREAD 4u
 
 typedef struct NgiRenderStats {
     uint64_t paths;              /* samples processed                                         */

@@ -28,6 +28,7 @@ RENDERER_PT, RENDERER_PTDIRECT, RENDERER_LT, RENDERER_LTDIRECT, RENDERER_BDPT = 
 RENDERERS = {"pt": RENDERER_PT, "ptdirect": RENDERER_PTDIRECT, "lt": RENDERER_LT, "ltdirect": RENDERER_LTDIRECT, "bdpt": RENDERER_BDPT}
 RENDER_TIME_KERNELS = 1  # NGI_RENDER_TIME_KERNELS
 RENDER_PER_RAY_TRACE = 2  # NGI_RENDER_PER_RAY_TRACE
+RENDER_BDPT_PER_THREAD = 4  # NGI_RENDER_BDPT_PER_THREAD
 NO_HIT = 0xFFFFFFFF
 
 d3 = C.c_double * 3

@@ -117,77 +117,95 @@ NGI_HD float ngi_bd_geometry_term(const NgiBdVertex& a, const NgiBdVertex& b) {
     return (float)((double)t / d2);
 }
 
-// ---- Path::SampleSubpath, bdpt.hpp:54-123. kind 0: light subpath (LE), 1: eye subpath (EL). Returns the vertex count. ----------
+// ---- Path::SampleSubpath, bdpt.hpp:54-123, in three pieces shared by the per-thread loop below and the wavefront kernels
+// (ngi_bdpt_wave.h). kind 0: light subpath (LE), 1: eye subpath (EL). --------------------------------------------------------
+// vertex 0 (bdpt.hpp:60-75): a sampled light point / the sensor point. false: the subpath is empty (no lights).
+NGI_BD_FN bool ngi_bd_vertex0(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind, NgiBdVertex& v) {
+    const NgiDevSensor& E = sc.sensor;
+    v.albedo = mk3(0.0f); v.pixel = -1;
+    if (kind == 0) {
+        if (sc.n_lights == 0) return false;
+        unsigned rb[4];
+        philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), 0u, 1u, bp.seed_lo, bp.seed_hi, rb);
+        double pd[3];
+        const NgiLightSample ls = ngi_sample_light(sc, u01(rb[0]), u01(rb[1]), u01(rb[2]), true, pd);     // :63-66
+        v.px = pd[0]; v.py = pd[1]; v.pz = pd[2]; v.sn = v.gn = ls.n; v.prim = ls.prim; v.type = NGI_L; v.degenerate = ls.degenerate;
+    } else if (E.kind == NGI_ET_PINHOLE) {
+        v.px = E.px; v.py = E.py; v.pz = E.pz; v.sn = v.gn = mk3(0.0f); v.prim = E.prim; v.type = NGI_E; v.degenerate = 1;
+    } else {
+        unsigned rc[4];
+        philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), 0u, 2u, bp.seed_lo, bp.seed_hi, rc);
+        f3 p; int tri; float bx, by; double pd[3];
+        ngi_sample_triangle_mesh(sc, E.first_tri, E.num_tris, E.cdf_offset, u01(rc[1]), u01(rc[2]), p, v.sn, tri, bx, by, pd);
+        v.gn = v.sn; v.px = pd[0]; v.py = pd[1]; v.pz = pd[2]; v.prim = E.prim; v.type = NGI_E; v.degenerate = 0;
+        v.pixel = ngi_area_sensor_pixel(sc, (unsigned)tri, bx, by, bp.width, bp.height);
+    }
+    return true;
+}
+// the direction sampled at the subpath's last vertex `pv` in iteration `step` >= 1 (bdpt.hpp:77-90); `prev` = the vertex before it
+// (nullptr at vertex 0). false: the subpath ends here. `rr` = the uniform of the Russian roulette that follows the hit (:108-113).
+NGI_BD_FN bool ngi_bd_sample_direction(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind, const int step,
+                                       const NgiBdVertex& pv, const NgiBdVertex* prev, f3& wo, float& rr) {
+    const NgiDevSensor& E = sc.sensor;
+    const f3 wi = prev ? ngi_bd_dir(pv, *prev) : mk3(0.0f);                                                  // :77
+    unsigned ra[4];
+    philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), (unsigned)(step - 1), kind == 0 ? 0u : 3u, bp.seed_lo, bp.seed_hi, ra);
+    const float u0 = u01(ra[0]), u1 = u01(ra[1]), uc = u01(ra[2]);
+    rr = u01(ra[3]);
+    const NgiDevPrim& P = sc.prims[pv.prim];
+    wo = mk3(0.0f);
+    bool wrote = true;
+    if (pv.type & NGI_L) {                                                                                   // SampleDirection, rt.hpp:698-715
+        if (P.l_type == NGI_LT_AREA) { const NgiGeom g = ngi_bd_geom(pv); wo = ngi_to_world(g, ngi_cosine_hemisphere(u0, u1)); }
+        else if (P.l_type == NGI_LT_POINT) wo = ngi_uniform_sphere(u0, u1);
+        else wo = P.l_vec;
+    } else if (pv.type & NGI_E) {                                                                            // rt.hpp:726-740
+        if (E.kind == NGI_ET_PINHOLE) wo = ngi_pinhole_sample(E, u0, u1);
+        else { const NgiGeom g = ngi_bd_geom(pv); wo = ngi_to_world(g, ngi_cosine_hemisphere(u0, u1)); }
+    } else {
+        const NgiGeom g = ngi_bd_geom(pv);
+        wrote = ngi_sample_bsdf(P, pv.type, g, wi, u0, u1, uc, wo);
+    }
+    if (!wrote) return false;                                                                                 // wo stays zero -> f == 0
+    float pdfUnused;
+    const f3 f = ngi_bd_eval_direction(sc, pv, pv.type, wi, wo, kind == 0, true, pdfUnused);                  // :81
+    return !is_zero(f);
+}
+// the vertex at the hit `h` of the ray (pv, wo) (bdpt.hpp:92-106)
+NGI_BD_FN void ngi_bd_hit_vertex(const NgiDevScene& sc, const NgiBdParams& bp, const double ppx, const double ppy, const double ppz, const f3 wo,
+                                 const NgiHitRec& h, NgiBdVertex& v) {
+    double ddx, ddy, ddz;
+    ngi_dither_direction(wo, make_float4(h.t, h.u, h.v, u2f(h.tri)), ddx, ddy, ddz);                          // see ngi_logic_surface
+    v.px = ppx + ddx * (double)h.t; v.py = ppy + ddy * (double)h.t; v.pz = ppz + ddz * (double)h.t;
+    NgiGeom g;
+    v.prim = ngi_reconstruct(sc, h.tri, h.u, h.v, g);
+    v.sn = g.sn; v.gn = g.gn; v.degenerate = 0;
+    const NgiDevPrim& HP = sc.prims[v.prim];
+    v.type = HP.type & ~NGI_EMITTER;                                                                          // :102
+    const int tex = (v.type & NGI_D) ? HP.d_tex : HP.g_tex;
+    v.albedo = (tex >= 0 && sc.shade_uv) ? ngi_texture_at_hit(sc, tex, h.tri, h.u, h.v) : ngi_constant_albedo(HP, v.type);
+    v.pixel = ((HP.type & NGI_E) && sc.sensor.kind == NGI_ET_AREA && sc.shade_uv) ? ngi_area_sensor_pixel(sc, h.tri, h.u, h.v, bp.width, bp.height) : -1;
+}
+NGI_HD int ngi_bd_vertex_cap(const NgiBdParams& bp) {
+    return bp.max_verts == -1 ? NGI_BD_MAX_VERTS : (bp.max_verts < NGI_BD_MAX_VERTS ? bp.max_verts : NGI_BD_MAX_VERTS);
+}
+// the whole subpath, one vertex after the other (per-thread form). Returns the vertex count.
 NGI_BD_FN int ngi_bd_sample_subpath(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind,
                                  NgiBdVertex* V, NgiBdCounters& cnt) {
-    const NgiDevSensor& E = sc.sensor;
-    int n = 0;
-    const int cap = bp.max_verts == -1 ? NGI_BD_MAX_VERTS : (bp.max_verts < NGI_BD_MAX_VERTS ? bp.max_verts : NGI_BD_MAX_VERTS);
-    for (int step = 0; step < cap; step++) {
-        if (step == 0) {
-            NgiBdVertex v;
-            v.albedo = mk3(0.0f); v.pixel = -1;
-            if (kind == 0) {
-                if (sc.n_lights == 0) return 0;
-                unsigned rb[4];
-                philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), 0u, 1u, bp.seed_lo, bp.seed_hi, rb);
-                double pd[3];
-                const NgiLightSample ls = ngi_sample_light(sc, u01(rb[0]), u01(rb[1]), u01(rb[2]), true, pd);     // :63-66
-                v.px = pd[0]; v.py = pd[1]; v.pz = pd[2]; v.sn = v.gn = ls.n; v.prim = ls.prim; v.type = NGI_L; v.degenerate = ls.degenerate;
-            } else if (E.kind == NGI_ET_PINHOLE) {
-                v.px = E.px; v.py = E.py; v.pz = E.pz; v.sn = v.gn = mk3(0.0f); v.prim = E.prim; v.type = NGI_E; v.degenerate = 1;
-            } else {
-                unsigned rc[4];
-                philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), 0u, 2u, bp.seed_lo, bp.seed_hi, rc);
-                f3 p; int tri; float bx, by; double pd[3];
-                ngi_sample_triangle_mesh(sc, E.first_tri, E.num_tris, E.cdf_offset, u01(rc[1]), u01(rc[2]), p, v.sn, tri, bx, by, pd);
-                v.gn = v.sn; v.px = pd[0]; v.py = pd[1]; v.pz = pd[2]; v.prim = E.prim; v.type = NGI_E; v.degenerate = 0;
-                v.pixel = ngi_area_sensor_pixel(sc, (unsigned)tri, bx, by, bp.width, bp.height);
-            }
-            V[n++] = v;
-            continue;
-        }
+    const int cap = ngi_bd_vertex_cap(bp);
+    if (cap < 1 || !ngi_bd_vertex0(sc, bp, sample, kind, V[0])) return 0;
+    int n = 1;
+    for (int step = 1; step < cap; step++) {
         const NgiBdVertex& pv = V[n - 1];
-        const f3 wi = n > 1 ? ngi_bd_dir(pv, V[n - 2]) : mk3(0.0f);                                              // :77
-        unsigned ra[4];
-        philox4x32_10((unsigned)sample, (unsigned)(sample >> 32), (unsigned)(step - 1), kind == 0 ? 0u : 3u, bp.seed_lo, bp.seed_hi, ra);
-        const float u0 = u01(ra[0]), u1 = u01(ra[1]), uc = u01(ra[2]);
-        const NgiDevPrim& P = sc.prims[pv.prim];
-        f3 wo = mk3(0.0f);
-        bool wrote = true;
-        if (pv.type & NGI_L) {                                                                                   // SampleDirection, rt.hpp:698-715
-            if (P.l_type == NGI_LT_AREA) { const NgiGeom g = ngi_bd_geom(pv); wo = ngi_to_world(g, ngi_cosine_hemisphere(u0, u1)); }
-            else if (P.l_type == NGI_LT_POINT) wo = ngi_uniform_sphere(u0, u1);
-            else wo = P.l_vec;
-        } else if (pv.type & NGI_E) {                                                                            // rt.hpp:726-740
-            if (E.kind == NGI_ET_PINHOLE) wo = ngi_pinhole_sample(E, u0, u1);
-            else { const NgiGeom g = ngi_bd_geom(pv); wo = ngi_to_world(g, ngi_cosine_hemisphere(u0, u1)); }
-        } else {
-            const NgiGeom g = ngi_bd_geom(pv);
-            wrote = ngi_sample_bsdf(P, pv.type, g, wi, u0, u1, uc, wo);
-        }
-        if (!wrote) break;                                                                                        // wo stays zero -> f == 0
-        float pdfUnused;
-        const f3 f = ngi_bd_eval_direction(sc, pv, pv.type, wi, wo, kind == 0, true, pdfUnused);                  // :81
-        if (is_zero(f)) break;
+        f3 wo; float rr;
+        if (!ngi_bd_sample_direction(sc, bp, sample, kind, step, pv, n > 1 ? &V[n - 2] : nullptr, wo, rr)) break;
         NgiHitRec h;
         cnt.extend++;
         const f3 o = mk3((float)pv.px, (float)pv.py, (float)pv.pz);
         if (!ngi_bd_trace_closest(sc, o, wo, h)) break;                                                            // :92
-        NgiBdVertex v;
-        double ddx, ddy, ddz;
-        ngi_dither_direction(wo, make_float4(h.t, h.u, h.v, u2f(h.tri)), ddx, ddy, ddz);                          // see ngi_logic_surface
-        v.px = pv.px + ddx * (double)h.t; v.py = pv.py + ddy * (double)h.t; v.pz = pv.pz + ddz * (double)h.t;
-        NgiGeom g;
-        v.prim = ngi_reconstruct(sc, h.tri, h.u, h.v, g);
-        v.sn = g.sn; v.gn = g.gn; v.degenerate = 0;
-        const NgiDevPrim& HP = sc.prims[v.prim];
-        v.type = HP.type & ~NGI_EMITTER;                                                                          // :102
-        const int tex = (v.type & NGI_D) ? HP.d_tex : HP.g_tex;
-        v.albedo = (tex >= 0 && sc.shade_uv) ? ngi_texture_at_hit(sc, tex, h.tri, h.u, h.v) : ngi_constant_albedo(HP, v.type);
-        v.pixel = ((HP.type & NGI_E) && E.kind == NGI_ET_AREA && sc.shade_uv) ? ngi_area_sensor_pixel(sc, h.tri, h.u, h.v, bp.width, bp.height) : -1;
-        V[n++] = v;
-        if (u01(ra[3]) > 0.5f) break;                                                                             // :108-113
+        ngi_bd_hit_vertex(sc, bp, pv.px, pv.py, pv.pz, wo, h, V[n]);
+        n++;
+        if (rr > 0.5f) break;                                                                                     // :108-113
     }
     return n;
 }
@@ -196,9 +214,11 @@ NGI_BD_FN int ngi_bd_sample_subpath(const NgiDevScene& sc, const NgiBdParams& bp
 // acts as (Connect overrides the end vertex's type when one subpath is empty, bdpt.hpp:139,153).
 struct NgiBdPath {
     const NgiBdVertex* L; const NgiBdVertex* E;
+    size_t stride;                  // distance between consecutive vertices of a subpath (1: per-thread arrays; the wavefront
+                                    // kernels keep vertex k of every walker together, ngi_bdpt_wave.h)
     int s, t, n;
     int type_first, type_last;      // overrides (or the vertex's own type)
-    NGI_HD const NgiBdVertex& v(int i) const { return i < s ? L[i] : E[n - 1 - i]; }
+    NGI_HD const NgiBdVertex& v(int i) const { return i < s ? L[(size_t)i * stride] : E[(size_t)(n - 1 - i) * stride]; }
     NGI_HD int type(int i) const { return i == 0 ? type_first : (i == n - 1 ? type_last : v(i).type); }
 };
 
@@ -310,28 +330,32 @@ NGI_BD_FN f3 ngi_bd_contribution(const NgiDevScene& sc, const NgiBdPath& p, NgiB
     return Cstar * (float)(1.0 / (invWeight * sel));
 }
 
-// One (n, s) strategy of a sample: Path::Connect (bdpt.hpp:125-177) + contribution + film splat (src/nanogi.cpp:1164-1181).
-// Not inlined: the CUDA kernel calls it from a per-lane state machine (k_bdpt), the simulator from the plain loop nest below.
-NGI_BD_FN void ngi_bd_connect(const NgiDevScene& sc, const NgiBdParams& bp, const NgiBdVertex* VL, const NgiBdVertex* VE, const int n, const int s,
-                                    NgiBdScratch& q, NgiBdCounters& cnt) {
+// One (n, s) strategy of a sample: Path::Connect (bdpt.hpp:125-177) + contribution + film splat (src/nanogi.cpp:1164-1181), in
+// two pieces around the visibility query: ngi_bd_connect_ray says whether the strategy needs one (and which), ngi_bd_connect_finish
+// evaluates and splats a strategy that passed. `stride`: see NgiBdPath.
+// Connect's tests that need no ray (bdpt.hpp:133-137, :147-151): can strategy (n, s) exist at all?
+NGI_HD bool ngi_bd_strategy_possible(const NgiDevScene& sc, const NgiBdVertex* VL, const NgiBdVertex* VE, const int n, const int s, const size_t stride = 1) {
     const int t = n - s;
-    NgiBdPath p; p.L = VL; p.E = VE; p.s = s; p.t = t; p.n = n;
-    if (s == 0) {
-        if (!(sc.prims[VE[t - 1].prim].type & NGI_L)) return;
-        p.type_first = NGI_L; p.type_last = VE[0].type;
-    } else if (t == 0) {
-        if (!(sc.prims[VL[s - 1].prim].type & NGI_E) || VL[s - 1].prim != sc.sensor.prim || VL[s - 1].pixel < 0) return;   // only THE sensor (last E primitive)
-        p.type_first = VL[0].type; p.type_last = NGI_E;
-    } else {
-        const NgiBdVertex& a = VL[s - 1];
-        const NgiBdVertex& b = VE[t - 1];
-        const double dx = b.px - a.px, dy = b.py - a.py, dz = b.pz - a.pz;           // Scene::Visible, rt.hpp:2251-2261
-        const double len = sqrt(dx * dx + dy * dy + dz * dz);
-        const f3 d = mk3((float)(dx / len), (float)(dy / len), (float)(dz / len));
-        cnt.shadow++;
-        if (ngi_bd_trace_any(sc, mk3((float)a.px, (float)a.py, (float)a.pz), d, (float)len * (1.0f - NGI_EPS_F))) return;
-        p.type_first = VL[0].type; p.type_last = VE[0].type;
-    }
+    if (s == 0) return (sc.prims[VE[(size_t)(t - 1) * stride].prim].type & NGI_L) != 0;
+    if (t == 0) { const NgiBdVertex& a = VL[(size_t)(s - 1) * stride]; return (sc.prims[a.prim].type & NGI_E) != 0 && a.prim == sc.sensor.prim && a.pixel >= 0; }   // only THE sensor (last E primitive)
+    return true;
+}
+// Scene::Visible's ray between the two end vertices a -> b (rt.hpp:2251-2261); only for s > 0 and t > 0
+NGI_HD void ngi_bd_connect_ray(const double ax, const double ay, const double az, const double bx, const double by, const double bz,
+                               f3& o, f3& d, float& tmax) {
+    const double dx = bx - ax, dy = by - ay, dz = bz - az;
+    const double len = sqrt(dx * dx + dy * dy + dz * dz);
+    o = mk3((float)ax, (float)ay, (float)az);
+    d = mk3((float)(dx / len), (float)(dy / len), (float)(dz / len));
+    tmax = (float)len * (1.0f - NGI_EPS_F);
+}
+NGI_BD_FN void ngi_bd_connect_finish(const NgiDevScene& sc, const NgiBdParams& bp, const NgiBdVertex* VL, const NgiBdVertex* VE, const size_t stride,
+                                     const int n, const int s, NgiBdScratch& q) {
+    const int t = n - s;
+    NgiBdPath p; p.L = VL; p.E = VE; p.stride = stride; p.s = s; p.t = t; p.n = n;
+    if (s == 0) { p.type_first = NGI_L; p.type_last = VE[0].type; }
+    else if (t == 0) { p.type_first = VL[0].type; p.type_last = NGI_E; }
+    else { p.type_first = VL[0].type; p.type_last = VE[0].type; }
     const f3 C = ngi_bd_contribution(sc, p, q);
     if (is_zero(C) || !(C.x == C.x && C.y == C.y && C.z == C.z)) return;
     // Path::RasterPosition of the last vertex, bdpt.hpp:207-215
@@ -346,13 +370,19 @@ NGI_BD_FN void ngi_bd_connect(const NgiDevScene& sc, const NgiBdParams& bp, cons
     }
     ngi_film_add(bp.film, pixel, C * bp.film_scale);
 }
-
-// Connect's tests that need no ray (bdpt.hpp:133-137, :147-151): can strategy (n, s) exist at all?
-NGI_HD bool ngi_bd_strategy_possible(const NgiDevScene& sc, const NgiBdVertex* VL, const NgiBdVertex* VE, const int n, const int s) {
+// per-thread form: tests, visibility query and evaluation in one go. Not inlined: the megakernel calls it from a per-lane state
+// machine (k_bdpt), the simulator from the plain loop nest below.
+NGI_BD_FN void ngi_bd_connect(const NgiDevScene& sc, const NgiBdParams& bp, const NgiBdVertex* VL, const NgiBdVertex* VE, const int n, const int s,
+                                    NgiBdScratch& q, NgiBdCounters& cnt) {
     const int t = n - s;
-    if (s == 0) return (sc.prims[VE[t - 1].prim].type & NGI_L) != 0;
-    if (t == 0) return (sc.prims[VL[s - 1].prim].type & NGI_E) != 0 && VL[s - 1].prim == sc.sensor.prim && VL[s - 1].pixel >= 0;
-    return true;
+    if (!ngi_bd_strategy_possible(sc, VL, VE, n, s)) return;
+    if (s > 0 && t > 0) {
+        f3 o, d; float tmax;
+        ngi_bd_connect_ray(VL[s - 1].px, VL[s - 1].py, VL[s - 1].pz, VE[t - 1].px, VE[t - 1].py, VE[t - 1].pz, o, d, tmax);
+        cnt.shadow++;
+        if (ngi_bd_trace_any(sc, o, d, tmax)) return;
+    }
+    ngi_bd_connect_finish(sc, bp, VL, VE, 1, n, s, q);
 }
 
 // the (n, s) strategies of a sample in the reference's order (src/nanogi.cpp:1148-1160): advances the cursor, returns false when done

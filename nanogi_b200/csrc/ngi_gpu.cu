@@ -29,6 +29,7 @@
 #include "ngi_scene_host.h"
 #include "ngi_wave.h"
 #include "ngi_bdpt.h"
+#include "ngi_bdpt_wave.h"
 #include "ngi_trace_warp.cuh"
 
 namespace {
@@ -426,6 +427,137 @@ __global__ void __launch_bounds__(kTraceBlock, NGI_TRACE_MIN_BLOCKS) k_shadow(Ng
     ngi_trace_warp<true>(sc.nodes8, sc.tris8, src, tune);
 }
 
+// ================================================================================================
+// wavefront bdpt (ngi_bdpt_wave.h): dense stages over a batch of samples
+// ================================================================================================
+constexpr int kBdwShadowCursor = 31;          // index into NgiBdWave::cursors
+__device__ __forceinline__ void bdw_push_ray(float4* q, const unsigned idx, const f3 o, const f3 wo, const float rr, const unsigned w) {
+    q[2 * (size_t)idx] = make_float4(o.x, o.y, o.z, rr);
+    q[2 * (size_t)idx + 1] = make_float4(wo.x, wo.y, wo.z, u2f(w));
+}
+__global__ void __launch_bounds__(kBlock) k_bdw_start(NgiDevScene sc, NgiBdParams bp, NgiBdWave wv, int cap) {
+    __shared__ unsigned s_warp[1][kBlock / 32];
+    __shared__ unsigned s_base[1];
+    unsigned* const counters[1] = {wv.counts + 1};
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    f3 o = mk3(0.0f), wo = mk3(0.0f); float rr = 0.0f;
+    bool push = false;
+    if (w < 2u * wv.batch) push = ngi_bdw_start(sc, bp, wv, w, cap, o, wo, rr);
+    const bool need[1] = {push};
+    unsigned idx[1];
+    block_reserve<1>(counters, need, idx, s_warp, s_base);
+    if (push) bdw_push_ray(wv.rays[1], idx[0], o, wo, rr, w);
+}
+__global__ void __launch_bounds__(kBlock) k_bdw_step(NgiDevScene sc, NgiBdParams bp, NgiBdWave wv, int step, int cap) {
+    __shared__ unsigned s_warp[1][kBlock / 32];
+    __shared__ unsigned s_base[1];
+    const unsigned n = wv.counts[step];
+    const float4* rq = wv.rays[step & 1];
+    float4* nq = wv.rays[(step + 1) & 1];
+    unsigned* const counters[1] = {wv.counts + step + 1};
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // block-uniform trip count
+        const unsigned e = base + threadIdx.x;
+        f3 o = mk3(0.0f), wo = mk3(0.0f); float rr = 0.0f; unsigned w = 0;
+        bool push = false;
+        if (e < n) push = ngi_bdw_step(sc, bp, wv, step, cap, rq[2 * (size_t)e], rq[2 * (size_t)e + 1], wv.hits[e], w, o, wo, rr);
+        const bool need[1] = {push};
+        unsigned idx[1];
+        block_reserve<1>(counters, need, idx, s_warp, s_base);
+        if (push) bdw_push_ray(nq, idx[0], o, wo, rr, w);
+    }
+}
+struct BdwExtendSource {
+    NgiBdWave wv; int step;
+    __device__ __forceinline__ unsigned count() const { return wv.counts[step]; }
+    __device__ __forceinline__ unsigned* cursor() const { return wv.cursors + step; }
+    __device__ __forceinline__ unsigned load(unsigned i, f3& o, f3& d, float& tmin, float& tmax) const {
+        const float4* q = wv.rays[step & 1] + 2 * (size_t)i;
+        const float4 r0 = q[0], r1 = q[1];
+        o = mk3(r0.x, r0.y, r0.z); d = mk3(r1.x, r1.y, r1.z); tmin = NGI_EPS_F; tmax = NGI_INF_F;
+        return i;
+    }
+    __device__ __forceinline__ void store(unsigned i, bool found, const NgiHitRec& h) const {
+        wv.hits[i] = found ? make_float4(h.t, h.u, h.v, u2f(h.tri)) : make_float4(0.0f, 0.0f, 0.0f, u2f(NGI_MISS));
+    }
+};
+struct BdwShadowSource {
+    NgiBdWave wv;
+    __device__ __forceinline__ unsigned count() const { return wv.n_ray_items; }
+    __device__ __forceinline__ unsigned* cursor() const { return wv.cursors + kBdwShadowCursor; }
+    __device__ __forceinline__ unsigned load(unsigned i, f3& o, f3& d, float& tmin, float& tmax) const {
+        const uint2 it = wv.ray_items[i];
+#ifdef NGI_BDW_DEBUG
+        { const int n = it.y & 0xFF, s = (it.y >> 8) & 0xFF;
+          if (it.x >= wv.batch || s <= 0 || n - s <= 0 || s > (int)wv.nverts[2 * it.x] || n - s > (int)wv.nverts[2 * it.x + 1]) {
+              printf("bad item i=%u of %u: x=%u y=%08x batch=%u\n", i, wv.n_ray_items, it.x, it.y, wv.batch); o = mk3(0.f); d = mk3(0.f,0.f,1.f); tmax = 0.f; tmin = 0.f; return i; } }
+#endif
+        ngi_bdw_item_ray(wv, it, o, d, tmax);
+        tmin = NGI_EPS_F;
+        return i;
+    }
+    __device__ __forceinline__ void store(unsigned i, bool occluded, const NgiHitRec&) const { wv.visible[i] = occluded ? 0 : 1; }
+};
+__global__ void __launch_bounds__(kTraceBlock, NGI_TRACE_MIN_BLOCKS) k_bdw_extend(NgiDevScene sc, NgiBdWave wv, int step, NgiTraceTuning tune) {
+    BdwExtendSource src; src.wv = wv; src.step = step;
+    ngi_trace_warp<false>(sc.nodes8, sc.tris8, src, tune);
+}
+__global__ void __launch_bounds__(kTraceBlock, NGI_TRACE_MIN_BLOCKS) k_bdw_shadow(NgiDevScene sc, NgiBdWave wv, NgiTraceTuning tune) {
+    BdwShadowSource src; src.wv = wv;
+    ngi_trace_warp<true>(sc.nodes8, sc.tris8, src, tune);
+}
+// per sample: (connecting strategies | ray-less strategies << 32), and where its items go: block-level exclusive scan of the packed
+// counts (neither half can carry: a batch has < 2^32 strategies) + one 64-bit atomic per block on the batch totals
+constexpr int kBdwTotals = 60;                // ctl[60..61] = totals (u64: ray items | ray-less items << 32)
+__global__ void __launch_bounds__(kBlock) k_bdw_count(NgiDevScene sc, NgiBdParams bp, NgiBdWave wv, unsigned long long* __restrict__ totals) {
+    __shared__ unsigned long long s_warp[kBlock / 32];
+    __shared__ unsigned long long s_base;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned nr = 0, nl = 0;
+    if (i < wv.batch) ngi_bdw_strategies(sc, bp, wv, i, nr, nl, false, 0u, 0u);
+    const unsigned long long v = (unsigned long long)nr | ((unsigned long long)nl << 32);
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += t;
+    }
+    if (lane == 31u) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int w = 0; w < kBlock / 32; w++) { const unsigned long long c = s_warp[w]; s_warp[w] = acc; acc += c; }
+        s_base = acc ? atomicAdd(totals, acc) : 0ull;
+    }
+    __syncthreads();
+    if (i < wv.batch) wv.offsets[i] = s_base + s_warp[warp] + (incl - v);
+}
+__global__ void __launch_bounds__(kBlock) k_bdw_expand(NgiDevScene sc, NgiBdParams bp, NgiBdWave wv) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wv.batch) return;
+    const unsigned long long off = wv.offsets[i];
+    unsigned nr, nl;
+    ngi_bdw_strategies(sc, bp, wv, i, nr, nl, true, (unsigned)(off & 0xFFFFFFFFull), (unsigned)(off >> 32));
+}
+__global__ void __launch_bounds__(kBlock) k_bdw_compact(NgiBdWave wv) {
+    __shared__ unsigned s_warp[1][kBlock / 32];
+    __shared__ unsigned s_base[1];
+    const unsigned n = wv.n_ray_items;
+    unsigned* const counters[1] = {wv.contrib_extra};
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned e = base + threadIdx.x;
+        const bool need[1] = {e < n && wv.visible[e] != 0};
+        unsigned idx[1];
+        block_reserve<1>(counters, need, idx, s_warp, s_base);
+        if (need[0]) wv.contrib_items[(size_t)wv.n_rayless + idx[0]] = wv.ray_items[e];
+    }
+}
+__global__ void __launch_bounds__(128) k_bdw_contrib(NgiDevScene sc, NgiBdParams bp, NgiBdWave wv) {
+    NgiBdScratch q;
+    const unsigned n = wv.n_rayless + *wv.contrib_extra;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_bdw_contrib(sc, bp, wv, wv.contrib_items[e], q);
+}
+
 __global__ void __launch_bounds__(kBlock) k_eval_bsdf(NgiDevScene sc, const float* __restrict__ q, const float* __restrict__ wo_in, size_t n,
                                                       int force_degenerated, float* __restrict__ out) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -538,9 +670,12 @@ struct Scene {
     // the extend and shadow kernels of one iteration are independent: the shadow kernel is forked onto the lane's second
     // stream so that its CTAs fill the SMs the extend kernel's tail leaves idle
     bool overlap_trace = true;
+    cudaStream_t bd_streams[2] = {nullptr, nullptr};   // wavefront bdpt: two batches in flight
+    unsigned grid_bdw_extend = 0, grid_bdw_shadow = 0;
 
     ~Scene() {
         cudaSetDevice(device);
+        for (cudaStream_t b : bd_streams) if (b) cudaStreamDestroy(b);
         for (Lane& l : lanes) {
             if (l.graph_exec) cudaGraphExecDestroy(l.graph_exec);
             for (auto e : l.events) cudaEventDestroy(e);
@@ -868,6 +1003,165 @@ int launch_iteration(Scene* s, Lane& l, bool timed, size_t& ev_used, bool per_ra
     return NGI_OK;
 }
 
+// ---- wavefront bdpt: host side -------------------------------------------------------------------------------------------
+// One batch context = the buffers of NgiBdWave + a stream. Two contexts alternate: while the host waits for the strategy totals of
+// batch b (the only host sync of a batch), the kernels of batch b + 1 are already queued on the other stream, and the tails of one
+// batch's persistent trace launches are filled by the other's kernels.
+struct BdwCtx {
+    cudaStream_t stream = nullptr;
+    NgiBdWave wv{};
+    unsigned* ctl = nullptr;                  // 64 words: counts[32] | cursors[28] | strategy totals (u64) | contrib_extra | shadow cursor
+    unsigned* ctl_host = nullptr;             // pinned copy
+    size_t ray_cap = 0, contrib_cap = 0;
+    bool pending = false;
+    cudaEvent_t done = nullptr;
+};
+
+int bdw_phase1(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64_t& launches) {
+    cudaStream_t st = c.stream;
+    NgiBdWave& wv = c.wv;
+    NGI_CUDA(cudaMemsetAsync(c.ctl, 0, 64 * sizeof(unsigned), st));
+    const unsigned walkers = 2u * wv.batch;
+    k_bdw_start<<<(walkers + kBlock - 1) / kBlock, kBlock, 0, st>>>(s->dev, bp, wv, cap);
+    launches++;
+    for (int step = 1; step < cap; step++) {
+        // the queue shrinks by about 2x per step (Russian roulette); the kernels loop grid-stride over the device-side count
+        const unsigned expect = std::max(walkers >> (step - 1), 1u);
+        k_bdw_extend<<<std::min(s->grid_bdw_extend, std::max(148u, (expect + kTraceBlock - 1) / kTraceBlock)), kTraceBlock, 0, st>>>(s->dev, wv, step, s->tune);
+        k_bdw_step<<<std::min(kStageGrid, std::max(148u, (2u * expect + kBlock - 1) / kBlock)), kBlock, 0, st>>>(s->dev, bp, wv, step, cap);
+        launches += 2;
+    }
+    k_bdw_count<<<(wv.batch + kBlock - 1) / kBlock, kBlock, 0, st>>>(s->dev, bp, wv, (unsigned long long*)(c.ctl + kBdwTotals));
+    launches++;
+    NGI_CUDA(cudaMemcpyAsync(c.ctl_host, c.ctl, 64 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    c.pending = true;
+    return NGI_OK;
+}
+
+int bdw_phase2(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64_t& launches, uint64_t& extend_rays, uint64_t& shadow_rays) {
+    if (!c.pending) return NGI_OK;
+    cudaStream_t st = c.stream;
+    NgiBdWave& wv = c.wv;
+    NGI_CUDA(cudaStreamSynchronize(st));
+    c.pending = false;
+    for (int k = 1; k < cap; k++) extend_rays += c.ctl_host[k];
+    wv.n_ray_items = c.ctl_host[kBdwTotals];
+    wv.n_rayless = c.ctl_host[kBdwTotals + 1];
+    shadow_rays += wv.n_ray_items;
+    const size_t need_ray = wv.n_ray_items, need_contrib = (size_t)wv.n_ray_items + wv.n_rayless;
+    if (need_ray > c.ray_cap) {
+        ngi_dfree(wv.ray_items, st); ngi_dfree(wv.visible, st);
+        c.ray_cap = need_ray + need_ray / 4;
+        NGI_CUDA(ngi_dmalloc((void**)&wv.ray_items, c.ray_cap * sizeof(uint2), st));
+        NGI_CUDA(ngi_dmalloc((void**)&wv.visible, c.ray_cap, st));
+    }
+    if (need_contrib > c.contrib_cap) {
+        ngi_dfree(wv.contrib_items, st);
+        c.contrib_cap = need_contrib + need_contrib / 4;
+        NGI_CUDA(ngi_dmalloc((void**)&wv.contrib_items, c.contrib_cap * sizeof(uint2), st));
+    }
+    if (need_contrib == 0) return NGI_OK;
+    k_bdw_expand<<<(wv.batch + kBlock - 1) / kBlock, kBlock, 0, st>>>(s->dev, bp, wv);
+    launches++;
+#ifdef NGI_BDW_DEBUG
+    {
+        cudaError_t e1 = cudaGetLastError();
+        cudaError_t e2 = cudaStreamSynchronize(st);
+        std::vector<uint2> items(wv.n_ray_items);
+        std::vector<unsigned long long> offs(wv.batch);
+        std::vector<unsigned> nv(2 * wv.batch);
+        cudaMemcpy(items.data(), wv.ray_items, items.size() * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(offs.data(), wv.offsets, offs.size() * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(nv.data(), wv.nverts, nv.size() * 4, cudaMemcpyDeviceToHost);
+        size_t zeros = 0; for (auto& it : items) zeros += (it.y == 0);
+        fprintf(stderr, "expand: launch err %d sync err %d; items %zu zero %zu; batch %u\n", (int)e1, (int)e2, items.size(), zeros, wv.batch);
+        for (unsigned i = 0; i < 12; i++) fprintf(stderr, "  sample %u nL %u nE %u off ray %u rayless %u\n", i, nv[2*i], nv[2*i+1], (unsigned)(offs[i] & 0xFFFFFFFF), (unsigned)(offs[i] >> 32));
+        for (unsigned i = 0; i < 40 && i < items.size(); i++) fprintf(stderr, "  item %u: x %u n %u s %u\n", i, items[i].x, items[i].y & 255, items[i].y >> 8);
+    }
+#endif
+    if (wv.n_ray_items) {
+        k_bdw_shadow<<<std::min(s->grid_bdw_shadow, std::max(148u, (wv.n_ray_items + kTraceBlock - 1) / kTraceBlock)), kTraceBlock, 0, st>>>(s->dev, wv, s->tune);
+        k_bdw_compact<<<std::min(kStageGrid, (wv.n_ray_items + kBlock - 1) / kBlock), kBlock, 0, st>>>(wv);
+        launches += 2;
+    }
+    k_bdw_contrib<<<(unsigned)std::min<size_t>(148u * 16u, (need_contrib + 127) / 128), 128, 0, st>>>(s->dev, bp, wv);
+    launches++;
+    return NGI_OK;
+}
+
+int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp, cudaStream_t st, NgiRenderStats* stats) {
+    const int cap = ngi_bd_vertex_cap(bp);
+    int rc;
+    if (!s->grid_bdw_extend) {
+        if ((rc = persistent_grid(k_bdw_extend, &s->grid_bdw_extend))) return rc;
+        if ((rc = persistent_grid(k_bdw_shadow, &s->grid_bdw_shadow))) return rc;
+    }
+    for (cudaStream_t& b : s->bd_streams) if (!b) NGI_CUDA(cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking));
+    // batch size: vertex storage cap x 2 B x 80 bytes (2 GB at 2^19 samples and 24 vertices), two batches in flight
+    unsigned B = rp->wave_capacity ? rp->wave_capacity : (1u << 19);
+    if (const char* e = getenv("NGI_BDPT_BATCH")) B = (unsigned)std::max(1, atoi(e));
+    B = (unsigned)std::min<long long>(B, rp->num_samples);
+    const long long n_batches = (rp->num_samples + B - 1) / B;
+    const int K = n_batches > 1 ? 2 : 1;
+    BdwCtx ctx[2];
+    cudaEvent_t ev0, ev1;
+    NGI_CUDA(cudaEventCreate(&ev0)); NGI_CUDA(cudaEventCreate(&ev1));
+    for (int k = 0; k < K; k++) {
+        BdwCtx& c = ctx[k];
+        c.stream = s->bd_streams[k];
+        NgiBdWave& wv = c.wv;
+        wv.walkers = 2u * B;
+        NGI_CUDA(ngi_dmalloc((void**)&wv.V, (size_t)cap * wv.walkers * sizeof(NgiBdVertex), st));
+        NGI_CUDA(ngi_dmalloc((void**)&wv.nverts, (size_t)wv.walkers * sizeof(unsigned), st));
+        NGI_CUDA(ngi_dmalloc((void**)&wv.rays[0], (size_t)wv.walkers * 2 * sizeof(float4), st));
+        NGI_CUDA(ngi_dmalloc((void**)&wv.rays[1], (size_t)wv.walkers * 2 * sizeof(float4), st));
+        NGI_CUDA(ngi_dmalloc((void**)&wv.hits, (size_t)wv.walkers * sizeof(float4), st));
+        NGI_CUDA(ngi_dmalloc((void**)&wv.offsets, (size_t)B * sizeof(unsigned long long), st));
+        NGI_CUDA(ngi_dmalloc((void**)&c.ctl, 64 * sizeof(unsigned), st));
+        wv.counts = c.ctl; wv.cursors = c.ctl + 32; wv.contrib_extra = c.ctl + 32 + 30;
+        NGI_CUDA(cudaMallocHost((void**)&c.ctl_host, 64 * sizeof(unsigned)));
+        c.ray_cap = (size_t)B * 12; c.contrib_cap = (size_t)B * 16;      // expected <= 16 strategies per sample; grown on demand
+        NGI_CUDA(ngi_dmalloc((void**)&wv.ray_items, c.ray_cap * sizeof(uint2), st));
+        NGI_CUDA(ngi_dmalloc((void**)&wv.visible, c.ray_cap, st));
+        NGI_CUDA(ngi_dmalloc((void**)&wv.contrib_items, c.contrib_cap * sizeof(uint2), st));
+        NGI_CUDA(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+    }
+    NGI_CUDA(cudaEventRecord(ev0, st));          // fork: the film memset and the allocations precede every batch
+    for (int k = 0; k < K; k++) NGI_CUDA(cudaStreamWaitEvent(ctx[k].stream, ev0, 0));
+    uint64_t launches = 0, extend_rays = 0, shadow_rays = 0;
+    for (long long b = 0; b < n_batches; b++) {
+        BdwCtx& c = ctx[b % K];
+        c.wv.first = (unsigned long long)(rp->sample_offset + b * (long long)B);
+        c.wv.batch = (unsigned)std::min<long long>(B, rp->num_samples - b * (long long)B);
+        if ((rc = bdw_phase1(s, c, bp, cap, launches))) return rc;
+        if (K > 1 && b > 0 && (rc = bdw_phase2(s, ctx[(b - 1) % K], bp, cap, launches, extend_rays, shadow_rays))) return rc;
+    }
+    if (K > 1 && n_batches > 1 && (rc = bdw_phase2(s, ctx[(n_batches - 2) % K], bp, cap, launches, extend_rays, shadow_rays))) return rc;   // no-op if done
+    if ((rc = bdw_phase2(s, ctx[(n_batches - 1) % K], bp, cap, launches, extend_rays, shadow_rays))) return rc;
+    for (int k = 0; k < K; k++) {                // join
+        NGI_CUDA(cudaEventRecord(ctx[k].done, ctx[k].stream));
+        NGI_CUDA(cudaStreamWaitEvent(st, ctx[k].done, 0));
+    }
+    NGI_CUDA(cudaEventRecord(ev1, st));
+    for (int k = 0; k < K; k++) {
+        BdwCtx& c = ctx[k];
+        ngi_dfree(c.wv.V, st); ngi_dfree(c.wv.nverts, st); ngi_dfree(c.wv.rays[0], st); ngi_dfree(c.wv.rays[1], st); ngi_dfree(c.wv.hits, st);
+        ngi_dfree(c.wv.offsets, st); ngi_dfree(c.ctl, st);
+        ngi_dfree(c.wv.ray_items, st); ngi_dfree(c.wv.visible, st); ngi_dfree(c.wv.contrib_items, st);
+    }
+    NGI_CUDA(cudaStreamSynchronize(st));
+    NGI_CUDA(cudaGetLastError());
+    float ms = 0;
+    NGI_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    for (int k = 0; k < K; k++) { cudaEventDestroy(ctx[k].done); cudaFreeHost(ctx[k].ctl_host); }
+    if (stats) {
+        stats->paths = (uint64_t)rp->num_samples; stats->extend_rays = extend_rays; stats->shadow_rays = shadow_rays;
+        stats->kernel_launches = launches; stats->wave_iterations = (uint64_t)n_batches; stats->gpu_seconds = ms * 1e-3;
+    }
+    return NGI_OK;
+}
+
 int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream_t st, NgiRenderStats* stats) {
     if (rp->struct_size != sizeof(NgiRenderParams)) return set_err(NGI_ERR_INVALID_ARGUMENT, "NgiRenderParams.struct_size mismatch (ABI)");
     if (rp->renderer < NGI_RENDERER_PT || rp->renderer > NGI_RENDERER_BDPT)
@@ -884,11 +1178,12 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         return NGI_OK;
     }
     if (rp->renderer == NGI_RENDERER_BDPT) {
-        // one thread per sample (ngi_bdpt.h): no wavefront state, a single launch over the shard
         NgiBdParams bp;
         bp.film = film_dev; bp.width = rp->width; bp.height = rp->height; bp.max_verts = rp->max_num_vertices;
         bp.seed_lo = (unsigned)rp->seed; bp.seed_hi = (unsigned)(rp->seed >> 32);
         bp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
+        if (!(rp->flags & NGI_RENDER_BDPT_PER_THREAD)) return render_bdpt_wave(s, rp, bp, st, stats);   // the product path (ngi_bdpt_wave.h)
+        // cross-check: one thread per sample (ngi_bdpt.h), a single launch over the shard
         unsigned long long* d_cnt = nullptr;
         NGI_CUDA(ngi_dmalloc((void**)&d_cnt, 2 * sizeof(unsigned long long), st));
         NGI_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));

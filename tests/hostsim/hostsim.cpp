@@ -20,6 +20,7 @@ static unsigned long long g_trace_count[2] = {0, 0};     // [0] BVH8 node steps,
 #include "../../nanogi_b200/csrc/ngi_scene_host.h"
 #include "../../nanogi_b200/csrc/ngi_wave.h"
 #include "../../nanogi_b200/csrc/ngi_bdpt.h"
+#include "../../nanogi_b200/csrc/ngi_bdpt_wave.h"
 
 namespace {
 
@@ -252,16 +253,86 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
     std::fill(film, film + npx * 3, 0.0f);
     if (stats) std::fill(stats, stats + 4, 0.0);
     if (rp->max_num_vertices != -1 && rp->max_num_vertices < 2) return 0;
-    if (rp->renderer == NGI_RENDERER_BDPT) {       // k_bdpt: one sample after the other
+    if (rp->renderer == NGI_RENDERER_BDPT) {
         NgiBdParams bp;
         bp.film = film; bp.width = rp->width; bp.height = rp->height; bp.max_verts = rp->max_num_vertices;
         bp.seed_lo = (unsigned)rp->seed; bp.seed_hi = (unsigned)(rp->seed >> 32);
         bp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
-        std::vector<NgiBdVertex> VL(NGI_BD_MAX_VERTS), VE(NGI_BD_MAX_VERTS);
         NgiBdCounters cnt; cnt.extend = 0; cnt.shadow = 0;
         std::vector<NgiBdScratch> q(1);
-        for (long long i = 0; i < rp->num_samples; i++) ngi_bdpt_sample(s->dev, bp, (unsigned long long)(rp->sample_offset + i), VL.data(), VE.data(), q[0], cnt);
-        if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)cnt.extend; stats[2] = (double)cnt.shadow; stats[3] = 1; }
+        if (rp->flags & NGI_RENDER_BDPT_PER_THREAD) {       // k_bdpt: one sample after the other
+            std::vector<NgiBdVertex> VL(NGI_BD_MAX_VERTS), VE(NGI_BD_MAX_VERTS);
+            for (long long i = 0; i < rp->num_samples; i++) ngi_bdpt_sample(s->dev, bp, (unsigned long long)(rp->sample_offset + i), VL.data(), VE.data(), q[0], cnt);
+            if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)cnt.extend; stats[2] = (double)cnt.shadow; stats[3] = 1; }
+            return 0;
+        }
+        // the wavefront stages (ngi_bdpt_wave.h) in the order the k_bdw_* kernels run, batch by batch
+        const int cap = ngi_bd_vertex_cap(bp);
+        const unsigned B = rp->wave_capacity ? rp->wave_capacity : 4096;
+        NgiBdWave wv;
+        std::memset(&wv, 0, sizeof(wv));
+        wv.walkers = 2 * B;
+        std::vector<NgiBdVertex> V((size_t)std::max(cap, 1) * wv.walkers);
+        std::vector<unsigned> nverts(wv.walkers);
+        std::vector<float4> rays0((size_t)2 * wv.walkers), rays1((size_t)2 * wv.walkers), hits(wv.walkers);
+        std::vector<unsigned long long> offsets(B + 1);
+        std::vector<uint2> ray_items, contrib_items;
+        std::vector<unsigned char> visible;
+        wv.V = V.data(); wv.nverts = nverts.data(); wv.rays[0] = rays0.data(); wv.rays[1] = rays1.data(); wv.hits = hits.data();
+        wv.offsets = offsets.data();
+        unsigned long long batches = 0;
+        for (long long b0 = 0; b0 < rp->num_samples; b0 += B, batches++) {
+            wv.first = (unsigned long long)(rp->sample_offset + b0);
+            wv.batch = (unsigned)std::min<long long>(B, rp->num_samples - b0);
+            unsigned count = 0;
+            for (unsigned w = 0; w < 2 * wv.batch; w++) {                                      // k_bdw_start
+                f3 o, wo; float rr;
+                if (ngi_bdw_start(s->dev, bp, wv, w, cap, o, wo, rr)) {
+                    wv.rays[1][2 * (size_t)count] = make_float4(o.x, o.y, o.z, rr); wv.rays[1][2 * (size_t)count + 1] = make_float4(wo.x, wo.y, wo.z, u2f(w)); count++;
+                }
+            }
+            for (int step = 1; step < cap && count > 0; step++) {
+                const float4* rq = wv.rays[step & 1];
+                float4* nq = wv.rays[(step + 1) & 1];
+                for (unsigned i = 0; i < count; i++) {                                         // k_bdw_extend
+                    NgiHitRec h;
+                    const bool hit = ngi_trace_bvh8<false>(s->dev.nodes8, s->dev.tris8, mk3(rq[2 * i].x, rq[2 * i].y, rq[2 * i].z), mk3(rq[2 * i + 1].x, rq[2 * i + 1].y, rq[2 * i + 1].z), NGI_EPS_F, NGI_INF_F, h);
+                    hits[i] = hit ? make_float4(h.t, h.u, h.v, u2f(h.tri)) : make_float4(0.0f, 0.0f, 0.0f, u2f(NGI_MISS));
+                }
+                cnt.extend += count;
+                unsigned next = 0;
+                for (unsigned i = 0; i < count; i++) {                                         // k_bdw_step
+                    unsigned w; f3 o, wo; float rr;
+                    if (ngi_bdw_step(s->dev, bp, wv, step, cap, rq[2 * i], rq[2 * i + 1], hits[i], w, o, wo, rr)) {
+                        nq[2 * (size_t)next] = make_float4(o.x, o.y, o.z, rr); nq[2 * (size_t)next + 1] = make_float4(wo.x, wo.y, wo.z, u2f(w)); next++;
+                    }
+                }
+                count = next;
+            }
+            unsigned long long acc = 0;
+            for (unsigned i = 0; i < wv.batch; i++) {                                          // k_bdw_count + scan
+                unsigned nr, nl;
+                ngi_bdw_strategies(s->dev, bp, wv, i, nr, nl, false, 0u, 0u);
+                offsets[i] = acc; acc += (unsigned long long)nr | ((unsigned long long)nl << 32);
+            }
+            offsets[wv.batch] = acc;
+            wv.n_ray_items = (unsigned)(acc & 0xFFFFFFFFull); wv.n_rayless = (unsigned)(acc >> 32);
+            ray_items.resize(wv.n_ray_items + 1); visible.resize(wv.n_ray_items + 1); contrib_items.resize((size_t)wv.n_ray_items + wv.n_rayless + 1);
+            wv.ray_items = ray_items.data(); wv.visible = visible.data(); wv.contrib_items = contrib_items.data();
+            for (unsigned i = 0; i < wv.batch; i++) {                                          // k_bdw_expand
+                unsigned nr, nl;
+                ngi_bdw_strategies(s->dev, bp, wv, i, nr, nl, true, (unsigned)(offsets[i] & 0xFFFFFFFFull), (unsigned)(offsets[i] >> 32));
+            }
+            unsigned extra = 0;
+            for (unsigned i = 0; i < wv.n_ray_items; i++) {                                    // k_bdw_shadow + k_bdw_compact
+                f3 o, d; float tmax; NgiHitRec h;
+                ngi_bdw_item_ray(wv, ray_items[i], o, d, tmax);
+                if (!ngi_trace_bvh8<true>(s->dev.nodes8, s->dev.tris8, o, d, NGI_EPS_F, tmax, h)) contrib_items[wv.n_rayless + extra++] = ray_items[i];
+            }
+            cnt.shadow += wv.n_ray_items;
+            for (unsigned i = 0; i < wv.n_rayless + extra; i++) ngi_bdw_contrib(s->dev, bp, wv, contrib_items[i], q[0]);   // k_bdw_contrib
+        }
+        if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)cnt.extend; stats[2] = (double)cnt.shadow; stats[3] = (double)batches; }
         return 0;
     }
     const unsigned P = rp->wave_capacity ? rp->wave_capacity : 4096;

@@ -75,7 +75,7 @@ class SimScene:
         return out[0] / max(rays.shape[0], 1), out[1] / max(rays.shape[0], 1)
 
     def render(self, renderer, num_samples, width, height, max_num_vertices=-1, seed=1, sample_offset=0, film_norm_samples=None,
-               wave_capacity=4096):
+               wave_capacity=4096, flags=0):
         p = capi.NgiRenderParams()
         p.struct_size = C.sizeof(capi.NgiRenderParams)
         p.renderer = capi.RENDERERS[renderer]
@@ -86,6 +86,7 @@ class SimScene:
         p.width, p.height = width, height
         p.seed = seed
         p.wave_capacity = wave_capacity
+        p.flags = flags
         film = np.zeros((height, width, 3), np.float32)
         stats = np.zeros(4)
         self.L.sim_render(self.h, C.byref(p), film.ctypes.data, stats.ctypes.data)

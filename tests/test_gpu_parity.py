@@ -146,6 +146,26 @@ def test_replay_bdpt(scene, m):
     g.close()
 
 
+@pytest.mark.parametrize("scene,m,batch", [("cornell_spheres", -1, 0), ("cornell_spheres", 5, 7777), ("cornell_raw_sensor", 6, 50000), ("cornell_mixed_lights", 3, 0)])
+def test_bdpt_wavefront_equals_per_thread(scene, m, batch):
+    """The wavefront bdpt (k_bdw_*: batches of samples through dense stages, warp-cooperative persistent trace kernels) against the
+    one-sample-per-thread megakernel (k_bdpt, NGI_RENDER_BDPT_PER_THREAD): same functions on the same Philox counters, so the ray
+    counts are identical and the films differ only by the order of the float atomics — any batch size, ragged last batch included,
+    several batches in flight on two streams."""
+    spec = scenes.cornell_raw_sensor(spheres=True) if scene == "cornell_raw_sensor" else getattr(scenes, scene)()
+    sd = scenes.to_scene_data(scaled_spec(spec, 0.01), 1.0)
+    g = capi.GpuScene(sd, 0)
+    n = 300000
+    fa, sa = g.render("bdpt", n, 64, 64, max_num_vertices=m, seed=5, sample_offset=77, wave_capacity=batch)
+    fb, sb = g.render("bdpt", n, 64, 64, max_num_vertices=m, seed=5, sample_offset=77, flags=capi.RENDER_BDPT_PER_THREAD)
+    g.close()
+    assert sa.extend_rays == sb.extend_rays and sa.shadow_rays == sb.shadow_rays, (sa.extend_rays, sb.extend_rays, sa.shadow_rays, sb.shadow_rays)
+    assert sa.kernel_launches > 1 and sb.kernel_launches == 1
+    assert fa.sum() > 0
+    np.testing.assert_allclose(fa, fb, rtol=1e-3, atol=1e-5 * float(fb.max()))
+    assert abs(float(fa.sum(dtype=np.float64)) / float(fb.sum(dtype=np.float64)) - 1.0) < 1e-5
+
+
 def test_bdpt_statistics_and_agreement_with_ptdirect(gpu_cornell, cornell):
     """bdpt at Cornell scale against the oracle (independent seeds). The reference's own bdpt is 2-3 % darker than its pt / ptdirect
     on this scene (oracle, 4 M samples, -m 6: 0.13141 vs 0.13489 — the oracle is bit-exact against the reference's code, so that

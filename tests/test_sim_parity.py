@@ -131,6 +131,21 @@ def test_replay_bdpt(scene, m):
     pc.check_replay(pysim.SimScene(sd), sd, "bdpt", n=15000, w=24, h=24, m=m)
 
 
+@pytest.mark.parametrize("scene,m,batch", [("cornell_spheres", -1, 1000), ("cornell_raw_sensor", 6, 4096), ("cornell_mixed_lights", 3, 333)])
+def test_bdpt_wavefront_equals_per_thread(scene, m, batch):
+    """The wavefront stages (ngi_bdpt_wave.h: batches of samples through start / extend / step / count / expand / shadow /
+    contrib) and the one-sample-per-thread form (ngi_bdpt.h) run the same functions on the same Philox counters: identical
+    ray counts, and films equal up to the order of the float additions — for any batch size (ragged last batch included)."""
+    spec = scenes.cornell_raw_sensor(spheres=True) if scene == "cornell_raw_sensor" else getattr(scenes, scene)()
+    sd = scenes.to_scene_data(scaled_spec(spec, 0.01), 1.0)
+    sim = pysim.SimScene(sd)
+    fa, sa = sim.render("bdpt", 10000, 24, 24, max_num_vertices=m, seed=5, sample_offset=77, wave_capacity=batch)
+    fb, sb = sim.render("bdpt", 10000, 24, 24, max_num_vertices=m, seed=5, sample_offset=77, flags=capi.RENDER_BDPT_PER_THREAD)
+    assert sa["extend_rays"] == sb["extend_rays"] and sa["shadow_rays"] == sb["shadow_rays"]
+    assert fa.sum() > 0
+    np.testing.assert_allclose(fa, fb, rtol=2e-5, atol=1e-6 * float(fb.max()))
+
+
 def test_bdpt_statistics_cornell_scale(cornell):
     pc.check_image_statistics(pysim.SimScene(cornell), cornell, "bdpt", w=16, h=16, spp=128, seeds=6, m=6, block=4)
 
