@@ -13,9 +13,11 @@
 //               (the queue shrinks by >= 2x per iteration; vertex k of every walker is stored together: V[k][walker])
 //   strategies  k_bdw_count   per sample: how many (n, s) strategies need a visibility ray / need none
 //               exclusive scan (cub) -> offsets; the host reads the two totals (the only host sync of a batch)
-//               k_bdw_expand  writes the strategy items (sample, n, s)
-//               k_bdw_shadow  Scene::Visible of every connecting strategy (persistent any-hit trace)
-//               k_bdw_compact visible items join the ray-less ones
+//               k_bdw_expand  writes the strategy items (sample, n, s): connecting ones first, ray-less ones behind them
+//               k_bdw_shadow  Scene::Visible of every connecting strategy (persistent any-hit trace); an occluded item's
+//                             key becomes NGI_BDW_DEAD
+//               radix sort (cub) of the items by (n, s): the lanes of a warp then run the same loop trip counts in the
+//                             contribution stage (unsorted it ran 6.2 of 32 lanes, profiles/r01_ncu_bdw_v1.txt); dead items go last
 //               k_bdw_contrib one item per lane: contribution x MIS weight (ngi_bd_connect_finish) -> film
 //
 // Same Philox counters as the per-thread form, so both produce the same samples; film sums differ only in the order of the
@@ -31,15 +33,16 @@ struct NgiBdWave {
     unsigned* counts;                // [NGI_BD_MAX_VERTS + 1] entries of ray queue k
     unsigned* cursors;               // [NGI_BD_MAX_VERTS + 1] dynamic-fetch cursors of the trace launches; [NGI_BD_MAX_VERTS] = shadow
     unsigned long long* offsets;     // [batch] where the items of each sample start: (ray items | ray-less items << 32)
-    uint2* ray_items;                // x = sample within the batch, y = n | s << 8
-    unsigned char* visible;          // per ray item
-    uint2* contrib_items;            // ray-less items, then the visible ray items
-    unsigned* contrib_extra;         // [1] visible ray items appended so far
+    uint2* items;                    // x = sample within the batch, y = n | s << 8 (NGI_BDW_DEAD: occluded); [0, n_ray_items) connect with
+                                     // a visibility ray, [n_ray_items, n_ray_items + n_rayless) need none
+    uint2* items_sorted;             // the same items ordered by y
     unsigned long long first;        // first sample index of the batch
     unsigned batch;                  // samples in this batch
     unsigned walkers;                // 2 * batch capacity = stride between V[k] and V[k + 1]
     unsigned n_ray_items, n_rayless; // totals (known to the host after the scan)
 };
+
+#define NGI_BDW_DEAD 0xFFFFu
 
 NGI_HD const NgiBdVertex* ngi_bdw_subpath(const NgiBdWave& wv, const unsigned sample_in_batch, const int kind) { return wv.V + 2u * sample_in_batch + (unsigned)kind; }
 
@@ -79,8 +82,8 @@ NGI_HD bool ngi_bdw_step(const NgiDevScene& sc, const NgiBdParams& bp, const Ngi
 }
 
 // k_bdw_count / k_bdw_expand: the strategies of one sample in the reference's order (src/nanogi.cpp:1148-1160). With items == nullptr
-// only counts; otherwise writes the connecting strategies from ray_items + ray_at and the ray-less ones that pass Connect's tests
-// (bdpt.hpp:133-137, :147-151) from contrib_items + rayless_at.
+// only counts; otherwise writes the connecting strategies from items + ray_at and the ray-less ones that pass Connect's tests
+// (bdpt.hpp:133-137, :147-151) from items + n_ray_items + rayless_at.
 NGI_HD void ngi_bdw_strategies(const NgiDevScene& sc, const NgiBdParams& bp, const NgiBdWave& wv, const unsigned i, unsigned& n_ray, unsigned& n_rayless,
                                const bool write, unsigned ray_at, unsigned rayless_at) {
     n_ray = 0u; n_rayless = 0u;
@@ -96,10 +99,10 @@ NGI_HD void ngi_bdw_strategies(const NgiDevScene& sc, const NgiBdParams& bp, con
     while (ngi_bd_next_strategy(bp, nL, nE, n, s)) {
         const uint2 item = make_uint2(i, (unsigned)n | ((unsigned)s << 8));
         if (s > 0 && n - s > 0) {
-            if (write) wv.ray_items[ray_at + n_ray] = item;
+            if (write) wv.items[ray_at + n_ray] = item;
             n_ray += one;
         } else if (ngi_bd_strategy_possible(sc, VL, VE, n, s, wv.walkers)) {
-            if (write) wv.contrib_items[rayless_at + n_rayless] = item;
+            if (write) wv.items[(size_t)wv.n_ray_items + rayless_at + n_rayless] = item;
             n_rayless += one;
         }
     }
@@ -115,6 +118,7 @@ NGI_HD void ngi_bdw_item_ray(const NgiBdWave& wv, const uint2 item, f3& o, f3& d
 
 // k_bdw_contrib: contribution, MIS weight and splat of one strategy that passed Connect
 NGI_HD void ngi_bdw_contrib(const NgiDevScene& sc, const NgiBdParams& bp, const NgiBdWave& wv, const uint2 item, NgiBdScratch& q) {
+    if (item.y == NGI_BDW_DEAD) return;
     const int n = (int)(item.y & 0xFFu), s = (int)((item.y >> 8) & 0xFFu);
     ngi_bd_connect_finish(sc, bp, ngi_bdw_subpath(wv, item.x, 0), ngi_bdw_subpath(wv, item.x, 1), wv.walkers, n, s, q);
 }

@@ -485,17 +485,12 @@ struct BdwShadowSource {
     __device__ __forceinline__ unsigned count() const { return wv.n_ray_items; }
     __device__ __forceinline__ unsigned* cursor() const { return wv.cursors + kBdwShadowCursor; }
     __device__ __forceinline__ unsigned load(unsigned i, f3& o, f3& d, float& tmin, float& tmax) const {
-        const uint2 it = wv.ray_items[i];
-#ifdef NGI_BDW_DEBUG
-        { const int n = it.y & 0xFF, s = (it.y >> 8) & 0xFF;
-          if (it.x >= wv.batch || s <= 0 || n - s <= 0 || s > (int)wv.nverts[2 * it.x] || n - s > (int)wv.nverts[2 * it.x + 1]) {
-              printf("bad item i=%u of %u: x=%u y=%08x batch=%u\n", i, wv.n_ray_items, it.x, it.y, wv.batch); o = mk3(0.f); d = mk3(0.f,0.f,1.f); tmax = 0.f; tmin = 0.f; return i; } }
-#endif
+        const uint2 it = wv.items[i];
         ngi_bdw_item_ray(wv, it, o, d, tmax);
         tmin = NGI_EPS_F;
         return i;
     }
-    __device__ __forceinline__ void store(unsigned i, bool occluded, const NgiHitRec&) const { wv.visible[i] = occluded ? 0 : 1; }
+    __device__ __forceinline__ void store(unsigned i, bool occluded, const NgiHitRec&) const { if (occluded) wv.items[i].y = NGI_BDW_DEAD; }
 };
 __global__ void __launch_bounds__(kTraceBlock, NGI_TRACE_MIN_BLOCKS) k_bdw_extend(NgiDevScene sc, NgiBdWave wv, int step, NgiTraceTuning tune) {
     BdwExtendSource src; src.wv = wv; src.step = step;
@@ -539,23 +534,10 @@ __global__ void __launch_bounds__(kBlock) k_bdw_expand(NgiDevScene sc, NgiBdPara
     unsigned nr, nl;
     ngi_bdw_strategies(sc, bp, wv, i, nr, nl, true, (unsigned)(off & 0xFFFFFFFFull), (unsigned)(off >> 32));
 }
-__global__ void __launch_bounds__(kBlock) k_bdw_compact(NgiBdWave wv) {
-    __shared__ unsigned s_warp[1][kBlock / 32];
-    __shared__ unsigned s_base[1];
-    const unsigned n = wv.n_ray_items;
-    unsigned* const counters[1] = {wv.contrib_extra};
-    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const unsigned e = base + threadIdx.x;
-        const bool need[1] = {e < n && wv.visible[e] != 0};
-        unsigned idx[1];
-        block_reserve<1>(counters, need, idx, s_warp, s_base);
-        if (need[0]) wv.contrib_items[(size_t)wv.n_rayless + idx[0]] = wv.ray_items[e];
-    }
-}
 __global__ void __launch_bounds__(128) k_bdw_contrib(NgiDevScene sc, NgiBdParams bp, NgiBdWave wv) {
     NgiBdScratch q;
-    const unsigned n = wv.n_rayless + *wv.contrib_extra;
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_bdw_contrib(sc, bp, wv, wv.contrib_items[e], q);
+    const unsigned n = wv.n_ray_items + wv.n_rayless;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_bdw_contrib(sc, bp, wv, wv.items_sorted[e], q);
 }
 
 __global__ void __launch_bounds__(kBlock) k_eval_bsdf(NgiDevScene sc, const float* __restrict__ q, const float* __restrict__ wo_in, size_t n,
@@ -1010,9 +992,10 @@ int launch_iteration(Scene* s, Lane& l, bool timed, size_t& ev_used, bool per_ra
 struct BdwCtx {
     cudaStream_t stream = nullptr;
     NgiBdWave wv{};
-    unsigned* ctl = nullptr;                  // 64 words: counts[32] | cursors[28] | strategy totals (u64) | contrib_extra | shadow cursor
+    unsigned* ctl = nullptr;                  // 64 words: counts[32] | cursors[28] | strategy totals (u64) | - | shadow cursor
     unsigned* ctl_host = nullptr;             // pinned copy
-    size_t ray_cap = 0, contrib_cap = 0;
+    size_t item_cap = 0;
+    void* sort_tmp = nullptr; size_t sort_bytes = 0;
     bool pending = false;
     cudaEvent_t done = nullptr;
 };
@@ -1038,6 +1021,18 @@ int bdw_phase1(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64
     return NGI_OK;
 }
 
+int bdw_alloc_items(BdwCtx& c, const size_t cap, cudaStream_t st) {
+    NgiBdWave& wv = c.wv;
+    ngi_dfree(wv.items, st); ngi_dfree(wv.items_sorted, st); ngi_dfree(c.sort_tmp, st);
+    c.item_cap = cap;
+    NGI_CUDA(ngi_dmalloc((void**)&wv.items, cap * sizeof(uint2), st));
+    NGI_CUDA(ngi_dmalloc((void**)&wv.items_sorted, cap * sizeof(uint2), st));
+    c.sort_bytes = 0;
+    NGI_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, c.sort_bytes, (const unsigned long long*)wv.items, (unsigned long long*)wv.items_sorted, (int)cap, 32, 48, st));
+    NGI_CUDA(ngi_dmalloc(&c.sort_tmp, c.sort_bytes, st));
+    return NGI_OK;
+}
+
 int bdw_phase2(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64_t& launches, uint64_t& extend_rays, uint64_t& shadow_rays) {
     if (!c.pending) return NGI_OK;
     cudaStream_t st = c.stream;
@@ -1048,43 +1043,20 @@ int bdw_phase2(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64
     wv.n_ray_items = c.ctl_host[kBdwTotals];
     wv.n_rayless = c.ctl_host[kBdwTotals + 1];
     shadow_rays += wv.n_ray_items;
-    const size_t need_ray = wv.n_ray_items, need_contrib = (size_t)wv.n_ray_items + wv.n_rayless;
-    if (need_ray > c.ray_cap) {
-        ngi_dfree(wv.ray_items, st); ngi_dfree(wv.visible, st);
-        c.ray_cap = need_ray + need_ray / 4;
-        NGI_CUDA(ngi_dmalloc((void**)&wv.ray_items, c.ray_cap * sizeof(uint2), st));
-        NGI_CUDA(ngi_dmalloc((void**)&wv.visible, c.ray_cap, st));
-    }
-    if (need_contrib > c.contrib_cap) {
-        ngi_dfree(wv.contrib_items, st);
-        c.contrib_cap = need_contrib + need_contrib / 4;
-        NGI_CUDA(ngi_dmalloc((void**)&wv.contrib_items, c.contrib_cap * sizeof(uint2), st));
-    }
-    if (need_contrib == 0) return NGI_OK;
+    const size_t need = (size_t)wv.n_ray_items + wv.n_rayless;
+    int rc;
+    if (need > c.item_cap && (rc = bdw_alloc_items(c, need + need / 4, st))) return rc;
+    if (need == 0) return NGI_OK;
     k_bdw_expand<<<(wv.batch + kBlock - 1) / kBlock, kBlock, 0, st>>>(s->dev, bp, wv);
     launches++;
-#ifdef NGI_BDW_DEBUG
-    {
-        cudaError_t e1 = cudaGetLastError();
-        cudaError_t e2 = cudaStreamSynchronize(st);
-        std::vector<uint2> items(wv.n_ray_items);
-        std::vector<unsigned long long> offs(wv.batch);
-        std::vector<unsigned> nv(2 * wv.batch);
-        cudaMemcpy(items.data(), wv.ray_items, items.size() * 8, cudaMemcpyDeviceToHost);
-        cudaMemcpy(offs.data(), wv.offsets, offs.size() * 8, cudaMemcpyDeviceToHost);
-        cudaMemcpy(nv.data(), wv.nverts, nv.size() * 4, cudaMemcpyDeviceToHost);
-        size_t zeros = 0; for (auto& it : items) zeros += (it.y == 0);
-        fprintf(stderr, "expand: launch err %d sync err %d; items %zu zero %zu; batch %u\n", (int)e1, (int)e2, items.size(), zeros, wv.batch);
-        for (unsigned i = 0; i < 12; i++) fprintf(stderr, "  sample %u nL %u nE %u off ray %u rayless %u\n", i, nv[2*i], nv[2*i+1], (unsigned)(offs[i] & 0xFFFFFFFF), (unsigned)(offs[i] >> 32));
-        for (unsigned i = 0; i < 40 && i < items.size(); i++) fprintf(stderr, "  item %u: x %u n %u s %u\n", i, items[i].x, items[i].y & 255, items[i].y >> 8);
-    }
-#endif
     if (wv.n_ray_items) {
         k_bdw_shadow<<<std::min(s->grid_bdw_shadow, std::max(148u, (wv.n_ray_items + kTraceBlock - 1) / kTraceBlock)), kTraceBlock, 0, st>>>(s->dev, wv, s->tune);
-        k_bdw_compact<<<std::min(kStageGrid, (wv.n_ray_items + kBlock - 1) / kBlock), kBlock, 0, st>>>(wv);
-        launches += 2;
+        launches++;
     }
-    k_bdw_contrib<<<(unsigned)std::min<size_t>(148u * 16u, (need_contrib + 127) / 128), 128, 0, st>>>(s->dev, bp, wv);
+    // order by y = n | s << 8 (bits 32..47 of the item read as one 64-bit key); dead items (0xFFFF) end up last
+    NGI_CUDA(cub::DeviceRadixSort::SortKeys(c.sort_tmp, c.sort_bytes, (const unsigned long long*)wv.items, (unsigned long long*)wv.items_sorted, (int)need, 32, 48, st));
+    launches += 3;
+    k_bdw_contrib<<<(unsigned)std::min<size_t>(148u * 16u, (need + 127) / 128), 128, 0, st>>>(s->dev, bp, wv);
     launches++;
     return NGI_OK;
 }
@@ -1118,12 +1090,9 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
         NGI_CUDA(ngi_dmalloc((void**)&wv.hits, (size_t)wv.walkers * sizeof(float4), st));
         NGI_CUDA(ngi_dmalloc((void**)&wv.offsets, (size_t)B * sizeof(unsigned long long), st));
         NGI_CUDA(ngi_dmalloc((void**)&c.ctl, 64 * sizeof(unsigned), st));
-        wv.counts = c.ctl; wv.cursors = c.ctl + 32; wv.contrib_extra = c.ctl + 32 + 30;
+        wv.counts = c.ctl; wv.cursors = c.ctl + 32;
         NGI_CUDA(cudaMallocHost((void**)&c.ctl_host, 64 * sizeof(unsigned)));
-        c.ray_cap = (size_t)B * 12; c.contrib_cap = (size_t)B * 16;      // expected <= 16 strategies per sample; grown on demand
-        NGI_CUDA(ngi_dmalloc((void**)&wv.ray_items, c.ray_cap * sizeof(uint2), st));
-        NGI_CUDA(ngi_dmalloc((void**)&wv.visible, c.ray_cap, st));
-        NGI_CUDA(ngi_dmalloc((void**)&wv.contrib_items, c.contrib_cap * sizeof(uint2), st));
+        if ((rc = bdw_alloc_items(c, (size_t)B * 16 + 1024, st))) return rc;     // expected <= 16 strategies per sample; grown on demand
         NGI_CUDA(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
     }
     NGI_CUDA(cudaEventRecord(ev0, st));          // fork: the film memset and the allocations precede every batch
@@ -1147,7 +1116,7 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
         BdwCtx& c = ctx[k];
         ngi_dfree(c.wv.V, st); ngi_dfree(c.wv.nverts, st); ngi_dfree(c.wv.rays[0], st); ngi_dfree(c.wv.rays[1], st); ngi_dfree(c.wv.hits, st);
         ngi_dfree(c.wv.offsets, st); ngi_dfree(c.ctl, st);
-        ngi_dfree(c.wv.ray_items, st); ngi_dfree(c.wv.visible, st); ngi_dfree(c.wv.contrib_items, st);
+        ngi_dfree(c.wv.items, st); ngi_dfree(c.wv.items_sorted, st); ngi_dfree(c.sort_tmp, st);
     }
     NGI_CUDA(cudaStreamSynchronize(st));
     NGI_CUDA(cudaGetLastError());

@@ -276,8 +276,7 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
         std::vector<unsigned> nverts(wv.walkers);
         std::vector<float4> rays0((size_t)2 * wv.walkers), rays1((size_t)2 * wv.walkers), hits(wv.walkers);
         std::vector<unsigned long long> offsets(B + 1);
-        std::vector<uint2> ray_items, contrib_items;
-        std::vector<unsigned char> visible;
+        std::vector<uint2> items, items_sorted;
         wv.V = V.data(); wv.nverts = nverts.data(); wv.rays[0] = rays0.data(); wv.rays[1] = rays1.data(); wv.hits = hits.data();
         wv.offsets = offsets.data();
         unsigned long long batches = 0;
@@ -317,20 +316,23 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
             }
             offsets[wv.batch] = acc;
             wv.n_ray_items = (unsigned)(acc & 0xFFFFFFFFull); wv.n_rayless = (unsigned)(acc >> 32);
-            ray_items.resize(wv.n_ray_items + 1); visible.resize(wv.n_ray_items + 1); contrib_items.resize((size_t)wv.n_ray_items + wv.n_rayless + 1);
-            wv.ray_items = ray_items.data(); wv.visible = visible.data(); wv.contrib_items = contrib_items.data();
+            const size_t n_items = (size_t)wv.n_ray_items + wv.n_rayless;
+            items.assign(n_items + 1, make_uint2(0u, 0u));
+            wv.items = items.data();
             for (unsigned i = 0; i < wv.batch; i++) {                                          // k_bdw_expand
                 unsigned nr, nl;
                 ngi_bdw_strategies(s->dev, bp, wv, i, nr, nl, true, (unsigned)(offsets[i] & 0xFFFFFFFFull), (unsigned)(offsets[i] >> 32));
             }
-            unsigned extra = 0;
-            for (unsigned i = 0; i < wv.n_ray_items; i++) {                                    // k_bdw_shadow + k_bdw_compact
+            for (unsigned i = 0; i < wv.n_ray_items; i++) {                                    // k_bdw_shadow
                 f3 o, d; float tmax; NgiHitRec h;
-                ngi_bdw_item_ray(wv, ray_items[i], o, d, tmax);
-                if (!ngi_trace_bvh8<true>(s->dev.nodes8, s->dev.tris8, o, d, NGI_EPS_F, tmax, h)) contrib_items[wv.n_rayless + extra++] = ray_items[i];
+                ngi_bdw_item_ray(wv, items[i], o, d, tmax);
+                if (ngi_trace_bvh8<true>(s->dev.nodes8, s->dev.tris8, o, d, NGI_EPS_F, tmax, h)) items[i].y = NGI_BDW_DEAD;
             }
             cnt.shadow += wv.n_ray_items;
-            for (unsigned i = 0; i < wv.n_rayless + extra; i++) ngi_bdw_contrib(s->dev, bp, wv, contrib_items[i], q[0]);   // k_bdw_contrib
+            items_sorted.assign(items.begin(), items.begin() + n_items);                       // radix sort by y (stable)
+            std::stable_sort(items_sorted.begin(), items_sorted.end(), [](const uint2& a, const uint2& b) { return a.y < b.y; });
+            wv.items_sorted = items_sorted.data();
+            for (size_t i = 0; i < n_items; i++) ngi_bdw_contrib(s->dev, bp, wv, items_sorted[i], q[0]);   // k_bdw_contrib
         }
         if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)cnt.extend; stats[2] = (double)cnt.shadow; stats[3] = (double)batches; }
         return 0;
