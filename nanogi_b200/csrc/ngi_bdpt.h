@@ -117,6 +117,25 @@ NGI_HD float ngi_bd_geometry_term(const NgiBdVertex& a, const NgiBdVertex& b) {
     return (float)((double)t / d2);
 }
 
+// direction and GeometryTerm (rt.hpp:2364-2374) of the edge a -> b
+NGI_HD void ngi_bd_edge(const NgiBdVertex& a, const NgiBdVertex& b, f3& w, float& G) {
+    const double dx = b.px - a.px, dy = b.py - a.py, dz = b.pz - a.pz;
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    const double inv = 1.0 / sqrt(d2);
+    w = mk3((float)(dx * inv), (float)(dy * inv), (float)(dz * inv));
+    float g = 1.0f;
+    if (!a.degenerate) g *= fabsf(dot(a.sn, w));
+    if (!b.degenerate) g *= fabsf(dot(b.sn, w));
+    G = (float)((double)g / d2);
+}
+// does EvaluateDirection(forceDegenerated = false) of a vertex acting as `type` equal the forceDegenerated = true value? It differs
+// only for specular lobes (-> 0, rt.hpp:1057-1060) and directional lights (-> 0, :934-937); precedence D > G > S
+NGI_HD bool ngi_bd_nondegenerate_vertex(const NgiDevScene& sc, const NgiBdVertex& v, const int type) {
+    if (type & NGI_L) return sc.prims[v.prim].l_type != NGI_LT_DIRECTIONAL;
+    if (type & NGI_E) return true;
+    return (type & (NGI_D | NGI_G)) != 0;
+}
+
 // ---- Path::SampleSubpath, bdpt.hpp:54-123, in three pieces shared by the per-thread loop below and the wavefront kernels
 // (ngi_bdpt_wave.h). kind 0: light subpath (LE), 1: eye subpath (EL). --------------------------------------------------------
 // vertex 0 (bdpt.hpp:60-75): a sampled light point / the sensor point. false: the subpath is empty (no lights).
@@ -263,10 +282,7 @@ NGI_HD f3 ngi_bd_cst(const NgiDevScene& sc, const NgiBdPath& p, const NgiBdScrat
 // (-> 0, rt.hpp:1057-1060), directional lights (-> 0, :934-937) and the position terms of point lights / the pinhole (-> 0,
 // :594-641); emitters do not depend on the transport direction.
 NGI_HD bool ngi_bd_nondegenerate(const NgiDevScene& sc, const NgiBdPath& p, const int k) {
-    const int type = p.type(k);
-    if (type & NGI_L) return sc.prims[p.v(k).prim].l_type != NGI_LT_DIRECTIONAL;
-    if (type & NGI_E) return true;
-    return (type & (NGI_D | NGI_G)) != 0;                  // precedence D > G > S: an S lobe is only reached without D and G
+    return ngi_bd_nondegenerate_vertex(sc, p.v(k), p.type(k));
 }
 NGI_HD bool ngi_bd_cst_nonzero(const NgiDevScene& sc, const NgiBdPath& p, const NgiBdScratch& q, const int i) {
     const int n = p.n;
@@ -279,17 +295,7 @@ NGI_HD bool ngi_bd_cst_nonzero(const NgiDevScene& sc, const NgiBdPath& p, const 
 NGI_BD_FN f3 ngi_bd_contribution(const NgiDevScene& sc, const NgiBdPath& p, NgiBdScratch& q) {
     const int n = p.n, s = p.s, t = p.t;
     for (int k = 0; k + 1 < n; k++) {                      // edges: direction and geometry term, once
-        const NgiBdVertex& a = p.v(k);
-        const NgiBdVertex& b = p.v(k + 1);
-        const double dx = b.px - a.px, dy = b.py - a.py, dz = b.pz - a.pz;
-        const double d2 = dx * dx + dy * dy + dz * dz;
-        const double inv = 1.0 / sqrt(d2);
-        const f3 w = mk3((float)(dx * inv), (float)(dy * inv), (float)(dz * inv));
-        float g = 1.0f;
-        if (!a.degenerate) g *= fabsf(dot(a.sn, w));
-        if (!b.degenerate) g *= fabsf(dot(b.sn, w));
-        q.w[k] = w;
-        q.G[k] = (float)((double)g / d2);                  // GeometryTerm, rt.hpp:2364-2374
+        ngi_bd_edge(p.v(k), p.v(k + 1), q.w[k], q.G[k]);
     }
     // unweighted contribution first (most connections end here with zero): alphaL * cst(s) * alphaE, bdpt.hpp:252-343
     const f3 cstS = ngi_bd_cst(sc, p, q, s);

@@ -535,9 +535,8 @@ __global__ void __launch_bounds__(kBlock) k_bdw_expand(NgiDevScene sc, NgiBdPara
     ngi_bdw_strategies(sc, bp, wv, i, nr, nl, true, (unsigned)(off & 0xFFFFFFFFull), (unsigned)(off >> 32));
 }
 __global__ void __launch_bounds__(128) k_bdw_contrib(NgiDevScene sc, NgiBdParams bp, NgiBdWave wv) {
-    NgiBdScratch q;
     const unsigned n = wv.n_ray_items + wv.n_rayless;
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_bdw_contrib(sc, bp, wv, wv.items_sorted[e], q);
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ngi_bdw_contrib(sc, bp, wv, wv.items_sorted[e]);
 }
 
 __global__ void __launch_bounds__(kBlock) k_eval_bsdf(NgiDevScene sc, const float* __restrict__ q, const float* __restrict__ wo_in, size_t n,
@@ -1069,7 +1068,7 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
         if ((rc = persistent_grid(k_bdw_shadow, &s->grid_bdw_shadow))) return rc;
     }
     for (cudaStream_t& b : s->bd_streams) if (!b) NGI_CUDA(cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking));
-    // batch size: vertex storage cap x 2 B x 80 bytes (2 GB at 2^19 samples and 24 vertices), two batches in flight
+    // batch size: vertex + cache storage cap x 2 B x 128 bytes (3.2 GB at 2^19 samples and 24 vertices), two batches in flight
     unsigned B = rp->wave_capacity ? rp->wave_capacity : (1u << 19);
     if (const char* e = getenv("NGI_BDPT_BATCH")) B = (unsigned)std::max(1, atoi(e));
     B = (unsigned)std::min<long long>(B, rp->num_samples);
@@ -1084,6 +1083,7 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
         NgiBdWave& wv = c.wv;
         wv.walkers = 2u * B;
         NGI_CUDA(ngi_dmalloc((void**)&wv.V, (size_t)cap * wv.walkers * sizeof(NgiBdVertex), st));
+        NGI_CUDA(ngi_dmalloc((void**)&wv.C, (size_t)cap * wv.walkers * sizeof(NgiBdCache), st));
         NGI_CUDA(ngi_dmalloc((void**)&wv.nverts, (size_t)wv.walkers * sizeof(unsigned), st));
         NGI_CUDA(ngi_dmalloc((void**)&wv.rays[0], (size_t)wv.walkers * 2 * sizeof(float4), st));
         NGI_CUDA(ngi_dmalloc((void**)&wv.rays[1], (size_t)wv.walkers * 2 * sizeof(float4), st));
@@ -1114,7 +1114,7 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
     NGI_CUDA(cudaEventRecord(ev1, st));
     for (int k = 0; k < K; k++) {
         BdwCtx& c = ctx[k];
-        ngi_dfree(c.wv.V, st); ngi_dfree(c.wv.nverts, st); ngi_dfree(c.wv.rays[0], st); ngi_dfree(c.wv.rays[1], st); ngi_dfree(c.wv.hits, st);
+        ngi_dfree(c.wv.V, st); ngi_dfree(c.wv.C, st); ngi_dfree(c.wv.nverts, st); ngi_dfree(c.wv.rays[0], st); ngi_dfree(c.wv.rays[1], st); ngi_dfree(c.wv.hits, st);
         ngi_dfree(c.wv.offsets, st); ngi_dfree(c.ctl, st);
         ngi_dfree(c.wv.items, st); ngi_dfree(c.wv.items_sorted, st); ngi_dfree(c.sort_tmp, st);
     }

@@ -273,6 +273,8 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
         std::memset(&wv, 0, sizeof(wv));
         wv.walkers = 2 * B;
         std::vector<NgiBdVertex> V((size_t)std::max(cap, 1) * wv.walkers);
+        std::vector<NgiBdCache> C((size_t)std::max(cap, 1) * wv.walkers);
+        wv.C = C.data();
         std::vector<unsigned> nverts(wv.walkers);
         std::vector<float4> rays0((size_t)2 * wv.walkers), rays1((size_t)2 * wv.walkers), hits(wv.walkers);
         std::vector<unsigned long long> offsets(B + 1);
@@ -332,7 +334,7 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
             items_sorted.assign(items.begin(), items.begin() + n_items);                       // radix sort by y (stable)
             std::stable_sort(items_sorted.begin(), items_sorted.end(), [](const uint2& a, const uint2& b) { return a.y < b.y; });
             wv.items_sorted = items_sorted.data();
-            for (size_t i = 0; i < n_items; i++) ngi_bdw_contrib(s->dev, bp, wv, items_sorted[i], q[0]);   // k_bdw_contrib
+            for (size_t i = 0; i < n_items; i++) ngi_bdw_contrib(s->dev, bp, wv, items_sorted[i]);   // k_bdw_contrib
         }
         if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)cnt.extend; stats[2] = (double)cnt.shadow; stats[3] = (double)batches; }
         return 0;
