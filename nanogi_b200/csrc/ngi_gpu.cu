@@ -651,7 +651,7 @@ struct Scene {
     // the extend and shadow kernels of one iteration are independent: the shadow kernel is forked onto the lane's second
     // stream so that its CTAs fill the SMs the extend kernel's tail leaves idle
     bool overlap_trace = true;
-    cudaStream_t bd_streams[2] = {nullptr, nullptr};   // wavefront bdpt: two batches in flight
+    cudaStream_t bd_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // wavefront bdpt: batches in flight
     unsigned grid_bdw_extend = 0, grid_bdw_shadow = 0;
 
     ~Scene() {
@@ -1068,13 +1068,21 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
         if ((rc = persistent_grid(k_bdw_shadow, &s->grid_bdw_shadow))) return rc;
     }
     for (cudaStream_t& b : s->bd_streams) if (!b) NGI_CUDA(cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking));
-    // batch size: vertex + cache storage cap x 2 B x 128 bytes (3.2 GB at 2^19 samples and 24 vertices), two batches in flight
-    unsigned B = rp->wave_capacity ? rp->wave_capacity : (1u << 19);
+    // batch size: every stage of a batch ends in a tail and the batches' ~50 launches are serially dependent, so throughput grows
+    // with the batch (profiles/r01_sweep_bdpt_batch.txt: 136 / 241 / 305 / 323 Mpaths/s at 2^17 / 2^19 / 2^21 / 2^22 samples);
+    // vertex + cache storage is cap x 2 B x 128 bytes (12.9 GB at 2^21 samples and 24 vertices) per batch in flight
+    unsigned B = rp->wave_capacity;
+    if (!B) {
+        B = 1u << 21;
+        while (B > (1u << 16) && (long long)B * 4 > rp->num_samples) B >>= 1;     // at least four batches, so that they overlap
+    }
     if (const char* e = getenv("NGI_BDPT_BATCH")) B = (unsigned)std::max(1, atoi(e));
     B = (unsigned)std::min<long long>(B, rp->num_samples);
     const long long n_batches = (rp->num_samples + B - 1) / B;
-    const int K = n_batches > 1 ? 2 : 1;
-    BdwCtx ctx[2];
+    int K = 2;
+    if (const char* e = getenv("NGI_BDPT_STREAMS")) K = std::min(4, std::max(1, atoi(e)));
+    K = (int)std::min<long long>(K, n_batches);
+    BdwCtx ctx[4];
     cudaEvent_t ev0, ev1;
     NGI_CUDA(cudaEventCreate(&ev0)); NGI_CUDA(cudaEventCreate(&ev1));
     for (int k = 0; k < K; k++) {
@@ -1100,13 +1108,13 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
     uint64_t launches = 0, extend_rays = 0, shadow_rays = 0;
     for (long long b = 0; b < n_batches; b++) {
         BdwCtx& c = ctx[b % K];
+        if ((rc = bdw_phase2(s, c, bp, cap, launches, extend_rays, shadow_rays))) return rc;      // batch b - K (no-op at the start)
         c.wv.first = (unsigned long long)(rp->sample_offset + b * (long long)B);
         c.wv.batch = (unsigned)std::min<long long>(B, rp->num_samples - b * (long long)B);
         if ((rc = bdw_phase1(s, c, bp, cap, launches))) return rc;
-        if (K > 1 && b > 0 && (rc = bdw_phase2(s, ctx[(b - 1) % K], bp, cap, launches, extend_rays, shadow_rays))) return rc;
     }
-    if (K > 1 && n_batches > 1 && (rc = bdw_phase2(s, ctx[(n_batches - 2) % K], bp, cap, launches, extend_rays, shadow_rays))) return rc;   // no-op if done
-    if ((rc = bdw_phase2(s, ctx[(n_batches - 1) % K], bp, cap, launches, extend_rays, shadow_rays))) return rc;
+    for (long long b = std::max<long long>(0, n_batches - K); b < n_batches; b++)
+        if ((rc = bdw_phase2(s, ctx[b % K], bp, cap, launches, extend_rays, shadow_rays))) return rc;
     for (int k = 0; k < K; k++) {                // join
         NGI_CUDA(cudaEventRecord(ctx[k].done, ctx[k].stream));
         NGI_CUDA(cudaStreamWaitEvent(st, ctx[k].done, 0));
