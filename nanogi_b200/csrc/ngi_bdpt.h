@@ -68,8 +68,10 @@ NGI_HD NgiGeom ngi_bd_geom(const NgiBdVertex& v) {
 }
 
 // Primitive::EvaluateDirection for any vertex kind (rt.hpp:912-1148) and, in `pdf`, Primitive::EvaluateDirectionPDF (:1150-1336)
-NGI_BD_FN f3 ngi_bd_eval_direction(const NgiDevScene& sc, const NgiBdVertex& v, const int type, const f3 wi, const f3 wo, const bool transLE,
-                                         const bool forceDegenerated, float& pdf) {
+// (the *_inl forms are for the wavefront kernels, which call each building block from one or two places; the NGI_BD_FN wrappers are
+// the single out-of-line copies the per-thread megakernel needs, see above)
+NGI_HD f3 ngi_bd_eval_direction_inl(const NgiDevScene& sc, const NgiBdVertex& v, const int type, const f3 wi, const f3 wo, const bool transLE,
+                                    const bool forceDegenerated, float& pdf) {
     const NgiDevPrim& P = sc.prims[v.prim];
     pdf = 0.0f;
     if (type & NGI_L) {
@@ -89,6 +91,10 @@ NGI_BD_FN f3 ngi_bd_eval_direction(const NgiDevScene& sc, const NgiBdVertex& v, 
     if (!(type & NGI_BSDF)) return mk3(0.0f);                                                                                      // assert(0), :1146
     const NgiGeom g = ngi_bd_geom(v);
     return ngi_eval_bsdf(P, type, g, wi, wo, forceDegenerated, pdf, transLE);
+}
+NGI_BD_FN f3 ngi_bd_eval_direction(const NgiDevScene& sc, const NgiBdVertex& v, const int type, const f3 wi, const f3 wo, const bool transLE,
+                                   const bool forceDegenerated, float& pdf) {
+    return ngi_bd_eval_direction_inl(sc, v, type, wi, wo, transLE, forceDegenerated, pdf);
 }
 // Primitive::EvaluatePosition (rt.hpp:594-641)
 NGI_HD float ngi_bd_eval_position(const NgiDevScene& sc, const NgiBdVertex& v, const int type, const bool forceDegenerated) {
@@ -139,7 +145,7 @@ NGI_HD bool ngi_bd_nondegenerate_vertex(const NgiDevScene& sc, const NgiBdVertex
 // ---- Path::SampleSubpath, bdpt.hpp:54-123, in three pieces shared by the per-thread loop below and the wavefront kernels
 // (ngi_bdpt_wave.h). kind 0: light subpath (LE), 1: eye subpath (EL). --------------------------------------------------------
 // vertex 0 (bdpt.hpp:60-75): a sampled light point / the sensor point. false: the subpath is empty (no lights).
-NGI_BD_FN bool ngi_bd_vertex0(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind, NgiBdVertex& v) {
+NGI_HD bool ngi_bd_vertex0_inl(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind, NgiBdVertex& v) {
     const NgiDevSensor& E = sc.sensor;
     v.albedo = mk3(0.0f); v.pixel = -1;
     if (kind == 0) {
@@ -161,10 +167,14 @@ NGI_BD_FN bool ngi_bd_vertex0(const NgiDevScene& sc, const NgiBdParams& bp, cons
     }
     return true;
 }
+NGI_BD_FN bool ngi_bd_vertex0(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind, NgiBdVertex& v) {
+    return ngi_bd_vertex0_inl(sc, bp, sample, kind, v);
+}
 // the direction sampled at the subpath's last vertex `pv` in iteration `step` >= 1 (bdpt.hpp:77-90); `prev` = the vertex before it
 // (nullptr at vertex 0). false: the subpath ends here. `rr` = the uniform of the Russian roulette that follows the hit (:108-113).
-NGI_BD_FN bool ngi_bd_sample_direction(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind, const int step,
-                                       const NgiBdVertex& pv, const NgiBdVertex* prev, f3& wo, float& rr) {
+template <bool INL>
+NGI_HD bool ngi_bd_sample_direction_t(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind, const int step,
+                                      const NgiBdVertex& pv, const NgiBdVertex* prev, f3& wo, float& rr) {
     const NgiDevSensor& E = sc.sensor;
     const f3 wi = prev ? ngi_bd_dir(pv, *prev) : mk3(0.0f);                                                  // :77
     unsigned ra[4];
@@ -187,12 +197,17 @@ NGI_BD_FN bool ngi_bd_sample_direction(const NgiDevScene& sc, const NgiBdParams&
     }
     if (!wrote) return false;                                                                                 // wo stays zero -> f == 0
     float pdfUnused;
-    const f3 f = ngi_bd_eval_direction(sc, pv, pv.type, wi, wo, kind == 0, true, pdfUnused);                  // :81
+    const f3 f = INL ? ngi_bd_eval_direction_inl(sc, pv, pv.type, wi, wo, kind == 0, true, pdfUnused)         // :81
+                     : ngi_bd_eval_direction(sc, pv, pv.type, wi, wo, kind == 0, true, pdfUnused);
     return !is_zero(f);
 }
+NGI_BD_FN bool ngi_bd_sample_direction(const NgiDevScene& sc, const NgiBdParams& bp, const unsigned long long sample, const int kind, const int step,
+                                       const NgiBdVertex& pv, const NgiBdVertex* prev, f3& wo, float& rr) {
+    return ngi_bd_sample_direction_t<false>(sc, bp, sample, kind, step, pv, prev, wo, rr);
+}
 // the vertex at the hit `h` of the ray (pv, wo) (bdpt.hpp:92-106)
-NGI_BD_FN void ngi_bd_hit_vertex(const NgiDevScene& sc, const NgiBdParams& bp, const double ppx, const double ppy, const double ppz, const f3 wo,
-                                 const NgiHitRec& h, NgiBdVertex& v) {
+NGI_HD void ngi_bd_hit_vertex_inl(const NgiDevScene& sc, const NgiBdParams& bp, const double ppx, const double ppy, const double ppz, const f3 wo,
+                                  const NgiHitRec& h, NgiBdVertex& v) {
     double ddx, ddy, ddz;
     ngi_dither_direction(wo, make_float4(h.t, h.u, h.v, u2f(h.tri)), ddx, ddy, ddz);                          // see ngi_logic_surface
     v.px = ppx + ddx * (double)h.t; v.py = ppy + ddy * (double)h.t; v.pz = ppz + ddz * (double)h.t;
@@ -204,6 +219,10 @@ NGI_BD_FN void ngi_bd_hit_vertex(const NgiDevScene& sc, const NgiBdParams& bp, c
     const int tex = (v.type & NGI_D) ? HP.d_tex : HP.g_tex;
     v.albedo = (tex >= 0 && sc.shade_uv) ? ngi_texture_at_hit(sc, tex, h.tri, h.u, h.v) : ngi_constant_albedo(HP, v.type);
     v.pixel = ((HP.type & NGI_E) && sc.sensor.kind == NGI_ET_AREA && sc.shade_uv) ? ngi_area_sensor_pixel(sc, h.tri, h.u, h.v, bp.width, bp.height) : -1;
+}
+NGI_BD_FN void ngi_bd_hit_vertex(const NgiDevScene& sc, const NgiBdParams& bp, const double ppx, const double ppy, const double ppz, const f3 wo,
+                                 const NgiHitRec& h, NgiBdVertex& v) {
+    ngi_bd_hit_vertex_inl(sc, bp, ppx, ppy, ppz, wo, h, v);
 }
 NGI_HD int ngi_bd_vertex_cap(const NgiBdParams& bp) {
     return bp.max_verts == -1 ? NGI_BD_MAX_VERTS : (bp.max_verts < NGI_BD_MAX_VERTS ? bp.max_verts : NGI_BD_MAX_VERTS);

@@ -68,7 +68,7 @@ NGI_HD bool ngi_bdw_start(const NgiDevScene& sc, const NgiBdParams& bp, const Ng
     const unsigned long long sample = wv.first + (w >> 1);
     const int kind = (int)(w & 1u);
     NgiBdVertex v;
-    if (cap < 1 || !ngi_bd_vertex0(sc, bp, sample, kind, v)) { wv.nverts[w] = 0u; return false; }
+    if (cap < 1 || !ngi_bd_vertex0_inl(sc, bp, sample, kind, v)) { wv.nverts[w] = 0u; return false; }
     wv.V[w] = v;
     wv.nverts[w] = 1u;
     {
@@ -81,7 +81,7 @@ NGI_HD bool ngi_bdw_start(const NgiDevScene& sc, const NgiBdParams& bp, const Ng
         wv.C[w] = c;
     }
     if (cap < 2) return false;
-    if (!ngi_bd_sample_direction(sc, bp, sample, kind, 1, v, nullptr, wo, rr)) return false;
+    if (!ngi_bd_sample_direction_t<true>(sc, bp, sample, kind, 1, v, nullptr, wo, rr)) return false;
     o = mk3((float)v.px, (float)v.py, (float)v.pz);
     return true;
 }
@@ -95,7 +95,7 @@ NGI_HD bool ngi_bdw_step(const NgiDevScene& sc, const NgiBdParams& bp, const Ngi
     const NgiBdVertex pv = wv.V[(size_t)(step - 1) * wv.walkers + w];
     NgiHitRec h; h.t = hit.x; h.u = hit.y; h.v = hit.z; h.tri = f2u(hit.w);
     NgiBdVertex v;
-    ngi_bd_hit_vertex(sc, bp, pv.px, pv.py, pv.pz, mk3(r1.x, r1.y, r1.z), h, v);
+    ngi_bd_hit_vertex_inl(sc, bp, pv.px, pv.py, pv.pz, mk3(r1.x, r1.y, r1.z), h, v);
     wv.V[(size_t)step * wv.walkers + w] = v;
     wv.nverts[w] = (unsigned)step + 1u;
     {   // the previous vertex now has a successor: complete its cache record and start the new vertex's
@@ -104,10 +104,10 @@ NGI_HD bool ngi_bdw_step(const NgiDevScene& sc, const NgiBdParams& bp, const Ngi
         NgiBdCache cp = *cpp;
         ngi_bd_edge(pv, v, cp.w, cp.G);
         const f3 back = step >= 2 ? -wv.C[(size_t)(step - 2) * wv.walkers + w].w : mk3(0.0f);      // towards vertex step - 2
-        const f3 f = ngi_bd_eval_direction(sc, pv, pv.type, back, cp.w, light, true, cp.fp);
+        const f3 f = ngi_bd_eval_direction_inl(sc, pv, pv.type, back, cp.w, light, true, cp.fp);
         if (!is_zero(f)) cp.flags |= NGI_BDC_F_NZ;
         if (step >= 2) {
-            const f3 r = ngi_bd_eval_direction(sc, pv, pv.type, cp.w, back, !light, true, cp.rp);
+            const f3 r = ngi_bd_eval_direction_inl(sc, pv, pv.type, cp.w, back, !light, true, cp.rp);
             if (!is_zero(r)) cp.flags |= NGI_BDC_R_NZ;
         }
         *cpp = cp;
@@ -120,7 +120,7 @@ NGI_HD bool ngi_bdw_step(const NgiDevScene& sc, const NgiBdParams& bp, const Ngi
     }
     if (r0.w > 0.5f) return false;                                                                                // :108-113
     if (step + 1 >= cap) return false;
-    if (!ngi_bd_sample_direction(sc, bp, wv.first + (w >> 1), (int)(w & 1u), step + 1, v, &pv, wo, rr)) return false;
+    if (!ngi_bd_sample_direction_t<true>(sc, bp, wv.first + (w >> 1), (int)(w & 1u), step + 1, v, &pv, wo, rr)) return false;
     o = mk3((float)v.px, (float)v.py, (float)v.pz);
     return true;
 }
@@ -198,15 +198,15 @@ NGI_HD void ngi_bdw_contrib(const NgiDevScene& sc, const NgiBdParams& bp, const 
     f3 cstS;                                                                                   // EvaluateCst(s), bdpt.hpp:217-250
     if (s >= 1 && t >= 1) {
         ngi_bd_edge(a, b, wc, Gc);
-        ffA = ngi_bd_eval_direction(sc, a, typeA, wiA, wc, true, true, fpA);                   // ff[s-1]
+        ffA = ngi_bd_eval_direction_inl(sc, a, typeA, wiA, wc, true, true, fpA);                   // ff[s-1]
         if (!ndA || is_zero(ffA)) return;
-        bfB = ngi_bd_eval_direction(sc, b, typeB, wiB, -wc, false, true, bpB);                 // bf[s]
+        bfB = ngi_bd_eval_direction_inl(sc, b, typeB, wiB, -wc, false, true, bpB);                 // bf[s]
         cstS = ndB ? ffA * bfB * Gc : zero;
     } else if (s == 0) {
-        ffB = ngi_bd_eval_direction(sc, b, typeB, zero, wiB, true, true, fpB);                 // ff[0]: b emits towards z_{t-2}
+        ffB = ngi_bd_eval_direction_inl(sc, b, typeB, zero, wiB, true, true, fpB);                 // ff[0]: b emits towards z_{t-2}
         cstS = ndB ? ffB * ngi_bd_eval_position(sc, b, typeB, false) : zero;
     } else {
-        bfA = ngi_bd_eval_direction(sc, a, typeA, zero, wiA, false, true, bpA);                // bf[n-1]: a senses from y_{s-2}
+        bfA = ngi_bd_eval_direction_inl(sc, a, typeA, zero, wiA, false, true, bpA);                // bf[n-1]: a senses from y_{s-2}
         cstS = ndA ? bfA * ngi_bd_eval_position(sc, a, typeA, false) : zero;
     }
     if (is_zero(cstS)) return;
@@ -215,8 +215,8 @@ NGI_HD void ngi_bdw_contrib(const NgiDevScene& sc, const NgiBdParams& bp, const 
     const f3 Cstar = alphaL * cstS * alphaE;
     if (is_zero(Cstar)) return;
     if (s >= 1 && t >= 1) {                                                                    // the other two, only needed for the weight
-        if (s >= 2) bfA = ngi_bd_eval_direction(sc, a, typeA, wc, wiA, false, true, bpA);      // bf[s-1]
-        if (t >= 2) ffB = ngi_bd_eval_direction(sc, b, typeB, -wc, wiB, true, true, fpB);      // ff[s]
+        if (s >= 2) bfA = ngi_bd_eval_direction_inl(sc, a, typeA, wc, wiA, false, true, bpA);      // bf[s-1]
+        if (t >= 2) ffB = ngi_bd_eval_direction_inl(sc, b, typeB, -wc, wiB, true, true, fpB);      // ff[s]
     }
 
     // EvaluatePowerHeuristicsMISWeightOpt: sum over the strategies i of (p_i / p_s)^2, p_i = PL[i] PE[i] if EvaluateCst(i) != 0

@@ -431,6 +431,9 @@ __global__ void __launch_bounds__(kTraceBlock, NGI_TRACE_MIN_BLOCKS) k_shadow(Ng
 // wavefront bdpt (ngi_bdpt_wave.h): dense stages over a batch of samples
 // ================================================================================================
 constexpr int kBdwShadowCursor = 31;          // index into NgiBdWave::cursors
+#ifndef NGI_BDW_STEP_MIN_BLOCKS
+#define NGI_BDW_STEP_MIN_BLOCKS 1
+#endif
 __device__ __forceinline__ void bdw_push_ray(float4* q, const unsigned idx, const f3 o, const f3 wo, const float rr, const unsigned w) {
     q[2 * (size_t)idx] = make_float4(o.x, o.y, o.z, rr);
     q[2 * (size_t)idx + 1] = make_float4(wo.x, wo.y, wo.z, u2f(w));
@@ -448,7 +451,7 @@ __global__ void __launch_bounds__(kBlock) k_bdw_start(NgiDevScene sc, NgiBdParam
     block_reserve<1>(counters, need, idx, s_warp, s_base);
     if (push) bdw_push_ray(wv.rays[1], idx[0], o, wo, rr, w);
 }
-__global__ void __launch_bounds__(kBlock) k_bdw_step(NgiDevScene sc, NgiBdParams bp, NgiBdWave wv, int step, int cap) {
+__global__ void __launch_bounds__(kBlock, NGI_BDW_STEP_MIN_BLOCKS) k_bdw_step(NgiDevScene sc, NgiBdParams bp, NgiBdWave wv, int step, int cap) {
     __shared__ unsigned s_warp[1][kBlock / 32];
     __shared__ unsigned s_base[1];
     const unsigned n = wv.counts[step];
