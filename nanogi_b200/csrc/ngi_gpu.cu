@@ -47,6 +47,9 @@ int set_err(int code, const std::string& msg) { g_err = msg; return code; }
         }                                                                                               \
     } while (0)
 
+#ifndef NGI_STREAM_RAYS
+#define NGI_STREAM_RAYS 1
+#endif
 constexpr int kBlock = 256;
 #ifndef NGI_TRACE_BLOCK
 #define NGI_TRACE_BLOCK 64   /* persistent trace kernels: small CTAs hand their SM slot back as soon as their 2 warps run dry */
@@ -381,14 +384,27 @@ struct ExtendSource {
     __device__ __forceinline__ unsigned* cursor() const { return wp.fetch_cursors + 1; }
     __device__ __forceinline__ unsigned load(unsigned i, f3& o, f3& d, float& tmin, float& tmax) const {
         const unsigned slot = wp.extend_q[i];
+#if NGI_STREAM_RAYS
+        // ray records are read once: streaming loads (evict-first) leave L1 / L2 to the BVH
+        const float4 di = __ldcs(&wp.sb[slot].dir_info);
+        const double2* sa2 = reinterpret_cast<const double2*>(wp.sa + slot);               // {sample, px} {py, pz}
+        const double2 a0 = __ldcs(sa2), a1 = __ldcs(sa2 + 1);
+        o = mk3((float)a0.y, (float)a1.x, (float)a1.y);                                      // rt.hpp:2166-2168
+#else
         const float4 di = wp.sb[slot].dir_info;
         const NgiSlotA* sa = wp.sa + slot;
         o = mk3((float)sa->px, (float)sa->py, (float)sa->pz);                                // rt.hpp:2166-2168
+#endif
         d = mk3(di.x, di.y, di.z); tmin = NGI_EPS_F; tmax = NGI_INF_F;                        // rt.hpp:2246-2249
         return slot;
     }
     __device__ __forceinline__ void store(unsigned slot, bool found, const NgiHitRec& h) const {
-        wp.hit[slot] = found ? make_float4(h.t, h.u, h.v, u2f(h.tri)) : make_float4(0.0f, 0.0f, 0.0f, u2f(NGI_MISS));
+        const float4 hv = found ? make_float4(h.t, h.u, h.v, u2f(h.tri)) : make_float4(0.0f, 0.0f, 0.0f, u2f(NGI_MISS));
+#if NGI_STREAM_RAYS
+        __stcs(wp.hit + slot, hv);
+#else
+        wp.hit[slot] = hv;
+#endif
     }
 };
 // Scene::Visible (rt.hpp:2251-2261) for the shadow queue + film accumulation (src/nanogi.cpp:706)
@@ -398,7 +414,11 @@ struct ShadowSource {
     __device__ __forceinline__ unsigned* cursor() const { return wp.fetch_cursors + 0; }
     __device__ __forceinline__ unsigned load(unsigned e, f3& o, f3& d, float& tmin, float& tmax) const {
         const float4* q = wp.shadow_q + 3 * (size_t)e;
+#if NGI_STREAM_RAYS
+        const float4 q0 = __ldcs(q), q1 = __ldcs(q + 1);
+#else
         const float4 q0 = q[0], q1 = q[1];
+#endif
         o = mk3(q0.x, q0.y, q0.z); d = mk3(q1.x, q1.y, q1.z); tmin = NGI_EPS_F; tmax = q0.w;
         return e;
     }
