@@ -725,6 +725,11 @@ int init_trace_launch(Scene* s) {
     if ((rc = persistent_grid(k_trace8<true>, &s->grid_trace[1]))) return rc;
     NGI_CUDA(ngi_dmalloc((void**)&s->trace_cursor, sizeof(unsigned), s->stream));
     NGI_CUDA(cudaStreamSynchronize(s->stream));
+    if (const char* e = getenv("NGI_TRACE_CARVEOUT")) {      // shared-memory carve-out (percent) of the trace kernels: they use none, L1 holds the BVH
+        const int pct = atoi(e);
+        cudaFuncSetAttribute(k_extend, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_shadow, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     if (const char* e = getenv("NGI_TRACE_REFILL_MIN")) s->tune.refill_min = atoi(e);
     if (const char* e = getenv("NGI_TRACE_TRI_MIN")) s->tune.tri_min = atoi(e);
     if (const char* e = getenv("NGI_TRACE_OVERLAP")) s->overlap_trace = atoi(e) != 0;
