@@ -1216,7 +1216,8 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     const bool timed = (rp->flags & NGI_RENDER_TIME_KERNELS) != 0 || per_ray;
     // default slot count per lane: 2 Mi, 4 Mi for long renders (profiles/r01_sweep_wave.txt: larger waves amortise the
     // fixed tail of every launch; small renders prefer the shorter ramp-up and drain)
-    unsigned P = rp->wave_capacity ? rp->wave_capacity : (rp->num_samples >= (1ll << 28) ? (1u << 22) : (1u << 21));
+    // (8 Mi from 2^30 samples on: C3 +2.2 %, C2 +0.6 % over 4 Mi, profiles/r01_sweep_wave.txt)
+    unsigned P = rp->wave_capacity ? rp->wave_capacity : (rp->num_samples >= (1ll << 30) ? (1u << 23) : rp->num_samples >= (1ll << 28) ? (1u << 22) : (1u << 21));
     P = std::max(P, 1024u);
     if ((unsigned long long)rp->num_samples < P) P = std::max(1024u, (unsigned)((rp->num_samples + 255) / 256 * 256));
     // lanes: concurrent pipelines on disjoint sample ranges; only worth it when every lane gets several waves of work
