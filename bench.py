@@ -354,6 +354,8 @@ def run_own(args, rank: int, local_rank: int, world: int):
             ref.orc.render(renderer, n_cpu, W, H, max_num_vertices=m, seed=12)
             cpu["oracle_port_value"] = n_cpu / (time.perf_counter() - t0) / 1e6
 
+    # the module's default slot count per lane (render_impl in ngi_gpu.cu)
+    wave_slots = args.wave_capacity or ((1 << 23) if n_rank >= (1 << 30) else (1 << 22) if n_rank >= (1 << 28) else (1 << 21))
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -363,8 +365,8 @@ def run_own(args, rank: int, local_rank: int, world: int):
                        "max_num_vertices": m, "tris": int(info.num_tris), "bvh8_nodes": int(info.bvh8_nodes),
                        "scene_device_bytes": int(info.device_bytes), "bvh_build_ms": info.build_gpu_seconds * 1e3,
                        "parallelism": f"samples sharded by index over {world} GPU(s); scene replicated; one NCCL film reduce",
-                       "l2": "256 MB memset between iterations flushes L2; wavefront state (%.0f MB) also exceeds it"
-                             % ((args.wave_capacity or (1 << 21)) * 176 / 1e6)},
+                       "l2": "256 MB memset between iterations flushes L2; wavefront state (%.0f MB: 188 B x %d slots x 2 lanes) also exceeds it"
+                             % (wave_slots * 188 * 2 / 1e6, wave_slots)},
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "includes": "scene H2D + GPU BVH build + render + film D2H (pinned) + destroy, wall clock",
                     "breakdown_s_per_step": {k: v / e2e_steps for k, v in e2e_parts.items()}},
