@@ -1025,6 +1025,25 @@ struct BdwCtx {
     void* sort_tmp = nullptr; size_t sort_bytes = 0;
     bool pending = false;
     cudaEvent_t done = nullptr;
+    void release(cudaStream_t st) {           // stream-ordered frees: safe once `st` is ordered after the batch streams (or on an error path)
+        ngi_dfree(wv.V, st); ngi_dfree(wv.C, st); ngi_dfree(wv.nverts, st); ngi_dfree(wv.rays[0], st); ngi_dfree(wv.rays[1], st);
+        ngi_dfree(wv.hits, st); ngi_dfree(wv.offsets, st); ngi_dfree(ctl, st);
+        ngi_dfree(wv.items, st); ngi_dfree(wv.items_sorted, st); ngi_dfree(sort_tmp, st);
+        if (ctl_host) cudaFreeHost(ctl_host);
+        if (done) cudaEventDestroy(done);
+        *this = BdwCtx();
+    }
+};
+// frees whatever a bdpt render holds when it leaves render_bdpt_wave, on success and on every error return
+struct BdwRender {
+    BdwCtx ctx[4];
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ~BdwRender() {
+        for (BdwCtx& c : ctx) { if (c.stream) cudaStreamSynchronize(c.stream); c.release(st); }     // (all released already on the success path)
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
 };
 
 int bdw_phase1(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64_t& launches) {
@@ -1106,12 +1125,28 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
     }
     if (const char* e = getenv("NGI_BDPT_BATCH")) B = (unsigned)std::max(1, atoi(e));
     B = (unsigned)std::min<long long>(B, rp->num_samples);
-    const long long n_batches = (rp->num_samples + B - 1) / B;
     int K = 2;
     if (const char* e = getenv("NGI_BDPT_STREAMS")) K = std::min(4, std::max(1, atoi(e)));
+    {   // fit the batches in flight into half of the memory that is free (or parked in the stream-ordered pool)
+        size_t free_b = 0, total_b = 0;
+        NGI_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        cudaMemPool_t pool;
+        if (pool_alloc_enabled() && cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess) {
+            unsigned long long reserved = 0, used = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used) free_b += (size_t)(reserved - used);
+        }
+        const size_t per_sample = (size_t)cap * 2 * (sizeof(NgiBdVertex) + sizeof(NgiBdCache)) + 2 * (4 * sizeof(float4) + sizeof(float4) + sizeof(unsigned)) +
+                                  sizeof(unsigned long long) + 3 * 16 * sizeof(uint2);
+        while (B > (1u << 12) && (size_t)B * per_sample * (size_t)K > free_b / 2) B >>= 1;
+    }
+    const long long n_batches = (rp->num_samples + B - 1) / B;
     K = (int)std::min<long long>(K, n_batches);
-    BdwCtx ctx[4];
-    cudaEvent_t ev0, ev1;
+    BdwRender R;
+    R.st = st;
+    BdwCtx* ctx = R.ctx;
+    cudaEvent_t& ev0 = R.ev0;
+    cudaEvent_t& ev1 = R.ev1;
     NGI_CUDA(cudaEventCreate(&ev0)); NGI_CUDA(cudaEventCreate(&ev1));
     for (int k = 0; k < K; k++) {
         BdwCtx& c = ctx[k];
@@ -1148,18 +1183,11 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
         NGI_CUDA(cudaStreamWaitEvent(st, ctx[k].done, 0));
     }
     NGI_CUDA(cudaEventRecord(ev1, st));
-    for (int k = 0; k < K; k++) {
-        BdwCtx& c = ctx[k];
-        ngi_dfree(c.wv.V, st); ngi_dfree(c.wv.C, st); ngi_dfree(c.wv.nverts, st); ngi_dfree(c.wv.rays[0], st); ngi_dfree(c.wv.rays[1], st); ngi_dfree(c.wv.hits, st);
-        ngi_dfree(c.wv.offsets, st); ngi_dfree(c.ctl, st);
-        ngi_dfree(c.wv.items, st); ngi_dfree(c.wv.items_sorted, st); ngi_dfree(c.sort_tmp, st);
-    }
+    for (int k = 0; k < K; k++) ctx[k].release(st);
     NGI_CUDA(cudaStreamSynchronize(st));
     NGI_CUDA(cudaGetLastError());
     float ms = 0;
     NGI_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-    for (int k = 0; k < K; k++) { cudaEventDestroy(ctx[k].done); cudaFreeHost(ctx[k].ctl_host); }
     if (stats) {
         stats->paths = (uint64_t)rp->num_samples; stats->extend_rays = extend_rays; stats->shadow_rays = shadow_rays;
         stats->kernel_launches = launches; stats->wave_iterations = (uint64_t)n_batches; stats->gpu_seconds = ms * 1e-3;
