@@ -58,8 +58,8 @@ enum { NGI_L_AREA = 0, NGI_L_POINT = 1, NGI_L_DIRECTIONAL = 2 };
 enum { NGI_E_AREA = 0, NGI_E_PINHOLE = 1 };
 enum { NGI_S_REFLECTION = 0, NGI_S_REFRACTION = 1, NGI_S_FRESNEL = 2 };
 /* reference src/nanogi.cpp:51-69. pt / ptdirect are the hot path; lt / ltdirect (src/nanogi.cpp:804-1131) run on the
- * same wavefront machinery; bdpt (src/nanogi.cpp:1133-1186, bdpt.hpp) as one sample per thread
- * (SURVEY 8f row 4). ptmnee is not accepted. */
+ * same wavefront machinery; bdpt (src/nanogi.cpp:1133-1186, bdpt.hpp) in batches of samples through
+ * its own dense stages on the same trace kernels. ptmnee is not accepted. */
 enum { NGI_RENDERER_PT = 0, NGI_RENDERER_PTDIRECT = 1, NGI_RENDERER_LT = 2, NGI_RENDERER_LTDIRECT = 3, NGI_RENDERER_BDPT = 4 };
 
 /*
@@ -130,7 +130,7 @@ typedef struct NgiRenderParams {
     int32_t width, height;
     int32_t accumulate;          /* render_device only: 1 = add into film, 0 = overwrite      */
     uint64_t seed;               /* Philox key                                                */
-    uint32_t wave_capacity;      /* path slots in flight; 0 = module default                  */
+    uint32_t wave_capacity;      /* path slots in flight per lane (bdpt: samples per batch); 0 = module default */
     uint32_t flags;              /* NGI_RENDER_* bits                                          */
 } NgiRenderParams;
 
