@@ -58,7 +58,7 @@ def test_shard_range_partitions_exactly():
         shard.shard_range(10, 2, 2)
 
 
-@pytest.mark.parametrize("renderer", ["pt", "ptdirect"])
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect", "bdpt"])
 def test_two_rank_gloo_render_equals_single_process(renderer, tmp_path):
     out = str(tmp_path / "film.npz")
     mp.spawn(_worker, args=(2, _free_port(), renderer, out), nprocs=2, join=True)

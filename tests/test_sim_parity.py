@@ -131,7 +131,7 @@ def test_replay_bdpt(scene, m):
     pc.check_replay(pysim.SimScene(sd), sd, "bdpt", n=15000, w=24, h=24, m=m)
 
 
-@pytest.mark.parametrize("scene,m,batch", [("cornell_spheres", -1, 1000), ("cornell_raw_sensor", 6, 4096), ("cornell_mixed_lights", 3, 333)])
+@pytest.mark.parametrize("scene,m,batch", [("cornell_spheres", -1, 1000), ("cornell_raw_sensor", 6, 4096), ("cornell_mixed_lights", 3, 333), ("cornell_textured", 4, 2048)])
 def test_bdpt_wavefront_equals_per_thread(scene, m, batch):
     """The wavefront stages (ngi_bdpt_wave.h: batches of samples through start / extend / step / count / expand / shadow /
     contrib) and the one-sample-per-thread form (ngi_bdpt.h) run the same functions on the same Philox counters: identical
