@@ -668,7 +668,7 @@ struct Scene {
     std::vector<Lane> lanes;
     int num_lanes = 2;
     // persistent trace kernels: grid = SM count x resident CTAs per SM (queried once per kernel)
-    NgiTraceTuning tune{4, 8, 0x3F800000u, 64u};   // best of the sweep in profiles/r01_sweep_trace.txt
+    NgiTraceTuning tune{4, 8, 0x3F800000u, 64u, 1u};   // best of the sweep in profiles/r01_sweep_trace.txt
     unsigned grid_extend = 0, grid_shadow = 0, grid_trace[2] = {0, 0};
     unsigned* trace_cursor = nullptr;
     // the extend and shadow kernels of one iteration are independent: the shadow kernel is forked onto the lane's second
@@ -735,6 +735,7 @@ int init_trace_launch(Scene* s) {
     if (const char* e = getenv("NGI_TRACE_OVERLAP")) s->overlap_trace = atoi(e) != 0;
     if (const char* e = getenv("NGI_LANES")) s->num_lanes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("NGI_TRACE_CHUNK")) s->tune.chunk = (unsigned)std::max(1, atoi(e));
+    if (const char* e = getenv("NGI_TRACE_SPREAD")) s->tune.spread = (unsigned)std::max(0, atoi(e));
     return NGI_OK;
 }
 
@@ -1056,7 +1057,7 @@ int bdw_phase1(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64
     for (int step = 1; step < cap; step++) {
         // the queue shrinks by about 2x per step (Russian roulette); the kernels loop grid-stride over the device-side count
         const unsigned expect = std::max(walkers >> (step - 1), 1u);
-        k_bdw_extend<<<std::min(s->grid_bdw_extend, std::max(148u, (expect + kTraceBlock - 1) / kTraceBlock)), kTraceBlock, 0, st>>>(s->dev, wv, step, s->tune);
+        k_bdw_extend<<<s->tune.spread ? s->grid_bdw_extend : std::min(s->grid_bdw_extend, std::max(148u, (expect + kTraceBlock - 1) / kTraceBlock)), kTraceBlock, 0, st>>>(s->dev, wv, step, s->tune);
         k_bdw_step<<<std::min(kStageGrid, std::max(148u, (2u * expect + kBlock - 1) / kBlock)), kBlock, 0, st>>>(s->dev, bp, wv, step, cap);
         launches += 2;
     }
@@ -1096,7 +1097,7 @@ int bdw_phase2(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64
     k_bdw_expand<<<(wv.batch + kBlock - 1) / kBlock, kBlock, 0, st>>>(s->dev, bp, wv);
     launches++;
     if (wv.n_ray_items) {
-        k_bdw_shadow<<<std::min(s->grid_bdw_shadow, std::max(148u, (wv.n_ray_items + kTraceBlock - 1) / kTraceBlock)), kTraceBlock, 0, st>>>(s->dev, wv, s->tune);
+        k_bdw_shadow<<<s->tune.spread ? s->grid_bdw_shadow : std::min(s->grid_bdw_shadow, std::max(148u, (wv.n_ray_items + kTraceBlock - 1) / kTraceBlock)), kTraceBlock, 0, st>>>(s->dev, wv, s->tune);
         launches++;
     }
     // order by y = n | s << 8 (bits 32..47 of the item read as one 64-bit key); dead items (0xFFFF) end up last

@@ -28,7 +28,10 @@ struct NgiTraceTuning {
     int refill_min;     // refill idle lanes when at least this many are idle (or all are)
     int tri_min;        // postpone the triangle phase when fewer lanes than this have triangles pending
     unsigned one_bits;  // 0x3F800000 as a run-time value (keeps it in a register for PRMT, see ngi_q1)
-    unsigned chunk;     // rays a warp takes from the queue per global atomic
+    unsigned chunk;     // rays a warp takes from the queue per global atomic (upper bound)
+    unsigned spread;    // != 0: short queues are spread over all warps — chunk = queue length / (2 x warps), at least 1. With a fixed chunk
+                        // a queue of a few thousand rays keeps a few dozen warps busy for two ray latencies while the rest of the GPU idles
+                        // (the nearly empty late steps of a bdpt batch: 50 us per launch for <= 30 k rays, profiles/r01_launches_bdw_final.txt)
 };
 
 // Source concept:
@@ -46,6 +49,11 @@ __device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, 
 
     // warp-uniform fetch state
     unsigned chunk_next = 0, chunk_end = 0;
+    unsigned chunk_size = tune.chunk;
+    if (tune.spread) {
+        const unsigned per = n / (2u * gridDim.x * (blockDim.x >> 5));
+        if (per < chunk_size) chunk_size = per ? per : 1u;
+    }
     bool exhausted = (n == 0);
 
     // per-lane ray state
@@ -69,10 +77,10 @@ __device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, 
             if (!exhausted && (nidle >= tune.refill_min || idle == FULL)) {
                 if (chunk_next >= chunk_end) {
                     unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(src.cursor(), tune.chunk);
+                    if (lane == 0) base = atomicAdd(src.cursor(), chunk_size);
                     base = __shfl_sync(FULL, base, 0);
                     chunk_next = base;
-                    chunk_end = base + tune.chunk < n ? base + tune.chunk : n;
+                    chunk_end = base + chunk_size < n ? base + chunk_size : n;
                     if (base >= n) { exhausted = true; chunk_next = chunk_end = 0; }
                 }
                 if (!exhausted) {
