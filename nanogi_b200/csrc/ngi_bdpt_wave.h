@@ -10,15 +10,16 @@
 //               k_bdw_start   vertex 0 + the first direction                               -> ray queue 1
 //               k_bdw_extend  closest hits of ray queue k (persistent warp-cooperative trace, ngi_trace_warp.cuh)
 //               k_bdw_step    hit -> vertex k, Russian roulette, next direction            -> ray queue k + 1
+//                             + the subpath cache of vertex k - 1 (NgiBdCache below)
 //               (the queue shrinks by >= 2x per iteration; vertex k of every walker is stored together: V[k][walker])
-//   strategies  k_bdw_count   per sample: how many (n, s) strategies need a visibility ray / need none
-//               exclusive scan (cub) -> offsets; the host reads the two totals (the only host sync of a batch)
+//   strategies  k_bdw_count   per sample: how many (n, s) strategies need a visibility ray / need none, and (block scan + one
+//                             atomic per block) where its items go; the host reads the two totals (the only host sync of a batch)
 //               k_bdw_expand  writes the strategy items (sample, n, s): connecting ones first, ray-less ones behind them
 //               k_bdw_shadow  Scene::Visible of every connecting strategy (persistent any-hit trace); an occluded item's
 //                             key becomes NGI_BDW_DEAD
 //               radix sort (cub) of the items by (n, s): the lanes of a warp then run the same loop trip counts in the
 //                             contribution stage (unsorted it ran 6.2 of 32 lanes, profiles/r01_ncu_bdw_v1.txt); dead items go last
-//               k_bdw_contrib one item per lane: contribution x MIS weight (ngi_bd_connect_finish) -> film
+//               k_bdw_contrib one item per lane: contribution x MIS weight from the subpath caches (4 BSDF evaluations) -> film
 //
 // Same Philox counters as the per-thread form, so both produce the same samples; film sums differ only in the order of the
 // float atomics.
@@ -48,7 +49,7 @@ struct NgiBdWave {
     float4* rays[2];                 // ray queue k lives in rays[k & 1]: (o.xyz, rr uniform) (d.xyz, walker bits)
     float4* hits;                    // (t, u, v, triangle) per entry of the queue being traced
     unsigned* counts;                // [NGI_BD_MAX_VERTS + 1] entries of ray queue k
-    unsigned* cursors;               // [NGI_BD_MAX_VERTS + 1] dynamic-fetch cursors of the trace launches; [NGI_BD_MAX_VERTS] = shadow
+    unsigned* cursors;               // dynamic-fetch cursors of the trace launches: [k] ray queue k, [31] the visibility rays
     unsigned long long* offsets;     // [batch] where the items of each sample start: (ray items | ray-less items << 32)
     uint2* items;                    // x = sample within the batch, y = n | s << 8 (NGI_BDW_DEAD: occluded); [0, n_ray_items) connect with
                                      // a visibility ray, [n_ray_items, n_ray_items + n_rayless) need none
@@ -56,7 +57,7 @@ struct NgiBdWave {
     unsigned long long first;        // first sample index of the batch
     unsigned batch;                  // samples in this batch
     unsigned walkers;                // 2 * batch capacity = stride between V[k] and V[k + 1]
-    unsigned n_ray_items, n_rayless; // totals (known to the host after the scan)
+    unsigned n_ray_items, n_rayless; // totals (known to the host after k_bdw_count)
 };
 
 #define NGI_BDW_DEAD 0xFFFFu
