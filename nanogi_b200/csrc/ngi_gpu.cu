@@ -730,6 +730,11 @@ int init_trace_launch(Scene* s) {
         cudaFuncSetAttribute(k_extend, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(k_shadow, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
+    if (const char* e = getenv("NGI_TRACE_GRID_PCT")) {      // fewer resident trace CTAs leave registers for the other lane's logic kernels
+        const int pct = std::min(100, std::max(10, atoi(e)));
+        s->grid_extend = std::max(148u, s->grid_extend * (unsigned)pct / 100u / 148u * 148u);
+        s->grid_shadow = std::max(148u, s->grid_shadow * (unsigned)pct / 100u / 148u * 148u);
+    }
     if (const char* e = getenv("NGI_TRACE_REFILL_MIN")) s->tune.refill_min = atoi(e);
     if (const char* e = getenv("NGI_TRACE_TRI_MIN")) s->tune.tri_min = atoi(e);
     if (const char* e = getenv("NGI_TRACE_OVERLAP")) s->overlap_trace = atoi(e) != 0;
