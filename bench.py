@@ -52,6 +52,9 @@ WORKLOADS = {
            "C4 procedural 10M-triangle interior (Sibenik-like layout, 256 small area lights), ptdirect 1920x1080 4096spp"),
     "c4pt": ("interior", "pt", 1920, 1080, 4096, -1,
              "C4 procedural 10M-triangle interior (Sibenik-like layout, 256 small area lights), pt 1920x1080 4096spp"),
+    # the wavefront bdpt (not a BASELINE config; same contract, so that its numbers are measured the same way)
+    "c2bdpt": ("cornell_spheres", "bdpt", 1024, 1024, 256, -1,
+               "C2's scene (Cornell box + glossy/glass icospheres, 2598 tris) bdpt 1024x1024 256spp"),
 }
 
 
@@ -191,7 +194,7 @@ def run_reference(args, rank: int):
     v = n_step * args.steps / dt / 1e6
     sample = f"{n_step} samples/step ({n_step / (W * H):.2f} spp of {spp}) x {args.steps} steps, same scene/resolution/renderer"
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC.replace("ptdirect", renderer), "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "mrays_per_s": rays / dt / 1e6,
         "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp": spp, "max_num_vertices": m,
@@ -318,14 +321,17 @@ def run_own(args, rank: int, local_rank: int, world: int):
                                   wave_capacity=args.wave_capacity)
         peak, peak_src = measured_peaks()
         br = b_ray(int(info.num_tris))
-        per = {"logic (k_classify + k_surface + k_eye)": (stt.logic_kernel_seconds, stt.logic_launches, None),
-               "k_extend": (stt.extend_kernel_seconds, stt.extend_launches, stt.extend_rays),
-               "k_shadow": (stt.shadow_kernel_seconds, stt.shadow_launches, stt.shadow_rays)}
+        bd = renderer == "bdpt"
+        k_ext, k_sh = ("k_bdw_extend", "k_bdw_shadow") if bd else ("k_extend", "k_shadow")
+        k_logic = "logic per batch (k_bdw_start + k_bdw_step + k_bdw_count + k_bdw_expand + sort + k_bdw_contrib)" if bd else "logic (k_classify + k_surface + k_eye)"
+        per = {k_logic: (stt.logic_kernel_seconds, stt.logic_launches, None),
+               k_ext: (stt.extend_kernel_seconds, stt.extend_launches, stt.extend_rays),
+               k_sh: (stt.shadow_kernel_seconds, stt.shadow_launches, stt.shadow_rays)}
         total_k = sum(v[0] for v in per.values()) or 1.0
         kern = {k: {"seconds": v[0], "launches": int(v[1]), "share": v[0] / total_k,
                     "avg_launch_ms": (v[0] / v[1] * 1e3 if v[1] else None)} for k, v in per.items()}
         # dominant TRACE kernel (the path's bytes are the BVH/triangle fetches of the ray queries)
-        dom = "k_extend" if stt.extend_kernel_seconds >= stt.shadow_kernel_seconds else "k_shadow"
+        dom = k_ext if stt.extend_kernel_seconds >= stt.shadow_kernel_seconds else k_sh
         sec, nl, rays = per[dom]
         achieved = rays * br / sec / 1e9 if sec > 0 else 0.0
         traffic, traffic_src = None, None
@@ -358,14 +364,16 @@ def run_own(args, rank: int, local_rank: int, world: int):
     wave_slots = args.wave_capacity or ((1 << 23) if n_rank >= (1 << 30) else (1 << 22) if n_rank >= (1 << 28) else (1 << 21))
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC.replace("ptdirect", renderer), "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "mrays_per_s": mrays,
             "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp_per_gpu": spp, "samples_per_step": n_total,
                        "max_num_vertices": m, "tris": int(info.num_tris), "bvh8_nodes": int(info.bvh8_nodes),
                        "scene_device_bytes": int(info.device_bytes), "bvh_build_ms": info.build_gpu_seconds * 1e3,
                        "parallelism": f"samples sharded by index over {world} GPU(s); scene replicated; one NCCL film reduce",
-                       "l2": "256 MB memset between iterations flushes L2; wavefront state (%.0f MB: 188 B x %d slots x 2 lanes) also exceeds it"
+                       "l2": ("256 MB memset between iterations flushes L2; a bdpt batch (vertex + cache records of 2 subpaths per sample, "
+                              "GBs per batch, two in flight) also exceeds it") if renderer == "bdpt" else
+                             "256 MB memset between iterations flushes L2; wavefront state (%.0f MB: 188 B x %d slots x 2 lanes) also exceeds it"
                              % (wave_slots * 188 * 2 / 1e6, wave_slots)},
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "includes": "scene H2D + GPU BVH build + render + film D2H (pinned) + destroy, wall clock",

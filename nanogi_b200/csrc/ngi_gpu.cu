@@ -1031,13 +1031,40 @@ struct BdwCtx {
     void* sort_tmp = nullptr; size_t sort_bytes = 0;
     bool pending = false;
     cudaEvent_t done = nullptr;
-    void release(cudaStream_t st) {           // stream-ordered frees: safe once `st` is ordered after the batch streams (or on an error path)
+    // NGI_RENDER_TIME_KERNELS: event pairs around the trace launches ([0] extend, [1] shadow) and around each phase
+    bool timed = false;
+    std::vector<cudaEvent_t> ev[3];
+    double seconds[3] = {0, 0, 0};
+    uint64_t timed_launches[3] = {0, 0, 0};
+    cudaError_t mark(int which, cudaStream_t st) {
+        if (!timed) return cudaSuccess;
+        cudaEvent_t e;
+        cudaError_t rc = cudaEventCreate(&e);
+        if (rc != cudaSuccess) return rc;
+        ev[which].push_back(e);
+        return cudaEventRecord(e, st);
+    }
+    void collect() {                           // after a stream synchronise: pairs -> seconds
+        for (int w = 0; w < 3; w++) {
+            for (size_t i = 0; i + 1 < ev[w].size(); i += 2) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, ev[w][i], ev[w][i + 1]) == cudaSuccess) { seconds[w] += ms * 1e-3; timed_launches[w]++; }
+            }
+            for (cudaEvent_t e : ev[w]) cudaEventDestroy(e);
+            ev[w].clear();
+        }
+    }
+    void release(cudaStream_t st) {
+        collect();           // stream-ordered frees: safe once `st` is ordered after the batch streams (or on an error path)
         ngi_dfree(wv.V, st); ngi_dfree(wv.C, st); ngi_dfree(wv.nverts, st); ngi_dfree(wv.rays[0], st); ngi_dfree(wv.rays[1], st);
         ngi_dfree(wv.hits, st); ngi_dfree(wv.offsets, st); ngi_dfree(ctl, st);
         ngi_dfree(wv.items, st); ngi_dfree(wv.items_sorted, st); ngi_dfree(sort_tmp, st);
         if (ctl_host) cudaFreeHost(ctl_host);
         if (done) cudaEventDestroy(done);
+        const double sec[3] = {seconds[0], seconds[1], seconds[2]};
+        const uint64_t tl[3] = {timed_launches[0], timed_launches[1], timed_launches[2]};
         *this = BdwCtx();
+        for (int w = 0; w < 3; w++) { seconds[w] = sec[w]; timed_launches[w] = tl[w]; }    // the totals survive the release
     }
 };
 // frees whatever a bdpt render holds when it leaves render_bdpt_wave, on success and on every error return
@@ -1055,6 +1082,7 @@ struct BdwRender {
 int bdw_phase1(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64_t& launches) {
     cudaStream_t st = c.stream;
     NgiBdWave& wv = c.wv;
+    NGI_CUDA(c.mark(2, st));
     NGI_CUDA(cudaMemsetAsync(c.ctl, 0, 64 * sizeof(unsigned), st));
     const unsigned walkers = 2u * wv.batch;
     k_bdw_start<<<(walkers + kBlock - 1) / kBlock, kBlock, 0, st>>>(s->dev, bp, wv, cap);
@@ -1062,12 +1090,15 @@ int bdw_phase1(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64
     for (int step = 1; step < cap; step++) {
         // the queue shrinks by about 2x per step (Russian roulette); the kernels loop grid-stride over the device-side count
         const unsigned expect = std::max(walkers >> (step - 1), 1u);
+        NGI_CUDA(c.mark(0, st));
         k_bdw_extend<<<s->tune.spread ? s->grid_bdw_extend : std::min(s->grid_bdw_extend, std::max(148u, (expect + kTraceBlock - 1) / kTraceBlock)), kTraceBlock, 0, st>>>(s->dev, wv, step, s->tune);
+        NGI_CUDA(c.mark(0, st));
         k_bdw_step<<<std::min(kStageGrid, std::max(148u, (2u * expect + kBlock - 1) / kBlock)), kBlock, 0, st>>>(s->dev, bp, wv, step, cap);
         launches += 2;
     }
     k_bdw_count<<<(wv.batch + kBlock - 1) / kBlock, kBlock, 0, st>>>(s->dev, bp, wv, (unsigned long long*)(c.ctl + kBdwTotals));
     launches++;
+    NGI_CUDA(c.mark(2, st));
     NGI_CUDA(cudaMemcpyAsync(c.ctl_host, c.ctl, 64 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     c.pending = true;
     return NGI_OK;
@@ -1091,6 +1122,7 @@ int bdw_phase2(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64
     NgiBdWave& wv = c.wv;
     NGI_CUDA(cudaStreamSynchronize(st));
     c.pending = false;
+    c.collect();
     for (int k = 1; k < cap; k++) extend_rays += c.ctl_host[k];
     wv.n_ray_items = c.ctl_host[kBdwTotals];
     wv.n_rayless = c.ctl_host[kBdwTotals + 1];
@@ -1099,10 +1131,13 @@ int bdw_phase2(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64
     int rc;
     if (need > c.item_cap && (rc = bdw_alloc_items(c, need + need / 4, st))) return rc;
     if (need == 0) return NGI_OK;
+    NGI_CUDA(c.mark(2, st));
     k_bdw_expand<<<(wv.batch + kBlock - 1) / kBlock, kBlock, 0, st>>>(s->dev, bp, wv);
     launches++;
     if (wv.n_ray_items) {
+        NGI_CUDA(c.mark(1, st));
         k_bdw_shadow<<<s->tune.spread ? s->grid_bdw_shadow : std::min(s->grid_bdw_shadow, std::max(148u, (wv.n_ray_items + kTraceBlock - 1) / kTraceBlock)), kTraceBlock, 0, st>>>(s->dev, wv, s->tune);
+        NGI_CUDA(c.mark(1, st));
         launches++;
     }
     // order by y = n | s << 8 (bits 32..47 of the item read as one 64-bit key); dead items (0xFFFF) end up last
@@ -1110,6 +1145,7 @@ int bdw_phase2(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64
     launches += 3;
     k_bdw_contrib<<<(unsigned)std::min<size_t>(148u * 16u, (need + 127) / 128), 128, 0, st>>>(s->dev, bp, wv);
     launches++;
+    NGI_CUDA(c.mark(2, st));
     return NGI_OK;
 }
 
@@ -1133,6 +1169,8 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
     B = (unsigned)std::min<long long>(B, rp->num_samples);
     int K = 2;
     if (const char* e = getenv("NGI_BDPT_STREAMS")) K = std::min(4, std::max(1, atoi(e)));
+    const bool timed = (rp->flags & NGI_RENDER_TIME_KERNELS) != 0;      // per-kernel CUDA events: one batch at a time
+    if (timed) K = 1;
     {   // fit the batches in flight into half of the memory that is free (or parked in the stream-ordered pool)
         size_t free_b = 0, total_b = 0;
         NGI_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -1157,6 +1195,7 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
     for (int k = 0; k < K; k++) {
         BdwCtx& c = ctx[k];
         c.stream = s->bd_streams[k];
+        c.timed = timed;
         NgiBdWave& wv = c.wv;
         wv.walkers = 2u * B;
         NGI_CUDA(ngi_dmalloc((void**)&wv.V, (size_t)cap * wv.walkers * sizeof(NgiBdVertex), st));
@@ -1197,6 +1236,13 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
     if (stats) {
         stats->paths = (uint64_t)rp->num_samples; stats->extend_rays = extend_rays; stats->shadow_rays = shadow_rays;
         stats->kernel_launches = launches; stats->wave_iterations = (uint64_t)n_batches; stats->gpu_seconds = ms * 1e-3;
+        if (timed) {       // "logic" = everything of a batch that is not a trace launch (start / step / count / expand / sort / contrib)
+            const BdwCtx& c = ctx[0];
+            stats->extend_kernel_seconds = c.seconds[0]; stats->extend_launches = c.timed_launches[0];
+            stats->shadow_kernel_seconds = c.seconds[1]; stats->shadow_launches = c.timed_launches[1];
+            stats->logic_kernel_seconds = std::max(0.0, c.seconds[2] - c.seconds[0] - c.seconds[1]); stats->logic_launches = (uint64_t)n_batches;
+            stats->trace_kernel_seconds = c.seconds[0] + c.seconds[1];
+        }
     }
     return NGI_OK;
 }
