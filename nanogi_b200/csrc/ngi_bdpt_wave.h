@@ -30,12 +30,16 @@
 // evaluations instead of O(n): everything ngi_bd_contribution (ngi_bdpt.h) computes per connection that depends on ONE subpath only.
 // "forward" = in the direction the subpath was sampled (k - 1 -> k -> k + 1) with the subpath's own transport mode (light: LE, eye:
 // EL), "reverse" = k + 1 -> k -> k - 1 with the opposite mode; both with forceDegenerated = true (bdpt.hpp:491-535).
-struct alignas(16) NgiBdCache {
-    f3 w; float G;      // edge k -> k + 1: direction, GeometryTerm                                        (k <= len - 2)
-    f3 A; float fp;     // A = alpha: EvaluatePosition / pdfA x prod_{j<k} f_j / pdf_j (bdpt.hpp:252-343); fp = forward pdf at k
+// 64 bytes = two 32-byte sectors: the second one holds everything the MIS sweep reads of a vertex that is not an end vertex.
+struct alignas(64) NgiBdCache {
+    f3 w;               // edge k -> k + 1: direction                                                       (k <= len - 2)
+    f3 A;               // alpha: EvaluatePosition / pdfA x prod_{j<k} f_j / pdf_j (bdpt.hpp:252-343)
+    float pad0, pad1;
     double P;           // pdfA x prod_{j<k} fp_j G_j: the density of sampling vertices 0..k (EvaluatePDF's subpath factor)
+    float G;            // GeometryTerm of the edge k -> k + 1                                              (k <= len - 2)
     float rp;           // reverse pdf at k                                                                 (1 <= k <= len - 2)
     unsigned flags;     // NGI_BDC_*
+    f3 back;            // direction k -> k - 1 (zero at vertex 0): the `wi` of every evaluation at k along its own subpath
 };
 #define NGI_BDC_ND 1u        /* ngi_bd_nondegenerate_vertex as its own type */
 #define NGI_BDC_F_NZ 2u      /* forward value != 0 */
@@ -75,7 +79,7 @@ NGI_HD bool ngi_bdw_start(const NgiDevScene& sc, const NgiBdParams& bp, const Ng
     {
         NgiBdCache c;
         const float pA = ngi_bd_position_pdf(sc, v, v.type);
-        c.w = mk3(0.0f); c.G = 0.0f; c.fp = 0.0f; c.rp = 0.0f;
+        c.w = mk3(0.0f); c.G = 0.0f; c.rp = 0.0f; c.back = mk3(0.0f); c.pad0 = c.pad1 = 0.0f;
         c.A = mk3(ngi_bd_eval_position(sc, v, v.type, true) / pA);
         c.P = (double)pA;
         c.flags = (ngi_bd_nondegenerate_vertex(sc, v, v.type) ? NGI_BDC_ND : 0u) | (ngi_bd_eval_position(sc, v, v.type, false) != 0.0f ? NGI_BDC_POS_NZ : 0u);
@@ -104,8 +108,9 @@ NGI_HD bool ngi_bdw_step(const NgiDevScene& sc, const NgiBdParams& bp, const Ngi
         NgiBdCache* cpp = wv.C + (size_t)(step - 1) * wv.walkers + w;
         NgiBdCache cp = *cpp;
         ngi_bd_edge(pv, v, cp.w, cp.G);
-        const f3 back = step >= 2 ? -wv.C[(size_t)(step - 2) * wv.walkers + w].w : mk3(0.0f);      // towards vertex step - 2
-        const f3 f = ngi_bd_eval_direction_inl(sc, pv, pv.type, back, cp.w, light, true, cp.fp);
+        const f3 back = cp.back;                                                                   // towards vertex step - 2
+        float fp;
+        const f3 f = ngi_bd_eval_direction_inl(sc, pv, pv.type, back, cp.w, light, true, fp);
         if (!is_zero(f)) cp.flags |= NGI_BDC_F_NZ;
         if (step >= 2) {
             const f3 r = ngi_bd_eval_direction_inl(sc, pv, pv.type, cp.w, back, !light, true, cp.rp);
@@ -113,9 +118,10 @@ NGI_HD bool ngi_bdw_step(const NgiDevScene& sc, const NgiBdParams& bp, const Ngi
         }
         *cpp = cp;
         NgiBdCache cn;
-        cn.w = mk3(0.0f); cn.G = 0.0f; cn.fp = 0.0f; cn.rp = 0.0f;
-        cn.A = (is_zero(cp.A) || is_zero(f)) ? mk3(0.0f) : cp.A * (f / cp.fp);
-        cn.P = cp.P * (double)cp.fp * (double)cp.G;
+        cn.w = mk3(0.0f); cn.G = 0.0f; cn.rp = 0.0f; cn.pad0 = cn.pad1 = 0.0f;
+        cn.back = -cp.w;
+        cn.A = (is_zero(cp.A) || is_zero(f)) ? mk3(0.0f) : cp.A * (f / fp);
+        cn.P = cp.P * (double)fp * (double)cp.G;
         cn.flags = ngi_bd_nondegenerate_vertex(sc, v, v.type) ? NGI_BDC_ND : 0u;
         wv.C[(size_t)step * wv.walkers + w] = cn;
     }
@@ -184,17 +190,21 @@ NGI_HD void ngi_bdw_contrib(const NgiDevScene& sc, const NgiBdParams& bp, const 
     float Gc = 0.0f;
     f3 ffA = zero, bfA = zero, ffB = zero, bfB = zero;
     float fpA = 0.0f, bpA = 0.0f, fpB = 0.0f, bpB = 0.0f;
+    f3 alphaL = mk3(1.0f), alphaE = mk3(1.0f);
+    double PLs = 1.0, PEs = 1.0;
     if (s >= 1) {
         a = VL[(size_t)(s - 1) * W];
         typeA = t == 0 ? NGI_E : a.type;
         ndA = ngi_bd_nondegenerate_vertex(sc, a, typeA);
-        if (s >= 2) wiA = -CL[(size_t)(s - 2) * W].w;
+        const NgiBdCache& ca = CL[(size_t)(s - 1) * W];
+        wiA = ca.back; alphaL = ca.A; PLs = ca.P;
     }
     if (t >= 1) {
         b = VE[(size_t)(t - 1) * W];
         typeB = s == 0 ? NGI_L : b.type;
         ndB = ngi_bd_nondegenerate_vertex(sc, b, typeB);
-        if (t >= 2) wiB = -CE[(size_t)(t - 2) * W].w;
+        const NgiBdCache& cb = CE[(size_t)(t - 1) * W];
+        wiB = cb.back; alphaE = cb.A; PEs = cb.P;
     }
     f3 cstS;                                                                                   // EvaluateCst(s), bdpt.hpp:217-250
     if (s >= 1 && t >= 1) {
@@ -211,8 +221,6 @@ NGI_HD void ngi_bdw_contrib(const NgiDevScene& sc, const NgiBdParams& bp, const 
         cstS = ndA ? bfA * ngi_bd_eval_position(sc, a, typeA, false) : zero;
     }
     if (is_zero(cstS)) return;
-    const f3 alphaL = s >= 1 ? CL[(size_t)(s - 1) * W].A : mk3(1.0f);
-    const f3 alphaE = t >= 1 ? CE[(size_t)(t - 1) * W].A : mk3(1.0f);
     const f3 Cstar = alphaL * cstS * alphaE;
     if (is_zero(Cstar)) return;
     if (s >= 1 && t >= 1) {                                                                    // the other two, only needed for the weight
@@ -221,8 +229,6 @@ NGI_HD void ngi_bdw_contrib(const NgiDevScene& sc, const NgiBdParams& bp, const 
     }
 
     // EvaluatePowerHeuristicsMISWeightOpt: sum over the strategies i of (p_i / p_s)^2, p_i = PL[i] PE[i] if EvaluateCst(i) != 0
-    const double PLs = s >= 1 ? CL[(size_t)(s - 1) * W].P : 1.0;
-    const double PEs = t >= 1 ? CE[(size_t)(t - 1) * W].P : 1.0;
     const double ps = PLs * PEs;
     double invWeight = ps > 0.0 ? 1.0 : 0.0;
     if (t >= 1) {       // strategies i = s + 1 .. n: the light side grows along the eye subpath; j = n - i eye vertices remain
