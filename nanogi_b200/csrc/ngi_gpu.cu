@@ -1159,7 +1159,7 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
     for (cudaStream_t& b : s->bd_streams) if (!b) NGI_CUDA(cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking));
     // batch size: every stage of a batch ends in a tail and the batches' ~50 launches are serially dependent, so throughput grows
     // with the batch (profiles/r01_sweep_bdpt_batch.txt: 136 / 241 / 305 / 323 Mpaths/s at 2^17 / 2^19 / 2^21 / 2^22 samples);
-    // vertex + cache storage is cap x 2 B x 128 bytes (12.9 GB at 2^21 samples and 24 vertices) per batch in flight
+    // vertex + cache storage is cap x 2 B x 144 bytes (14.5 GB at 2^21 samples and 24 vertices) per batch in flight
     unsigned B = rp->wave_capacity;
     if (!B) {
         B = 1u << 21;
