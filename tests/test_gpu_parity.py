@@ -150,7 +150,7 @@ def test_replay_bdpt(scene, m):
 def test_bdpt_wavefront_equals_per_thread(scene, m, batch):
     """The wavefront bdpt (k_bdw_*: batches of samples through dense stages, warp-cooperative persistent trace kernels) against the
     one-sample-per-thread megakernel (k_bdpt, NGI_RENDER_BDPT_PER_THREAD): same functions on the same Philox counters, so the ray
-    counts are identical and the films differ only by the order of the float atomics — any batch size, ragged last batch included,
+    counts agree (exactly on the simulator) and the films differ only by the order of the float atomics — any batch size, ragged last batch included,
     several batches in flight on two streams."""
     spec = scenes.cornell_raw_sensor(spheres=True) if scene == "cornell_raw_sensor" else getattr(scenes, scene)()
     sd = scenes.to_scene_data(scaled_spec(spec, 0.01), 1.0)
@@ -159,7 +159,10 @@ def test_bdpt_wavefront_equals_per_thread(scene, m, batch):
     fa, sa = g.render("bdpt", n, 64, 64, max_num_vertices=m, seed=5, sample_offset=77, wave_capacity=batch)
     fb, sb = g.render("bdpt", n, 64, 64, max_num_vertices=m, seed=5, sample_offset=77, flags=capi.RENDER_BDPT_PER_THREAD)
     g.close()
-    assert sa.extend_rays == sb.extend_rays and sa.shadow_rays == sb.shadow_rays, (sa.extend_rays, sb.extend_rays, sa.shadow_rays, sb.shadow_rays)
+    # the two kernels are separate compilations of the same functions (inlined here, out of line there): nvcc may contract a * b + c
+    # differently, and on the 1 M-triangle scene 1 path in 10^7 then branches differently (tools/bdpt_c3.py) — allow that much
+    assert abs(sa.extend_rays - sb.extend_rays) <= 1e-5 * sb.extend_rays and abs(sa.shadow_rays - sb.shadow_rays) <= 1e-5 * sb.shadow_rays, \
+        (sa.extend_rays, sb.extend_rays, sa.shadow_rays, sb.shadow_rays)
     assert sa.kernel_launches > 1 and sb.kernel_launches == 1
     assert fa.sum() > 0
     np.testing.assert_allclose(fa, fb, rtol=1e-3, atol=1e-5 * float(fb.max()))
