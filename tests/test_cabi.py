@@ -68,3 +68,12 @@ def test_gpu_path_fails_loudly_without_a_device():
     with pytest.raises(capi.NgiError, match="no CUDA device"):
         capi.GpuScene(sd, 0)
     assert capi.device_count() == -2
+
+
+def test_render_flag_constants_match_the_header():
+    """capi's NGI_RENDER_* mirrors vs the macros of include/nanogi_gpu.h."""
+    text = open(os.path.join(ROOT, "include", "nanogi_gpu.h")).read()
+    macros = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+NGI_RENDER_(\w+)\s+(\d+)u", text)}
+    assert macros == {"TIME_KERNELS": capi.RENDER_TIME_KERNELS, "PER_RAY_TRACE": capi.RENDER_PER_RAY_TRACE,
+                      "BDPT_PER_THREAD": capi.RENDER_BDPT_PER_THREAD}
+    assert len(set(macros.values())) == len(macros) and all(v & (v - 1) == 0 for v in macros.values())      # distinct single bits
