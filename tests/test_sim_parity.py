@@ -146,6 +146,31 @@ def test_bdpt_wavefront_equals_per_thread(scene, m, batch):
     np.testing.assert_allclose(fa, fb, rtol=2e-5, atol=1e-6 * float(fb.max()))
 
 
+@pytest.mark.parametrize("n", [1, 7, 1000])
+@pytest.mark.parametrize("m", [2, 3, -1])
+def test_bdpt_wavefront_edge_sizes(n, m):
+    """Edge sizes of the batch machinery: fewer samples than a batch, batches of 3 samples (ragged last batch), the shortest paths."""
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_spheres(), 0.01), 1.0)
+    sim = pysim.SimScene(sd)
+    fb, sb = sim.render("bdpt", n, 16, 16, max_num_vertices=m, seed=11, sample_offset=5, film_norm_samples=1000, flags=capi.RENDER_BDPT_PER_THREAD)
+    for batch in (3, 4096):
+        fa, sa = sim.render("bdpt", n, 16, 16, max_num_vertices=m, seed=11, sample_offset=5, film_norm_samples=1000, wave_capacity=batch)
+        assert sa["extend_rays"] == sb["extend_rays"] and sa["shadow_rays"] == sb["shadow_rays"]
+        np.testing.assert_allclose(fa, fb, rtol=2e-5, atol=1e-6 * max(float(fb.max()), 1e-30))
+
+
+def test_bdpt_wavefront_without_lights():
+    """No light primitive: the light subpaths are empty, every sample ends after the eye subpath was traced (src/nanogi.cpp:1137-1146), the
+    film stays black — in both forms."""
+    spec = [p for p in scaled_spec(scenes.cornell_box(), 0.01) if "L" not in p["type"]]
+    sd = scenes.to_scene_data(spec, 1.0)
+    sim = pysim.SimScene(sd)
+    fa, sa = sim.render("bdpt", 2000, 16, 16, max_num_vertices=5, seed=3, wave_capacity=512)
+    fb, sb = sim.render("bdpt", 2000, 16, 16, max_num_vertices=5, seed=3, flags=capi.RENDER_BDPT_PER_THREAD)
+    assert not fa.any() and not fb.any()
+    assert sa["shadow_rays"] == sb["shadow_rays"] == 0 and sa["extend_rays"] == sb["extend_rays"] > 0
+
+
 def test_bdpt_statistics_cornell_scale(cornell):
     pc.check_image_statistics(pysim.SimScene(cornell), cornell, "bdpt", w=16, h=16, spp=128, seeds=6, m=6, block=4)
 
