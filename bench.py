@@ -4,18 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c4pt] [--impl reference]
 
 Own arm (default)
-  step      one full render of the workload (one pass of the hot path over one batch of samples): at N = 1 the
-            workload is BASELINE.json configs[1] — Cornell box + glossy/glass spheres, `ptdirect`, 1024 x 1024,
-            1024 spp = 2^30 samples, unbounded path length. N > 1: every rank renders 2^30 samples of the SAME
-            image (disjoint Philox sample-index ranges, weak scaling: N * 1024 spp) and the per-rank films are
-            summed by ONE NCCL reduce to rank 0 inside the timed region.
+  step      one full render of the workload (one pass of the hot path over one batch of samples). The default workload
+            is the configuration BASELINE.json's metric and target are quoted on — configs[2] = C3: procedural
+            1M-triangle instanced-sphere scene, mixed diffuse / glossy / specular BSDFs, `ptdirect`, 1920 x 1080,
+            1024 spp = 2 123 366 400 samples, unbounded path length (it fits one GPU; `--workload c2` is configs[1]).
+            STRONG scaling: at any N the job is the same 2 123 366 400 samples; rank r renders the index range
+            nanogi_b200.shard.shard_range gives it (disjoint Philox sample indices: the sample SET does not depend on
+            N) and the per-rank films are summed by ONE NCCL reduce to rank 0 — the product's own ncclReduce
+            (ngi_gpu_comm_reduce_film) — inside the timed region. (`--scaling weak` multiplies the job by N instead.)
   value     Mpaths/s of the whole job, device-timed (torch CUDA events on the stream the kernels are launched on),
             scene + BVH resident in HBM, film left in HBM; max over ranks.
   e2e       the same metric through the C-ABI call a host application makes, with HOST buffers, every step:
             ngi_gpu_scene_create (H2D of the flattened scene + GPU BVH build) -> render -> film D2H into pinned
             host memory -> ngi_gpu_scene_destroy; wall clock around the calls (they synchronise), max over ranks.
   roofline  dominant kernel (named in the JSON) timed live with CUDA events around every launch
-            (NGI_RENDER_TIME_KERNELS pass on the same stream), algorithmic bytes per ray from SURVEY.md §8(d).
+            (NGI_RENDER_TIME_KERNELS pass on the same stream), algorithmic bytes per ray from SURVEY.md §8(d) against the
+            measured HBM peak. The trace kernels are bound by instruction issue, not by HBM, on every BASELINE scene, so
+            `bound` says "sm_issue" and the line carries issue-slot utilisation, active lanes per instruction, thread
+            instructions per ray and the measured DRAM traffic from the committed `ncu --set full` capture of THIS build
+            (profiles/r02_ncu_metrics.json, keyed by a hash of nanogi_b200/csrc; another build -> those fields are null).
   cpu_baseline  nanogi's own CPU code on all host cores (oracle/_ref: the reference's sources on stand-in third-party
             headers, Embree replaced by a scalar BVH; the oracle port when oracle/_ref is absent), bounded sample of the
             same workload; rank 0, N = 1 only.
@@ -40,6 +47,8 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "Mpaths/s (ptdirect; Mrays/s and image checks alongside)"
+
+DEFAULT_WORKLOAD = "c3"     # the configuration BASELINE.json's metric / target is stated on (fits one GPU)
 
 WORKLOADS = {
     # name: (scene generator, renderer, W, H, spp, max_num_vertices, description)
@@ -67,18 +76,28 @@ def b_ray(n_tris: int) -> int:
     return max(d, 1) * 80 + 4 * 48 + 96
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE steady-state launch of the dominant trace kernel, from the committed
-# `ncu --set full` captures (profiles/r01_ncu_c2_final.txt, profiles/r01_ncu_c3_final.txt). Those runs used 2 Mi-slot waves,
-# where a steady-state launch traces one ray per slot (ended paths are regenerated in the same iteration), so the figure is
-# kept per ray and scaled to this run's rays per launch.
-NCU_DRAM_BYTES_PER_LAUNCH = {
-    "c2": {"k_extend": (176.288512e6 + 30.705664e6, 1 << 21, "profiles/r01_ncu_c2_final.txt"),
-           "k_shadow": (93.781760e6 + 3.983104e6, 1 << 21, "profiles/r01_ncu_c2_final.txt")},
-    "c3": {"k_extend": (350.019840e6 + 48.704768e6, 1 << 21, "profiles/r01_ncu_c3_final.txt"),
-           "k_shadow": (114.695168e6 + 7.332608e6, 1 << 21, "profiles/r01_ncu_c3_final.txt")},
-    "c4": {"k_extend": (1.420079e9 + 60.782080e6, 1 << 21, "profiles/r01_ncu_c4.txt"),
-           "k_shadow": (0.439095e9 + 21.539584e6, 1 << 21, "profiles/r01_ncu_c4.txt")},
-}
+def csrc_sha() -> str:
+    """Hash of the CUDA sources the loaded module was built from (ties profiles/r02_ncu_metrics.json to a build)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "nanogi_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".h", ".cuh", ".cu")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_metrics(workload: str, kernel: str):
+    """Counters of ONE steady-state launch of `kernel` from the committed `ncu --set full` capture (tools/ncu_metrics.py),
+    or None when the capture is of another build of the CUDA sources."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
+    try:
+        j = json.load(open(p))
+    except Exception:
+        return None
+    if j.get("csrc_sha") != csrc_sha():
+        return None
+    return (j.get("workloads", {}).get(workload, {}) or {}).get(kernel)
 
 
 def measured_peaks():
@@ -152,7 +171,8 @@ class CpuReference:
         self.cores = os.cpu_count() or 1
         self.orc = pyoracle.OracleScene(sd)
         self.ref = None
-        if pyref.available() and sd.num_tris <= 200000 and not os.environ.get("NGI_BENCH_CPU_PORT"):
+        # (C3's 983 k triangles load in ~25 s through the reference's loader; C4's 10 M would take minutes: the port runs there)
+        if pyref.available() and sd.num_tris <= 2000000 and not os.environ.get("NGI_BENCH_CPU_PORT"):
             # the reference loads scene FILES: write the workload as schema.yml + OBJ (not part of any timed region)
             self.ref = pyref.RefScene(getattr(scenes, WORKLOADS[workload][0])(), aspect)
         self.kind = "reference" if self.ref is not None else "port"
@@ -195,7 +215,7 @@ def run_reference(args, rank: int):
     sample = f"{n_step} samples/step ({n_step / (W * H):.2f} spp of {spp}) x {args.steps} steps, same scene/resolution/renderer"
     line = {
         "impl": "reference", "metric": METRIC.replace("ptdirect", renderer), "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "mrays_per_s": rays / dt / 1e6,
         "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp": spp, "max_num_vertices": m,
                    "note": cpu.note},
@@ -211,7 +231,7 @@ def run_own(args, rank: int, local_rank: int, world: int):
     import torch
     import torch.distributed as dist
 
-    from nanogi_b200 import capi
+    from nanogi_b200 import capi, shard
 
     if not torch.cuda.is_available() or capi.device_count() <= 0:
         raise RuntimeError("bench.py: no CUDA device — the GPU path has no CPU fallback")
@@ -223,8 +243,11 @@ def run_own(args, rank: int, local_rank: int, world: int):
     gen, renderer, W, H, spp, m, desc = WORKLOADS[args.workload]
     if args.spp:
         spp = args.spp
-    n_rank = W * H * spp                      # samples per rank per step (weak scaling)
-    n_total = n_rank * world
+    # STRONG scaling (default): the job is the workload's W*H*spp samples at any N, rank r takes the index range shard_range gives
+    # it (src/nanogi.cpp:281: one parallel_for over [0, NumSamples)). --scaling weak: N times the job, fixed work per GPU.
+    n_total = W * H * spp * (world if args.scaling == "weak" else 1)
+    sample_offset, n_rank = shard.shard_range(n_total, rank, world)
+    comm = shard.make_comm(local_rank)         # the product's NCCL communicator (ncclCommInitRank; id broadcast over the process group)
     sd = build_scene(args.workload, W / H)
     scene = capi.GpuScene(sd, local_rank)
     info = scene.info()
@@ -240,10 +263,9 @@ def run_own(args, rank: int, local_rank: int, world: int):
     def step(i: int, flags: int = 0):
         flush.zero_()                                               # L2 flush between iterations
         st = scene.render_device(film.data_ptr(), stream.cuda_stream, renderer, n_rank, W, H, max_num_vertices=m,
-                                 seed=1000 + i, sample_offset=rank * n_rank, film_norm_samples=n_total, flags=flags,
+                                 seed=1000 + i, sample_offset=sample_offset, film_norm_samples=n_total, flags=flags,
                                  wave_capacity=args.wave_capacity)
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)           # the one exchange of the path
+        shard.reduce_film(film, 0, comm, stream.cuda_stream)        # the one exchange of the path (src/nanogi.cpp:429-437): ncclReduce
         return st
 
     for i in range(args.warmup):
@@ -289,8 +311,8 @@ def run_own(args, rank: int, local_rank: int, world: int):
                         "ngi_gpu_render")                           # render + film D2H into pinned host memory
         else:
             sc.render_device(film.data_ptr(), stream.cuda_stream, renderer, n_rank, W, H, max_num_vertices=m, seed=5000 + i,
-                             sample_offset=rank * n_rank, film_norm_samples=n_total, wave_capacity=args.wave_capacity)
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+                             sample_offset=sample_offset, film_norm_samples=n_total, wave_capacity=args.wave_capacity)
+            shard.reduce_film(film, 0, comm, stream.cuda_stream)
             if rank == 0:
                 pinned.copy_(film, non_blocking=True)
             torch.cuda.synchronize(dev)
@@ -334,16 +356,27 @@ def run_own(args, rank: int, local_rank: int, world: int):
         dom = k_ext if stt.extend_kernel_seconds >= stt.shadow_kernel_seconds else k_sh
         sec, nl, rays = per[dom]
         achieved = rays * br / sec / 1e9 if sec > 0 else 0.0
-        traffic, traffic_src = None, None
-        ncu = NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload if args.workload in NCU_DRAM_BYTES_PER_LAUNCH else "", {}).get(dom)
-        if ncu:
-            traffic = ncu[0] / ncu[1] * (rays / max(nl, 1))          # bytes per launch of THIS run's size
-            traffic_src = "%s: %.0f B/ray of DRAM traffic (x %.0f rays per launch here) vs %d algorithmic B/ray" % (ncu[2], ncu[0] / ncu[1], rays / max(nl, 1), br)
-        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_ray": br, "rays_per_launch": rays / max(nl, 1),
+        rays_per_launch = rays / max(nl, 1)
+        # counters of one steady-state launch of the same kernel from the committed ncu capture of THIS build
+        nm = ncu_metrics(args.workload, dom)
+        traffic = traffic_src = None
+        counters = None
+        if nm:
+            per_ray = nm["dram_bytes"] / nm["rays"]
+            traffic = per_ray * rays_per_launch                        # bytes per launch of THIS run's size
+            traffic_src = "%s: %.0f B/ray of DRAM traffic (x %.0f rays per launch here) vs %d algorithmic B/ray" % (nm["source"], per_ray, rays_per_launch, br)
+            counters = {k: nm.get(k) for k in ("issue_active_pct", "active_lanes", "thread_inst_per_ray", "warp_inst_per_ray", "alu_pipe_pct", "fma_pipe_pct",
+                                               "dram_throughput_pct", "l1_hit_pct", "l2_hit_pct", "warps_active_pct", "registers", "local_load_inst_per_ray",
+                                               "local_store_inst_per_ray")}
+        roof = {"bound": "sm_issue", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_ray": br, "rays_per_launch": rays_per_launch,
                 "avg_launch_ms": sec / max(nl, 1) * 1e3, "grays_per_s": rays / sec / 1e9 if sec > 0 else 0.0,
-                "note": "algorithmic bytes (SURVEY 8d) / CUDA-event launch time; the scene (%.1f MB incl. BVH) is L2-resident, so "
-                        "HBM is not the physical limiter of this workload — see profiles/ for L2/issue counters" % (info.device_bytes / 1e6)}
+                "ncu": counters,
+                "note": "achieved = algorithmic bytes (SURVEY 8d: %d B/ray) x rays per launch / CUDA-event launch time, against the measured HBM "
+                        "copy peak: an ALGORITHMIC fraction. The kernel is bound by instruction issue (BVH8 node steps + triangle tests; the "
+                        "BVH, %.1f MB of nodes + triangles, is served from L1/L2), so `ncu` carries the physical counters of one steady-state "
+                        "launch of this build: issue-slot utilisation, active lanes, thread instructions per ray, measured DRAM bytes"
+                        % (br, (int(info.bvh8_nodes) * 80 + int(info.num_tris) * 48) / 1e6)}
 
     # ---- CPU baseline (oracle port) on the host cores: rank 0, N = 1 only -----------------------------------
     cpu = None
@@ -365,12 +398,14 @@ def run_own(args, rank: int, local_rank: int, world: int):
     if rank == 0:
         line = {
             "metric": METRIC.replace("ptdirect", renderer), "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "mrays_per_s": mrays,
-            "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp_per_gpu": spp, "samples_per_step": n_total,
+            "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp": n_total // (W * H), "samples_per_step": n_total,
+                       "samples_per_gpu": n_rank,
                        "max_num_vertices": m, "tris": int(info.num_tris), "bvh8_nodes": int(info.bvh8_nodes),
                        "scene_device_bytes": int(info.device_bytes), "bvh_build_ms": info.build_gpu_seconds * 1e3,
-                       "parallelism": f"samples sharded by index over {world} GPU(s); scene replicated; one NCCL film reduce",
+                       "parallelism": f"one job of {n_total} samples sharded by index over {world} GPU(s) ({args.scaling} scaling); scene replicated; "
+                                      "one ncclReduce of the films inside the timed region (libnanogi_gpu.so: ngi_gpu_comm_reduce_film)",
                        "l2": ("256 MB memset between iterations flushes L2; a bdpt batch (vertex + cache records of 2 subpaths per sample, "
                               "GBs per batch, two in flight) also exceeds it") if renderer == "bdpt" else
                              "256 MB memset between iterations flushes L2; wavefront state (%.0f MB: 188 B x %d slots x 2 lanes) also exceeds it"
@@ -383,6 +418,8 @@ def run_own(args, rank: int, local_rank: int, world: int):
         }
         emit(line)
     scene.close()
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -411,8 +448,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (default: the workload's)")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the same job at any N; weak: N times the job")
+    ap.add_argument("--spp", type=int, default=0, help="override the samples per pixel of the job (default: the workload's)")
     ap.add_argument("--wave-capacity", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="size of the cpu_baseline sample")

@@ -40,7 +40,8 @@ typedef enum NgiStatus {
     NGI_ERR_NO_DEVICE = -2,       /* no CUDA device: the GPU path never falls back to the CPU   */
     NGI_ERR_CUDA = -3,
     NGI_ERR_UNSUPPORTED = -4,     /* renderer outside pt / ptdirect / lt / ltdirect / bdpt (ptmnee) */
-    NGI_ERR_OUT_OF_MEMORY = -5
+    NGI_ERR_OUT_OF_MEMORY = -5,
+    NGI_ERR_NCCL = -6             /* libnccl.so.2 missing or an NCCL call failed (multi-GPU entry points only) */
 } NgiStatus;
 
 /* ---- primitive type bitmask: reference include/nanogi/rt.hpp:338-351 ---------------------- */
@@ -159,6 +160,7 @@ typedef struct NgiRenderStats {
     double extend_kernel_seconds;
     double shadow_kernel_seconds;
     uint64_t logic_launches, extend_launches, shadow_launches;
+    double reduce_seconds;       /* ngi_gpu_group_render: CUDA-event time of the NCCL film reduce on the root device */
 } NgiRenderStats;
 
 typedef struct NgiSceneInfo {
@@ -222,6 +224,36 @@ NGI_API int ngi_gpu_trace_device(void* scene, const void* rays_device, uint64_t 
  * out : per query 8 floats   {wo[3], fs[3], pdf, wo_valid}                                     */
 NGI_API int ngi_gpu_eval_bsdf(void* scene, const float* queries_host, const float* wo_in_host,
                               uint64_t n, int force_degenerated, float* out_host);
+
+/* ---- multi-GPU: samples sharded by index, ONE NCCL reduce of the per-GPU films ---------------
+ * Replaces, across GPUs, the reference's split of [0, NumSamples) into independent chunks with private films
+ * (tbb::parallel_for, reference src/nanogi.cpp:281-337) and its final gather `film += ctx.film * (W*H/N)`
+ * (src/nanogi.cpp:429-437). Counter-based Philox keyed by the sample index makes the sample SET independent of the
+ * GPU count; every GPU pre-scales its splats by W*H/film_norm_samples, so the gather is one ncclReduce(SUM) over NVLink.
+ * NCCL is opened with dlopen("libnccl.so.2") on first use: without it these entry points return NGI_ERR_NCCL and the
+ * single-GPU entry points are unaffected. */
+
+/* rank r of world_size takes sample indices [offset, offset + count) = [r N / G, (r+1) N / G) */
+NGI_API void ngi_gpu_shard_range(int64_t num_samples, int rank, int world_size, int64_t* out_offset, int64_t* out_count);
+
+/* (a) ONE process, several devices: ncclCommInitAll. The scene is uploaded and its BVH built once, on devices[0], and
+ * every built array is handed to the other devices with ncclBroadcast. devices = NULL means 0 .. num_devices-1. */
+NGI_API int ngi_gpu_group_create(const NgiSceneDesc* desc, const int* devices, int num_devices, void** out_group);
+/* Renderer::Render for the whole group: shards params->num_samples (from params->sample_offset) over the devices, renders
+ * the shards concurrently, reduces the films onto devices[0] (ncclReduce, SUM) and copies the result to host memory. */
+NGI_API int ngi_gpu_group_render(void* group, const NgiRenderParams* params, float* film_rgb_host, NgiRenderStats* out_stats);
+/* the scene handle of the group's index-th device (borrowed: valid until ngi_gpu_group_destroy) */
+NGI_API int ngi_gpu_group_scene(void* group, int index, void** out_scene);
+NGI_API void ngi_gpu_group_destroy(void* group);
+
+/* (b) one process PER GPU (torchrun, MPI): ncclCommInitRank. Rank 0 calls ngi_gpu_comm_get_id and hands the 128 bytes
+ * to the other ranks by any host channel; every rank then creates its communicator, renders its shard with
+ * ngi_gpu_render_device and calls ngi_gpu_comm_reduce_film (in place; the sum lands on `root`) on the same stream. */
+typedef struct NgiCommId { char bytes[128]; } NgiCommId;
+NGI_API int ngi_gpu_comm_get_id(NgiCommId* out_id);
+NGI_API int ngi_gpu_comm_create(const NgiCommId* id, int rank, int world_size, int device, void** out_comm);
+NGI_API int ngi_gpu_comm_reduce_film(void* comm, void* film_rgb_device, uint64_t num_floats, int root, void* cuda_stream);
+NGI_API void ngi_gpu_comm_destroy(void* comm);
 
 /* thread-local message of the last failing call */
 NGI_API const char* ngi_gpu_last_error(void);

@@ -76,7 +76,12 @@ class NgiRenderStats(C.Structure):
         ("gpu_seconds", C.c_double), ("trace_kernel_seconds", C.c_double),
         ("logic_kernel_seconds", C.c_double), ("extend_kernel_seconds", C.c_double), ("shadow_kernel_seconds", C.c_double),
         ("logic_launches", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
+        ("reduce_seconds", C.c_double),
     ]
+
+
+class NgiCommId(C.Structure):
+    _fields_ = [("bytes", C.c_char * 128)]
 
 
 class NgiSceneInfo(C.Structure):
@@ -110,7 +115,11 @@ GPU_SYMBOLS = [
     "ngi_gpu_device_count", "ngi_gpu_scene_create", "ngi_gpu_scene_info", "ngi_gpu_scene_destroy",
     "ngi_gpu_render", "ngi_gpu_render_device", "ngi_gpu_trace", "ngi_gpu_trace_device",
     "ngi_gpu_eval_bsdf", "ngi_gpu_last_error", "ngi_gpu_abi_version",
+    "ngi_gpu_shard_range", "ngi_gpu_group_create", "ngi_gpu_group_render", "ngi_gpu_group_scene", "ngi_gpu_group_destroy",
+    "ngi_gpu_comm_get_id", "ngi_gpu_comm_create", "ngi_gpu_comm_reduce_film", "ngi_gpu_comm_destroy",
 ]
+ABI_VERSION = 2
+ERR_NCCL = -6
 HOST_SYMBOLS = [
     "ngi_host_scene_load", "ngi_host_scene_desc", "ngi_host_scene_sensor", "ngi_host_scene_num_lights",
     "ngi_host_scene_free", "ngi_host_save_image", "ngi_host_load_image", "ngi_host_parse_cli", "ngi_host_usage", "ngi_host_last_error",
@@ -231,6 +240,18 @@ def gpu_lib():
         lib.ngi_gpu_trace_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
         lib.ngi_gpu_eval_bsdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         lib.ngi_gpu_last_error.restype = C.c_char_p
+        lib.ngi_gpu_shard_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        lib.ngi_gpu_shard_range.restype = None
+        lib.ngi_gpu_group_create.argtypes = [C.POINTER(NgiSceneDesc), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        lib.ngi_gpu_group_render.argtypes = [C.c_void_p, C.POINTER(NgiRenderParams), C.c_void_p, C.POINTER(NgiRenderStats)]
+        lib.ngi_gpu_group_scene.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        lib.ngi_gpu_group_destroy.argtypes = [C.c_void_p]
+        lib.ngi_gpu_group_destroy.restype = None
+        lib.ngi_gpu_comm_get_id.argtypes = [C.POINTER(NgiCommId)]
+        lib.ngi_gpu_comm_create.argtypes = [C.POINTER(NgiCommId), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        lib.ngi_gpu_comm_reduce_film.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        lib.ngi_gpu_comm_destroy.argtypes = [C.c_void_p]
+        lib.ngi_gpu_comm_destroy.restype = None
         _gpu = lib
     return _gpu
 
@@ -326,7 +347,8 @@ class GpuScene:
         _check(self.lib.ngi_gpu_scene_info(self.handle, C.byref(out)), "ngi_gpu_scene_info")
         return out
 
-    def _params(self, renderer, num_samples, width, height, max_num_vertices=-1, seed=1, sample_offset=0,
+    @staticmethod
+    def _params(renderer, num_samples, width, height, max_num_vertices=-1, seed=1, sample_offset=0,
                 film_norm_samples=None, wave_capacity=0, accumulate=0, flags=0) -> NgiRenderParams:
         p = NgiRenderParams()
         p.struct_size = C.sizeof(NgiRenderParams)
@@ -378,6 +400,70 @@ class GpuScene:
         _check(self.lib.ngi_gpu_eval_bsdf(self.handle, queries.ctypes.data, wo.ctypes.data, n, int(force_degenerated), out.ctypes.data),
                "ngi_gpu_eval_bsdf")
         return out
+
+
+class GpuGroup:
+    """ngi_gpu_group_*: every device of ONE process — scene built once and broadcast, samples sharded by index, one NCCL
+    film reduce per render (what `nanogi --gpus N` runs)."""
+
+    def __init__(self, scene: SceneData, devices):
+        self.lib = gpu_lib()
+        self.handle = C.c_void_p()
+        self.scene = scene
+        self.devices = list(devices)
+        d = scene.desc()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        _check(self.lib.ngi_gpu_group_create(C.byref(d), arr, len(self.devices), C.byref(self.handle)), "ngi_gpu_group_create")
+
+    def close(self):
+        if self.handle:
+            self.lib.ngi_gpu_group_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, renderer, num_samples, width, height, **kw):
+        p = GpuScene._params(renderer, num_samples, width, height, **kw)
+        film = np.empty((height, width, 3), np.float32)
+        stats = NgiRenderStats()
+        _check(self.lib.ngi_gpu_group_render(self.handle, C.byref(p), film.ctypes.data, C.byref(stats)), "ngi_gpu_group_render")
+        return film, stats
+
+
+class GpuComm:
+    """ngi_gpu_comm_*: this process's rank of an NCCL communicator that spans one process per GPU. `exchange` hands rank 0's
+    128-byte id to the other ranks (any host channel: bench.py passes a torch.distributed broadcast)."""
+
+    def __init__(self, rank: int, world_size: int, device: int, exchange):
+        self.lib = gpu_lib()
+        self.handle = C.c_void_p()
+        cid = NgiCommId()
+        if rank == 0:
+            _check(self.lib.ngi_gpu_comm_get_id(C.byref(cid)), "ngi_gpu_comm_get_id")
+        blob = exchange(C.string_at(C.byref(cid), 128) if rank == 0 else None)
+        assert len(blob) == 128
+        C.memmove(C.byref(cid), blob, 128)
+        _check(self.lib.ngi_gpu_comm_create(C.byref(cid), rank, world_size, device, C.byref(self.handle)), "ngi_gpu_comm_create")
+
+    def reduce_film(self, film_ptr: int, num_floats: int, root: int = 0, stream_ptr: int = 0):
+        _check(self.lib.ngi_gpu_comm_reduce_film(self.handle, C.c_void_p(film_ptr), num_floats, root, C.c_void_p(stream_ptr)),
+               "ngi_gpu_comm_reduce_film")
+
+    def close(self):
+        if self.handle:
+            self.lib.ngi_gpu_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+def shard_range(num_samples: int, rank: int, world_size: int):
+    """ngi_gpu_shard_range: (offset, count) of `rank` — the product's own arithmetic (no device needed)."""
+    off, cnt = C.c_int64(), C.c_int64()
+    gpu_lib().ngi_gpu_shard_range(int(num_samples), int(rank), int(world_size), C.byref(off), C.byref(cnt))
+    return off.value, cnt.value
 
 
 def device_count() -> int:

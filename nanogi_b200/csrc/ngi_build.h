@@ -119,6 +119,68 @@ NGI_HD unsigned ngi_ploc_keep(const int* __restrict__ nn, const int i) {
     const int j = nn[i];
     return (j >= 0 && nn[j] == i && j < i) ? 0u : 1u;
 }
+// ---- SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1) -------------------------------------------------------
+// C(n, i) = cheapest way to turn the binary subtree of n into a forest of at most i wide-BVH subtrees:
+//     C(n, 1) = min( leaf:      A_n * P_n * c_prim          (P_n <= NGI_LEAF_MAX_TRIS triangles in one leaf slot),
+//                    internal:  A_n * c_node + D(n, 8) )     (n becomes an 8-wide node)
+//     C(n, i) = min( D(n, i), C(n, i - 1) )                  i = 2 .. 7
+//     D(n, j) = min over 0 < k < j of  C(left, k) + C(right, j - k)
+// One row per binary inner node, filled bottom-up: PLOC creates a node after both of its children (ngi_ploc_merge), so the row is
+// computed right where the node is made. The collapse then follows the recorded decisions (ngi_collapse_node) instead of opening
+// the child with the largest area until the node is full. A node step costs the same whether 3 or 8 slots are occupied, so the
+// model's constant per-node cost is exact for this traversal; the greedy collapse left the nodes of the 1 M-triangle scene 3.9 / 8
+// full on average (tools/bvh_quality.py).
+#define NGI_LEAF_MAX_TRIS 3
+#define NGI_DP_INF 3.0e38f
+#ifndef NGI_SAH_C_PRIM
+#define NGI_SAH_C_PRIM 0.3f        /* cost of a triangle test relative to an 8-wide node step (tools/bvh_quality.py sweep) */
+#endif
+struct alignas(16) NgiDpRow {
+    float c[7];        // c[i - 1] = C(n, i)
+    unsigned dec;      // bit 0: C(n, 1) is the leaf; bits 1 + 3 (j - 2) .. +2, j = 2 .. 8: the split k of D(n, j), or 0 = "C(n, j) is C(n, j - 1)"
+};
+NGI_HD unsigned ngi_dp_split(const unsigned dec, const int j) { return (dec >> (1 + 3 * (j - 2))) & 7u; }
+// m: binary node id; leaves (m >= n - 1) cost A * c_prim whatever the budget
+NGI_HD float ngi_dp_get(const NgiDpRow* __restrict__ dp, const float4* __restrict__ lo, const float4* __restrict__ hi, const int n, const int m,
+                        const int i, const float c_prim) {
+    if (m >= n - 1) {
+        const float4 a = lo[m], b = hi[m];
+        const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+        return (dx * dy + dy * dz + dz * dx) * c_prim;
+    }
+    return dp[m].c[i - 1];
+}
+NGI_HD void ngi_dp_node(NgiDpRow* __restrict__ dp, const float4* __restrict__ lo, const float4* __restrict__ hi, const int n, const int id,
+                        const int a, const int b, const unsigned count, const float area, const float c_node, const float c_prim) {
+    float ca[7], cb[7];
+#pragma unroll
+    for (int i = 1; i <= 7; i++) { ca[i - 1] = ngi_dp_get(dp, lo, hi, n, a, i, c_prim); cb[i - 1] = ngi_dp_get(dp, lo, hi, n, b, i, c_prim); }
+    float D[9]; unsigned K[9];
+#pragma unroll
+    for (int j = 2; j <= 8; j++) {
+        float best = NGI_DP_INF; unsigned bk = 1;
+#pragma unroll
+        for (int k = 1; k < j; k++) {
+            if (k > 7 || j - k > 7) continue;
+            const float v = ca[k - 1] + cb[j - k - 1];
+            if (v < best) { best = v; bk = (unsigned)k; }
+        }
+        D[j] = best; K[j] = bk;
+    }
+    NgiDpRow r;
+    const float leaf = count <= NGI_LEAF_MAX_TRIS ? area * (float)count * c_prim : NGI_DP_INF;
+    const float inner = area * c_node + D[8];
+    r.dec = leaf <= inner ? 1u : 0u;
+    r.c[0] = leaf <= inner ? leaf : inner;
+#pragma unroll
+    for (int i = 2; i <= 7; i++) {
+        if (D[i] < r.c[i - 2]) { r.c[i - 1] = D[i]; r.dec |= K[i] << (1 + 3 * (i - 2)); }
+        else r.c[i - 1] = r.c[i - 2];
+    }
+    r.dec |= K[8] << (1 + 3 * 6);
+    dp[id] = r;
+}
+
 struct NgiPlocCtx {
     const int* nn; const unsigned* pos;          // nearest neighbour, exclusive scan of the keep flags
     const int* cid_in; const float4* clo_in; const float4* chi_in;
@@ -127,6 +189,8 @@ struct NgiPlocCtx {
     int* left; int* right; unsigned* cnt;        // [n-1]
     int n;                                       // leaves
     int next_id;                                 // id of the first merge of this round (ids go downwards)
+    NgiDpRow* dp;                                // [n-1] collapse decisions (ngi_dp_node), or NULL
+    float c_node, c_prim;
 };
 NGI_HD void ngi_ploc_merge(const NgiPlocCtx& c, const int i) {
     const int j = c.nn[i];
@@ -144,6 +208,10 @@ NGI_HD void ngi_ploc_merge(const NgiPlocCtx& c, const int i) {
         c.cnt[id] = (a >= c.n - 1 ? 1u : c.cnt[a]) + (b >= c.n - 1 ? 1u : c.cnt[b]);
         c.lo[id] = u0; c.hi[id] = u1;
         c.cid_out[p] = id; c.clo_out[p] = u0; c.chi_out[p] = u1;
+        if (c.dp) {
+            const float dx = u1.x - u0.x, dy = u1.y - u0.y, dz = u1.z - u0.z;
+            ngi_dp_node(c.dp, c.lo, c.hi, c.n, id, a, b, c.cnt[id], dx * dy + dy * dz + dz * dx, c.c_node, c.c_prim);
+        }
     } else {
         c.cid_out[p] = c.cid_in[i]; c.clo_out[p] = c.clo_in[i]; c.chi_out[p] = c.chi_in[i];
     }
@@ -163,7 +231,6 @@ NGI_HD void ngi_pack2(const float4* __restrict__ lo, const float4* __restrict__ 
 }
 
 // ---- 6. collapse to BVH8 -------------------------------------------------------------------------
-#define NGI_LEAF_MAX_TRIS 3
 
 struct NgiCollapseCtx {
     // BVH2 (node numbering as above)
@@ -177,6 +244,7 @@ struct NgiCollapseCtx {
     float4* tris8;                           // [n][3]
     unsigned* counters;                      // [0] = nodes allocated, [1] = triangles allocated, [2] = next-level task count
     NgiBuildTask* out_tasks;
+    const NgiDpRow* dp;                      // SAH-optimal collapse decisions, or NULL = greedy (open the largest child until 8)
 };
 
 NGI_HD unsigned ngi_atomic_add(unsigned* p, unsigned v) {
@@ -197,7 +265,26 @@ NGI_HD float ngi_half_area(float4 lo, float4 hi) {
 NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTask task) {
     const int n = c.n;
     int child[8];
-    int cnt = 2;
+    bool dp_leaf[8];                          // DP: this child becomes a leaf slot (else: every child with <= NGI_LEAF_MAX_TRIS triangles does)
+    int cnt = 0;
+    if (c.dp) {
+        // follow the recorded decisions: the 8 child slots of this node are distributed over the two binary subtrees
+        int st_m[16], st_j[16]; int sp = 0;
+        const unsigned k8 = ngi_dp_split(c.dp[task.node2].dec, 8);
+        st_m[sp] = c.right[task.node2]; st_j[sp++] = 8 - (int)k8;
+        st_m[sp] = c.left[task.node2]; st_j[sp++] = (int)k8;
+        while (sp > 0) {
+            const int m = st_m[--sp]; int j = st_j[sp];
+            if (m >= n - 1) { dp_leaf[cnt] = true; child[cnt++] = m; continue; }
+            const unsigned dec = c.dp[m].dec;
+            unsigned k = 0;
+            while (j > 1 && (k = ngi_dp_split(dec, j)) == 0u) j--;             // C(m, j) = C(m, j - 1)
+            if (j == 1) { dp_leaf[cnt] = (dec & 1u) != 0u; child[cnt++] = m; continue; }
+            st_m[sp] = c.right[m]; st_j[sp++] = j - (int)k;
+            st_m[sp] = c.left[m]; st_j[sp++] = (int)k;
+        }
+    } else {
+    cnt = 2;
     child[0] = c.left[task.node2];
     child[1] = c.right[task.node2];
     // greedily open the inner child with the largest surface area until 8 children
@@ -214,6 +301,8 @@ NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTa
         const int nd = child[best];
         child[best] = c.left[nd];
         child[cnt++] = c.right[nd];
+    }
+    for (int k = 0; k < cnt; k++) dp_leaf[k] = child[k] >= n - 1 || c.cnt[child[k]] <= NGI_LEAF_MAX_TRIS;
     }
     // node frame: origin one quantisation step below the node box and 252 steps of usable range, so that the
     // outward-rounded planes (widened by 2^-7 step, see below) never need clamping on either side
@@ -244,7 +333,7 @@ NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTa
     for (int k = 0; k < cnt; k++) {
         const int nd = child[k];
         if (nd >= n - 1) { inner[k] = false; ntri[k] = 1; leafTri[k][0] = nd - (n - 1); }
-        else if (c.cnt[nd] <= NGI_LEAF_MAX_TRIS) {
+        else if (dp_leaf[k]) {
             // gather the (at most NGI_LEAF_MAX_TRIS) leaves of the small subtree, left first
             inner[k] = false; ntri[k] = 0;
             int st[NGI_LEAF_MAX_TRIS + 1]; int sp = 0;

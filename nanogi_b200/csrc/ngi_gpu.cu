@@ -16,8 +16,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -31,6 +33,7 @@
 #include "ngi_bdpt.h"
 #include "ngi_bdpt_wave.h"
 #include "ngi_trace_warp.cuh"
+#include "ngi_comm.h"
 
 namespace {
 
@@ -216,9 +219,11 @@ struct NgiRenderCounters {
     unsigned stage[4];  // [0] surface queue entries, [1] regenerate queue entries
 };
 
-__global__ void k_iter_begin(NgiRenderCounters* c, unsigned long long sample_end) {
+constexpr unsigned kIterLogCap = 8192;     // NGI_ITER_LOG: (shadow, extend) ray counts of the first iterations of a lane
+__global__ void k_iter_begin(NgiRenderCounters* c, unsigned long long sample_end, unsigned* __restrict__ iter_log) {
     // the eye kernel of the previous iteration started samples next_sample .. next_sample + stage[1] - 1
     const unsigned long long ns = c->next_sample + c->stage[1];
+    if (iter_log && c->iterations < kIterLogCap) { iter_log[2 * c->iterations] = c->iter[0]; iter_log[2 * c->iterations + 1] = c->iter[1]; }
     c->next_sample = ns < sample_end ? ns : sample_end;
     c->total_shadow += c->iter[0];
     c->total_extend += c->iter[1];
@@ -232,6 +237,32 @@ __global__ void k_iter_begin(NgiRenderCounters* c, unsigned long long sample_end
     c->stage[1] = 0u;
     c->iterations += 1ull;
 }
+
+// ---- fp64 film behind the fp32 atomics ------------------------------------------------------------------------------
+// The reference accumulates in double (std::vector<glm::dvec3>, src/nanogi.cpp:203, :297). The kernels splat with fp32 atomics
+// (RED.ADD.F32 is the fast path), and a fp32 sum stops growing once a splat falls below ulp(sum)/2, ~6e-8 of the sum: a pixel that
+// collects > 1e7 splats (the eye-vertex connections of ptdirect / bdpt onto a small visible light at 1080p x 1024 spp) would come
+// out too dark. So the fp32 film is only a staging buffer: once per wavefront iteration (bdpt: per batch) k_film_fold moves it into
+// a fp64 accumulator — atomicExch fetches AND zeroes an element, so splats of kernels running concurrently on other streams are
+// never lost — and k_film_finish writes the rounded sums back at the end of the render. 25 MB + 50 MB of traffic per fold at
+// 1080p, < 1 % of an iteration.
+__global__ void __launch_bounds__(kBlock) k_film_begin(float* __restrict__ film, double* __restrict__ acc, size_t n, int accumulate) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        acc[i] = accumulate ? (double)film[i] : 0.0;
+        film[i] = 0.0f;
+    }
+}
+__global__ void __launch_bounds__(kBlock) k_film_fold(float* __restrict__ film, double* __restrict__ acc, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = atomicExch(film + i, 0.0f);
+        if (v != 0.0f) atomicAdd(acc + i, (double)v);
+    }
+}
+__global__ void __launch_bounds__(kBlock) k_film_finish(float* __restrict__ film, const double* __restrict__ acc, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        film[i] = (float)(acc[i] + (double)film[i]);
+}
+constexpr unsigned kFilmGrid = 148u * 8u;
 
 // Logic stage = three dense kernels over compacted queues (warp ballot/popc + one atomic per warp, ngi_queue_alloc):
 //   k_classify  every slot: idle / miss / RR / vertex cap (+ pt emission) -> surface_q | regen_q
@@ -654,6 +685,10 @@ struct Lane {
     cudaGraphExec_t graph_exec = nullptr;
     NgiWaveParams graph_wp{};
     int graph_iters = 0;
+    double* fold_acc = nullptr;                  // lane 0 only: fp64 film accumulator folded into after every iteration (k_film_fold)
+    size_t fold_n = 0;
+    double* graph_acc = nullptr;                 // what the captured graph folds into
+    unsigned* iter_log = nullptr;                // NGI_ITER_LOG=<file>: per-iteration ray counts (profiling sessions: rays of an ncu-captured launch)
     std::vector<cudaEvent_t> events;             // per-kernel timing (NGI_RENDER_TIME_KERNELS)
     NgiWaveParams wp{};
     bool running = false;
@@ -665,6 +700,7 @@ struct Scene {
     NgiDevScene dev{};
     NgiSceneInfo info{};
     std::vector<void*> allocs;
+    std::vector<size_t> alloc_bytes;             // parallel to `allocs` (a built scene is cloned to other devices array by array)
     std::vector<Lane> lanes;
     int num_lanes = 2;
     // persistent trace kernels: grid = SM count x resident CTAs per SM (queried once per kernel)
@@ -675,6 +711,8 @@ struct Scene {
     // stream so that its CTAs fill the SMs the extend kernel's tail leaves idle
     bool overlap_trace = true;
     cudaStream_t bd_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // wavefront bdpt: batches in flight
+    double* film_acc = nullptr;                  // fp64 film accumulator (k_film_fold), kept across renders of the same size
+    size_t film_acc_n = 0;
     unsigned grid_bdw_extend = 0, grid_bdw_shadow = 0;
 
     ~Scene() {
@@ -684,6 +722,7 @@ struct Scene {
             if (l.graph_exec) cudaGraphExecDestroy(l.graph_exec);
             for (auto e : l.events) cudaEventDestroy(e);
             if (l.wave_mem) wave_cache_put(device, l.wave_mem, l.wave_capacity);
+            if (l.iter_log) cudaFree(l.iter_log);
             if (l.counters) cudaFree(l.counters);
             if (l.counters_host) cudaFreeHost(l.counters_host);
             if (l.ev_fork) cudaEventDestroy(l.ev_fork);
@@ -694,6 +733,7 @@ struct Scene {
         }
         for (void* p : allocs) ngi_dfree(p, stream);
         if (trace_cursor) ngi_dfree(trace_cursor, stream);
+        if (film_acc) cudaFree(film_acc);
         if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
     }
 };
@@ -702,7 +742,7 @@ template <class T>
 int dev_alloc(Scene* s, T** out, size_t count, bool keep) {
     void* p = nullptr;
     NGI_CUDA(ngi_dmalloc(&p, std::max<size_t>(count * sizeof(T), 16), s->stream));
-    if (keep) { s->allocs.push_back(p); s->info.device_bytes += count * sizeof(T); }
+    if (keep) { s->allocs.push_back(p); s->alloc_bytes.push_back(std::max<size_t>(count * sizeof(T), 16)); s->info.device_bytes += count * sizeof(T); }
     *out = (T*)p;
     return NGI_OK;
 }
@@ -846,6 +886,12 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     if ((rc = dev_alloc(s, &d_keep, n, false))) return rc;
     if ((rc = dev_alloc(s, &d_spos, n, false))) return rc;
     if ((rc = dev_alloc(s, &d_newc, 1, false))) return rc;
+    // SAH-optimal collapse decisions, one row per binary node, filled by the PLOC merges (ngi_dp_node); NGI_COLLAPSE_GREEDY=1 keeps
+    // round 1's greedy collapse for A/B runs
+    NgiDpRow* d_dp = nullptr;
+    const bool greedy_collapse = getenv("NGI_COLLAPSE_GREEDY") && atoi(getenv("NGI_COLLAPSE_GREEDY"));
+    const float sah_c_prim = getenv("NGI_SAH_CPRIM") ? (float)atof(getenv("NGI_SAH_CPRIM")) : NGI_SAH_C_PRIM;
+    if (!greedy_collapse && (rc = dev_alloc(s, &d_dp, n - 1, false))) return rc;
     size_t scan_bytes = 0;
     NGI_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_keep, d_spos, (int)n, st));
     if ((rc = dev_alloc(s, &d_scan_tmp, scan_bytes, false))) return rc;
@@ -862,6 +908,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
             pc.cid_out = d_cid[cur ^ 1]; pc.clo_out = d_clo[cur ^ 1]; pc.chi_out = d_chi[cur ^ 1];
             pc.lo = d_lo; pc.hi = d_hi; pc.left = d_left; pc.right = d_right; pc.cnt = d_ncnt; pc.n = (int)n;
             pc.next_id = (int)(n - 2) - (int)merges_done;
+            pc.dp = d_dp; pc.c_node = 1.0f; pc.c_prim = sah_c_prim;
             k_ploc_merge<<<grid_for(C), kBlock, 0, st>>>(pc, (int)C, d_keep, d_newc);
             unsigned newC = 0;
             NGI_CUDA(cudaMemcpyAsync(&newC, d_newc, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -890,7 +937,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     }
     NgiCollapseCtx ctx;
     ctx.lo = d_lo; ctx.hi = d_hi; ctx.left = d_left; ctx.right = d_right; ctx.cnt = d_ncnt; ctx.tris2 = d_tris2; ctx.n = (int)n;
-    ctx.nodes8 = d_nodes8_tmp; ctx.tris8 = d_tris8; ctx.counters = d_cnt;
+    ctx.nodes8 = d_nodes8_tmp; ctx.tris8 = d_tris8; ctx.counters = d_cnt; ctx.dp = d_dp;
     unsigned n_tasks = 1, depth = 0;
     unsigned hc[4] = {1, 0, 0, 0};
     NgiBuildTask *qin = d_q0, *qout = d_q1;
@@ -921,7 +968,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     for (void* p : {(void*)d_pos, (void*)d_bounds, (void*)d_rec, (void*)d_tlo, (void*)d_thi, (void*)d_keys, (void*)d_keys2, (void*)d_vals, (void*)d_vals2,
                     (void*)d_tmp, (void*)d_lo, (void*)d_hi, (void*)d_left, (void*)d_right, (void*)d_ncnt, (void*)d_cid[0], (void*)d_cid[1],
                     (void*)d_clo[0], (void*)d_clo[1], (void*)d_chi[0], (void*)d_chi[1], (void*)d_nn, (void*)d_keep, (void*)d_spos, (void*)d_newc, (void*)d_scan_tmp,
-                    (void*)d_nodes8_tmp, (void*)d_cnt, (void*)d_q0, (void*)d_q1})
+                    (void*)d_nodes8_tmp, (void*)d_cnt, (void*)d_q0, (void*)d_q1, (void*)d_dp})
         ngi_dfree(p, st);
 
     NgiDevScene& d = s->dev;
@@ -946,6 +993,7 @@ int ensure_lane(Scene* s, Lane& l, unsigned P) {
         NGI_CUDA(cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
         NGI_CUDA(cudaMalloc((void**)&l.counters, sizeof(NgiRenderCounters)));
         NGI_CUDA(cudaMallocHost((void**)&l.counters_host, sizeof(NgiRenderCounters)));
+        if (getenv("NGI_ITER_LOG")) NGI_CUDA(cudaMalloc((void**)&l.iter_log, 2 * kIterLogCap * sizeof(unsigned)));
     }
     if (l.wave_capacity == P && l.wave_mem) return NGI_OK;
     if (l.graph_exec) { cudaGraphExecDestroy(l.graph_exec); l.graph_exec = nullptr; }
@@ -983,7 +1031,7 @@ int launch_iteration(Scene* s, Lane& l, bool timed, size_t& ev_used, bool per_ra
     const unsigned P = wp.capacity;
     const bool direct = wp.renderer == NGI_RENDERER_PTDIRECT || wp.renderer == NGI_RENDERER_LTDIRECT;   // renderers with a shadow queue
     const bool lt = wp.renderer >= NGI_RENDERER_LT || s->dev.sensor.kind == NGI_ET_AREA;   // generic kernels
-    k_iter_begin<<<1, 1, 0, st>>>(l.counters, wp.sample_end);
+    k_iter_begin<<<1, 1, 0, st>>>(l.counters, wp.sample_end, l.iter_log);
     if (timed) {
         while (l.events.size() < ev_used + 4) { cudaEvent_t e; NGI_CUDA(cudaEventCreate(&e)); l.events.push_back(e); }
         NGI_CUDA(cudaEventRecord(l.events[ev_used], st));
@@ -1007,6 +1055,7 @@ int launch_iteration(Scene* s, Lane& l, bool timed, size_t& ev_used, bool per_ra
         k_shadow<<<s->grid_shadow, kTraceBlock, 0, l.stream2>>>(s->dev, wp, s->tune);
         NGI_CUDA(cudaEventRecord(l.ev_join, l.stream2));
         NGI_CUDA(cudaStreamWaitEvent(st, l.ev_join, 0));
+        if (l.fold_acc) k_film_fold<<<kFilmGrid, kBlock, 0, st>>>(wp.film, l.fold_acc, l.fold_n);
         return NGI_OK;
     }
     if (per_ray) k_extend_per_ray<<<std::min(grid_for(P), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
@@ -1015,6 +1064,7 @@ int launch_iteration(Scene* s, Lane& l, bool timed, size_t& ev_used, bool per_ra
     if (direct && per_ray) k_shadow_per_ray<<<std::min(grid_for((size_t)P * 2), 148u * 16u), kBlock, 0, st>>>(s->dev, wp);
     else if (direct) k_shadow<<<s->grid_shadow, kTraceBlock, 0, st>>>(s->dev, wp, s->tune);
     if (timed) { NGI_CUDA(cudaEventRecord(l.events[ev_used + 3], st)); ev_used += 4; }
+    if (l.fold_acc) k_film_fold<<<kFilmGrid, kBlock, 0, st>>>(wp.film, l.fold_acc, l.fold_n);
     return NGI_OK;
 }
 
@@ -1144,7 +1194,8 @@ int bdw_phase2(Scene* s, BdwCtx& c, const NgiBdParams& bp, const int cap, uint64
     NGI_CUDA(cub::DeviceRadixSort::SortKeys(c.sort_tmp, c.sort_bytes, (const unsigned long long*)wv.items, (unsigned long long*)wv.items_sorted, (int)need, 32, 48, st));
     launches += 3;
     k_bdw_contrib<<<(unsigned)std::min<size_t>(148u * 16u, (need + 127) / 128), 128, 0, st>>>(s->dev, bp, wv);
-    launches++;
+    k_film_fold<<<kFilmGrid, kBlock, 0, st>>>(bp.film, s->film_acc, s->film_acc_n);
+    launches += 2;
     NGI_CUDA(c.mark(2, st));
     return NGI_OK;
 }
@@ -1227,6 +1278,8 @@ int render_bdpt_wave(Scene* s, const NgiRenderParams* rp, const NgiBdParams& bp,
         NGI_CUDA(cudaEventRecord(ctx[k].done, ctx[k].stream));
         NGI_CUDA(cudaStreamWaitEvent(st, ctx[k].done, 0));
     }
+    k_film_finish<<<kFilmGrid, kBlock, 0, st>>>(bp.film, s->film_acc, s->film_acc_n);
+    launches += 2;                                // k_film_begin (render_impl) + k_film_finish
     NGI_CUDA(cudaEventRecord(ev1, st));
     for (int k = 0; k < K; k++) ctx[k].release(st);
     NGI_CUDA(cudaStreamSynchronize(st));
@@ -1255,13 +1308,22 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     if (rp->width <= 0 || rp->height <= 0 || rp->num_samples < 0 || rp->sample_offset < 0) return set_err(NGI_ERR_INVALID_ARGUMENT, "invalid width/height/num_samples");
     const size_t npx = (size_t)rp->width * rp->height;
     if (stats) memset(stats, 0, sizeof(*stats));
-    if (!rp->accumulate) NGI_CUDA(cudaMemsetAsync(film_dev, 0, npx * 3 * sizeof(float), st));
     if (rp->num_samples == 0 || (rp->max_num_vertices != -1 && rp->max_num_vertices < 2)) {
         // MaxNumVertices <= 1: the loop exits before the first direction is sampled (src/nanogi.cpp:485)
+        if (!rp->accumulate) NGI_CUDA(cudaMemsetAsync(film_dev, 0, npx * 3 * sizeof(float), st));
         NGI_CUDA(cudaStreamSynchronize(st));
         if (stats) stats->paths = (uint64_t)rp->num_samples;
         return NGI_OK;
     }
+    // fp64 accumulation behind the fp32 film (k_film_fold): the accumulator is kept with the scene handle
+    const size_t nfilm = npx * 3;
+    if (s->film_acc_n != nfilm) {
+        for (Lane& l : s->lanes) if (l.graph_exec) { cudaGraphExecDestroy(l.graph_exec); l.graph_exec = nullptr; }
+        if (s->film_acc) { NGI_CUDA(cudaFree(s->film_acc)); s->film_acc = nullptr; s->film_acc_n = 0; }
+        NGI_CUDA(cudaMalloc((void**)&s->film_acc, nfilm * sizeof(double)));
+        s->film_acc_n = nfilm;
+    }
+    k_film_begin<<<kFilmGrid, kBlock, 0, st>>>(film_dev, s->film_acc, nfilm, rp->accumulate);
     if (rp->renderer == NGI_RENDERER_BDPT) {
         NgiBdParams bp;
         bp.film = film_dev; bp.width = rp->width; bp.height = rp->height; bp.max_verts = rp->max_num_vertices;
@@ -1277,6 +1339,7 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         NGI_CUDA(cudaEventRecord(e0, st));
         const unsigned grid = (unsigned)std::min<unsigned long long>(((unsigned long long)rp->num_samples + 127ull) / 128ull, 148ull * 64ull);
         k_bdpt<<<grid, 128, 0, st>>>(s->dev, bp, (unsigned long long)rp->sample_offset, (unsigned long long)rp->num_samples, d_cnt);
+        k_film_finish<<<kFilmGrid, kBlock, 0, st>>>(film_dev, s->film_acc, nfilm);
         NGI_CUDA(cudaEventRecord(e1, st));
         unsigned long long h_cnt[2] = {0, 0};
         NGI_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
@@ -1288,7 +1351,7 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         ngi_dfree(d_cnt, st);
         if (stats) {
             stats->paths = (uint64_t)rp->num_samples; stats->extend_rays = h_cnt[0]; stats->shadow_rays = h_cnt[1];
-            stats->kernel_launches = 1; stats->wave_iterations = 1; stats->gpu_seconds = ms * 1e-3;
+            stats->kernel_launches = 3; stats->wave_iterations = 1; stats->gpu_seconds = ms * 1e-3;
         }
         return NGI_OK;
     }
@@ -1326,6 +1389,8 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         wp.sample_end = (unsigned long long)(rp->sample_offset + lo + cnt);
         wp.seed_lo = (unsigned)rp->seed; wp.seed_hi = (unsigned)(rp->seed >> 32);
         wp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
+        l.fold_acc = k == 0 ? s->film_acc : nullptr;          // one fold per iteration of lane 0 covers every lane's splats
+        l.fold_n = nfilm;
         NgiRenderCounters init;
         memset(&init, 0, sizeof(init));
         init.next_sample = (unsigned long long)(rp->sample_offset + lo);
@@ -1333,7 +1398,7 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
         NGI_CUDA(cudaStreamWaitEvent(l.stream, ev0, 0));
         NGI_CUDA(cudaMemcpyAsync(l.counters, l.counters_host, sizeof(init), cudaMemcpyHostToDevice, l.stream));
         NGI_CUDA(cudaMemsetAsync(wp.sb, 0, (size_t)P * 32, l.stream));         // every slot starts idle (dir_info.w = 0)
-        if (!timed && (!l.graph_exec || !same_wp(l.graph_wp, wp) || l.graph_iters != kItersPerBatch)) {
+        if (!timed && (!l.graph_exec || !same_wp(l.graph_wp, wp) || l.graph_iters != kItersPerBatch || l.graph_acc != l.fold_acc)) {
             // the batch of kItersPerBatch iterations is captured once into a CUDA graph and replayed
             if (l.graph_exec) { cudaGraphExecDestroy(l.graph_exec); l.graph_exec = nullptr; }
             cudaGraph_t graph;
@@ -1343,7 +1408,7 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
             NGI_CUDA(cudaStreamEndCapture(l.stream, &graph));
             NGI_CUDA(cudaGraphInstantiate(&l.graph_exec, graph, 0));
             cudaGraphDestroy(graph);
-            l.graph_wp = wp; l.graph_iters = kItersPerBatch;
+            l.graph_wp = wp; l.graph_iters = kItersPerBatch; l.graph_acc = l.fold_acc;
         }
         l.running = true;
     }
@@ -1363,7 +1428,7 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
             } else {
                 NGI_CUDA(cudaGraphLaunch(l.graph_exec, l.stream));
             }
-            launches += (uint64_t)kItersPerBatch * kernels_per_iter;
+            launches += (uint64_t)kItersPerBatch * (kernels_per_iter + (l.fold_acc ? 1 : 0));
             NGI_CUDA(cudaMemcpyAsync(l.counters_host, l.counters, sizeof(NgiRenderCounters), cudaMemcpyDeviceToHost, l.stream));
         }
         for (int k = 0; k < K; k++) {
@@ -1388,6 +1453,22 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
             }
         }
     }
+    if (const char* path = getenv("NGI_ITER_LOG")) {        // entry i = rays of iteration i - 1 (the counters roll at the start of an iteration)
+        if (FILE* f = fopen(path, "a")) {
+            std::vector<unsigned> h(2 * kIterLogCap);
+            for (int k = 0; k < K; k++) {
+                Lane& l = s->lanes[k];
+                if (!l.iter_log) continue;
+                cudaMemcpy(h.data(), l.iter_log, h.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
+                const unsigned long long its = std::min<unsigned long long>(l.counters_host->iterations, kIterLogCap);
+                fprintf(f, "# render: renderer %d samples %lld slots %u lane %d of %d iterations %llu\n", rp->renderer, (long long)rp->num_samples, P, k, K, its);
+                for (unsigned long long i = 1; i < its; i++) fprintf(f, "%d %llu %u %u\n", k, i - 1, h[2 * i], h[2 * i + 1]);
+            }
+            fclose(f);
+        }
+    }
+    k_film_finish<<<kFilmGrid, kBlock, 0, st>>>(film_dev, s->film_acc, nfilm);      // every lane has joined `st`
+    launches += 2;                                                                  // k_film_begin + k_film_finish
     NGI_CUDA(cudaEventRecord(ev1, st));
     NGI_CUDA(cudaStreamSynchronize(st));
     NGI_CUDA(cudaGetLastError());
@@ -1454,6 +1535,194 @@ int trace_impl(Scene* s, const NgiRay* rays_dev, size_t n, NgiHit* hits_dev, int
     return NGI_OK;
 }
 
+// ================================================================================================
+// multi-GPU: samples sharded by index, one NCCL reduce of the per-GPU films (ngi_comm.h)
+// ================================================================================================
+#define NGI_NCCL(api, call)                                                                             \
+    do {                                                                                                \
+        ncclResult_t r__ = (call);                                                                      \
+        if (r__ != ncclSuccess) return set_err(NGI_ERR_NCCL, std::string(#call) + ": " + (api)->GetErrorString(r__)); \
+    } while (0)
+
+int nccl_or_error(NgiNccl** out) {
+    NgiNccl* api = ngi_nccl();
+    if (!api->handle) return set_err(NGI_ERR_NCCL, api->error);
+    *out = api;
+    return NGI_OK;
+}
+
+void log_nccl_once(NgiNccl* api, const char* what, int ranks) {
+    if (const char* q = getenv("NGI_QUIET")) if (atoi(q)) return;
+    int v = 0;
+    api->GetVersion(&v);
+    fprintf(stderr, "[nanogi_gpu] NCCL %d.%d.%d: %s over %d GPU(s)\n", v / 10000, (v / 100) % 100, v % 100, what, ranks);
+}
+
+// one rank of a communicator that spans processes (one process per GPU)
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+};
+
+// every device of one process: scene built on the first, cloned to the others; per-device film; one communicator per device
+struct Group {
+    std::vector<int> devices;
+    std::vector<Scene*> scenes;
+    std::vector<ncclComm_t> comms;
+    std::vector<float*> films;
+    size_t film_floats = 0;
+    ~Group() {
+        NgiNccl* api = ngi_nccl();
+        for (size_t g = 0; g < devices.size(); g++) {
+            cudaSetDevice(devices[g]);
+            if (g < films.size() && films[g]) cudaFree(films[g]);
+            if (g < comms.size() && comms[g] && api->handle) api->CommDestroy(comms[g]);
+            if (g < scenes.size()) delete scenes[g];
+        }
+    }
+};
+
+// A second scene handle on `device` with the arrays of `src` (built on another device): same sizes, contents broadcast by the caller
+int clone_scene_layout(const Scene* src, int device, Scene** out) {
+    NGI_CUDA(cudaSetDevice(device));
+    Scene* c = new Scene;
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return set_err(NGI_ERR_CUDA, cudaGetErrorString(e)); }
+    for (size_t i = 0; i < src->allocs.size(); i++) {
+        void* p = nullptr;
+        e = ngi_dmalloc(&p, src->alloc_bytes[i], c->stream);
+        if (e != cudaSuccess) { delete c; return set_err(e == cudaErrorMemoryAllocation ? NGI_ERR_OUT_OF_MEMORY : NGI_ERR_CUDA, cudaGetErrorString(e)); }
+        c->allocs.push_back(p); c->alloc_bytes.push_back(src->alloc_bytes[i]);
+    }
+    auto map = [&](const void* p) -> void* {
+        if (!p) return nullptr;
+        for (size_t i = 0; i < src->allocs.size(); i++) if (src->allocs[i] == p) return c->allocs[i];
+        return nullptr;
+    };
+    const NgiDevScene& a = src->dev;
+    NgiDevScene& d = c->dev;
+    d = a;
+    d.nodes8 = (const uint4*)map(a.nodes8); d.tris8 = (const float4*)map(a.tris8); d.nodes2 = (const float4*)map(a.nodes2); d.tris2 = (const float4*)map(a.tris2);
+    d.shade_tris = (const float4*)map(a.shade_tris); d.prims = (const NgiDevPrim*)map(a.prims); d.light_prims = (const unsigned*)map(a.light_prims);
+    d.cdf = (const float*)map(a.cdf); d.shade_uv = (const float*)map(a.shade_uv); d.textures = (const NgiDevTex*)map(a.textures); d.tex_data = (const float*)map(a.tex_data);
+    c->info = src->info;
+    *out = c;
+    return NGI_OK;
+}
+
+int group_create(const NgiSceneDesc* desc, const int* devices, int n, Group** out) {
+    NgiNccl* api = nullptr;
+    int rc;
+    if (n > 1 && (rc = nccl_or_error(&api))) return rc;
+    std::unique_ptr<Group> g(new Group);
+    g->devices.assign(devices, devices + n);
+    // the scene is uploaded and its BVH built ONCE, on the first device
+    NGI_CUDA(cudaSetDevice(devices[0]));
+    {
+        Scene* s0 = new Scene;
+        s0->device = devices[0];
+        cudaError_t e = cudaStreamCreateWithFlags(&s0->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete s0; return set_err(NGI_ERR_CUDA, cudaGetErrorString(e)); }
+        rc = build_scene(s0, desc);
+        if (rc != NGI_OK) { delete s0; return rc; }
+        g->scenes.push_back(s0);
+    }
+    if (n > 1) {
+        g->comms.assign(n, nullptr);
+        NGI_NCCL(api, api->CommInitAll(g->comms.data(), n, devices));
+        log_nccl_once(api, "ncclCommInitAll; scene broadcast from the first device + one film reduce per render", n);
+        for (int k = 1; k < n; k++) {
+            Scene* c = nullptr;
+            if ((rc = clone_scene_layout(g->scenes[0], devices[k], &c))) return rc;
+            g->scenes.push_back(c);
+        }
+        // every array of the built scene (BVH8 nodes, traversal + shading triangles, primitives, CDFs, textures) goes over NVLink
+        const Scene* s0 = g->scenes[0];
+        NGI_CUDA(cudaSetDevice(devices[0]));
+        NGI_CUDA(cudaStreamSynchronize(s0->stream));
+        NGI_NCCL(api, api->GroupStart());
+        for (size_t i = 0; i < s0->allocs.size(); i++)
+            for (int k = 0; k < n; k++)
+                NGI_NCCL(api, api->Broadcast(s0->allocs[i], g->scenes[k]->allocs[i], s0->alloc_bytes[i], ncclChar, 0, g->comms[k], g->scenes[k]->stream));
+        NGI_NCCL(api, api->GroupEnd());
+        for (int k = 0; k < n; k++) {
+            NGI_CUDA(cudaSetDevice(devices[k]));
+            NGI_CUDA(cudaStreamSynchronize(g->scenes[k]->stream));
+            if (k > 0 && (rc = init_trace_launch(g->scenes[k]))) return rc;
+        }
+    }
+    *out = g.release();
+    return NGI_OK;
+}
+
+int group_render(Group* g, const NgiRenderParams* rp, float* film_host, NgiRenderStats* stats) {
+    const int n = (int)g->devices.size();
+    if (rp->width <= 0 || rp->height <= 0 || rp->num_samples < 0) return set_err(NGI_ERR_INVALID_ARGUMENT, "invalid width/height/num_samples");
+    const size_t floats = (size_t)rp->width * rp->height * 3;
+    if (g->film_floats != floats) {
+        for (int k = 0; k < (int)g->films.size(); k++) { cudaSetDevice(g->devices[k]); cudaFree(g->films[k]); }
+        g->films.assign(n, nullptr);
+        g->film_floats = 0;
+        for (int k = 0; k < n; k++) { NGI_CUDA(cudaSetDevice(g->devices[k])); NGI_CUDA(cudaMalloc((void**)&g->films[k], floats * sizeof(float))); }
+        g->film_floats = floats;
+    }
+    // samples sharded by index (ngi_gpu_shard_range); every device renders its shard concurrently, one host thread each
+    std::vector<NgiRenderStats> st(n);
+    std::vector<int> rcs(n, NGI_OK);
+    std::vector<std::string> errs(n);
+    auto work = [&](int k) {
+        cudaSetDevice(g->devices[k]);
+        NgiRenderParams p = *rp;
+        int64_t off = 0, cnt = 0;
+        ngi_gpu_shard_range(rp->num_samples, k, n, &off, &cnt);
+        p.sample_offset = rp->sample_offset + off; p.num_samples = cnt; p.accumulate = 0;
+        rcs[k] = render_impl(g->scenes[k], &p, g->films[k], g->scenes[k]->stream, &st[k]);
+        if (rcs[k] != NGI_OK) errs[k] = g_err;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int k = 1; k < n; k++) th.emplace_back(work, k);
+        work(0);
+        for (auto& t : th) t.join();
+    }
+    for (int k = 0; k < n; k++) if (rcs[k] != NGI_OK) return set_err(rcs[k], "GPU " + std::to_string(g->devices[k]) + ": " + errs[k]);
+    // the gather of src/nanogi.cpp:429-437: one reduce(SUM) onto the first device
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    NGI_CUDA(cudaSetDevice(g->devices[0]));
+    NGI_CUDA(cudaEventCreate(&e0)); NGI_CUDA(cudaEventCreate(&e1));
+    NGI_CUDA(cudaEventRecord(e0, g->scenes[0]->stream));
+    if (n > 1) {
+        NgiNccl* api = nullptr;
+        int rc;
+        if ((rc = nccl_or_error(&api))) return rc;
+        NGI_NCCL(api, api->GroupStart());
+        for (int k = 0; k < n; k++)
+            NGI_NCCL(api, api->Reduce(g->films[k], g->films[k], floats, ncclFloat, ncclSum, 0, g->comms[k], g->scenes[k]->stream));
+        NGI_NCCL(api, api->GroupEnd());
+    }
+    NGI_CUDA(cudaEventRecord(e1, g->scenes[0]->stream));
+    NGI_CUDA(cudaMemcpyAsync(film_host, g->films[0], floats * sizeof(float), cudaMemcpyDeviceToHost, g->scenes[0]->stream));
+    for (int k = 0; k < n; k++) { NGI_CUDA(cudaSetDevice(g->devices[k])); NGI_CUDA(cudaStreamSynchronize(g->scenes[k]->stream)); }
+    NGI_CUDA(cudaSetDevice(g->devices[0]));
+    float reduce_ms = 0;
+    NGI_CUDA(cudaEventElapsedTime(&reduce_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (int k = 0; k < n; k++) {
+            stats->paths += st[k].paths; stats->extend_rays += st[k].extend_rays; stats->shadow_rays += st[k].shadow_rays;
+            stats->wave_iterations += st[k].wave_iterations; stats->kernel_launches += st[k].kernel_launches;
+            stats->gpu_seconds = std::max(stats->gpu_seconds, st[k].gpu_seconds);
+            stats->trace_kernel_seconds += st[k].trace_kernel_seconds; stats->logic_kernel_seconds += st[k].logic_kernel_seconds;
+            stats->extend_kernel_seconds += st[k].extend_kernel_seconds; stats->shadow_kernel_seconds += st[k].shadow_kernel_seconds;
+            stats->logic_launches += st[k].logic_launches; stats->extend_launches += st[k].extend_launches; stats->shadow_launches += st[k].shadow_launches;
+        }
+        stats->reduce_seconds = reduce_ms * 1e-3;
+    }
+    return NGI_OK;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1461,7 +1730,7 @@ int trace_impl(Scene* s, const NgiRay* rays_dev, size_t n, NgiHit* hits_dev, int
 // ================================================================================================
 extern "C" {
 
-int ngi_gpu_abi_version(void) { return 1; }
+int ngi_gpu_abi_version(void) { return 2; }   // 2: NgiRenderStats.reduce_seconds, multi-GPU entry points
 
 const char* ngi_gpu_last_error(void) { return g_err.c_str(); }
 
@@ -1570,5 +1839,100 @@ int ngi_gpu_eval_bsdf(void* scene, const float* queries_host, const float* wo_in
     cudaFree(d_q); cudaFree(d_wo); cudaFree(d_out);
     return NGI_OK;
 }
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------------------------
+void ngi_gpu_shard_range(int64_t num_samples, int rank, int world_size, int64_t* out_offset, int64_t* out_count) {
+    // rank r of G takes the contiguous index range [r N / G, (r + 1) N / G): sizes differ by at most one (128-bit product: N can
+    // exceed 2^60 / G in principle)
+    const __int128 n = num_samples;
+    const int64_t lo = (int64_t)(n * rank / world_size), hi = (int64_t)(n * (rank + 1) / world_size);
+    if (out_offset) *out_offset = lo;
+    if (out_count) *out_count = hi - lo;
+}
+
+int ngi_gpu_comm_get_id(NgiCommId* out_id) {
+    if (!out_id) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    static_assert(sizeof(NgiCommId) >= sizeof(ncclUniqueId), "NgiCommId too small");
+    NgiNccl* api = nullptr;
+    int rc;
+    if ((rc = nccl_or_error(&api))) return rc;
+    ncclUniqueId id;
+    NGI_NCCL(api, api->GetUniqueId(&id));
+    memset(out_id, 0, sizeof(*out_id));
+    memcpy(out_id, &id, sizeof(id));
+    return NGI_OK;
+}
+
+int ngi_gpu_comm_create(const NgiCommId* id, int rank, int world_size, int device, void** out_comm) {
+    if (!id || !out_comm || world_size < 1 || rank < 0 || rank >= world_size) return set_err(NGI_ERR_INVALID_ARGUMENT, "bad id / rank / world_size");
+    *out_comm = nullptr;
+    NgiNccl* api = nullptr;
+    int rc;
+    if ((rc = nccl_or_error(&api))) return rc;
+    const int nd = ngi_gpu_device_count();
+    if (nd < 0) return nd;
+    if (device < 0 || device >= nd) return set_err(NGI_ERR_INVALID_ARGUMENT, "device index out of range");
+    NGI_CUDA(cudaSetDevice(device));
+    ncclUniqueId nid;
+    memcpy(&nid, id, sizeof(nid));
+    Comm* c = new Comm;
+    c->rank = rank; c->world = world_size; c->device = device;
+    ncclResult_t r = api->CommInitRank(&c->comm, world_size, nid, rank);
+    if (r != ncclSuccess) { delete c; return set_err(NGI_ERR_NCCL, std::string("ncclCommInitRank: ") + api->GetErrorString(r)); }
+    if (rank == 0) log_nccl_once(api, "ncclCommInitRank (one process per GPU); one film reduce per render", world_size);
+    *out_comm = c;
+    return NGI_OK;
+}
+
+int ngi_gpu_comm_reduce_film(void* comm, void* film_rgb_device, uint64_t num_floats, int root, void* cuda_stream) {
+    if (!comm || !film_rgb_device) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    Comm* c = (Comm*)comm;
+    NgiNccl* api = nullptr;
+    int rc;
+    if ((rc = nccl_or_error(&api))) return rc;
+    NGI_CUDA(cudaSetDevice(c->device));
+    NGI_NCCL(api, api->Reduce(film_rgb_device, film_rgb_device, (size_t)num_floats, ncclFloat, ncclSum, root, c->comm, (cudaStream_t)cuda_stream));
+    return NGI_OK;
+}
+
+void ngi_gpu_comm_destroy(void* comm) {
+    Comm* c = (Comm*)comm;
+    if (!c) return;
+    NgiNccl* api = ngi_nccl();
+    if (c->comm && api->handle) { cudaSetDevice(c->device); api->CommDestroy(c->comm); }
+    delete c;
+}
+
+int ngi_gpu_group_create(const NgiSceneDesc* desc, const int* devices, int num_devices, void** out_group) {
+    if (!desc || !out_group || num_devices < 1) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument / no devices");
+    *out_group = nullptr;
+    const int nd = ngi_gpu_device_count();
+    if (nd < 0) return nd;
+    std::vector<int> dv(num_devices);
+    for (int k = 0; k < num_devices; k++) {
+        dv[k] = devices ? devices[k] : k;
+        if (dv[k] < 0 || dv[k] >= nd) return set_err(NGI_ERR_INVALID_ARGUMENT, "device index out of range");
+        for (int j = 0; j < k; j++) if (dv[j] == dv[k]) return set_err(NGI_ERR_INVALID_ARGUMENT, "duplicate device index");
+    }
+    Group* g = nullptr;
+    const int rc = group_create(desc, dv.data(), num_devices, &g);
+    if (rc != NGI_OK) return rc;
+    *out_group = g;
+    return NGI_OK;
+}
+
+int ngi_gpu_group_render(void* group, const NgiRenderParams* params, float* film_rgb_host, NgiRenderStats* out_stats) {
+    if (!group || !params || !film_rgb_host) return set_err(NGI_ERR_INVALID_ARGUMENT, "null argument");
+    return group_render((Group*)group, params, film_rgb_host, out_stats);
+}
+
+int ngi_gpu_group_scene(void* group, int index, void** out_scene) {
+    Group* g = (Group*)group;
+    if (!g || !out_scene || index < 0 || index >= (int)g->scenes.size()) return set_err(NGI_ERR_INVALID_ARGUMENT, "bad group / index");
+    *out_scene = g->scenes[index];
+    return NGI_OK;
+}
+
+void ngi_gpu_group_destroy(void* group) { delete (Group*)group; }
 
 }  // extern "C"

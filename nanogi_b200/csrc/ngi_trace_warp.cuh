@@ -21,6 +21,9 @@
 #pragma once
 #include "ngi_bvh.h"
 
+#ifndef NGI_TRACE_BLOCK
+#define NGI_TRACE_BLOCK 64         /* threads per CTA of the persistent trace kernels (see ngi_gpu.cu) */
+#endif
 #define NGI_WARP_STACK 48          /* >= NGI_BVH8_MAX_DEPTH (node groups) + NGI_POSTPONE_MAX_SP (postponed triangle groups) */
 #define NGI_POSTPONE_MAX_SP 16
 
@@ -40,7 +43,7 @@ struct NgiTraceTuning {
 //   unsigned load(unsigned i, f3& o, f3& d, float& tmin, float& tmax);   returns a token handed back to store()
 //   void store(unsigned token, bool found, const NgiHitRec& h);
 template <bool ANY_HIT, class Source>
-__device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Source src,
+__device__ __forceinline__ void ngi_trace_warp_postpone(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Source src,
                                                const NgiTraceTuning tune) {
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
@@ -158,4 +161,162 @@ __device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, 
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second form of the loop (NGI_TRACE_TQ, the product default): the triangle backlog lives in SHARED memory.
+//
+// What the first form (ngi_trace_warp_postpone below) loses, from profiles/r01_ncu_c3_extend_blocks.txt: 29.0 lanes hold a ray
+// but only 23.9 take the node step — the other 5.1 have just popped a POSTPONED triangle group off their stack and sit the node
+// phase out — and the triangle phase runs at 10.3 lanes. Here a lane keeps traversing while its triangle groups wait in a small
+// per-lane LIFO in shared memory (NGI_TQ entries of 8 bytes, [entry][thread]: conflict-free), so
+//   * the stack in local memory holds node groups only (depth <= NGI_BVH8_MAX_DEPTH) and every lane with a ray takes the node
+//     step of every round (unless its backlog is full);
+//   * the triangle phase starts when at least tune.tri_min lanes have a group waiting (or fewer lanes could step nodes than test
+//     triangles), and leaves again when it runs out of lanes: both phases run dense.
+// A deferred triangle test only delays the shrinking of best.t (a few more node steps pass the culling test); the result is the
+// same order-free minimum of (t, id).
+#ifndef NGI_TQ
+#define NGI_TQ 2          /* s40 sweep on C3: 2 entries 1.449 ms, 4 entries 1.466 ms, 6 entries 1.469 ms per k_extend launch */
+#endif
+template <bool ANY_HIT, class Source>
+__device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Source src,
+                                                  const NgiTraceTuning tune, uint2 (*s_tq)[NGI_TRACE_BLOCK], unsigned (*s_aux)[NGI_TRACE_BLOCK]) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned tid = threadIdx.x;
+    const unsigned lane = tid & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned n = src.count();
+
+    unsigned chunk_next = 0, chunk_end = 0;
+    unsigned chunk_size = tune.chunk;
+    if (tune.spread) {
+        const unsigned per = n / (2u * gridDim.x * (blockDim.x >> 5));
+        if (per < chunk_size) chunk_size = per ? per : 1u;
+    }
+    bool exhausted = (n == 0);
+
+    // per-lane ray state. What a ray needs only when it retires — its queue token and the (u, v) of its best hit — is parked in
+    // shared memory (s_aux[0..2][thread]): with those three in registers ptxas spilled four values around every node step
+    bool active = false;
+    NgiRayCtx r;
+    float tmax = 0.0f;
+    float best_t = 0.0f; unsigned best_tri = NGI_MISS;
+    bool found = false;
+    uint2 stack[NGI_BVH8_MAX_DEPTH + 1];
+    int sp = 0;
+    int tqn = 0;              // triangle groups waiting in s_tq[0 .. tqn) of this thread; tqn > 0 implies tgroup.y != 0
+    unsigned skipped = 0;     // warp-uniform: consecutive rounds whose triangle phase was put off (starvation guard)
+    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+
+    while (true) {
+        __syncwarp();
+        // ---------------- dynamic fetch ----------------
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle != 0u) {
+            const int nidle = __popc(idle);
+            if (!exhausted && (nidle >= tune.refill_min || idle == FULL)) {
+                if (chunk_next >= chunk_end) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(src.cursor(), chunk_size);
+                    base = __shfl_sync(FULL, base, 0);
+                    chunk_next = base;
+                    chunk_end = base + chunk_size < n ? base + chunk_size : n;
+                    if (base >= n) { exhausted = true; chunk_next = chunk_end = 0; }
+                }
+                if (!exhausted) {
+                    const unsigned my = chunk_next + (unsigned)__popc(idle & lt_mask);
+                    if (!active && my < chunk_end) {
+                        f3 o, d; float tmin;
+                        s_aux[0][tid] = src.load(my, o, d, tmin, tmax);
+                        ngi_ray_ctx(r, o, d, tmin);
+                        r.one = tune.one_bits;
+                        best_t = tmax; best_tri = NGI_MISS;
+                        found = false; sp = 0; tqn = 0;
+                        ngroup = make_uint2(0u, 0x80000000u);   // root: base 0, pseudo-slot 7
+                        tgroup = make_uint2(0u, 0u);
+                        active = true;
+                    }
+                    chunk_next = chunk_next + (unsigned)nidle < chunk_end ? chunk_next + (unsigned)nidle : chunk_end;
+                }
+            }
+            if (exhausted && __ballot_sync(FULL, active) == 0u) break;
+        }
+
+        // ---------------- node phase: one node step per lane ----------------
+        if (active && ngroup.y > 0x00FFFFFFu && tqn < NGI_TQ) {
+            size_t ni;
+            ngi_bvh8_pop_child(ngroup, r.octinv, ni);
+            if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;            // never full: the build bounds the depth
+            uint2 tnew;
+            ngi_bvh8_node_step(nodes, ni, r, best_t, ngroup, tnew);
+            if (tnew.y != 0u) {
+                if (tgroup.y == 0u) tgroup = tnew;
+                else s_tq[tqn++][tid] = tnew;
+            }
+        }
+        if (active && ngroup.y <= 0x00FFFFFFu && sp > 0) ngroup = stack[--sp];
+        __syncwarp();
+
+        // ---------------- triangle phase: one triangle per lane per trip ----------------
+        while (true) {
+            const bool has = active && tgroup.y != 0u;
+            const unsigned m = __ballot_sync(FULL, has);
+            if (m == 0u) break;
+            const int nm = __popc(m);
+            if (nm < tune.tri_min) {
+                // few lanes have triangles: go on with node steps if more lanes can take one (at most 4 rounds in a row, so that
+                // a lane that has nothing but triangles left is not kept waiting)
+                const unsigned ready = __ballot_sync(FULL, active && ngroup.y > 0x00FFFFFFu && tqn < NGI_TQ);
+                if (__popc(ready) > nm && skipped < 4u) { skipped++; break; }
+            }
+            skipped = 0u;
+            if (has) {
+                const int bit = ngi_bfind(tgroup.y);
+                tgroup.y &= ~(1u << bit);
+                const size_t ti = (size_t)tgroup.x + (unsigned)bit;
+                const float4 a = ngi_ldg(tris + 3 * ti), b = ngi_ldg(tris + 3 * ti + 1), c = ngi_ldg(tris + 3 * ti + 2);
+                float t, u, v;
+                if (ngi_tri_test(a, b, c, r.o, r.d, r.tmin, tmax, t, u, v)) {
+                    if (ANY_HIT) {
+                        found = true; tgroup.y = 0u; tqn = 0; ngroup.y = 0u; sp = 0;   // occluded: this ray is finished
+                    } else {
+                        const unsigned id = f2u(a.w);
+                        if (t < best_t || (t == best_t && id < best_tri)) {      // ngi_accept: lexicographic minimum of (t, id)
+                            best_t = t; best_tri = id;
+                            s_aux[1][tid] = f2u(u); s_aux[2][tid] = f2u(v);
+                        }
+                        found = true;
+                    }
+                }
+                if (tgroup.y == 0u && tqn > 0) tgroup = s_tq[--tqn][tid];
+            }
+        }
+
+        // ---------------- retire ----------------
+        if (active && ngroup.y <= 0x00FFFFFFu && sp == 0 && tgroup.y == 0u) {
+            NgiHitRec best; best.t = best_t; best.tri = best_tri;
+            best.u = 0.0f; best.v = 0.0f;
+            if (!ANY_HIT && found) { best.u = u2f(s_aux[1][tid]); best.v = u2f(s_aux[2][tid]); }
+            src.store(s_aux[0][tid], found, best);
+            active = false;
+        }
+    }
+}
+
+
+// what the kernels call: NGI_TRACE_TQ = 1 (default) the shared-memory backlog form, 0 the postponing form (A/B builds)
+#ifndef NGI_TRACE_TQ
+#define NGI_TRACE_TQ 1
+#endif
+template <bool ANY_HIT, class Source>
+__device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Source src,
+                                               const NgiTraceTuning tune) {
+#if NGI_TRACE_TQ
+    __shared__ uint2 s_tq[NGI_TQ][NGI_TRACE_BLOCK];
+    __shared__ unsigned s_aux[3][NGI_TRACE_BLOCK];
+    ngi_trace_warp_tq<ANY_HIT>(nodes, tris, src, tune, s_tq, s_aux);
+#else
+    ngi_trace_warp_postpone<ANY_HIT>(nodes, tris, src, tune);
+#endif
 }

@@ -3,7 +3,8 @@
 // Host-side mirror of the reference application (src/nanogi.cpp): Run (:1993-2121), Renderer::Load
 // (:117-180) and Renderer::Render (:182-221). The CLI, scene YAML, renderer names and film outputs are
 // the reference's; the per-sample loop is replaced by ONE call across the C ABI (include/nanogi_gpu.h):
-//     Renderer::Render(scene, film)   ->   ngi_gpu_scene_create + ngi_gpu_render
+//     Scene's Embree commit           ->   ngi_gpu_group_create   (BVH built once on the first GPU, broadcast over NCCL to the others)
+//     Renderer::Render(scene, film)   ->   ngi_gpu_group_render   (samples sharded by index, one NCCL reduce of the per-GPU films)
 // `pt` and `ptdirect` (the hot path) and `lt` / `ltdirect` / `bdpt` are on the GPU path; ptmnee is reported
 // as unsupported instead of silently differing. --render-time and progress images follow RenderProcess's pass loop.
 // There is no CPU fallback.
@@ -13,7 +14,6 @@
 #include <ctime>
 #include <iostream>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/nanogi_gpu.h"
@@ -39,6 +39,8 @@ struct Renderer {
     unsigned WaveCapacity = 0;
     long long SampleOffset = 0;          // [b200] first sample index (resume: continue the Philox sample sequence)
     std::string ResumeFrom;              // [b200] film of an earlier run (.pfm) rendered with SampleOffset samples
+    void* Group = nullptr;               // [b200] ngi_gpu_group handle: the scene on every GPU + the NCCL communicators
+    ~Renderer() { if (Group) ngi_gpu_group_destroy(Group); }
 
     // Renderer::Load, src/nanogi.cpp:117-180
     bool Load(const CliOptions& vm) {
@@ -68,6 +70,25 @@ struct Renderer {
         return true;
     }
 
+    // The accelerator build of the reference lives in Scene::Load (rtcCommit, rt.hpp:2085-2143) and is therefore outside its
+    // "Rendering" timer; here it is the upload of the flattened scene + the GPU BVH build on the first device, the NCCL
+    // communicator (--gpus > 1) and the broadcast of the built scene to the other devices.
+    bool Build(const HostScene& scene) {
+        const auto start = std::chrono::high_resolution_clock::now();
+        const NgiSceneDesc desc = scene.desc();
+        if (ngi_gpu_group_create(&desc, nullptr, NumGpus, &Group) != NGI_OK) { NGI_LOG_ERROR(ngi_gpu_last_error()); return false; }
+        void* s0 = nullptr; NgiSceneInfo info{};
+        if (ngi_gpu_group_scene(Group, 0, &s0) == NGI_OK && ngi_gpu_scene_info(s0, &info) == NGI_OK) {
+            char buf[256];
+            std::snprintf(buf, sizeof(buf), "BVH8: %llu triangles, %llu nodes, depth %u, %.1f MB on each of %d GPU(s), built in %.1f ms (GPU) / %.1f ms (total)",
+                          (unsigned long long)info.num_tris, (unsigned long long)info.bvh8_nodes, info.bvh8_max_depth, info.device_bytes / 1e6, NumGpus,
+                          info.build_gpu_seconds * 1e3,
+                          (double)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::high_resolution_clock::now() - start).count() / 1e3);
+            NGI_LOG_INFO(buf);
+        }
+        return true;
+    }
+
     // {{count}} expansion of the progress image path, src/nanogi.cpp:374-393 (ctemplate there)
     static std::string ProgressPath(const std::string& format, long long count) {
         char num[32];
@@ -84,23 +105,9 @@ struct Renderer {
     // mode is a single pass unless progress images are requested; --render-time mode runs passes until the time is up
     // (:336-346), sized to ~0.25 s of GPU work. Raw (unscaled) pass films are accumulated in fp64 and normalised by
     // W*H / processedSamples like :429-437.
-    bool Render(const HostScene& scene, std::vector<float>& film) const {
+    bool Render(std::vector<float>& film) const {
         const auto start = std::chrono::high_resolution_clock::now();
         const size_t npx = (size_t)Params.Width * Params.Height;
-        const NgiSceneDesc desc = scene.desc();
-        std::vector<void*> handles(NumGpus, nullptr);
-        std::vector<std::string> errors(NumGpus);
-        auto for_each_gpu = [&](const std::function<void(int)>& fn) {
-            std::vector<std::thread> th;
-            for (int g = 1; g < NumGpus; g++) th.emplace_back(fn, g);
-            fn(0);
-            for (auto& t : th) t.join();
-            for (int g = 0; g < NumGpus; g++) if (!errors[g].empty()) { NGI_LOG_ERROR("GPU " + std::to_string(g) + ": " + errors[g]); return false; }
-            return true;
-        };
-        struct Cleanup { std::vector<void*>& h; ~Cleanup() { for (void* p : h) if (p) ngi_gpu_scene_destroy(p); } } cleanup{handles};
-        if (!for_each_gpu([&](int g) { if (ngi_gpu_scene_create(&desc, g, &handles[g]) != NGI_OK) errors[g] = ngi_gpu_last_error(); })) return false;
-
         std::vector<double> acc(npx * 3, 0.0);                 // raw sum of sample contributions
         long long processed = 0;                               // samples behind `acc` (incl. a resumed film's)
         if (!ResumeFrom.empty()) {
@@ -115,9 +122,9 @@ struct Renderer {
             processed = SampleOffset;
         }
         const long long first = SampleOffset;
-        std::vector<std::vector<float>> films(NumGpus, std::vector<float>(npx * 3));
-        std::vector<NgiRenderStats> stats(NumGpus);
-        unsigned long long ext = 0, sh = 0; double gpu_s = 0;
+        std::vector<float> pass_film(npx * 3);
+        NgiRenderStats stats{};
+        unsigned long long ext = 0, sh = 0; double gpu_s = 0, reduce_s = 0;
         auto gather = [&](std::vector<float>& out) {
             const double scale = processed > 0 ? (double)npx / (double)processed : 0.0;
             out.resize(npx * 3);
@@ -137,22 +144,18 @@ struct Renderer {
             if (n > 0) {
                 const long long base = first + done;
                 const auto pass_start = std::chrono::high_resolution_clock::now();
-                if (!for_each_gpu([&](int g) {
-                        NgiRenderParams p{};
-                        p.struct_size = sizeof(p);
-                        p.renderer = Type;
-                        // samples sharded by index: GPU g takes the contiguous range [g n/G, (g+1) n/G) of this pass
-                        const long long lo = n * g / NumGpus, hi = n * (g + 1) / NumGpus;
-                        p.num_samples = hi - lo; p.sample_offset = base + lo; p.film_norm_samples = 0;   // raw sums
-                        p.max_num_vertices = Params.MaxNumVertices; p.width = Params.Width; p.height = Params.Height;
-                        p.seed = Seed; p.wave_capacity = WaveCapacity;
-                        if (ngi_gpu_render(handles[g], &p, films[g].data(), &stats[g]) != NGI_OK) errors[g] = ngi_gpu_last_error();
-                    })) return false;
-                double pass_gpu = 0;
-                for (int g = 0; g < NumGpus; g++) {
-                    for (size_t i = 0; i < npx * 3; i++) acc[i] += (double)films[g][i];
-                    ext += stats[g].extend_rays; sh += stats[g].shadow_rays; pass_gpu = std::max(pass_gpu, stats[g].gpu_seconds);
-                }
+                // one call for all GPUs: the module shards [base, base + n) by index, renders the shards concurrently and sums the
+                // films with one NCCL reduce; raw sums (film_norm_samples = 0) so that passes add up in fp64 here
+                NgiRenderParams p{};
+                p.struct_size = sizeof(p);
+                p.renderer = Type;
+                p.num_samples = n; p.sample_offset = base; p.film_norm_samples = 0;
+                p.max_num_vertices = Params.MaxNumVertices; p.width = Params.Width; p.height = Params.Height;
+                p.seed = Seed; p.wave_capacity = WaveCapacity;
+                if (ngi_gpu_group_render(Group, &p, pass_film.data(), &stats) != NGI_OK) { NGI_LOG_ERROR(ngi_gpu_last_error()); return false; }
+                for (size_t i = 0; i < npx * 3; i++) acc[i] += (double)pass_film[i];
+                ext += stats.extend_rays; sh += stats.shadow_rays; reduce_s += stats.reduce_seconds;
+                const double pass_gpu = stats.gpu_seconds + stats.reduce_seconds;
                 gpu_s += pass_gpu;
                 done += n; processed += n;
                 if (passes && seconds_since(pass_start) < 0.25 && pass_size < (1ll << 34)) pass_size *= 2;
@@ -186,6 +189,10 @@ struct Renderer {
         std::snprintf(buf, sizeof(buf), "GPU render: %.3f s, %.1f Mpaths/s, %.1f Mrays/s (extend %llu, shadow %llu)", gpu_s,
                       gpu_s > 0 ? done / gpu_s / 1e6 : 0.0, gpu_s > 0 ? (ext + sh) / gpu_s / 1e6 : 0.0, ext, sh);
         NGI_LOG_INFO(buf);
+        if (NumGpus > 1) {
+            std::snprintf(buf, sizeof(buf), "NCCL film reduce over %d GPUs: %.3f ms", NumGpus, reduce_s * 1e3);
+            NGI_LOG_INFO(buf);
+        }
         return true;
     }
 };
@@ -217,11 +224,16 @@ bool Run(int argc, char** argv) {
         NGI_LOG_INDENTER();
         if (!renderer.Load(vm)) return false;
     }
+    {
+        NGI_LOG_INFO("Building GPU scene");
+        NGI_LOG_INDENTER();
+        if (!renderer.Build(scene)) return false;
+    }
     std::vector<float> film;
     {
         NGI_LOG_INFO("Rendering");
         NGI_LOG_INDENTER();
-        if (!renderer.Render(scene, film)) return false;
+        if (!renderer.Render(film)) return false;
     }
     {
         NGI_LOG_INFO("Saving rendered image");

@@ -32,6 +32,7 @@ struct SimScene {
     std::vector<uint4> nodes8;
     std::vector<int> left, right;
     std::vector<unsigned> cnt;
+    std::vector<NgiDpRow> dp;                  // SAH-optimal collapse decisions (ngi_dp_node)
     unsigned n_nodes8 = 0, depth8 = 0;
     float smin[3], smax[3], pad = 0;
     NgiDevScene dev;
@@ -83,6 +84,9 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
         for (int j = 0; j < 3; j++) s->tris2[(size_t)k * 3 + j] = s->rec_in[(size_t)i * 3 + j];
         s->lo[n - 1 + k] = tlo[i]; s->hi[n - 1 + k] = thi[i];
     }
+    const float c_node = 1.0f, c_prim = getenv("NGI_SAH_CPRIM") ? (float)atof(getenv("NGI_SAH_CPRIM")) : NGI_SAH_C_PRIM;
+    const bool greedy = getenv("NGI_COLLAPSE_GREEDY") != nullptr;
+    s->dp.assign(n - 1, NgiDpRow());
     if (getenv("NGI_SIM_SAH")) {
         // EXPERIMENT (build-quality yardstick, not a product path): top-down binned-SAH binary tree over the same leaves,
         // collapsed by the same ngi_collapse_node — how much traversal cost is left in the PLOC topology?
@@ -152,6 +156,12 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
             s->left[t.node] = child(t.b, mid);
             s->right[t.node] = child(mid, t.e);
         }
+        // children carry larger ids than their parent here: rows bottom-up = ids downwards
+        for (int id = (int)n - 2; id >= 0; id--) {
+            const float4 a = lo[id], b = hi[id];
+            const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+            ngi_dp_node(s->dp.data(), lo.data(), hi.data(), (int)n, id, s->left[id], s->right[id], s->cnt[id], dx * dy + dy * dz + dz * dx, c_node, c_prim);
+        }
     } else {
     // PLOC rounds, same per-item functions as the CUDA kernels (k_ploc_*)
     s->left.assign(n - 1, 0); s->right.assign(n - 1, 0); s->cnt.assign(n - 1, 0u);
@@ -171,6 +181,7 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
             pc.cid_out = cid[cur ^ 1].data(); pc.clo_out = clo[cur ^ 1].data(); pc.chi_out = chi[cur ^ 1].data();
             pc.lo = s->lo.data(); pc.hi = s->hi.data(); pc.left = s->left.data(); pc.right = s->right.data(); pc.cnt = s->cnt.data();
             pc.n = (int)n; pc.next_id = (int)(n - 2) - (int)merges;
+            pc.dp = s->dp.data(); pc.c_node = c_node; pc.c_prim = c_prim;
             for (unsigned i = 0; i < C; i++) ngi_ploc_merge(pc, (int)i);
             merges += C - acc; C = acc; cur ^= 1;
         }
@@ -186,6 +197,7 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
     NgiCollapseCtx c;
     c.lo = s->lo.data(); c.hi = s->hi.data(); c.left = s->left.data(); c.right = s->right.data(); c.cnt = s->cnt.data();
     c.tris2 = s->tris2.data(); c.n = (int)n; c.nodes8 = s->nodes8.data(); c.tris8 = s->tris8.data(); c.counters = counters;
+    c.dp = greedy ? nullptr : s->dp.data();
     unsigned depth = 0;
     while (!cur.empty()) {
         depth++;
@@ -251,7 +263,7 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
     SimScene* s = (SimScene*)h;
     const size_t npx = (size_t)rp->width * rp->height;
     std::fill(film, film + npx * 3, 0.0f);
-    if (stats) std::fill(stats, stats + 4, 0.0);
+    if (stats) std::fill(stats, stats + 8, 0.0);
     if (rp->max_num_vertices != -1 && rp->max_num_vertices < 2) return 0;
     if (rp->renderer == NGI_RENDERER_BDPT) {
         NgiBdParams bp;
@@ -355,6 +367,7 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
     wp.seed_lo = (unsigned)rp->seed; wp.seed_hi = (unsigned)(rp->seed >> 32);
     wp.film_scale = rp->film_norm_samples > 0 ? (float)((double)npx / (double)rp->film_norm_samples) : 1.0f;
     unsigned long long extend = 0, shadow = 0, iters = 0;
+    unsigned long long cost[4] = {0, 0, 0, 0};   // BVH8 node steps / triangle tests of the extend rays, then of the shadow rays (stats[4..7])
     while (true) {
         iter_counters[0] = iter_counters[1] = 0;
         if (rp->renderer >= NGI_RENDERER_LT || s->dev.sensor.kind == NGI_ET_AREA) for (unsigned i = 0; i < P; i++) ngi_logic_step<true>(s->dev, wp, i);
@@ -362,10 +375,17 @@ __attribute__((visibility("default"))) int sim_render(void* h, const NgiRenderPa
         extend += iter_counters[1]; shadow += iter_counters[0];
         iters++;
         if (iter_counters[1] == 0 && iter_counters[0] == 0 && next_sample >= wp.sample_end) break;
+        g_trace_count[0] = g_trace_count[1] = 0;
         for (unsigned q = 0; q < iter_counters[1]; q++) ngi_extend_step(s->dev, wp, extend_q[q]);   // compacted extend queue
+        cost[0] += g_trace_count[0]; cost[1] += g_trace_count[1];
+        g_trace_count[0] = g_trace_count[1] = 0;
         for (unsigned e = 0; e < iter_counters[0]; e++) ngi_shadow_step(s->dev, wp, e);
+        cost[2] += g_trace_count[0]; cost[3] += g_trace_count[1];
     }
-    if (stats) { stats[0] = (double)rp->num_samples; stats[1] = (double)extend; stats[2] = (double)shadow; stats[3] = (double)iters; }
+    if (stats) {
+        stats[0] = (double)rp->num_samples; stats[1] = (double)extend; stats[2] = (double)shadow; stats[3] = (double)iters;
+        for (int k = 0; k < 4; k++) stats[4 + k] = (double)cost[k];
+    }
     return 0;
 }
 

@@ -88,9 +88,11 @@ class SimScene:
         p.wave_capacity = wave_capacity
         p.flags = flags
         film = np.zeros((height, width, 3), np.float32)
-        stats = np.zeros(4)
+        stats = np.zeros(8)
         self.L.sim_render(self.h, C.byref(p), film.ctypes.data, stats.ctypes.data)
-        return film, {"paths": stats[0], "extend_rays": stats[1], "shadow_rays": stats[2], "iterations": stats[3]}
+        return film, {"paths": stats[0], "extend_rays": stats[1], "shadow_rays": stats[2], "iterations": stats[3],
+                      # BVH8 traversal cost inside the render (pt / ptdirect / lt / ltdirect): node steps and triangle tests
+                      "extend_node_steps": stats[4], "extend_tri_tests": stats[5], "shadow_node_steps": stats[6], "shadow_tri_tests": stats[7]}
 
     def eval_bsdf(self, queries, wo_in, force_degenerated):
         queries = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, 16)

@@ -32,7 +32,7 @@ def test_gpu_library_exports_header_symbols():
     for n in names:
         assert hasattr(lib, n), n
     lib.ngi_gpu_abi_version.restype = ctypes.c_int
-    assert lib.ngi_gpu_abi_version() == 1
+    assert lib.ngi_gpu_abi_version() == capi.ABI_VERSION
 
 
 def test_struct_sizes_match_the_header():

@@ -66,8 +66,9 @@ def test_cli_render_time_and_progress_images(scene_file, tmp_path):
                   "--progress-image-update-format", fmt, "--seed", 3)
     assert rc == 0, log
     assert out.exists()
+    assert (tmp_path / "progress").is_dir(), log
     shots = sorted(os.listdir(tmp_path / "progress"))
-    assert len(shots) >= 2 and shots[0] == "0000000001.hdr"
+    assert len(shots) >= 2 and shots[0] == "0000000001.hdr", log
     n = [int(line.split(":")[-1]) for line in log.splitlines() if "# of samples" in line][0]
     assert n > 10_000_000                                       # far more than a CPU would do in 1.5 s
     a = capi.load_image(str(tmp_path / "progress" / shots[0])); b = capi.load_image(str(out))

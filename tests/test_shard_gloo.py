@@ -1,5 +1,7 @@
-"""Multi-rank host logic on CPU: world_size-2 gloo process group, samples sharded by index, one
-reduce(SUM) of the per-rank films to rank 0 — the same nanogi_b200.shard code bench.py runs over NCCL.
+"""Multi-rank host logic on CPU: world_size-2 gloo process group. What runs here is what `bench.py --gpus N` runs
+over NCCL: nanogi_b200.shard.shard_range (-> ngi_gpu_shard_range in libnanogi_gpu.so, the arithmetic ngi_gpu_group_render
+uses too), shard.exchange_comm_id (rank 0's NCCL id, made by ngi_gpu_comm_get_id, to every rank) and shard.reduce_film (one
+reduce(SUM) of the per-rank films to rank 0; over gloo here, through the product's ncclReduce when a communicator exists).
 The per-rank renderer here is the CPU oracle in Philox mode (test infrastructure), so the sharded film must equal
 the single-process film of the same sample set up to fp64 summation order."""
 import os
@@ -33,6 +35,18 @@ def _worker(rank, world, port, renderer, out_path):
     sd = scenes.to_scene_data(scenes.cornell_box(), 1.0)
     orc = pyoracle.OracleScene(sd)
     off, cnt = shard.shard_range(N, rank, world)
+    # the communicator id travels like in bench.py: made by the product on rank 0, broadcast over the process group
+    import ctypes
+    from nanogi_b200 import capi
+    blob = None
+    if rank == 0:
+        cid = capi.NgiCommId()
+        rc = capi.gpu_lib().ngi_gpu_comm_get_id(ctypes.byref(cid))
+        blob = ctypes.string_at(ctypes.byref(cid), 128) if rc == 0 else bytes(range(128))     # no libnccl on this host: any 128 bytes
+    got = shard.exchange_comm_id(blob)
+    ids = [None, None]
+    dist.all_gather_object(ids, got)
+    assert ids[0] == ids[1] and len(got) == 128 and (rank != 0 or got == blob)
     film, st = orc.render(renderer, cnt, W, H, max_num_vertices=6, seed=SEED, rng_mode=1, num_threads=1,
                           sample_offset=off, film_norm_samples=N)
     t = torch.from_numpy(film)
