@@ -133,7 +133,7 @@ NGI_HD unsigned ngi_ploc_keep(const int* __restrict__ nn, const int i) {
 #define NGI_LEAF_MAX_TRIS 3
 #define NGI_DP_INF 3.0e38f
 #ifndef NGI_SAH_C_PRIM
-#define NGI_SAH_C_PRIM 0.3f        /* cost of a triangle test relative to an 8-wide node step (tools/bvh_quality.py sweep) */
+#define NGI_SAH_C_PRIM 0.5f        /* cost of a triangle test relative to an 8-wide node step (C3 k_extend: 1.385 / 1.379 / 1.366 ms at 0.2 / 0.3 / 0.5, s41) */
 #endif
 struct alignas(16) NgiDpRow {
     float c[7];        // c[i - 1] = C(n, i)
@@ -413,4 +413,30 @@ NGI_HD_NOINLINE void ngi_collapse_node(const NgiCollapseCtx& c, const NgiBuildTa
     out[2] = make_uint4(ngi_pack4(q[0]), ngi_pack4(q[0] + 4), ngi_pack4(q[1]), ngi_pack4(q[1] + 4));
     out[3] = make_uint4(ngi_pack4(q[2]), ngi_pack4(q[2] + 4), ngi_pack4(q[3]), ngi_pack4(q[3] + 4));
     out[4] = make_uint4(ngi_pack4(q[4]), ngi_pack4(q[4] + 4), ngi_pack4(q[5]), ngi_pack4(q[5] + 4));
+}
+
+// ---- 7. traversal form of a node --------------------------------------------------------------------
+// The collapse writes n1 = (child_base, tri_base, meta[0..3], meta[4..7]) with the leaf triangles packed from tri_base on
+// (meta = unary count << 5 | offset). The traversal wants n1 = (child_base, -, valid24, -) and triangle j of slot s at the fixed
+// place 24 * node + 3 * s + j (ngi_bvh.h). One item = one node; `out_nodes` may be `in_nodes`.
+NGI_HD void ngi_expand_node(const uint4* __restrict__ in_nodes, const float4* __restrict__ tris_compact, const unsigned ni,
+                            uint4* out_nodes, float4* __restrict__ tris_fixed) {
+    const uint4 n0 = in_nodes[5 * (size_t)ni], n1 = in_nodes[5 * (size_t)ni + 1];
+    const uint4 n2 = in_nodes[5 * (size_t)ni + 2], n3 = in_nodes[5 * (size_t)ni + 3], n4 = in_nodes[5 * (size_t)ni + 4];
+    const unsigned imask = n0.w >> 24;
+    unsigned valid = 0;
+    for (int s = 0; s < 8; s++) {
+        const unsigned meta = ((s < 4 ? n1.z : n1.w) >> (8 * (s & 3))) & 0xFFu;
+        if (meta == 0u || ((imask >> s) & 1u)) continue;
+        const int cnt = ngi_popc(meta >> 5);
+        const unsigned off = meta & 31u;
+        for (int j = 0; j < cnt; j++) {
+            const size_t src = ((size_t)n1.y + off + (unsigned)j) * 3, dst = ((size_t)24 * ni + 3 * (unsigned)s + (unsigned)j) * 3;
+            tris_fixed[dst] = tris_compact[src]; tris_fixed[dst + 1] = tris_compact[src + 1]; tris_fixed[dst + 2] = tris_compact[src + 2];
+        }
+        valid |= ((1u << cnt) - 1u) << (3 * s);
+    }
+    out_nodes[5 * (size_t)ni] = n0;
+    out_nodes[5 * (size_t)ni + 1] = make_uint4(n1.x, 0u, valid, 0u);
+    out_nodes[5 * (size_t)ni + 2] = n2; out_nodes[5 * (size_t)ni + 3] = n3; out_nodes[5 * (size_t)ni + 4] = n4;
 }

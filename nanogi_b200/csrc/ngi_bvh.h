@@ -121,15 +121,22 @@ NGI_HD bool ngi_trace_bvh2(const float4* __restrict__ nodes, const float4* __res
 // ------------------------------------------------------------------------------------------------
 // BVH8 — compressed wide node, 80 bytes = 5 x uint4:
 //   n0 = (p.x, p.y, p.z as float bits,  ex | ey<<8 | ez<<16 | imask<<24)       e* = biased float exponents
-//   n1 = (child_base, tri_base, meta[0..3], meta[4..7])
+//   n1 = (child_base, -, valid24, -)
 //   n2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])
 //   n3 = (qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7])
 //   n4 = (qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7])
 // child box = p + q * 2^(e-127) per axis, q in [0,255] rounded outward.
-// meta[i]: 0 = empty slot; inner child: 0b001'11sss (low5 = 24 + slot); leaf: (unary triangle count) << 5 |
-// offset of its first triangle relative to tri_base (0..23). imask bit i = slot i is an inner child.
-// Inner children are stored contiguously from child_base in slot order. Children sit in slots so that
-// (slot ^ octant) approximates front-to-back order (slot bit0/1/2 = child lies towards +x/+y/+z).
+// imask bit s = slot s is an inner child; inner children are stored contiguously from child_base in slot order. Children sit
+// in slots so that (slot ^ octant) approximates front-to-back order (slot bit0/1/2 = child lies towards +x/+y/+z).
+// Triangles have FIXED places: triangle j (j < 3) of the leaf in slot s of node ni is record 24 * ni + 3 * s + j of the triangle
+// array, and valid24 bit 3 s + j says whether it exists. The places of inner and empty slots are never referenced (nor fetched:
+// the array is only touched through the hit masks), so the padding costs address space, not bandwidth — and the node step needs no
+// per-child bit arithmetic: an 8-bit box-hit mask h turns into the node group (h & imask, its bits permuted by the ray octant:
+// one table lookup) and the triangle group (every bit of h repeated three times & valid24: one table lookup). Round 1 assembled
+// both masks child by child from meta bytes (count << offset): 44 ALU-pipe instructions of a node step whose ALU pipe is the
+// busiest unit of the trace kernels (profiles/r02_ncu_c3_tq.txt).
+// (The collapse, ngi_collapse_node, still emits the compact round-1 form — n1 = (child_base, tri_base, meta[0..3], meta[4..7]),
+// meta = unary count << 5 | offset — and ngi_expand_node rewrites it once the node count is known.)
 // ------------------------------------------------------------------------------------------------
 #define NGI_BVH8_STACK 40
 // test-only instrumentation hook (tests/hostsim counts node steps / triangle tests per ray with it); empty in the product
@@ -139,6 +146,41 @@ NGI_HD bool ngi_trace_bvh2(const float4* __restrict__ nodes, const float4* __res
 #define NGI_BVH8_MAX_DEPTH 32     /* enforced by the build; traversal stacks are sized from it */
 
 NGI_HD unsigned ngi_byte(unsigned w, int i) { return (w >> (8 * i)) & 0xFFu; }
+
+// bit s of an 8-bit mask -> bit (s ^ o): the order in which a ray of octant-code o wants to visit the slots
+NGI_HD unsigned ngi_perm8_calc(unsigned x, const unsigned o) {
+    if (o & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+    if (o & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+    if (o & 4u) x = ((x & 0x0Fu) << 4) | ((x >> 4) & 0x0Fu);
+    return x;
+}
+// bit s of an 8-bit mask -> bits 3 s, 3 s + 1, 3 s + 2
+NGI_HD unsigned ngi_spread3_calc(unsigned x) {
+    x = (x | (x << 8)) & 0x00F00Fu;
+    x = (x | (x << 4)) & 0x0C30C3u;
+    x = (x | (x << 2)) & 0x249249u;
+    return x * 7u;
+}
+#if defined(__CUDACC__)
+// the two lookups of the node step as tables in global memory (3 KB, L1-resident; read with ld.global.nc): filled once per module
+// load by ngi_bvh_tables_init (ngi_gpu.cu)
+__device__ unsigned char g_ngi_perm8[8 * 256];
+__device__ unsigned g_ngi_spread3[256];
+#endif
+NGI_HD unsigned ngi_perm8(const unsigned x, const unsigned o) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned)__ldg(g_ngi_perm8 + (o << 8) + x);
+#else
+    return ngi_perm8_calc(x, o);
+#endif
+}
+NGI_HD unsigned ngi_spread3(const unsigned x) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(g_ngi_spread3 + x);
+#else
+    return ngi_spread3_calc(x);
+#endif
+}
 
 // Quantised plane -> float without a conversion instruction. I2F.U8 runs on the XU pipe at 16 lanes/clk/SM and
 // was the busiest pipe of the first traversal kernel (profiles/r01_ncu_c2_steady.txt: XU 71 %). Instead one PRMT
@@ -157,17 +199,6 @@ NGI_HD float ngi_q1(unsigned w, int i, unsigned one) {
     return u2f(0x3F800000u | (((w >> (8 * i)) & 0xFFu) << 8));
 #endif
 }
-// per byte: 0xFF if the byte's top bit is set, else 0x00
-NGI_HD unsigned ngi_sext_s8x4(unsigned x) {
-#if defined(__CUDA_ARCH__)
-    unsigned r;
-    asm("prmt.b32 %0, %1, 0, 0x0000ba98;" : "=r"(r) : "r"(x));
-    return r;
-#else
-    return ((x >> 7) & 0x01010101u) * 0xFFu;
-#endif
-}
-
 // Two plane distances with ONE instruction: sm_100's packed FFMA2 (PTX fma.rn.f32x2) computes (q0, q1) * s + b with the scale
 // and the offset as scalar operands; each half is an IEEE fma.rn, i.e. bit-identical to two fmaf(). The traversal kernels are
 // issue-bound (profiles/r01_ncu_c3_final.txt: 68 % issue slots, the node step is half of all issued instructions and 48 of its
@@ -228,18 +259,11 @@ NGI_HD void ngi_bvh8_node_step(const uint4* __restrict__ nodes, const size_t ni,
     const float sy = u2f((((n0.w >> 8) & 0xFFu) + 15u) << 23) * r.idy;
     const float sz = u2f((((n0.w >> 16) & 0xFFu) + 15u) << 23) * r.idz;
     const float bx = (u2f(n0.x) - r.o.x) * r.idx - sx, by = (u2f(n0.y) - r.o.y) * r.idy - sy, bz = (u2f(n0.z) - r.o.z) * r.idz - sz;
-    const unsigned octinv4 = r.octinv * 0x01010101u;
     const unsigned one = r.one;
 
-    unsigned hitmask = 0;
+    unsigned hit8 = 0;                    // bit s = the ray meets the box of slot s (empty slots: a degenerate box, masked out below)
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        const unsigned meta4 = h ? n1.w : n1.z;
-        // 4 children at a time (Ylitie et al. 2017): bit position and bit pattern each child contributes
-        const unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const unsigned inner_mask4 = ngi_sext_s8x4(is_inner4 << 3);
-        const unsigned bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-        const unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
         // near / far plane words per axis, chosen by the ray's sign
         const unsigned lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
         const unsigned hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
@@ -260,14 +284,15 @@ NGI_HD void ngi_bvh8_node_step(const uint4* __restrict__ nodes, const size_t ni,
             for (int k = 0; k < 2; k++) {
                 const float tn = fmaxf(fmaxf(tnx[k], tny[k]), fmaxf(tnz[k], r.tmin));
                 const float tf = fminf(fminf(tfx[k], tfy[k]), fminf(tfz[k], limit));
-                if (tn <= tf) hitmask |= ngi_byte(child_bits4, i + k) << ngi_byte(bit_index4, i + k);   // empty slots have no bits
+                if (tn <= tf) hit8 |= 1u << (4 * h + i + k);
             }
         }
     }
+    const unsigned imask = n0.w >> 24;
     ngroup.x = n1.x;
-    ngroup.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
-    tgroup.x = n1.y;
-    tgroup.y = hitmask & 0x00FFFFFFu;
+    ngroup.y = (ngi_perm8(hit8 & imask, r.octinv) << 24) | imask;
+    tgroup.x = 24u * (unsigned)ni;
+    tgroup.y = ngi_spread3(hit8) & n1.z;
 }
 
 // per-ray traversal (one thread = one ray, no cooperation): the reference form of the algorithm. The product

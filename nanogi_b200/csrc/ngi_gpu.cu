@@ -161,6 +161,27 @@ __global__ void __launch_bounds__(128) k_collapse8(NgiCollapseCtx ctx, const Ngi
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_tasks) ngi_collapse_node(ctx, tasks[i]);
 }
+__global__ void __launch_bounds__(kBlock) k_expand8(const uint4* __restrict__ in_nodes, const float4* __restrict__ tris_compact, unsigned n_nodes,
+                                                    uint4* __restrict__ out_nodes, float4* __restrict__ tris_fixed) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) ngi_expand_node(in_nodes, tris_compact, i, out_nodes, tris_fixed);
+}
+// the node step's two lookup tables (ngi_bvh.h), once per device
+int bvh_tables_init() {
+    static std::mutex m;
+    static bool done[64] = {};
+    int dev = 0;
+    NGI_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(m);
+    if (dev >= 0 && dev < 64 && done[dev]) return NGI_OK;
+    unsigned char perm[8 * 256]; unsigned spread[256];
+    for (unsigned o = 0; o < 8; o++) for (unsigned x = 0; x < 256; x++) perm[(o << 8) + x] = (unsigned char)ngi_perm8_calc(x, o);
+    for (unsigned x = 0; x < 256; x++) spread[x] = ngi_spread3_calc(x);
+    NGI_CUDA(cudaMemcpyToSymbol(g_ngi_perm8, perm, sizeof(perm)));
+    NGI_CUDA(cudaMemcpyToSymbol(g_ngi_spread3, spread, sizeof(spread)));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return NGI_OK;
+}
 
 // ================================================================================================
 // ray-query kernels (ngi_gpu_trace*)
@@ -704,7 +725,7 @@ struct Scene {
     std::vector<Lane> lanes;
     int num_lanes = 2;
     // persistent trace kernels: grid = SM count x resident CTAs per SM (queried once per kernel)
-    NgiTraceTuning tune{4, 8, 0x3F800000u, 64u, 1u};   // best of the sweep in profiles/r01_sweep_trace.txt
+    NgiTraceTuning tune{4, 12, 0x3F800000u, 64u, 1u};  // refill_min / tri_min: sweeps in profiles/r01_sweep_trace.txt, profiles/r02_sweep_trace_tq.txt
     unsigned grid_extend = 0, grid_shadow = 0, grid_trace[2] = {0, 0};
     unsigned* trace_cursor = nullptr;
     // the extend and shadow kernels of one iteration are independent: the shadow kernel is forked onto the lane's second
@@ -923,9 +944,9 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     k_pack2<<<grid_for(n - 1), kBlock, 0, st>>>(d_lo, d_hi, d_left, d_right, (int)n, d_nodes2);
 
     // ---- 6. collapse to BVH8, one launch per level ----
-    uint4* d_nodes8_tmp = nullptr; float4* d_tris8 = nullptr; unsigned* d_cnt = nullptr; NgiBuildTask *d_q0 = nullptr, *d_q1 = nullptr;
+    uint4* d_nodes8_tmp = nullptr; float4* d_tris8_compact = nullptr; unsigned* d_cnt = nullptr; NgiBuildTask *d_q0 = nullptr, *d_q1 = nullptr;
     if ((rc = dev_alloc(s, &d_nodes8_tmp, (size_t)n * 5, false))) return rc;
-    if ((rc = dev_alloc(s, &d_tris8, (size_t)n * 3, true))) return rc;
+    if ((rc = dev_alloc(s, &d_tris8_compact, (size_t)n * 3, false))) return rc;
     if ((rc = dev_alloc(s, &d_cnt, 4, false))) return rc;
     if ((rc = dev_alloc(s, &d_q0, n, false))) return rc;
     if ((rc = dev_alloc(s, &d_q1, n, false))) return rc;
@@ -937,7 +958,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     }
     NgiCollapseCtx ctx;
     ctx.lo = d_lo; ctx.hi = d_hi; ctx.left = d_left; ctx.right = d_right; ctx.cnt = d_ncnt; ctx.tris2 = d_tris2; ctx.n = (int)n;
-    ctx.nodes8 = d_nodes8_tmp; ctx.tris8 = d_tris8; ctx.counters = d_cnt; ctx.dp = d_dp;
+    ctx.nodes8 = d_nodes8_tmp; ctx.tris8 = d_tris8_compact; ctx.counters = d_cnt; ctx.dp = d_dp;
     unsigned n_tasks = 1, depth = 0;
     unsigned hc[4] = {1, 0, 0, 0};
     NgiBuildTask *qin = d_q0, *qout = d_q1;
@@ -956,9 +977,14 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     if (hc[1] != n) return set_err(NGI_ERR_CUDA, "BVH8 collapse lost triangles: " + std::to_string(hc[1]) + " of " + std::to_string(n));
     if (depth > NGI_BVH8_MAX_DEPTH) return set_err(NGI_ERR_UNSUPPORTED, "BVH8 depth " + std::to_string(depth) + " exceeds the traversal stack");
     const unsigned n_nodes8 = hc[0];
-    uint4* d_nodes8 = nullptr;
+    if ((unsigned long long)n_nodes8 * 24ull >= 0xFFFFFFFFull) return set_err(NGI_ERR_UNSUPPORTED, "more than 2^32 / 24 BVH8 nodes");
+    // traversal form: exact-size node array with valid24 masks, triangles at their fixed places 24 * node + 3 * slot + j (ngi_bvh.h)
+    uint4* d_nodes8 = nullptr; float4* d_tris8 = nullptr;
     if ((rc = dev_alloc(s, &d_nodes8, (size_t)n_nodes8 * 5, true))) return rc;
-    NGI_CUDA(cudaMemcpyAsync(d_nodes8, d_nodes8_tmp, (size_t)n_nodes8 * 5 * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
+    if ((rc = dev_alloc(s, &d_tris8, (size_t)n_nodes8 * 24 * 3, true))) return rc;
+    NGI_CUDA(cudaMemsetAsync(d_tris8, 0, (size_t)n_nodes8 * 24 * 3 * sizeof(float4), st));
+    k_expand8<<<grid_for(n_nodes8), kBlock, 0, st>>>(d_nodes8_tmp, d_tris8_compact, n_nodes8, d_nodes8, d_tris8);
+    if ((rc = bvh_tables_init())) return rc;
     NGI_CUDA(cudaEventRecord(ev1, st));
     NGI_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
@@ -968,7 +994,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     for (void* p : {(void*)d_pos, (void*)d_bounds, (void*)d_rec, (void*)d_tlo, (void*)d_thi, (void*)d_keys, (void*)d_keys2, (void*)d_vals, (void*)d_vals2,
                     (void*)d_tmp, (void*)d_lo, (void*)d_hi, (void*)d_left, (void*)d_right, (void*)d_ncnt, (void*)d_cid[0], (void*)d_cid[1],
                     (void*)d_clo[0], (void*)d_clo[1], (void*)d_chi[0], (void*)d_chi[1], (void*)d_nn, (void*)d_keep, (void*)d_spos, (void*)d_newc, (void*)d_scan_tmp,
-                    (void*)d_nodes8_tmp, (void*)d_cnt, (void*)d_q0, (void*)d_q1, (void*)d_dp})
+                    (void*)d_nodes8_tmp, (void*)d_tris8_compact, (void*)d_cnt, (void*)d_q0, (void*)d_q1, (void*)d_dp})
         ngi_dfree(p, st);
 
     NgiDevScene& d = s->dev;
@@ -1649,7 +1675,7 @@ int group_create(const NgiSceneDesc* desc, const int* devices, int n, Group** ou
         for (int k = 0; k < n; k++) {
             NGI_CUDA(cudaSetDevice(devices[k]));
             NGI_CUDA(cudaStreamSynchronize(g->scenes[k]->stream));
-            if (k > 0 && (rc = init_trace_launch(g->scenes[k]))) return rc;
+            if (k > 0 && ((rc = bvh_tables_init()) || (rc = init_trace_launch(g->scenes[k])))) return rc;
         }
     }
     *out = g.release();

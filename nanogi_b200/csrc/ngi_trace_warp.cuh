@@ -176,25 +176,25 @@ __device__ __forceinline__ void ngi_trace_warp_postpone(const uint4* __restrict_
 //     triangles), and leaves again when it runs out of lanes: both phases run dense.
 // A deferred triangle test only delays the shrinking of best.t (a few more node steps pass the culling test); the result is the
 // same order-free minimum of (t, id).
+#ifndef NGI_SSTACK
+#define NGI_SSTACK 0       /* levels of the node-group stack kept in shared memory (A/B: profiles/r02_sweep_sstack.txt) */
+#endif
 #ifndef NGI_TQ
 #define NGI_TQ 2          /* s40 sweep on C3: 2 entries 1.449 ms, 4 entries 1.466 ms, 6 entries 1.469 ms per k_extend launch */
 #endif
 template <bool ANY_HIT, class Source>
 __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Source src,
-                                                  const NgiTraceTuning tune, uint2 (*s_tq)[NGI_TRACE_BLOCK], unsigned (*s_aux)[NGI_TRACE_BLOCK]) {
+                                                  const NgiTraceTuning tune, uint2 (*s_tq)[NGI_TRACE_BLOCK], unsigned (*s_aux)[NGI_TRACE_BLOCK],
+                                                  unsigned (*s_chunk)[2], uint2 (*s_stack)[NGI_TRACE_BLOCK]) {
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned tid = threadIdx.x;
     const unsigned lane = tid & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned n = src.count();
-
-    unsigned chunk_next = 0, chunk_end = 0;
-    unsigned chunk_size = tune.chunk;
-    if (tune.spread) {
-        const unsigned per = n / (2u * gridDim.x * (blockDim.x >> 5));
-        if (per < chunk_size) chunk_size = per ? per : 1u;
-    }
-    bool exhausted = (n == 0);
+    const unsigned warp = tid >> 5;
+    // warp-uniform fetch state: the chunk of the queue this warp is handing out lives in shared memory (s_chunk[warp] = {next, end}),
+    // it is only touched when lanes are refilled and would otherwise hold two registers of every thread through the node step
+    if (lane == 0) { s_chunk[warp][0] = 0u; s_chunk[warp][1] = 0u; }
+    bool exhausted = (src.count() == 0);
 
     // per-lane ray state. What a ray needs only when it retires — its queue token and the (u, v) of its best hit — is parked in
     // shared memory (s_aux[0..2][thread]): with those three in registers ptxas spilled four values around every node step
@@ -203,7 +203,8 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
     float tmax = 0.0f;
     float best_t = 0.0f; unsigned best_tri = NGI_MISS;
     bool found = false;
-    uint2 stack[NGI_BVH8_MAX_DEPTH + 1];
+    // node-group stack: the first NGI_SSTACK levels in shared memory ([level][thread]: conflict-free), deeper ones in local memory
+    uint2 stack[NGI_BVH8_MAX_DEPTH + 1 - NGI_SSTACK];
     int sp = 0;
     int tqn = 0;              // triangle groups waiting in s_tq[0 .. tqn) of this thread; tqn > 0 implies tgroup.y != 0
     unsigned skipped = 0;     // warp-uniform: consecutive rounds whose triangle phase was put off (starvation guard)
@@ -216,7 +217,14 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
         if (idle != 0u) {
             const int nidle = __popc(idle);
             if (!exhausted && (nidle >= tune.refill_min || idle == FULL)) {
+                unsigned chunk_next = s_chunk[warp][0], chunk_end = s_chunk[warp][1];
                 if (chunk_next >= chunk_end) {
+                    const unsigned n = src.count();
+                    unsigned chunk_size = tune.chunk;
+                    if (tune.spread) {
+                        const unsigned per = n / (2u * gridDim.x * (blockDim.x >> 5));
+                        if (per < chunk_size) chunk_size = per ? per : 1u;
+                    }
                     unsigned base = 0;
                     if (lane == 0) base = atomicAdd(src.cursor(), chunk_size);
                     base = __shfl_sync(FULL, base, 0);
@@ -239,6 +247,8 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
                     }
                     chunk_next = chunk_next + (unsigned)nidle < chunk_end ? chunk_next + (unsigned)nidle : chunk_end;
                 }
+                __syncwarp();
+                if (lane == 0) { s_chunk[warp][0] = chunk_next; s_chunk[warp][1] = chunk_end; }
             }
             if (exhausted && __ballot_sync(FULL, active) == 0u) break;
         }
@@ -247,7 +257,10 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
         if (active && ngroup.y > 0x00FFFFFFu && tqn < NGI_TQ) {
             size_t ni;
             ngi_bvh8_pop_child(ngroup, r.octinv, ni);
-            if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;            // never full: the build bounds the depth
+            if (ngroup.y > 0x00FFFFFFu) {                                // never full: the build bounds the depth
+                if (NGI_SSTACK > 0 && sp < NGI_SSTACK) s_stack[sp][tid] = ngroup; else stack[sp - NGI_SSTACK] = ngroup;
+                sp++;
+            }
             uint2 tnew;
             ngi_bvh8_node_step(nodes, ni, r, best_t, ngroup, tnew);
             if (tnew.y != 0u) {
@@ -255,7 +268,10 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
                 else s_tq[tqn++][tid] = tnew;
             }
         }
-        if (active && ngroup.y <= 0x00FFFFFFu && sp > 0) ngroup = stack[--sp];
+        if (active && ngroup.y <= 0x00FFFFFFu && sp > 0) {
+            --sp;
+            if (NGI_SSTACK > 0 && sp < NGI_SSTACK) ngroup = s_stack[sp][tid]; else ngroup = stack[sp - NGI_SSTACK];
+        }
         __syncwarp();
 
         // ---------------- triangle phase: one triangle per lane per trip ----------------
@@ -315,7 +331,9 @@ __device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, 
 #if NGI_TRACE_TQ
     __shared__ uint2 s_tq[NGI_TQ][NGI_TRACE_BLOCK];
     __shared__ unsigned s_aux[3][NGI_TRACE_BLOCK];
-    ngi_trace_warp_tq<ANY_HIT>(nodes, tris, src, tune, s_tq, s_aux);
+    __shared__ unsigned s_chunk[NGI_TRACE_BLOCK / 32][2];
+    __shared__ uint2 s_stack[NGI_SSTACK > 0 ? NGI_SSTACK : 1][NGI_TRACE_BLOCK];
+    ngi_trace_warp_tq<ANY_HIT>(nodes, tris, src, tune, s_tq, s_aux, s_chunk, s_stack);
 #else
     ngi_trace_warp_postpone<ANY_HIT>(nodes, tris, src, tune);
 #endif

@@ -209,6 +209,11 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
     s->n_nodes8 = counters[0];
     s->depth8 = depth;
     if (counters[1] != n) { g_err = "collapse lost triangles: " + std::to_string(counters[1]) + " of " + std::to_string(n); delete s; return nullptr; }
+    {   // traversal form: valid24 masks + triangles at their fixed places (k_expand8)
+        std::vector<float4> fixed((size_t)s->n_nodes8 * 24 * 3, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        for (unsigned i = 0; i < s->n_nodes8; i++) ngi_expand_node(s->nodes8.data(), s->tris8.data(), i, s->nodes8.data(), fixed.data());
+        s->tris8.swap(fixed);
+    }
     NgiDevScene& d = s->dev;
     d.nodes8 = s->nodes8.data(); d.tris8 = s->tris8.data(); d.nodes2 = s->nodes2.data(); d.tris2 = s->tris2.data();
     d.shade_tris = s->ha.shade_tris.data(); d.prims = s->ha.prims.data(); d.light_prims = s->ha.light_prims.data();

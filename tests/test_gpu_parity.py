@@ -29,7 +29,7 @@ def gpu_c2(cornell_spheres):
 def test_extension_is_loaded_and_device_present():
     assert capi.device_count() >= 1
     import ctypes
-    assert ctypes.CDLL(capi.GPU_LIB_PATH).ngi_gpu_abi_version() == 1
+    assert ctypes.CDLL(capi.GPU_LIB_PATH).ngi_gpu_abi_version() == capi.ABI_VERSION
 
 
 @pytest.mark.parametrize("name", ["cornell", "cornell_spheres", "furnace"])
@@ -163,7 +163,7 @@ def test_bdpt_wavefront_equals_per_thread(scene, m, batch):
     # differently, and on the 1 M-triangle scene 1 path in 10^7 then branches differently (tools/bdpt_c3.py) — allow that much
     assert abs(sa.extend_rays - sb.extend_rays) <= 1e-5 * sb.extend_rays and abs(sa.shadow_rays - sb.shadow_rays) <= 1e-5 * sb.shadow_rays, \
         (sa.extend_rays, sb.extend_rays, sa.shadow_rays, sb.shadow_rays)
-    assert sa.kernel_launches > 1 and sb.kernel_launches == 1
+    assert sa.kernel_launches > 3 and sb.kernel_launches == 3        # per-thread form: k_film_begin, k_bdpt, k_film_finish
     assert fa.sum() > 0
     np.testing.assert_allclose(fa, fb, rtol=1e-3, atol=1e-5 * float(fb.max()))
     assert abs(float(fa.sum(dtype=np.float64)) / float(fb.sum(dtype=np.float64)) - 1.0) < 1e-5

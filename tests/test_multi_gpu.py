@@ -47,8 +47,10 @@ def test_film_is_accumulated_in_fp64_behind_the_fp32_atomics():
     big, _ = s.render("ptdirect", 1 << 26, 1, 1, max_num_vertices=6, seed=5)
     small, _ = s.render("ptdirect", 1 << 20, 1, 1, max_num_vertices=6, seed=6)          # few enough adds for plain fp32
     ref, _ = pyoracle.OracleScene(sd).render("ptdirect", 1 << 20, 1, 1, max_num_vertices=6, seed=7)
-    assert abs(small.mean() - ref.mean()) < 0.02 * ref.mean()
-    assert abs(big.mean() - small.mean()) < 0.01 * small.mean(), (big.mean(), small.mean())
+    # (a plain fp32 sum of 1.3e8 such terms stalls around 1/3 of the true value; the tolerances below are Monte-Carlo noise of
+    # the 2^20-sample runs)
+    assert abs(small.mean() - ref.mean()) < 0.03 * ref.mean()
+    assert abs(big.mean() - small.mean()) < 0.03 * small.mean() and abs(big.mean() - ref.mean()) < 0.03 * ref.mean(), (big.mean(), small.mean(), ref.mean())
     s.close()
 
 

@@ -71,6 +71,14 @@ def main():
         v = num(r[ix[key]])
         return scaled(v, units[ix[key]]) if unit_scaled else v
 
+    def per_ray(r, key, rays):
+        v = get(r, key)
+        return None if v is None else v / rays
+
+    def time_us(r):
+        v = get(r, "gpu__time_duration.sum")
+        return None if v is None else v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[ix["gpu__time_duration.sum"]], 1.0)
+
     seen = {"k_extend": 0, "k_shadow": 0}
     per = {}
     for r in rows:
@@ -87,7 +95,7 @@ def main():
         winst = get(r, "smsp__inst_executed.sum")
         lanes = get(r, "smsp__thread_inst_executed_per_inst_executed.ratio")
         m = {
-            "source": os.path.basename(args.rep), "iteration": it, "rays": rays, "duration_us": (get(r, "gpu__time_duration.sum") or 0) / 1e3,
+            "source": os.path.basename(args.rep), "iteration": it, "rays": rays, "duration_us": time_us(r),
             "dram_bytes": dram, "dram_bytes_per_ray": dram / rays,
             "issue_active_pct": get(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "active_lanes": lanes,
@@ -99,10 +107,12 @@ def main():
             "l1_hit_pct": get(r, "l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": get(r, "lts__t_sector_hit_rate.pct"),
             "warps_active_pct": get(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
             "registers": get(r, "launch__registers_per_thread"),
-            "local_load_inst_per_ray": (get(r, "smsp__inst_executed_op_local_ld.sum") or 0) / rays,
-            "local_store_inst_per_ray": (get(r, "smsp__inst_executed_op_local_st.sum") or 0) / rays,
-            "shared_load_inst_per_ray": (get(r, "smsp__inst_executed_op_shared_ld.sum") or 0) / rays,
-            "shared_store_inst_per_ray": (get(r, "smsp__inst_executed_op_shared_st.sum") or 0) / rays,
+            # the traversal stack (node groups) is thread-local memory, the triangle backlog shared memory: warp instructions per ray
+            "local_load_inst_per_ray": per_ray(r, "smsp__sass_inst_executed_op_local_ld.sum", rays),
+            "local_store_inst_per_ray": per_ray(r, "smsp__sass_inst_executed_op_local_st.sum", rays),
+            "local_load_l1_hit_pct": get(r, "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct"),
+            "shared_load_inst_per_ray": per_ray(r, "smsp__sass_inst_executed_op_shared_ld.sum", rays),
+            "shared_store_inst_per_ray": per_ray(r, "smsp__sass_inst_executed_op_shared_st.sum", rays),
         }
         per.setdefault(kern, m)          # the first captured launch of each kernel
     j = {}
