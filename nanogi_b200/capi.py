@@ -21,6 +21,7 @@ HOST_LIB_PATH = os.path.join(_HERE, "libnanogi_host.so")
 
 # ---- enums (include/nanogi_gpu.h) -------------------------------------------------------------
 TYPE_D, TYPE_G, TYPE_S, TYPE_L, TYPE_E = 1, 2, 4, 8, 16
+TYPE_BSDF_MASK = TYPE_D | TYPE_G | TYPE_S
 L_AREA, L_POINT, L_DIRECTIONAL = 0, 1, 2
 E_AREA, E_PINHOLE = 0, 1
 S_REFLECTION, S_REFRACTION, S_FRESNEL = 0, 1, 2

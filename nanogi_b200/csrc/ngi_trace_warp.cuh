@@ -176,6 +176,9 @@ __device__ __forceinline__ void ngi_trace_warp_postpone(const uint4* __restrict_
 //     triangles), and leaves again when it runs out of lanes: both phases run dense.
 // A deferred triangle test only delays the shrinking of best.t (a few more node steps pass the culling test); the result is the
 // same order-free minimum of (t, id).
+#ifndef NGI_NODE_REPS
+#define NGI_NODE_REPS 1
+#endif
 #ifndef NGI_SSTACK
 #define NGI_SSTACK 0       /* levels of the node-group stack kept in shared memory (A/B: profiles/r02_sweep_sstack.txt) */
 #endif
@@ -253,24 +256,29 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
             if (exhausted && __ballot_sync(FULL, active) == 0u) break;
         }
 
-        // ---------------- node phase: one node step per lane ----------------
-        if (active && ngroup.y > 0x00FFFFFFu && tqn < NGI_TQ) {
-            size_t ni;
-            ngi_bvh8_pop_child(ngroup, r.octinv, ni);
-            if (ngroup.y > 0x00FFFFFFu) {                                // never full: the build bounds the depth
-                if (NGI_SSTACK > 0 && sp < NGI_SSTACK) s_stack[sp][tid] = ngroup; else stack[sp - NGI_SSTACK] = ngroup;
-                sp++;
+        // ---------------- node phase: NGI_NODE_REPS node steps per lane ----------------
+        // (every round of this loop pays ~150 warp instructions of fetch / vote / phase-change bookkeeping, profiles/r02_ncu_c3_extend_blocks_s42.txt:
+        // taking more than one node step per round spreads them; the triangle backlog absorbs what the extra steps find)
+#pragma unroll 1
+        for (int rep = 0; rep < NGI_NODE_REPS; rep++) {
+            if (active && ngroup.y > 0x00FFFFFFu && tqn < NGI_TQ) {
+                size_t ni;
+                ngi_bvh8_pop_child(ngroup, r.octinv, ni);
+                if (ngroup.y > 0x00FFFFFFu) {                                // never full: the build bounds the depth
+                    if (NGI_SSTACK > 0 && sp < NGI_SSTACK) s_stack[sp][tid] = ngroup; else stack[sp - NGI_SSTACK] = ngroup;
+                    sp++;
+                }
+                uint2 tnew;
+                ngi_bvh8_node_step(nodes, ni, r, best_t, ngroup, tnew);
+                if (tnew.y != 0u) {
+                    if (tgroup.y == 0u) tgroup = tnew;
+                    else s_tq[tqn++][tid] = tnew;
+                }
             }
-            uint2 tnew;
-            ngi_bvh8_node_step(nodes, ni, r, best_t, ngroup, tnew);
-            if (tnew.y != 0u) {
-                if (tgroup.y == 0u) tgroup = tnew;
-                else s_tq[tqn++][tid] = tnew;
+            if (active && ngroup.y <= 0x00FFFFFFu && sp > 0) {
+                --sp;
+                if (NGI_SSTACK > 0 && sp < NGI_SSTACK) ngroup = s_stack[sp][tid]; else ngroup = stack[sp - NGI_SSTACK];
             }
-        }
-        if (active && ngroup.y <= 0x00FFFFFFu && sp > 0) {
-            --sp;
-            if (NGI_SSTACK > 0 && sp < NGI_SSTACK) ngroup = s_stack[sp][tid]; else ngroup = stack[sp - NGI_SSTACK];
         }
         __syncwarp();
 

@@ -398,6 +398,43 @@ def light_over_plane(le: float = 5.0, height: float = 1.0, half: float = 0.5, rh
     ]
 
 
+# ---- branch coverage: the primitive kinds no BASELINE scene contains -----------------------------------------------
+def cornell_branches(light_res: int = 0) -> Spec:
+    """Cornell box whose blocks are replaced by primitives that exercise the branches C1-C4 never take:
+      * a [D, G] and a [G, S] primitive — the lobe is resolved by precedence D > G > S (rt.hpp:808-859: the `if (type & D) ... else if
+        (type & G) ...` chains; src/nanogi.cpp:601 strips only the emitter bits), so the first renders as D, the second as G;
+      * S.reflection (a mirror block) and S.refraction (a sphere), rt.hpp:808-859, :1066-1098;
+      * a pure [L] mesh: an emitter with no BSDF — a path that hits it from outside a direct-light connection finds no lobe to
+        sample and ends there (rt.hpp:909, :1146, :1334);
+      * light_res > 0: the ceiling light tessellated into 2 * light_res^2 triangles (131 072 at 256): a large area CDF
+        (basic.hpp:440-497, rt.hpp:1747-1765)."""
+    spec = [p for p in _cornell_prims() if p["mesh"]["name"] not in ("largebox", "smallbox", "light")]
+    lx0, lx1, lz0, lz1, ly = 213.0, 343.0, 227.0, 332.0, 548.75
+    if light_res > 0:
+        xs = np.linspace(lx1, lx0, light_res + 1); zs = np.linspace(lz0, lz1, light_res + 1)
+        X, Z = np.meshgrid(xs, zs, indexing="ij")
+        P = np.stack([X, np.full_like(X, ly), Z], axis=-1)
+        q = np.stack([P[:-1, :-1], P[:-1, 1:], P[1:, 1:], P[1:, :-1]], axis=2).reshape(-1, 4, 3)
+        light = quads_to_tris(q)
+    else:
+        light = quads_to_tris([[[lx1, ly, lz0], [lx1, ly, lz1], [lx0, ly, lz1], [lx0, ly, lz0]]])
+    spec.insert(0, mesh_prim(["L", "D"], light, name="light", L={"type": "area", "Le": [10.0] * 3}, D={"R": [0, 0, 0]}))
+    tris, nrm = icosphere(2)
+    spec.append(mesh_prim(["D", "G"], tris * 60.0 + np.array([120.0, 60.0, 150.0]), nrm, name="dg", D={"R": [0.2, 0.7, 0.9]}, G=dict(COPPER, Roughness=0.2)))
+    spec.append(mesh_prim(["G", "S"], tris * 60.0 + np.array([420.0, 60.0, 150.0]), nrm, name="gs", G=dict(COPPER, Roughness=0.15),
+                          S={"type": "fresnel", "R": [1, 1, 1], "eta1": 1.0, "eta2": 1.5}))
+    spec.append(mesh_prim(["S"], tris * 70.0 + np.array([278.0, 70.0, 330.0]), nrm, name="refr",
+                          S={"type": "refraction", "R": [0.95, 0.95, 1.0], "eta1": 1.0, "eta2": 1.5}))
+    mirror = box_quads(np.array([60.0, 0.0, 380.0]), np.array([200.0, 300.0, 520.0]), inward=False)
+    spec.append(mesh_prim(["S"], quads_to_tris(mirror), name="mirror", S={"type": "reflection", "R": [0.9, 0.9, 0.9]}))
+    # a small emissive quad on the floor with NO BSDF lobe at all
+    ex0, ex1, ez0, ez1, ey = 380.0, 470.0, 380.0, 470.0, 0.5
+    spec.append(mesh_prim(["L"], quads_to_tris([[[ex0, ey, ez0], [ex0, ey, ez1], [ex1, ey, ez1], [ex1, ey, ez0]]]), name="bare_light",
+                          L={"type": "area", "Le": [4.0, 3.0, 2.0]}))
+    spec.append(pinhole(**CORNELL_CAMERA))
+    return spec
+
+
 # ---- C3: ~1M-triangle flattened "instanced" spheres -------------------------------------------
 def instanced_spheres(seed: int = 1, subdiv: int = 5, grid=(4, 4, 3)) -> Spec:
     rng = np.random.default_rng(seed)

@@ -12,6 +12,14 @@ from nanogi_b200 import capi, scenes
 from oracle import pyoracle
 
 
+def prim_index(spec, mesh_name):
+    """index (YAML order = NgiSceneDesc order) of the primitive whose mesh is called `mesh_name`"""
+    for i, p in enumerate(spec):
+        if p.get("mesh") is not None and p["mesh"]["name"] == mesh_name:
+            return i
+    raise KeyError(mesh_name)
+
+
 def film_and_stats(result):
     film, st = result
     if not isinstance(st, dict):

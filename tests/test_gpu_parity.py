@@ -166,7 +166,9 @@ def test_bdpt_wavefront_equals_per_thread(scene, m, batch):
     assert sa.kernel_launches > 3 and sb.kernel_launches == 3        # per-thread form: k_film_begin, k_bdpt, k_film_finish
     assert fa.sum() > 0
     np.testing.assert_allclose(fa, fb, rtol=1e-3, atol=1e-5 * float(fb.max()))
-    assert abs(float(fa.sum(dtype=np.float64)) / float(fb.sum(dtype=np.float64)) - 1.0) < 1e-5
+    # (the wavefront path folds its fp32 film into fp64 after every batch, the single-launch per-thread form sums in fp32 only:
+    # with point lights a few pixels collect most splats and the per-thread sum is the less accurate one)
+    assert abs(float(fa.sum(dtype=np.float64)) / float(fb.sum(dtype=np.float64)) - 1.0) < 5e-4
 
 
 def test_bdpt_statistics_and_agreement_with_ptdirect(gpu_cornell, cornell):

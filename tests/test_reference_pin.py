@@ -31,6 +31,8 @@ SCENES = {
     "cornell_raw_sensor": (lambda: scenes.cornell_raw_sensor(spheres=True), 7),   # E.area sensor
     "cornell_textured": (scenes.cornell_textured, -1),            # D.TexR / G.TexR through the reference's Texture::Load / Evaluate
     "furnace": (lambda: scenes.furnace(0.5, 1.0), 5),             # six [L, D] walls: uniform light pick over 6 lights
+    # [D, G] / [G, S] primitives (lobe precedence), S.reflection, S.refraction, a pure [L] mesh; the ceiling light as 512 triangles
+    "cornell_branches": (lambda: scenes.cornell_branches(light_res=16), -1),
 }
 RENDERERS = ["pt", "ptdirect", "lt", "ltdirect", "bdpt"]
 

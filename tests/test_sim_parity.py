@@ -77,6 +77,33 @@ def test_bsdf_parity_reflection_refraction():
     pc.check_bsdf_parity(sim, sd, 1, capi.TYPE_S, n=800, seed=1)
 
 
+@pytest.fixture(scope="module")
+def branches_sim():
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_branches(), 0.01), 1.0)
+    return pysim.SimScene(sd), sd
+
+
+@pytest.mark.parametrize("name,bits", [("dg", capi.TYPE_D | capi.TYPE_G), ("gs", capi.TYPE_G | capi.TYPE_S), ("refr", capi.TYPE_S), ("mirror", capi.TYPE_S)])
+def test_bsdf_parity_by_precedence(branches_sim, name, bits):
+    """CPU twin of tests/test_gpu_branches.py: [D, G] evaluates as D, [G, S] as G (rt.hpp:808-859)"""
+    sim, sd = branches_sim
+    prim = pc.prim_index(scenes.cornell_branches(), name)
+    assert sd.prims[prim].type & capi.TYPE_BSDF_MASK == bits
+    pc.check_bsdf_parity(sim, sd, prim, bits, n=600, seed=3)
+
+
+@pytest.mark.parametrize("renderer", ["pt", "ptdirect", "ltdirect"])
+def test_replay_branches(branches_sim, renderer):
+    """S.reflection / S.refraction, two-lobe primitives, a pure [L] mesh: sample-exact against the oracle"""
+    sim, sd = branches_sim
+    pc.check_replay(sim, sd, renderer, n=20000, m=-1, wave_capacity=2048, max_bad_pixels=0.006)
+
+
+def test_replay_large_light_cdf():
+    sd = scenes.to_scene_data(scaled_spec(scenes.cornell_branches(light_res=64), 0.01), 1.0)      # 8 192-triangle light
+    pc.check_replay(pysim.SimScene(sd), sd, "ptdirect", n=20000, m=4, wave_capacity=2048, max_bad_pixels=0.006)
+
+
 @pytest.mark.parametrize("renderer", ["pt", "ptdirect"])
 @pytest.mark.parametrize("m", [-1, 3])
 def test_replay_small_scale(renderer, m):
