@@ -394,7 +394,7 @@ def run_own(args, rank: int, local_rank: int, world: int):
             cpu["oracle_port_value"] = n_cpu / (time.perf_counter() - t0) / 1e6
 
     # the module's default slot count per lane (render_impl in ngi_gpu.cu)
-    wave_slots = args.wave_capacity or ((1 << 23) if n_rank >= (1 << 30) else (1 << 22) if n_rank >= (1 << 28) else (1 << 21))
+    wave_slots = args.wave_capacity or ((1 << 23) if n_rank >= (1 << 30) else (1 << 22) if n_rank >= (1 << 27) else (1 << 21))
     if rank == 0:
         line = {
             "metric": METRIC.replace("ptdirect", renderer), "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -172,6 +172,8 @@ typedef struct NgiSceneInfo {
     float scene_min[3], scene_max[3];
     uint32_t num_lights;
     uint32_t bvh8_max_depth;
+    uint32_t bvh2_max_depth;     /* height of the binary BVH; accel = 1 (cross-check traversal) needs it < 64 */
+    uint32_t reserved0;
 } NgiSceneInfo;
 
 /* ray / hit records of the geometry-parity and ray-throughput entry point */

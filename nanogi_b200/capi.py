@@ -89,7 +89,7 @@ class NgiSceneInfo(C.Structure):
     _fields_ = [
         ("num_tris", C.c_uint64), ("bvh8_nodes", C.c_uint64), ("bvh2_nodes", C.c_uint64), ("device_bytes", C.c_uint64),
         ("build_gpu_seconds", C.c_double), ("scene_min", C.c_float * 3), ("scene_max", C.c_float * 3),
-        ("num_lights", C.c_uint32), ("bvh8_max_depth", C.c_uint32),
+        ("num_lights", C.c_uint32), ("bvh8_max_depth", C.c_uint32), ("bvh2_max_depth", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 

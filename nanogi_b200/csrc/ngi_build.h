@@ -187,6 +187,7 @@ struct NgiPlocCtx {
     int* cid_out; float4* clo_out; float4* chi_out;
     float4* lo; float4* hi;                      // [2n-1] node boxes
     int* left; int* right; unsigned* cnt;        // [n-1]
+    unsigned* depth;                             // [n-1] height of the binary subtree (the BVH2 cross-check traversal has a 64-entry stack)
     int n;                                       // leaves
     int next_id;                                 // id of the first merge of this round (ids go downwards)
     NgiDpRow* dp;                                // [n-1] collapse decisions (ngi_dp_node), or NULL
@@ -206,6 +207,10 @@ NGI_HD void ngi_ploc_merge(const NgiPlocCtx& c, const int i) {
         const float4 u1 = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.0f);
         c.left[id] = a; c.right[id] = b;
         c.cnt[id] = (a >= c.n - 1 ? 1u : c.cnt[a]) + (b >= c.n - 1 ? 1u : c.cnt[b]);
+        if (c.depth) {
+            const unsigned da = a >= c.n - 1 ? 0u : c.depth[a], db = b >= c.n - 1 ? 0u : c.depth[b];
+            c.depth[id] = 1u + (da > db ? da : db);
+        }
         c.lo[id] = u0; c.hi[id] = u1;
         c.cid_out[p] = id; c.clo_out[p] = u0; c.chi_out[p] = u1;
         if (c.dp) {

@@ -722,6 +722,8 @@ struct Scene {
     NgiSceneInfo info{};
     std::vector<void*> allocs;
     std::vector<size_t> alloc_bytes;             // parallel to `allocs` (a built scene is cloned to other devices array by array)
+    std::vector<void*> build_temps;              // temporaries of build_scene: released by its guard on every exit path
+    unsigned bvh2_depth = 0;                     // height of the binary BVH (accel = 1 needs it <= its traversal stack)
     std::vector<Lane> lanes;
     int num_lanes = 2;
     // persistent trace kernels: grid = SM count x resident CTAs per SM (queried once per kernel)
@@ -764,6 +766,7 @@ int dev_alloc(Scene* s, T** out, size_t count, bool keep) {
     void* p = nullptr;
     NGI_CUDA(ngi_dmalloc(&p, std::max<size_t>(count * sizeof(T), 16), s->stream));
     if (keep) { s->allocs.push_back(p); s->alloc_bytes.push_back(std::max<size_t>(count * sizeof(T), 16)); s->info.device_bytes += count * sizeof(T); }
+    else s->build_temps.push_back(p);
     *out = (T*)p;
     return NGI_OK;
 }
@@ -812,7 +815,18 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     const unsigned nr = ha.n_real;
     const unsigned n = nr < 2 ? 2 : nr;
 
-    cudaEvent_t ev0, ev1;
+    // events and every keep = false allocation below are released when this function returns, whichever way
+    struct BuildGuard {
+        Scene* s; cudaStream_t st; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        ~BuildGuard() {
+            for (void* p : s->build_temps) ngi_dfree(p, st);
+            s->build_temps.clear();
+            if (ev0) cudaEventDestroy(ev0);
+            if (ev1) cudaEventDestroy(ev1);
+        }
+    } guard{s, st};
+    cudaEvent_t& ev0 = guard.ev0;
+    cudaEvent_t& ev1 = guard.ev1;
     NGI_CUDA(cudaEventCreate(&ev0));
     NGI_CUDA(cudaEventCreate(&ev1));
 
@@ -894,6 +908,8 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     if ((rc = dev_alloc(s, &d_left, n - 1, false))) return rc;
     if ((rc = dev_alloc(s, &d_right, n - 1, false))) return rc;
     if ((rc = dev_alloc(s, &d_ncnt, n - 1, false))) return rc;
+    unsigned* d_depth2 = nullptr;
+    if ((rc = dev_alloc(s, &d_depth2, n - 1, false))) return rc;
     k_gather_sorted<<<grid_for(n), kBlock, 0, st>>>(d_vals2, n, d_rec, d_tlo, d_thi, d_tris2, d_lo, d_hi);
     // the sort buffers are dead now; cluster arrays ping-pong
     int *d_cid[2] = {nullptr, nullptr}, *d_nn = nullptr; float4 *d_clo[2] = {nullptr, nullptr}, *d_chi[2] = {nullptr, nullptr};
@@ -929,7 +945,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
             pc.cid_out = d_cid[cur ^ 1]; pc.clo_out = d_clo[cur ^ 1]; pc.chi_out = d_chi[cur ^ 1];
             pc.lo = d_lo; pc.hi = d_hi; pc.left = d_left; pc.right = d_right; pc.cnt = d_ncnt; pc.n = (int)n;
             pc.next_id = (int)(n - 2) - (int)merges_done;
-            pc.dp = d_dp; pc.c_node = 1.0f; pc.c_prim = sah_c_prim;
+            pc.dp = d_dp; pc.c_node = 1.0f; pc.c_prim = sah_c_prim; pc.depth = d_depth2;
             k_ploc_merge<<<grid_for(C), kBlock, 0, st>>>(pc, (int)C, d_keep, d_newc);
             unsigned newC = 0;
             NGI_CUDA(cudaMemcpyAsync(&newC, d_newc, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -940,6 +956,8 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
             if (++rounds > 100000) return set_err(NGI_ERR_CUDA, "PLOC did not terminate");
         }
         if (merges_done != n - 1) return set_err(NGI_ERR_CUDA, "PLOC merge count mismatch");
+        NGI_CUDA(cudaMemcpyAsync(&s->bvh2_depth, d_depth2, sizeof(unsigned), cudaMemcpyDeviceToHost, st));     // node 0 = root
+        NGI_CUDA(cudaStreamSynchronize(st));
     }
     k_pack2<<<grid_for(n - 1), kBlock, 0, st>>>(d_lo, d_hi, d_left, d_right, (int)n, d_nodes2);
 
@@ -989,14 +1007,6 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     NGI_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     NGI_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-
-    for (void* p : {(void*)d_pos, (void*)d_bounds, (void*)d_rec, (void*)d_tlo, (void*)d_thi, (void*)d_keys, (void*)d_keys2, (void*)d_vals, (void*)d_vals2,
-                    (void*)d_tmp, (void*)d_lo, (void*)d_hi, (void*)d_left, (void*)d_right, (void*)d_ncnt, (void*)d_cid[0], (void*)d_cid[1],
-                    (void*)d_clo[0], (void*)d_clo[1], (void*)d_chi[0], (void*)d_chi[1], (void*)d_nn, (void*)d_keep, (void*)d_spos, (void*)d_newc, (void*)d_scan_tmp,
-                    (void*)d_nodes8_tmp, (void*)d_tris8_compact, (void*)d_cnt, (void*)d_q0, (void*)d_q1, (void*)d_dp})
-        ngi_dfree(p, st);
-
     NgiDevScene& d = s->dev;
     d.nodes8 = d_nodes8; d.tris8 = d_tris8; d.nodes2 = d_nodes2; d.tris2 = d_tris2;
     d.shade_tris = d_shade; d.prims = d_prims; d.light_prims = d_lights; d.cdf = d_cdf;
@@ -1005,7 +1015,7 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     s->info.num_tris = nr; s->info.bvh8_nodes = n_nodes8; s->info.bvh2_nodes = n - 1;
     s->info.build_gpu_seconds = ms * 1e-3;
     for (int k = 0; k < 3; k++) { s->info.scene_min[k] = smin[k]; s->info.scene_max[k] = smax[k]; }
-    s->info.num_lights = d.n_lights; s->info.bvh8_max_depth = depth;
+    s->info.num_lights = d.n_lights; s->info.bvh8_max_depth = depth; s->info.bvh2_max_depth = s->bvh2_depth;
     return init_trace_launch(s);
 }
 
@@ -1386,7 +1396,8 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     // default slot count per lane: 2 Mi, 4 Mi for long renders (profiles/r01_sweep_wave.txt: larger waves amortise the
     // fixed tail of every launch; small renders prefer the shorter ramp-up and drain)
     // (8 Mi from 2^30 samples on: C3 +2.2 %, C2 +0.6 % over 4 Mi, profiles/r01_sweep_wave.txt)
-    unsigned P = rp->wave_capacity ? rp->wave_capacity : (rp->num_samples >= (1ll << 30) ? (1u << 23) : rp->num_samples >= (1ll << 28) ? (1u << 22) : (1u << 21));
+    // (4 Mi already from 2^27 samples: the 8-GPU shard of C3, 265 M samples, is just below 2^28)
+    unsigned P = rp->wave_capacity ? rp->wave_capacity : (rp->num_samples >= (1ll << 30) ? (1u << 23) : rp->num_samples >= (1ll << 27) ? (1u << 22) : (1u << 21));
     P = std::max(P, 1024u);
     if ((unsigned long long)rp->num_samples < P) P = std::max(1024u, (unsigned)((rp->num_samples + 255) / 256 * 256));
     // lanes: concurrent pipelines on disjoint sample ranges; only worth it when every lane gets several waves of work
@@ -1395,7 +1406,9 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     if ((int)s->lanes.size() < K) s->lanes.resize(K);
     int rc;
 
-    cudaEvent_t ev0, ev1;
+    struct EventPair { cudaEvent_t a = nullptr, b = nullptr; ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evp;
+    cudaEvent_t& ev0 = evp.a;
+    cudaEvent_t& ev1 = evp.b;
     NGI_CUDA(cudaEventCreate(&ev0));
     NGI_CUDA(cudaEventCreate(&ev1));
     NGI_CUDA(cudaEventRecord(ev0, st));          // also the fork point: the film memset above precedes every lane
@@ -1500,7 +1513,6 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     NGI_CUDA(cudaGetLastError());
     float ms = 0;
     NGI_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) {
         stats->paths = (uint64_t)rp->num_samples;
         for (int k = 0; k < K; k++) {
@@ -1539,8 +1551,12 @@ void launch_trace8(Scene* s, const NgiRay* rays, size_t n, NgiHit* hits, cudaStr
 
 int trace_impl(Scene* s, const NgiRay* rays_dev, size_t n, NgiHit* hits_dev, int any_hit, int accel, double* seconds) {
     if (accel < 0 || accel > 2) return set_err(NGI_ERR_INVALID_ARGUMENT, "accel must be 0 (BVH8), 1 (BVH2) or 2 (brute force)");
+    if (accel == 1 && s->bvh2_depth >= 64u)      // ngi_trace_bvh2 keeps one stack entry per level in int stack[64]
+        return set_err(NGI_ERR_UNSUPPORTED, "binary BVH of height " + std::to_string(s->bvh2_depth) + " exceeds the cross-check traversal's stack (accel = 1)");
     cudaStream_t st = s->stream;
-    cudaEvent_t ev0, ev1;
+    struct EventPair { cudaEvent_t a = nullptr, b = nullptr; ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evp;
+    cudaEvent_t& ev0 = evp.a;
+    cudaEvent_t& ev1 = evp.b;
     NGI_CUDA(cudaEventCreate(&ev0));
     NGI_CUDA(cudaEventCreate(&ev1));
     if (n >= 0xFFFFFF00ull) return set_err(NGI_ERR_INVALID_ARGUMENT, "at most 2^32 - 256 rays per call");
@@ -1556,7 +1572,6 @@ int trace_impl(Scene* s, const NgiRay* rays_dev, size_t n, NgiHit* hits_dev, int
     NGI_CUDA(cudaGetLastError());
     float ms = 0;
     NGI_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (seconds) *seconds = ms * 1e-3;
     return NGI_OK;
 }

@@ -177,7 +177,7 @@ __device__ __forceinline__ void ngi_trace_warp_postpone(const uint4* __restrict_
 // A deferred triangle test only delays the shrinking of best.t (a few more node steps pass the culling test); the result is the
 // same order-free minimum of (t, id).
 #ifndef NGI_NODE_REPS
-#define NGI_NODE_REPS 1
+#define NGI_NODE_REPS 2   /* C3 k_extend per launch: 1.301 ms (1 step per round), 1.229 ms (2), 1.218 ms (3, but C2 +8 %): profiles/r02_sweep_trace_tq.txt */
 #endif
 #ifndef NGI_SSTACK
 #define NGI_SSTACK 0       /* levels of the node-group stack kept in shared memory (A/B: profiles/r02_sweep_sstack.txt) */

@@ -210,7 +210,10 @@ inline bool decode_png(const std::vector<uint8_t>& f, int& w, int& h, std::vecto
         const std::string type((const char*)&f[pos + 4], 4);
         if (pos + 12 + len > f.size()) { err = "truncated PNG"; return false; }
         const uint8_t* d = &f[pos + 8];
-        if (type == "IHDR") { w = (int)be32(d); h = (int)be32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+        if (type == "IHDR") {
+            if (len < 13) { err = "malformed PNG (IHDR shorter than 13 bytes)"; return false; }
+            w = (int)be32(d); h = (int)be32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12];
+        }
         else if (type == "IDAT") idat.insert(idat.end(), d, d + len);
         else if (type == "IEND") break;
         pos += 12 + len;

@@ -98,6 +98,7 @@ struct HostScene {
             for (size_t i = 0; i < primitivesNode.size(); i++) {
                 NgiPrimitive prim{};
                 prim.first_tri = -1; prim.d_tex = -1; prim.g_tex = -1;
+                bool mesh_has_uv = false;                                               // THIS primitive's mesh carries texture coordinates
                 const yaml::Node& primitiveNode = primitivesNode[i];
 
                 // ---- type, rt.hpp:1583-1616 ----
@@ -132,6 +133,7 @@ struct HostScene {
                     prim.num_tris = (int32_t)mesh.num_tris();
                     positions.insert(positions.end(), mesh.positions.begin(), mesh.positions.end());
                     normals.insert(normals.end(), mesh.normals.begin(), mesh.normals.end());
+                    mesh_has_uv = !mesh.texcoords.empty();
                     if (!mesh.texcoords.empty()) { any_uv = true; texcoords.resize((size_t)prim.first_tri * 6, 0.f); texcoords.insert(texcoords.end(), mesh.texcoords.begin(), mesh.texcoords.end()); }
                     else all_uv = false;
                 }
@@ -175,14 +177,15 @@ struct HostScene {
                     } else if (type == "area") {                                       // rt.hpp:1910-1929
                         prim.e_type = NGI_E_AREA;
                         ParseVec3(ENode["area"]["We"], prim.e_we);
-                        if (prim.first_tri < 0 || !any_uv) { error = "Raw sensor must be associated with mesh with UV coordinates"; NGI_LOG_ERROR(error); return false; }
+                        // the reference looks at the sensor's OWN mesh (rt.hpp:1919-1924): a sensor mesh without uv would map every splat to pixel 0
+                        if (prim.first_tri < 0 || !mesh_has_uv) { error = "Raw sensor must be associated with mesh with UV coordinates"; NGI_LOG_ERROR(error); return false; }
                     }
                 }
                 if ((prim.type & NGI_TYPE_D) > 0) {                                    // rt.hpp:1940-1957
                     const yaml::Node& DNode = paramsNode["D"];
                     if (DNode["R"]) ParseVec3(DNode["R"], prim.d_r);
                     else if (DNode["TexR"]) { if ((prim.d_tex = LoadTexture(basePath + DNode["TexR"].as_string())) < 0) return false; }   // rt.hpp:1947-1951
-                    else { error = "D requires R or TexR"; return false; }
+                    else { error = "D requires R or TexR"; NGI_LOG_ERROR(error); return false; }
                 }
                 if ((prim.type & NGI_TYPE_G) > 0) {                                    // rt.hpp:1965-1985
                     const yaml::Node& GNode = paramsNode["G"];
@@ -191,7 +194,7 @@ struct HostScene {
                     prim.g_roughness = GNode["Roughness"].as_double();
                     if (GNode["R"]) ParseVec3(GNode["R"], prim.g_r);
                     else if (GNode["TexR"]) { if ((prim.g_tex = LoadTexture(basePath + GNode["TexR"].as_string())) < 0) return false; }   // rt.hpp:1975-1979
-                    else { error = "G requires R or TexR"; return false; }
+                    else { error = "G requires R or TexR"; NGI_LOG_ERROR(error); return false; }
                 }
                 if ((prim.type & NGI_TYPE_S) > 0) {                                    // rt.hpp:1993-2040
                     const yaml::Node& SNode = paramsNode["S"];

@@ -181,7 +181,7 @@ __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc
             pc.cid_out = cid[cur ^ 1].data(); pc.clo_out = clo[cur ^ 1].data(); pc.chi_out = chi[cur ^ 1].data();
             pc.lo = s->lo.data(); pc.hi = s->hi.data(); pc.left = s->left.data(); pc.right = s->right.data(); pc.cnt = s->cnt.data();
             pc.n = (int)n; pc.next_id = (int)(n - 2) - (int)merges;
-            pc.dp = s->dp.data(); pc.c_node = c_node; pc.c_prim = c_prim;
+            pc.dp = s->dp.data(); pc.c_node = c_node; pc.c_prim = c_prim; pc.depth = nullptr;
             for (unsigned i = 0; i < C; i++) ngi_ploc_merge(pc, (int)i);
             merges += C - acc; C = acc; cur ^= 1;
         }

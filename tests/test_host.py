@@ -100,6 +100,31 @@ def test_yaml_and_loader_errors(tmp_path):
     assert sd.num_tris == 1 and np.allclose(sd.normals[0], [[0, 0, 1]] * 3) and sd.prims[1].e_aspect == 2.0
 
 
+def test_area_sensor_needs_uv_on_its_own_mesh(tmp_path):
+    """rt.hpp:1919-1924 checks the SENSOR's mesh: an earlier mesh with texture coordinates must not satisfy it"""
+    (tmp_path / "uv.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nvn 0 0 1\nf 1/1/1 2/2/1 3/3/1\n")
+    (tmp_path / "nouv.obj").write_text("v 0 0 2\nv 1 0 2\nv 0 1 2\nvn 0 0 -1\nf 1//1 2//1 3//1\n")
+    y = ("version: 5\nscene:\n  primitives:\n    - type: [D]\n      mesh:\n        path: uv.obj\n      params:\n        D:\n          R: [1, 1, 1]\n"
+         "    - type: [E]\n      mesh:\n        path: nouv.obj\n      params:\n        E:\n          type: area\n          area:\n            We: [1, 1, 1]\n")
+    p = tmp_path / "scene.yml"
+    p.write_text(y)
+    with pytest.raises(capi.NgiError, match="UV coordinates"):
+        capi.load_scene_file(str(p), 1.0)
+    p.write_text(y.replace("nouv.obj", "uv.obj"))
+    assert capi.load_scene_file(str(p), 1.0).num_tris == 2
+
+
+def test_malformed_png_is_rejected(tmp_path):
+    import struct, zlib
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    bad = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", b"\0\0\0\1\0\0\0\1") + chunk(b"IEND", b"")       # IHDR of 8 bytes instead of 13
+    f = tmp_path / "bad.png"
+    f.write_bytes(bad)
+    with pytest.raises(capi.NgiError, match="IHDR"):
+        capi.load_image(str(f))
+
+
 def test_obj_features(tmp_path):
     (tmp_path / "m.obj").write_text(
         "# quad + negative indices + vt\no first\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"

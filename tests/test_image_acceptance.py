@@ -97,6 +97,10 @@ def test_image_acceptance(name):
     se_mean_cpu = math.sqrt(mc.var(ddof=1) / K) / R.mean()
     mean_gpu_vs_cpu = (mg.mean() - mc.mean()) / mc.mean()
     se_mean_pair = math.sqrt(mc.var(ddof=1) / K + mg.var(ddof=1) / K) / mc.mean()
+    # the same on the clamped films: fireflies dominate the standard error of a plain mean (a single sample can carry 1e3 x a pixel)
+    mgc, mcc = np.minimum(Ig, cap).mean(axis=(1, 2, 3)), np.minimum(Ic, cap).mean(axis=(1, 2, 3))
+    meanc_gpu_vs_cpu = (mgc.mean() - mcc.mean()) / mcc.mean()
+    se_meanc_pair = math.sqrt(mcc.var(ddof=1) / K + mgc.var(ddof=1) / K) / mcc.mean()
 
     def blocks(F):
         k = F.shape[0]
@@ -112,7 +116,8 @@ def test_image_acceptance(name):
                              "clamp": "pixel values clamped at 20 x the reference mean, both sides"},
         "rel_rmse_unclamped": {"gpu": float(rg.mean()), "cpu": float(rc.mean()), "diff_pct_of_cpu": 100 * diff_u, "standard_error_pct": 100 * se_u},
         "image_mean": {"cpu_vs_reference_pct": 100 * mean_cpu_vs_ref, "cpu_standard_error_pct": 100 * se_mean_cpu,
-                       "gpu_vs_cpu_pct": 100 * mean_gpu_vs_cpu, "pair_standard_error_pct": 100 * se_mean_pair},
+                       "gpu_vs_cpu_pct": 100 * mean_gpu_vs_cpu, "pair_standard_error_pct": 100 * se_mean_pair,
+                       "clamped_gpu_vs_cpu_pct": 100 * meanc_gpu_vs_cpu, "clamped_pair_standard_error_pct": 100 * se_meanc_pair},
         "blocks": {"count": int(z.size), "pixels": f"{blk}x{blk}", "z_max": float(np.abs(z).max()), "beyond_3_sigma": n_gt3,
                    "expected_beyond_3_sigma": 0.0027 * z.size},
     }
@@ -127,4 +132,6 @@ def test_image_acceptance(name):
     assert abs(diff_c) <= 0.01 + 1.0 * se_c, f"relRMSE (clamped) {rgc.mean():.4f} vs CPU {rcc.mean():.4f}: {100 * diff_c:+.2f} % (s.e. {100 * se_c:.2f} %)"
     assert abs(mean_cpu_vs_ref) <= max(0.004, 3.5 * se_mean_cpu), f"CPU pooled mean vs the 64k-spp reference: {100 * mean_cpu_vs_ref:+.3f} % (s.e. {100 * se_mean_cpu:.3f} %)"
     assert abs(mean_gpu_vs_cpu) <= max(0.004, 3.5 * se_mean_pair), f"image means: {100 * mean_gpu_vs_cpu:+.3f} % (s.e. {100 * se_mean_pair:.3f} %)"
+    assert se_meanc_pair <= 0.0025 and abs(meanc_gpu_vs_cpu) <= max(0.003, 3.5 * se_meanc_pair), \
+        f"clamped image means: {100 * meanc_gpu_vs_cpu:+.3f} % (s.e. {100 * se_meanc_pair:.3f} %)"
     assert n_gt3 <= 2 and np.abs(z).max() < 4.5, f"block bias: {n_gt3} of {z.size} blocks beyond 3 sigma, max |z| = {np.abs(z).max():.2f}"
