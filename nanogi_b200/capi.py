@@ -403,11 +403,22 @@ class GpuScene:
         return out
 
 
+def _map_torchs_nccl_first():
+    """libnanogi_gpu.so opens "libnccl.so.2" with dlopen on first use. In a Python process that ALSO imports torch, torch's own
+    (newer) NCCL must be the copy mapped under that soname: if the system library got there first, a later `import torch` fails
+    with an undefined NCCL symbol. So the glue imports torch (when installed) before the first NCCL entry point is called."""
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
+
+
 class GpuGroup:
     """ngi_gpu_group_*: every device of ONE process — scene built once and broadcast, samples sharded by index, one NCCL
     film reduce per render (what `nanogi --gpus N` runs)."""
 
     def __init__(self, scene: SceneData, devices):
+        _map_torchs_nccl_first()
         self.lib = gpu_lib()
         self.handle = C.c_void_p()
         self.scene = scene
@@ -440,6 +451,7 @@ class GpuComm:
     128-byte id to the other ranks (any host channel: bench.py passes a torch.distributed broadcast)."""
 
     def __init__(self, rank: int, world_size: int, device: int, exchange):
+        _map_torchs_nccl_first()
         self.lib = gpu_lib()
         self.handle = C.c_void_p()
         cid = NgiCommId()

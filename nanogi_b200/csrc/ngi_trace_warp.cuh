@@ -166,50 +166,64 @@ __device__ __forceinline__ void ngi_trace_warp_postpone(const uint4* __restrict_
 // ------------------------------------------------------------------------------------------------
 // Second form of the loop (NGI_TRACE_TQ, the product default): the triangle backlog lives in SHARED memory.
 //
-// What the first form (ngi_trace_warp_postpone below) loses, from profiles/r01_ncu_c3_extend_blocks.txt: 29.0 lanes hold a ray
+// What the first form (ngi_trace_warp_postpone above) loses, from profiles/r01_ncu_c3_extend_blocks.txt: 29.0 lanes hold a ray
 // but only 23.9 take the node step — the other 5.1 have just popped a POSTPONED triangle group off their stack and sit the node
 // phase out — and the triangle phase runs at 10.3 lanes. Here a lane keeps traversing while its triangle groups wait in a small
 // per-lane LIFO in shared memory (NGI_TQ entries of 8 bytes, [entry][thread]: conflict-free), so
 //   * the stack in local memory holds node groups only (depth <= NGI_BVH8_MAX_DEPTH) and every lane with a ray takes the node
-//     step of every round (unless its backlog is full);
+//     steps of every round (unless its backlog is full);
 //   * the triangle phase starts when at least tune.tri_min lanes have a group waiting (or fewer lanes could step nodes than test
-//     triangles), and leaves again when it runs out of lanes: both phases run dense.
+//     triangles), and leaves again when it runs out of lanes: both phases run dense;
+//   * a round takes NGI_NODE_REPS node steps per lane: every round pays ~150 warp instructions of fetch / vote / phase-change
+//     bookkeeping (profiles/r02_ncu_c3_extend_blocks_s42.txt), two steps per round halve that share.
 // A deferred triangle test only delays the shrinking of best.t (a few more node steps pass the culling test); the result is the
 // same order-free minimum of (t, id).
+//
+// Everything a thread keeps in shared memory sits in ONE pool, [slot][thread] with 8-byte slots, addressed from a per-thread base
+// register with immediate offsets (ld.shared / st.shared through inline PTX): with ordinary __shared__ arrays ptxas re-derived the
+// addresses from S2R SR_TID.X / SR_CgaCtaId at every use inside the loop (9 S2R per round, ~10 % of the stall samples).
+//   slots 0 .. NGI_TQ-1   triangle backlog entries (tri base, 24-bit mask)
+//   slot  NGI_TQ          (queue token of the ray, u of its best hit)      needed only when the ray retires: with these three in
+//   slot  NGI_TQ + 1      (v of its best hit, -)                           registers ptxas spilled four values around every node step
+//   then one 8-byte slot per WARP: {next, end} of the chunk of the queue the warp is handing out (touched only when lanes are refilled)
 #ifndef NGI_NODE_REPS
 #define NGI_NODE_REPS 2   /* C3 k_extend per launch: 1.301 ms (1 step per round), 1.229 ms (2), 1.218 ms (3, but C2 +8 %): profiles/r02_sweep_trace_tq.txt */
-#endif
-#ifndef NGI_SSTACK
-#define NGI_SSTACK 0       /* levels of the node-group stack kept in shared memory (A/B: profiles/r02_sweep_sstack.txt) */
 #endif
 #ifndef NGI_TQ
 #define NGI_TQ 2          /* s40 sweep on C3: 2 entries 1.449 ms, 4 entries 1.466 ms, 6 entries 1.469 ms per k_extend launch */
 #endif
+#define NGI_POOL_SLOT_BYTES (NGI_TRACE_BLOCK * 8)
+#define NGI_POOL_BYTES ((NGI_TQ + 2) * NGI_POOL_SLOT_BYTES + (NGI_TRACE_BLOCK / 32) * 8)
+
+__device__ __forceinline__ void ngi_sts64(const unsigned addr, const uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y)); }
+__device__ __forceinline__ uint2 ngi_lds64(const unsigned addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
+__device__ __forceinline__ void ngi_sts32(const unsigned addr, const unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ unsigned ngi_lds32(const unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
 template <bool ANY_HIT, class Source>
 __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Source src,
-                                                  const NgiTraceTuning tune, uint2 (*s_tq)[NGI_TRACE_BLOCK], unsigned (*s_aux)[NGI_TRACE_BLOCK],
-                                                  unsigned (*s_chunk)[2], uint2 (*s_stack)[NGI_TRACE_BLOCK]) {
+                                                  const NgiTraceTuning tune, unsigned char* pool) {
     const unsigned FULL = 0xFFFFFFFFu;
-    const unsigned tid = threadIdx.x;
-    const unsigned lane = tid & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned warp = tid >> 5;
-    // warp-uniform fetch state: the chunk of the queue this warp is handing out lives in shared memory (s_chunk[warp] = {next, end}),
-    // it is only touched when lanes are refilled and would otherwise hold two registers of every thread through the node step
-    if (lane == 0) { s_chunk[warp][0] = 0u; s_chunk[warp][1] = 0u; }
+    unsigned sbase;           // shared-space address of this thread's slot 0; `mov` through asm so that it stays in a register
+    {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(pool) + threadIdx.x * 8u;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(a));
+    }
+    const unsigned kAux0 = NGI_TQ * NGI_POOL_SLOT_BYTES, kAux1 = (NGI_TQ + 1) * NGI_POOL_SLOT_BYTES;
+    const unsigned lane = threadIdx.x & 31u;
+    // warp-uniform fetch state {next, end}, see above
+    const unsigned cbase = (unsigned)__cvta_generic_to_shared(pool) + (NGI_TQ + 2) * NGI_POOL_SLOT_BYTES + (threadIdx.x >> 5) * 8u;
+    if (lane == 0) ngi_sts64(cbase, make_uint2(0u, 0u));
     bool exhausted = (src.count() == 0);
 
-    // per-lane ray state. What a ray needs only when it retires — its queue token and the (u, v) of its best hit — is parked in
-    // shared memory (s_aux[0..2][thread]): with those three in registers ptxas spilled four values around every node step
     bool active = false;
     NgiRayCtx r;
     float tmax = 0.0f;
     float best_t = 0.0f; unsigned best_tri = NGI_MISS;
     bool found = false;
-    // node-group stack: the first NGI_SSTACK levels in shared memory ([level][thread]: conflict-free), deeper ones in local memory
-    uint2 stack[NGI_BVH8_MAX_DEPTH + 1 - NGI_SSTACK];
+    uint2 stack[NGI_BVH8_MAX_DEPTH + 1];      // node groups only
     int sp = 0;
-    int tqn = 0;              // triangle groups waiting in s_tq[0 .. tqn) of this thread; tqn > 0 implies tgroup.y != 0
+    int tqn = 0;              // triangle groups waiting in backlog slots [0, tqn) of this thread; tqn > 0 implies tgroup.y != 0
     unsigned skipped = 0;     // warp-uniform: consecutive rounds whose triangle phase was put off (starvation guard)
     uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
 
@@ -220,7 +234,8 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
         if (idle != 0u) {
             const int nidle = __popc(idle);
             if (!exhausted && (nidle >= tune.refill_min || idle == FULL)) {
-                unsigned chunk_next = s_chunk[warp][0], chunk_end = s_chunk[warp][1];
+                const uint2 ck = ngi_lds64((unsigned)__cvta_generic_to_shared(pool) + (NGI_TQ + 2) * NGI_POOL_SLOT_BYTES + (threadIdx.x >> 5) * 8u);
+                unsigned chunk_next = ck.x, chunk_end = ck.y;
                 if (chunk_next >= chunk_end) {
                     const unsigned n = src.count();
                     unsigned chunk_size = tune.chunk;
@@ -229,17 +244,18 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
                         if (per < chunk_size) chunk_size = per ? per : 1u;
                     }
                     unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(src.cursor(), chunk_size);
+                    if ((threadIdx.x & 31u) == 0) base = atomicAdd(src.cursor(), chunk_size);
                     base = __shfl_sync(FULL, base, 0);
                     chunk_next = base;
                     chunk_end = base + chunk_size < n ? base + chunk_size : n;
                     if (base >= n) { exhausted = true; chunk_next = chunk_end = 0; }
                 }
                 if (!exhausted) {
-                    const unsigned my = chunk_next + (unsigned)__popc(idle & lt_mask);
+                    const unsigned my = chunk_next + (unsigned)__popc(idle & ((1u << (threadIdx.x & 31u)) - 1u));
                     if (!active && my < chunk_end) {
                         f3 o, d; float tmin;
-                        s_aux[0][tid] = src.load(my, o, d, tmin, tmax);
+                        const unsigned token = src.load(my, o, d, tmin, tmax);
+                        ngi_sts32(sbase + kAux0, token);
                         ngi_ray_ctx(r, o, d, tmin);
                         r.one = tune.one_bits;
                         best_t = tmax; best_tri = NGI_MISS;
@@ -251,34 +267,27 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
                     chunk_next = chunk_next + (unsigned)nidle < chunk_end ? chunk_next + (unsigned)nidle : chunk_end;
                 }
                 __syncwarp();
-                if (lane == 0) { s_chunk[warp][0] = chunk_next; s_chunk[warp][1] = chunk_end; }
+                if ((threadIdx.x & 31u) == 0)
+                    ngi_sts64((unsigned)__cvta_generic_to_shared(pool) + (NGI_TQ + 2) * NGI_POOL_SLOT_BYTES + (threadIdx.x >> 5) * 8u, make_uint2(chunk_next, chunk_end));
             }
             if (exhausted && __ballot_sync(FULL, active) == 0u) break;
         }
 
         // ---------------- node phase: NGI_NODE_REPS node steps per lane ----------------
-        // (every round of this loop pays ~150 warp instructions of fetch / vote / phase-change bookkeeping, profiles/r02_ncu_c3_extend_blocks_s42.txt:
-        // taking more than one node step per round spreads them; the triangle backlog absorbs what the extra steps find)
 #pragma unroll 1
         for (int rep = 0; rep < NGI_NODE_REPS; rep++) {
             if (active && ngroup.y > 0x00FFFFFFu && tqn < NGI_TQ) {
                 size_t ni;
                 ngi_bvh8_pop_child(ngroup, r.octinv, ni);
-                if (ngroup.y > 0x00FFFFFFu) {                                // never full: the build bounds the depth
-                    if (NGI_SSTACK > 0 && sp < NGI_SSTACK) s_stack[sp][tid] = ngroup; else stack[sp - NGI_SSTACK] = ngroup;
-                    sp++;
-                }
+                if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;            // never full: the build bounds the depth
                 uint2 tnew;
                 ngi_bvh8_node_step(nodes, ni, r, best_t, ngroup, tnew);
                 if (tnew.y != 0u) {
                     if (tgroup.y == 0u) tgroup = tnew;
-                    else s_tq[tqn++][tid] = tnew;
+                    else { ngi_sts64(sbase + (unsigned)tqn * NGI_POOL_SLOT_BYTES, tnew); tqn++; }
                 }
             }
-            if (active && ngroup.y <= 0x00FFFFFFu && sp > 0) {
-                --sp;
-                if (NGI_SSTACK > 0 && sp < NGI_SSTACK) ngroup = s_stack[sp][tid]; else ngroup = stack[sp - NGI_SSTACK];
-            }
+            if (active && ngroup.y <= 0x00FFFFFFu && sp > 0) ngroup = stack[--sp];
         }
         __syncwarp();
 
@@ -308,12 +317,12 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
                         const unsigned id = f2u(a.w);
                         if (t < best_t || (t == best_t && id < best_tri)) {      // ngi_accept: lexicographic minimum of (t, id)
                             best_t = t; best_tri = id;
-                            s_aux[1][tid] = f2u(u); s_aux[2][tid] = f2u(v);
+                            ngi_sts32(sbase + kAux0 + 4u, f2u(u)); ngi_sts32(sbase + kAux1, f2u(v));
                         }
                         found = true;
                     }
                 }
-                if (tgroup.y == 0u && tqn > 0) tgroup = s_tq[--tqn][tid];
+                if (tgroup.y == 0u && tqn > 0) { --tqn; tgroup = ngi_lds64(sbase + (unsigned)tqn * NGI_POOL_SLOT_BYTES); }
             }
         }
 
@@ -321,8 +330,8 @@ __device__ __forceinline__ void ngi_trace_warp_tq(const uint4* __restrict__ node
         if (active && ngroup.y <= 0x00FFFFFFu && sp == 0 && tgroup.y == 0u) {
             NgiHitRec best; best.t = best_t; best.tri = best_tri;
             best.u = 0.0f; best.v = 0.0f;
-            if (!ANY_HIT && found) { best.u = u2f(s_aux[1][tid]); best.v = u2f(s_aux[2][tid]); }
-            src.store(s_aux[0][tid], found, best);
+            if (!ANY_HIT && found) { best.u = u2f(ngi_lds32(sbase + kAux0 + 4u)); best.v = u2f(ngi_lds32(sbase + kAux1)); }
+            src.store(ngi_lds32(sbase + kAux0), found, best);
             active = false;
         }
     }
@@ -337,11 +346,8 @@ template <bool ANY_HIT, class Source>
 __device__ __forceinline__ void ngi_trace_warp(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Source src,
                                                const NgiTraceTuning tune) {
 #if NGI_TRACE_TQ
-    __shared__ uint2 s_tq[NGI_TQ][NGI_TRACE_BLOCK];
-    __shared__ unsigned s_aux[3][NGI_TRACE_BLOCK];
-    __shared__ unsigned s_chunk[NGI_TRACE_BLOCK / 32][2];
-    __shared__ uint2 s_stack[NGI_SSTACK > 0 ? NGI_SSTACK : 1][NGI_TRACE_BLOCK];
-    ngi_trace_warp_tq<ANY_HIT>(nodes, tris, src, tune, s_tq, s_aux, s_chunk, s_stack);
+    __shared__ __align__(16) unsigned char s_pool[NGI_POOL_BYTES];
+    ngi_trace_warp_tq<ANY_HIT>(nodes, tris, src, tune, s_pool);
 #else
     ngi_trace_warp_postpone<ANY_HIT>(nodes, tris, src, tune);
 #endif
