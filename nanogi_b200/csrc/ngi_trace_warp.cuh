@@ -178,6 +178,10 @@ __device__ __forceinline__ void ngi_trace_warp_postpone(const uint4* __restrict_
 //     bookkeeping (profiles/r02_ncu_c3_extend_blocks_s42.txt), two steps per round halve that share.
 // A deferred triangle test only delays the shrinking of best.t (a few more node steps pass the culling test); the result is the
 // same order-free minimum of (t, id).
+// (Measured and rejected, profiles/r02_sweep_trace_tq.txt: software prefetch — the next node of every lane into L1 with
+// prefetch.global.L1 = CCTL.E.PF1 made k_extend 2.3x SLOWER on C3, the first triangle of a new group or the ray records of a new
+// chunk into L1 / L2 1 % slower; 40 instead of 36 warps per SM (48 registers, 13 spill instructions) 14 % slower; levels of the
+// node stack in shared memory: no effect.)
 //
 // Everything a thread keeps in shared memory sits in ONE pool, [slot][thread] with 8-byte slots, addressed from a per-thread base
 // register with immediate offsets (ld.shared / st.shared through inline PTX): with ordinary __shared__ arrays ptxas re-derived the

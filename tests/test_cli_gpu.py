@@ -110,3 +110,35 @@ def test_cli_matches_the_reference_binary(scene_file, tmp_path):
     assert abs(a.mean() - b.mean()) < 0.02 * a.mean()
     blk = lambda f: f.reshape(8, 8, 8, 8, 3).mean(axis=(1, 3, 4))
     assert np.allclose(blk(a), blk(b), rtol=0.15, atol=0.02 * a.mean())
+
+
+def test_reference_binary_with_the_gpu_bridge(scene_file, tmp_path):
+    """INTEGRATION.md B, compiled: oracle/_ref/nanogi_ref_gpu is the REFERENCE application (its Run, CLI, Scene::Load, SaveImage) with
+    oracle/ref_gpu_bridge.hpp's RenderOnGpu behind Renderer::Render (one inserted statement, src/nanogi.cpp:203), linked to
+    libnanogi_gpu.so. NANOGI_DEVICE=gpu selects the GPU module; without it the same binary runs the reference's CPU path. The GPU image
+    equals the drop-in `nanogi`'s (same seed: same Philox sample set) and agrees with the CPU image within Monte-Carlo noise."""
+    from oracle import pyref
+    exe = os.path.join(os.path.dirname(pyref.BIN_PATH), "nanogi_ref_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/nanogi_ref_gpu not built")
+    n, w = 64 * 64 * 256, 64
+    cpu_img, gpu_img, drop_img = tmp_path / "cpu.exr", tmp_path / "gpu.exr", tmp_path / "drop.pfm"
+    args = ["ptdirect", scene_file, None, str(w), str(w), "-n", str(n), "-m", "6"]
+    r = subprocess.run([exe] + [a if a is not None else str(cpu_img) for a in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and cpu_img.exists(), r.stdout[-2000:]
+    env = dict(os.environ, NANOGI_DEVICE="gpu", NANOGI_GPUS="1", NANOGI_SEED="11")
+    r = subprocess.run([exe] + [a if a is not None else str(gpu_img) for a in args], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and gpu_img.exists() and "GPU module:" in r.stdout + r.stderr, (r.stdout + r.stderr)[-2000:]
+    rc, log = run("ptdirect", scene_file, drop_img, w, w, "-n", n, "-m", 6, "--seed", 11)
+    assert rc == 0, log
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    a = cv2.imread(str(cpu_img), cv2.IMREAD_UNCHANGED)[:, :, ::-1].astype(np.float64)     # BGR -> RGB, top-down
+    b = cv2.imread(str(gpu_img), cv2.IMREAD_UNCHANGED)[:, :, ::-1].astype(np.float64)
+    c = capi.load_image(str(drop_img)).astype(np.float64)
+    assert a.shape == b.shape == c.shape == (w, w, 3)
+    # the reference's loader (Assimp stand-in) and this repository's loader hand the module the same scene: same samples, same film
+    assert np.allclose(b, c, rtol=2e-3, atol=1e-5 * c.max())
+    assert abs(a.mean() - b.mean()) < 0.02 * a.mean()
+    blk = lambda f: f.reshape(8, 8, 8, 8, 3).mean(axis=(1, 3, 4))
+    assert np.allclose(blk(a), blk(b), rtol=0.15, atol=0.02 * a.mean())

@@ -132,6 +132,7 @@ def test_image_acceptance(name):
     assert abs(diff_c) <= 0.01 + 1.0 * se_c, f"relRMSE (clamped) {rgc.mean():.4f} vs CPU {rcc.mean():.4f}: {100 * diff_c:+.2f} % (s.e. {100 * se_c:.2f} %)"
     assert abs(mean_cpu_vs_ref) <= max(0.004, 3.5 * se_mean_cpu), f"CPU pooled mean vs the 64k-spp reference: {100 * mean_cpu_vs_ref:+.3f} % (s.e. {100 * se_mean_cpu:.3f} %)"
     assert abs(mean_gpu_vs_cpu) <= max(0.004, 3.5 * se_mean_pair), f"image means: {100 * mean_gpu_vs_cpu:+.3f} % (s.e. {100 * se_mean_pair:.3f} %)"
-    assert se_meanc_pair <= 0.0025 and abs(meanc_gpu_vs_cpu) <= max(0.003, 3.5 * se_meanc_pair), \
+    # (s.e. of the clamped mean difference: 0.1 - 0.2 % for ptdirect, 0.3 - 0.4 % for pt, whose light hits are rarer and larger)
+    assert se_meanc_pair <= 0.006 and abs(meanc_gpu_vs_cpu) <= max(0.003, 3.5 * se_meanc_pair), \
         f"clamped image means: {100 * meanc_gpu_vs_cpu:+.3f} % (s.e. {100 * se_meanc_pair:.3f} %)"
     assert n_gt3 <= 2 and np.abs(z).max() < 4.5, f"block bias: {n_gt3} of {z.size} blocks beyond 3 sigma, max |z| = {np.abs(z).max():.2f}"
