@@ -756,7 +756,7 @@ struct Scene {
         }
         for (void* p : allocs) ngi_dfree(p, stream);
         if (trace_cursor) ngi_dfree(trace_cursor, stream);
-        if (film_acc) cudaFree(film_acc);
+        if (film_acc) ngi_dfree(film_acc, stream);
         if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
     }
 };
@@ -1355,8 +1355,11 @@ int render_impl(Scene* s, const NgiRenderParams* rp, float* film_dev, cudaStream
     const size_t nfilm = npx * 3;
     if (s->film_acc_n != nfilm) {
         for (Lane& l : s->lanes) if (l.graph_exec) { cudaGraphExecDestroy(l.graph_exec); l.graph_exec = nullptr; }
-        if (s->film_acc) { NGI_CUDA(cudaFree(s->film_acc)); s->film_acc = nullptr; s->film_acc_n = 0; }
-        NGI_CUDA(cudaMalloc((void**)&s->film_acc, nfilm * sizeof(double)));
+        // from the stream-ordered pool like every other scene array: as a cudaMalloc / cudaFree pair per scene handle it cost the e2e
+        // path (one handle per render) 0.2 - 0.36 s per step in scene_destroy (profiles/r02_sweep_l2_persist_and_film_pool.txt)
+        if (s->film_acc) { ngi_dfree(s->film_acc, s->stream); s->film_acc = nullptr; s->film_acc_n = 0; }
+        NGI_CUDA(ngi_dmalloc((void**)&s->film_acc, nfilm * sizeof(double), s->stream));
+        NGI_CUDA(cudaStreamSynchronize(s->stream));          // usable from the caller's stream and the lanes' streams from here on
         s->film_acc_n = nfilm;
     }
     k_film_begin<<<kFilmGrid, kBlock, 0, st>>>(film_dev, s->film_acc, nfilm, rp->accumulate);
