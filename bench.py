@@ -203,8 +203,12 @@ def run_reference(args, rank: int):
     cpu = CpuReference(args.workload, sd, W / H)
     cores = cpu.cores
     # bounded sample: calibrate on 2^18 samples, then size a step to ~ args.cpu_step_seconds of wall time
-    rate = (1 << 18) / cpu.render(renderer, 1 << 18, W, H, m, 11)
-    n_step = int(max(1 << 18, min(rate * args.cpu_step_seconds, W * H * spp)))
+    n_step = 1 << 18
+    while True:
+        dt0 = cpu.render(renderer, n_step, W, H, m, 11)
+        if dt0 >= 0.6 * args.cpu_step_seconds or n_step >= W * H * spp:
+            break
+        n_step = int(min(W * H * spp, n_step * min(8.0, max(1.5, args.cpu_step_seconds / max(dt0, 1e-3)))))
     for i in range(args.warmup):
         cpu.render(renderer, n_step, W, H, m, 100 + i)
     dt = 0.0
@@ -382,9 +386,14 @@ def run_own(args, rank: int, local_rank: int, world: int):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         ref = CpuReference(args.workload, sd, W / H)
-        rate = (1 << 18) / ref.render(renderer, 1 << 18, W, H, m, 11)
-        n_cpu = int(max(1 << 18, min(rate * args.cpu_seconds, n_rank)))
-        dtc = ref.render(renderer, n_cpu, W, H, m, 12)
+        # bounded sample: grow it until one render takes about --cpu-seconds (a short render over-states the rate: thread start-up
+        # and the per-thread films are paid per call)
+        n_cpu, dtc = 1 << 18, 0.0
+        while True:
+            dtc = ref.render(renderer, n_cpu, W, H, m, 12)
+            if dtc >= 0.6 * args.cpu_seconds or n_cpu >= n_rank:
+                break
+            n_cpu = int(min(n_rank, n_cpu * min(8.0, max(1.5, args.cpu_seconds / max(dtc, 1e-3)))))
         cpu = {"value": n_cpu / dtc / 1e6, "unit": "Mpaths/s", "cores": ref.cores, "kind": ref.kind,
                "sample": f"{n_cpu} samples ({n_cpu / (W * H):.2f} spp of {spp}) of the same scene/resolution/renderer, {dtc:.1f} s",
                "mrays_per_s": ref.rays_per_path(renderer, W, H, m) * n_cpu / dtc / 1e6, "note": ref.note}
