@@ -256,7 +256,12 @@ def run_own(args, rank: int, local_rank: int, world: int):
     scene = capi.GpuScene(sd, local_rank)
     info = scene.info()
     film = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    # ONE explicit stream for everything: the module forks its lanes from it and joins them back, the product's ncclReduce runs on it,
+    # the timing events are recorded on it. (With torch's default stream — handle 0 — the module would render on its own non-blocking
+    # stream and the reduce on the legacy default stream: nothing orders the next step's film reset after a reduce still in flight.
+    # At N = 8 that race added 3 of the 8 ring chunks of the previous image to the next one, s48.)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():

@@ -254,6 +254,9 @@ NGI_API void ngi_gpu_group_destroy(void* group);
 typedef struct NgiCommId { char bytes[128]; } NgiCommId;
 NGI_API int ngi_gpu_comm_get_id(NgiCommId* out_id);
 NGI_API int ngi_gpu_comm_create(const NgiCommId* id, int rank, int world_size, int device, void** out_comm);
+/* `cuda_stream`: pass the stream the film was rendered on (the one given to ngi_gpu_render_device), so that the reduce is ordered
+ * after that render and before the next one. NULL = the legacy default stream; the call then returns only after the reduce has
+ * completed (the module's own streams are non-blocking and would not wait for it). */
 NGI_API int ngi_gpu_comm_reduce_film(void* comm, void* film_rgb_device, uint64_t num_floats, int root, void* cuda_stream);
 NGI_API void ngi_gpu_comm_destroy(void* comm);
 

@@ -1936,6 +1936,9 @@ int ngi_gpu_comm_reduce_film(void* comm, void* film_rgb_device, uint64_t num_flo
     if ((rc = nccl_or_error(&api))) return rc;
     NGI_CUDA(cudaSetDevice(c->device));
     NGI_NCCL(api, api->Reduce(film_rgb_device, film_rgb_device, (size_t)num_floats, ncclFloat, ncclSum, root, c->comm, (cudaStream_t)cuda_stream));
+    // NULL = the legacy default stream, which does NOT order itself against the non-blocking streams this module renders on: return
+    // only when the reduce is done, so that a following render cannot reset a film the reduce is still reading / writing
+    if (!cuda_stream) NGI_CUDA(cudaStreamSynchronize(nullptr));
     return NGI_OK;
 }
 

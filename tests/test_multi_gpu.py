@@ -63,6 +63,7 @@ def test_accumulate_adds_passes_into_the_callers_film():
     n, w = 1 << 22, 64
     one, _ = s.render("ptdirect", n, w, w, seed=5)
     film = torch.zeros((w, w, 3), dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()                                   # stream 0 below = the module's own (non-blocking) stream
     for k in range(8):
         s.render_device(film.data_ptr(), 0, "ptdirect", n // 8, w, w, seed=5, sample_offset=k * (n // 8), film_norm_samples=n, accumulate=1)
     torch.cuda.synchronize()
