@@ -107,6 +107,12 @@ __global__ void __launch_bounds__(kBlock) k_tri_setup(const float* __restrict__ 
     if (i < n) ngi_tri_setup(positions, i, n_real, pad, anchor, rec, lo, hi);
 }
 
+__global__ void __launch_bounds__(kBlock) k_shade_setup(const float* __restrict__ positions, const float* __restrict__ normals, const int* __restrict__ tri_prim,
+                                                        unsigned n, float4* __restrict__ shade) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) ngi_shade_setup(positions, normals, tri_prim, t, shade);
+}
+
 __global__ void __launch_bounds__(kBlock) k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, unsigned n, f3 mmin, f3 sinv,
                                                    unsigned long long* __restrict__ keys, unsigned* __restrict__ vals) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -836,11 +842,20 @@ int build_scene(Scene* s, const NgiSceneDesc* desc) {
     if ((rc = dev_alloc(s, &d_pos, (size_t)std::max(nr, 1u) * 9, false))) return rc;
     if (nr) NGI_CUDA(cudaMemcpyAsync(d_pos, desc->positions, (size_t)nr * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
     float4* d_shade = nullptr; NgiDevPrim* d_prims = nullptr; unsigned* d_lights = nullptr; float* d_cdf = nullptr;
-    if ((rc = dev_alloc(s, &d_shade, ha.shade_tris.size(), true))) return rc;
+    // shading records are assembled on the device from positions + normals + the per-triangle primitive index (k_shade_setup): the
+    // host loop and the 80 B / triangle upload it replaces were a third of scene_create on the 1 M-triangle scene
+    float* d_nrm = nullptr; int* d_triprim = nullptr;
+    if ((rc = dev_alloc(s, &d_shade, (size_t)nr * 5, true))) return rc;
+    if ((rc = dev_alloc(s, &d_nrm, (size_t)std::max(nr, 1u) * 9, false))) return rc;
+    if ((rc = dev_alloc(s, &d_triprim, std::max(nr, 1u), false))) return rc;
+    if (nr) {
+        NGI_CUDA(cudaMemcpyAsync(d_nrm, desc->normals, (size_t)nr * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+        NGI_CUDA(cudaMemcpyAsync(d_triprim, ha.tri_prim.data(), (size_t)nr * sizeof(int), cudaMemcpyHostToDevice, st));
+        k_shade_setup<<<grid_for(nr), kBlock, 0, st>>>(d_pos, d_nrm, d_triprim, nr, d_shade);
+    }
     if ((rc = dev_alloc(s, &d_prims, ha.prims.size(), true))) return rc;
     if ((rc = dev_alloc(s, &d_lights, ha.light_prims.size(), true))) return rc;
     if ((rc = dev_alloc(s, &d_cdf, ha.cdf.size(), true))) return rc;
-    if (!ha.shade_tris.empty()) NGI_CUDA(cudaMemcpyAsync(d_shade, ha.shade_tris.data(), ha.shade_tris.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
     NGI_CUDA(cudaMemcpyAsync(d_prims, ha.prims.data(), ha.prims.size() * sizeof(NgiDevPrim), cudaMemcpyHostToDevice, st));
     if (!ha.light_prims.empty()) NGI_CUDA(cudaMemcpyAsync(d_lights, ha.light_prims.data(), ha.light_prims.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
     if (!ha.cdf.empty()) NGI_CUDA(cudaMemcpyAsync(d_cdf, ha.cdf.data(), ha.cdf.size() * sizeof(float), cudaMemcpyHostToDevice, st));

@@ -16,7 +16,8 @@
 #include "ngi_shade.h"
 
 struct NgiHostArrays {
-    std::vector<float4> shade_tris;     // [n_real][5]
+    std::vector<float4> shade_tris;     // [n_real][5]: only filled on request (the CPU simulator); the CUDA module builds it on the device
+    std::vector<int> tri_prim;          // [n_real] primitive index of every triangle
     std::vector<NgiDevPrim> prims;
     std::vector<unsigned> light_prims;
     std::vector<float> cdf;
@@ -50,23 +51,41 @@ inline float ngi_area_cdf(const NgiSceneDesc* d, const int first_tri, const int 
     return (float)(1.0 / sumArea);
 }
 
-inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out) {
+// shading record of triangle t: 3 positions + 3 vertex normals + primitive index, 5 x float4 (one item of k_shade_setup)
+NGI_HD void ngi_shade_setup(const float* __restrict__ positions, const float* __restrict__ normals, const int* __restrict__ tri_prim,
+                            const size_t t, float4* __restrict__ shade) {
+    const float* p = positions + t * 9;
+    const float* q = normals + t * 9;
+    float4* r = shade + t * 5;
+    r[0] = make_float4(p[0], p[1], p[2], p[3]);
+    r[1] = make_float4(p[4], p[5], p[6], p[7]);
+    r[2] = make_float4(p[8], q[0], q[1], q[2]);
+    r[3] = make_float4(q[3], q[4], q[5], q[6]);
+    r[4] = make_float4(q[7], q[8], u2f((unsigned)tri_prim[t]), 0.0f);
+}
+
+inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out, const bool host_shade_tris = false) {
     if (!d || d->struct_size != sizeof(NgiSceneDesc)) { out.error = "NgiSceneDesc.struct_size mismatch (ABI)"; return false; }
     if (d->num_tris > 0 && (!d->positions || !d->normals)) { out.error = "positions / normals are NULL"; return false; }
     if (d->num_prims == 0 || !d->prims) { out.error = "scene has no primitives"; return false; }
     if (d->num_tris >= 0x7FFFFFF0ull) { out.error = "too many triangles (max 2^31 - 16)"; return false; }
     const size_t n = (size_t)d->num_tris;
     out.n_real = (unsigned)n;
-    std::vector<int> triPrim(n, -1);
+    std::vector<int>& triPrim = out.tri_prim;
+    triPrim.assign(n, -1);
     out.prims.resize(d->num_prims);
     int sensor = -1;
+    // scene bounds: only the bounding disk of a directional light needs them (rt.hpp:2067-2073)
     double bmin[3] = {1e300, 1e300, 1e300}, bmax[3] = {-1e300, -1e300, -1e300};
-    for (size_t i = 0; i < n * 3; i++)
-        for (int k = 0; k < 3; k++) {
-            const double v = d->positions[i * 3 + k];
-            if (v < bmin[k]) bmin[k] = v;
-            if (v > bmax[k]) bmax[k] = v;
-        }
+    bool any_directional = false;
+    for (uint32_t i = 0; i < d->num_prims; i++) if ((d->prims[i].type & NGI_TYPE_L) && d->prims[i].l_type == NGI_L_DIRECTIONAL) any_directional = true;
+    if (any_directional)
+        for (size_t i = 0; i < n * 3; i++)
+            for (int k = 0; k < 3; k++) {
+                const double v = d->positions[i * 3 + k];
+                if (v < bmin[k]) bmin[k] = v;
+                if (v > bmax[k]) bmax[k] = v;
+            }
     for (uint32_t i = 0; i < d->num_prims; i++) {
         const NgiPrimitive& s = d->prims[i];
         NgiDevPrim p;
@@ -138,17 +157,11 @@ inline bool ngi_prepare_scene(const NgiSceneDesc* d, NgiHostArrays& out) {
         E.inv_a = (float)(1.0 / (tanFov * tanFov * s.e_aspect * 4.0));                  // rt.hpp:974
         E.prim = sensor;
     }
-    out.shade_tris.resize(n * 5);
-    for (size_t t = 0; t < n; t++) {
+    for (size_t t = 0; t < n; t++)
         if (triPrim[t] < 0) { out.error = "triangle " + std::to_string(t) + " belongs to no primitive"; return false; }
-        const float* p = d->positions + t * 9;
-        const float* q = d->normals + t * 9;
-        float4* r = &out.shade_tris[t * 5];
-        r[0] = make_float4(p[0], p[1], p[2], p[3]);
-        r[1] = make_float4(p[4], p[5], p[6], p[7]);
-        r[2] = make_float4(p[8], q[0], q[1], q[2]);
-        r[3] = make_float4(q[3], q[4], q[5], q[6]);
-        r[4] = make_float4(q[7], q[8], u2f((unsigned)triPrim[t]), 0.0f);
+    if (host_shade_tris) {
+        out.shade_tris.resize(n * 5);
+        for (size_t t = 0; t < n; t++) ngi_shade_setup(d->positions, d->normals, triPrim.data(), t, out.shade_tris.data());
     }
     return true;
 }

@@ -48,7 +48,7 @@ __attribute__((visibility("default"))) const char* sim_last_error() { return g_e
 
 __attribute__((visibility("default"))) void* sim_scene_create(const NgiSceneDesc* desc) {
     SimScene* s = new SimScene;
-    if (!ngi_prepare_scene(desc, s->ha)) { g_err = s->ha.error; delete s; return nullptr; }
+    if (!ngi_prepare_scene(desc, s->ha, true)) { g_err = s->ha.error; delete s; return nullptr; }
     const unsigned nr = s->ha.n_real;
     const unsigned n = nr < 2 ? 2 : nr;
     s->n = n;

@@ -17,7 +17,28 @@ def line(name):
 
 
 def main():
-    prefix = sys.argv[1] if len(sys.argv) > 1 else "r02_final_"
+    """`--write`: replaces the blocks between <!-- TABLE:x --> and <!-- /TABLE:x --> in DESIGN.md (x = main, scaling, image)"""
+    import contextlib
+    import io
+    import re
+    write = "--write" in sys.argv
+    args = [a for a in sys.argv[1:] if a != "--write"]
+    prefix = args[0] if args else "r02_final_"
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        tables(prefix)
+    parts = buf.getvalue().strip("\n").split("\n\n")
+    if not write:
+        print(buf.getvalue())
+        return
+    p = os.path.join(ROOT, "DESIGN.md")
+    doc = open(p).read()
+    for name, body in zip(("main", "scaling", "image"), parts):
+        doc = re.sub(rf"<!-- TABLE:{name} -->.*?<!-- /TABLE:{name} -->", lambda m: f"<!-- TABLE:{name} -->\n{body}\n<!-- /TABLE:{name} -->", doc, flags=re.S)
+    open(p, "w").write(doc)
+
+
+def tables(prefix):
     print("| workload | Mpaths/s | e2e | Mrays/s | `roofline.frac` | extend Grays/s | CPU (16 cores) | file |")
     print("|---|---|---|---|---|---|---|---|")
     for wl, f in (("C1", "bench_c1"), ("C2", "bench_c2"), ("**C3** (headline)", "bench_c3"), ("C4 `ptdirect` 256 spp", "bench_c4"), ("C4 `pt` 256 spp", "bench_c4pt"),
@@ -44,7 +65,7 @@ def main():
     print("|---|---|---|---|---|---|---|")
     base = None
     for n in (1, 2, 4, 8):
-        for pat in (f"r02_bench_c3_n{n}_n8.json", f"r02_bench_c3_n{n}_s44.json"):
+        for pat in (f"r02_bench_c3_n{n}_n8v.json", f"r02_bench_c3_n{n}_n8.json", f"r02_bench_c3_n{n}_s44.json"):
             j = line(pat)
             if j:
                 if n == 1:
