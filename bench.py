@@ -221,7 +221,8 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC.replace("ptdirect", renderer), "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "mrays_per_s": rays / dt / 1e6,
-        "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp": spp, "max_num_vertices": m,
+        "config": {"workload": desc, "renderer": renderer, "width": W, "height": H, "spp": spp, "samples_per_step": W * H * spp, "max_num_vertices": m,
+                   "sampled": f"each step renders {n_step} samples of the job (bounded CPU sample)",
                    "note": cpu.note},
         "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
