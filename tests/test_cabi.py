@@ -77,3 +77,26 @@ def test_render_flag_constants_match_the_header():
     assert macros == {"TIME_KERNELS": capi.RENDER_TIME_KERNELS, "PER_RAY_TRACE": capi.RENDER_PER_RAY_TRACE,
                       "BDPT_PER_THREAD": capi.RENDER_BDPT_PER_THREAD}
     assert len(set(macros.values())) == len(macros) and all(v & (v - 1) == 0 for v in macros.values())      # distinct single bits
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_a_device():
+    """ngi_gpu_group_* / ngi_gpu_comm_* (multi-GPU, NCCL): argument errors and the no-device error come back as status codes with a
+    message, never as a fallback; ngi_gpu_shard_range is pure arithmetic and works anywhere."""
+    import torch
+    if not os.path.exists(capi.GPU_LIB_PATH):
+        pytest.skip("libnanogi_gpu.so not built")
+    lib = capi.gpu_lib()
+    assert capi.shard_range(10, 0, 3) == (0, 3) and capi.shard_range(10, 2, 3) == (6, 4)
+    h = ctypes.c_void_p()
+    assert lib.ngi_gpu_group_create(None, None, 1, ctypes.byref(h)) == -1            # NGI_ERR_INVALID_ARGUMENT
+    cid = capi.NgiCommId()
+    assert lib.ngi_gpu_comm_create(ctypes.byref(cid), 3, 2, 0, ctypes.byref(h)) == -1      # rank >= world_size
+    assert lib.ngi_gpu_comm_reduce_film(None, None, 0, 0, None) == -1
+    if torch.cuda.is_available():
+        return
+    from nanogi_b200 import scenes
+    sd = scenes.to_scene_data(scenes.cornell_box(), 1.0)
+    with pytest.raises(capi.NgiError, match="no CUDA device"):
+        capi.GpuGroup(sd, [0])
+    rc = lib.ngi_gpu_comm_create(ctypes.byref(cid), 0, 1, 0, ctypes.byref(h))
+    assert rc in (-2, -6), rc                                                          # no device (or no libnccl on this host): an error either way
