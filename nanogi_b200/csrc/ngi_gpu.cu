@@ -343,7 +343,10 @@ __device__ __forceinline__ void block_reserve(unsigned* const (&counters)[NQ], c
     if (threadIdx.x < NQ) {
         unsigned acc = 0;
         for (int w = 0; w < kBlock / 32; w++) { const unsigned c = s_warp[threadIdx.x][w]; s_warp[threadIdx.x][w] = acc; acc += c; }
-        s_base[threadIdx.x] = acc ? atomicAdd(counters[threadIdx.x], acc) : 0u;
+        unsigned* ctr = counters[0];
+#pragma unroll
+        for (int q = 1; q < NQ; q++) if (threadIdx.x == (unsigned)q) ctr = counters[q];          // (a select chain: indexing `counters` puts it in local memory)
+        s_base[threadIdx.x] = acc ? atomicAdd(ctr, acc) : 0u;
     }
     __syncthreads();
 #pragma unroll

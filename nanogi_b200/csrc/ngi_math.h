@@ -51,6 +51,35 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 struct f3 { float x, y, z; };
 struct d3v { double x, y, z; };
 
+// ---- division, square root, sin / cos of the SHADING code -----------------------------------------
+// ngi_shade.h / ngi_wave.h / ngi_bdpt*.h compute in fp32 what the reference computes in fp64, so their last bits are this
+// module's choice. With NGI_FAST_SHADE the device takes them from the special-function unit (MUFU.RCP / RSQ / SQRT: <= 2 ulp;
+// MUFU.SIN / COS: 2^-21 absolute on [-pi, pi]) — one or two instructions where the correctly rounded sequences are ~10
+// (division: MUFU.RCP + FCHK + 5 FFMA + a slow-path call), ~8 (sqrtf) and ~40 (sincosf). Not used by the texel lookup
+// (fp64 like the reference, ngi_wave.h) nor by the ray queries (the explicitly rounded NGI_* macros above). The host build of these
+// headers (tests/hostsim) keeps the IEEE operations.
+#ifndef NGI_FAST_SHADE
+#define NGI_FAST_SHADE 1
+#endif
+#if defined(__CUDA_ARCH__) && NGI_FAST_SHADE
+#define NGI_SFU1(op, x) float r_; asm(op " %0, %1;" : "=f"(r_) : "f"(x)); return r_
+NGI_HD float ngi_rcpf(const float x) { NGI_SFU1("rcp.approx.ftz.f32", x); }
+NGI_HD float ngi_sqrtf(const float x) { NGI_SFU1("sqrt.approx.ftz.f32", x); }
+NGI_HD float ngi_rsqrtf(const float x) { NGI_SFU1("rsqrt.approx.ftz.f32", x); }
+NGI_HD float ngi_divf(const float a, const float b) { return a * ngi_rcpf(b); }
+// theta in [-pi, 2 pi]: brought into [-pi, pi], where the SFU's error bound holds
+NGI_HD void ngi_sincosf(float theta, float* s, float* c) {
+    if (theta > NGI_PI_F) theta -= 2.0f * NGI_PI_F;
+    __sincosf(theta, s, c);
+}
+#else
+NGI_HD float ngi_rcpf(const float x) { return 1.0f / x; }
+NGI_HD float ngi_sqrtf(const float x) { return sqrtf(x); }
+NGI_HD float ngi_rsqrtf(const float x) { return 1.0f / sqrtf(x); }
+NGI_HD float ngi_divf(const float a, const float b) { return a / b; }
+NGI_HD void ngi_sincosf(const float theta, float* s, float* c) { sincosf(theta, s, c); }
+#endif
+
 NGI_HD f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
 NGI_HD f3 mk3(float a) { return mk3(a, a, a); }
 NGI_HD f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -59,14 +88,14 @@ NGI_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
 NGI_HD f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
 NGI_HD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 NGI_HD f3 operator*(float s, f3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
-NGI_HD f3 operator/(f3 a, f3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
-NGI_HD f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+NGI_HD f3 operator/(f3 a, f3 b) { return mk3(ngi_divf(a.x, b.x), ngi_divf(a.y, b.y), ngi_divf(a.z, b.z)); }
+NGI_HD f3 operator/(f3 a, float s) { return mk3(ngi_divf(a.x, s), ngi_divf(a.y, s), ngi_divf(a.z, s)); }   // (one MUFU.RCP: the asm is CSE'd)
 NGI_HD f3 operator+(f3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
 NGI_HD float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 NGI_HD f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
-NGI_HD float length(f3 a) { return sqrtf(dot(a, a)); }
-// glm::normalize(v) = v * inversesqrt(dot(v, v)); a zero vector yields NaN (relied upon by the sn fallback)
-NGI_HD f3 normalize(f3 a) { const float s = 1.0f / sqrtf(dot(a, a)); return a * s; }
+NGI_HD float length(f3 a) { return ngi_sqrtf(dot(a, a)); }
+// glm::normalize(v) = v * inversesqrt(dot(v, v)); a zero vector yields NaN (relied upon by the sn fallback; 0 * MUFU.RSQ(0) = 0 * inf too)
+NGI_HD f3 normalize(f3 a) { const float s = ngi_rsqrtf(dot(a, a)); return a * s; }
 NGI_HD bool is_zero(f3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
 NGI_HD float fmin2(float a, float b) { return fminf(a, b); }
 NGI_HD float fmax2(float a, float b) { return fmaxf(a, b); }

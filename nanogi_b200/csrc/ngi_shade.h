@@ -77,7 +77,7 @@ NGI_HD void ngi_tangent_space(NgiGeom& g) { ngi_orthonormal_basis(g.sn, g.dpdu, 
 NGI_HD f3 ngi_to_local(const NgiGeom& g, const f3 w) { return mk3(dot(g.dpdu, w), dot(g.dpdv, w), dot(g.sn, w)); }
 NGI_HD f3 ngi_to_world(const NgiGeom& g, const f3 l) { return g.dpdu * l.x + g.dpdv * l.y + g.sn * l.z; }
 // rt.hpp:71-75
-NGI_HD float ngi_local_tan(const f3 v) { const float t = 1.0f - v.z * v.z; return t <= 0.0f ? 0.0f : sqrtf(t) / v.z; }
+NGI_HD float ngi_local_tan(const f3 v) { const float t = 1.0f - v.z * v.z; return t <= 0.0f ? 0.0f : ngi_divf(ngi_sqrtf(t), v.z); }
 
 // rt.hpp:87-103
 NGI_HD void ngi_concentric_disk(const float u0, const float u1, float& sx, float& sy) {
@@ -85,28 +85,28 @@ NGI_HD void ngi_concentric_disk(const float u0, const float u1, float& sx, float
     if (vx == 0.0f && vy == 0.0f) { sx = 0.0f; sy = 0.0f; return; }
     float r, theta;
     if (vx > -vy) {
-        if (vx > vy) { r = vx; theta = (NGI_PI_F * 0.25f) * vy / vx; }
-        else         { r = vy; theta = (NGI_PI_F * 0.25f) * (2.0f - vx / vy); }
+        if (vx > vy) { r = vx; theta = ngi_divf((NGI_PI_F * 0.25f) * vy, vx); }
+        else         { r = vy; theta = (NGI_PI_F * 0.25f) * (2.0f - ngi_divf(vx, vy)); }
     } else {
-        if (vx < vy) { r = -vx; theta = (NGI_PI_F * 0.25f) * (4.0f + vy / vx); }
-        else         { r = -vy; theta = (NGI_PI_F * 0.25f) * (6.0f - vx / vy); }
+        if (vx < vy) { r = -vx; theta = (NGI_PI_F * 0.25f) * (4.0f + ngi_divf(vy, vx)); }
+        else         { r = -vy; theta = (NGI_PI_F * 0.25f) * (6.0f - ngi_divf(vx, vy)); }
     }
     float s, c;
-    sincosf(theta, &s, &c);
+    ngi_sincosf(theta, &s, &c);                                                               // theta in [-pi/4, 7 pi/4]
     sx = r * c; sy = r * s;
 }
 // rt.hpp:105-109
 NGI_HD f3 ngi_cosine_hemisphere(const float u0, const float u1) {
     float sx, sy;
     ngi_concentric_disk(u0, u1, sx, sy);
-    return mk3(sx, sy, sqrtf(fmaxf(0.0f, 1.0f - sx * sx - sy * sy)));
+    return mk3(sx, sy, ngi_sqrtf(fmaxf(0.0f, 1.0f - sx * sx - sy * sy)));
 }
 // rt.hpp:116-122
 NGI_HD f3 ngi_uniform_sphere(const float u0, const float u1) {
     const float z = 1.0f - 2.0f * u0;
-    const float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    const float r = ngi_sqrtf(fmaxf(0.0f, 1.0f - z * z));
     float s, c;
-    sincosf(2.0f * NGI_PI_F * u1, &s, &c);
+    ngi_sincosf(2.0f * NGI_PI_F * u1, &s, &c);
     return mk3(r * c, r * s, z);
 }
 // rt.hpp:135-140
@@ -120,8 +120,8 @@ NGI_HD int ngi_pixel_index(const float rx, const float ry, const int w, const in
 NGI_HD bool ngi_raster_position(const NgiDevSensor& E, const f3 wo, float& rx, float& ry, float& cosTheta) {
     const f3 woEye = mk3(dot(E.vx, wo), dot(E.vy, wo), dot(E.vz, wo));
     if (woEye.z >= 0.0f) return false;
-    rx = (-woEye.x / woEye.z / E.tan_fov / E.aspect + 1.0f) * 0.5f;
-    ry = (-woEye.y / woEye.z / E.tan_fov + 1.0f) * 0.5f;
+    rx = (ngi_divf(ngi_divf(ngi_divf(-woEye.x, woEye.z), E.tan_fov), E.aspect) + 1.0f) * 0.5f;   // (SFU quotients move a sample across a
+    ry = (ngi_divf(ngi_divf(-woEye.y, woEye.z), E.tan_fov) + 1.0f) * 0.5f;                        //  pixel edge it is within ~3e-7 of, like any fp32 rounding)
     cosTheta = -woEye.z;
     if (rx < 0.0f || rx > 1.0f || ry < 0.0f || ry > 1.0f) return false;
     return true;
@@ -130,7 +130,7 @@ NGI_HD bool ngi_raster_position(const NgiDevSensor& E, const f3 wo, float& rx, f
 NGI_HD float ngi_pinhole_importance(const NgiDevSensor& E, const f3 wo, float& rx, float& ry) {
     float cosTheta;
     if (!ngi_raster_position(E, wo, rx, ry, cosTheta)) return 0.0f;
-    const float inv = 1.0f / cosTheta;
+    const float inv = ngi_rcpf(cosTheta);
     return inv * inv * inv * E.inv_a;
 }
 // SampleDirection for E.pinhole, rt.hpp:733-740
@@ -143,17 +143,17 @@ NGI_HD f3 ngi_pinhole_sample(const NgiDevSensor& E, const float u0, const float 
 // ---- type G helpers, rt.hpp:1407-1442 ---------------------------------------------------------
 NGI_HD float ngi_beckmann(const float rough, const f3 H) {                                   // :1407-1414
     if (H.z <= 0.0f) return 0.0f;
-    const float ex = ngi_local_tan(H) / rough;
+    const float ex = ngi_divf(ngi_local_tan(H), rough);
     const float t1 = expf(-(ex * ex));
     const float c2 = H.z * H.z;
     const float t2 = NGI_PI_F * rough * rough * (c2 * c2);
-    return t1 / t2;
+    return ngi_divf(t1, t2);
 }
 NGI_HD float ngi_shadow_masking(const f3 wi, const f3 wo, const f3 H) {                       // :1423-1431 (typo kept)
     const float n_dot_H = H.z, n_dot_wo = wo.z, n_dot_wi = wi.z;
     const float wo_dot_H = fabsf(dot(wo, H));
     const float wi_dot_H = fabsf(dot(wo, H));  // sic: the reference uses `wo` here too
-    return fminf(1.0f, fminf(2.0f * n_dot_H * n_dot_wo / wo_dot_H, 2.0f * n_dot_H * n_dot_wi / wi_dot_H));
+    return fminf(1.0f, fminf(ngi_divf(2.0f * n_dot_H * n_dot_wo, wo_dot_H), ngi_divf(2.0f * n_dot_H * n_dot_wi, wi_dot_H)));
 }
 NGI_HD f3 ngi_fr_conductor(const f3 eta, const f3 k, const float cosThetaI) {                 // :1433-1442
     const f3 e2k2 = eta * eta + k * k;
@@ -165,13 +165,13 @@ NGI_HD f3 ngi_fr_conductor(const f3 eta, const f3 k, const float cosThetaI) {   
 }
 // rt.hpp:1450-1466
 NGI_HD float ngi_fresnel(const float wiDotN, const float etaI, const float etaT) {
-    const float eta = etaI / etaT;
+    const float eta = ngi_divf(etaI, etaT);
     const float cosThetaTSq = 1.0f - eta * eta * (1.0f - wiDotN * wiDotN);
     if (cosThetaTSq <= 0.0f) return 1.0f;
     const float absCosThetaI = fabsf(wiDotN);
-    const float absCosThetaT = sqrtf(cosThetaTSq);
-    const float rhoS = (etaI * absCosThetaI - etaT * absCosThetaT) / (etaI * absCosThetaI + etaT * absCosThetaT);
-    const float rhoT = (etaI * absCosThetaT - etaT * absCosThetaI) / (etaI * absCosThetaT + etaT * absCosThetaI);
+    const float absCosThetaT = ngi_sqrtf(cosThetaTSq);
+    const float rhoS = ngi_divf(etaI * absCosThetaI - etaT * absCosThetaT, etaI * absCosThetaI + etaT * absCosThetaT);
+    const float rhoT = ngi_divf(etaI * absCosThetaT - etaT * absCosThetaI, etaI * absCosThetaT + etaT * absCosThetaI);
     return (rhoS * rhoS + rhoT * rhoT) * 0.5f;
 }
 
@@ -188,10 +188,10 @@ NGI_HD bool ngi_sample_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& 
     if (type & NGI_G) {                                                                       // :769-796
         if (localWi.z <= 0.0f) return false;
         const float tanThetaHSqr = -P.g_rough * P.g_rough * logf(1.0f - u0);
-        const float cosThetaH = 1.0f / sqrtf(1.0f + tanThetaHSqr);
-        const float sinThetaH = sqrtf(fmaxf(0.0f, 1.0f - cosThetaH * cosThetaH));
+        const float cosThetaH = ngi_rsqrtf(1.0f + tanThetaHSqr);
+        const float sinThetaH = ngi_sqrtf(fmaxf(0.0f, 1.0f - cosThetaH * cosThetaH));
         float s, c;
-        sincosf(2.0f * NGI_PI_F * u1, &s, &c);
+        ngi_sincosf(2.0f * NGI_PI_F * u1, &s, &c);
         const f3 H = mk3(sinThetaH * c, sinThetaH * s, cosThetaH);
         const f3 localWo = -localWi - H * (2.0f * dot(-localWi, H));
         if (localWo.z <= 0.0f) return false;
@@ -207,11 +207,11 @@ NGI_HD bool ngi_sample_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& 
         float etaI = P.s_eta1, etaT = P.s_eta2;
         if (localWi.z < 0.0f) { const float t = etaI; etaI = etaT; etaT = t; }
         const float wiDotN = localWi.z;
-        const float eta = etaI / etaT;
+        const float eta = ngi_divf(etaI, etaT);
         const float cosThetaTSq = 1.0f - eta * eta * (1.0f - wiDotN * wiDotN);
         if (P.s_type == NGI_ST_REFRACTION) {                                                  // :828-859
             if (cosThetaTSq <= 0.0f) { wo = ngi_to_world(g, mk3(-localWi.x, -localWi.y, localWi.z)); return true; }
-            const float cosThetaT = sqrtf(cosThetaTSq) * (wiDotN > 0.0f ? -1.0f : 1.0f);
+            const float cosThetaT = ngi_sqrtf(cosThetaTSq) * (wiDotN > 0.0f ? -1.0f : 1.0f);
             wo = ngi_to_world(g, mk3(-eta * localWi.x, -eta * localWi.y, cosThetaT));
             return true;
         }
@@ -220,7 +220,7 @@ NGI_HD bool ngi_sample_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& 
             if (uComp <= Fr) {
                 wo = ngi_to_world(g, mk3(-localWi.x, -localWi.y, localWi.z));
             } else {
-                const float cosThetaT = sqrtf(cosThetaTSq) * (wiDotN > 0.0f ? -1.0f : 1.0f);
+                const float cosThetaT = ngi_sqrtf(cosThetaTSq) * (wiDotN > 0.0f ? -1.0f : 1.0f);
                 wo = ngi_to_world(g, mk3(-eta * localWi.x, -eta * localWi.y, cosThetaT));
             }
             return true;
@@ -240,7 +240,7 @@ NGI_HD f3 ngi_eval_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& g, c
     // shadingNormalCorrection, :994-1005 (EL => 1 unless the sides disagree; LE => wiDotNs * woDotNg / (woDotNs * wiDotNg))
     const float wiDotNg = dot(wi, g.gn), woDotNg = dot(wo, g.gn);
     float snc = (wiDotNg * localWi.z <= 0.0f || woDotNg * localWo.z <= 0.0f) ? 0.0f : 1.0f;
-    if (transLE && snc != 0.0f) snc = localWi.z * woDotNg / (localWo.z * wiDotNg);
+    if (transLE && snc != 0.0f) snc = ngi_divf(localWi.z * woDotNg, localWo.z * wiDotNg);
     if (type & NGI_D) {                                                                       // :1013-1024, :1221-1231
         if (localWi.z <= 0.0f || localWo.z <= 0.0f) return mk3(0.0f);
         pdf = NGI_INV_PI_F;
@@ -252,8 +252,8 @@ NGI_HD f3 ngi_eval_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& g, c
         const float D = ngi_beckmann(P.g_rough, H);
         const float G = ngi_shadow_masking(localWi, localWo, H);
         const f3 F = ngi_fr_conductor(P.g_eta, P.g_k, dot(localWi, H));
-        pdf = D * H.z / (4.0f * dot(localWo, H)) / localWo.z;
-        return g.albedo * F * (D * G / (4.0f * localWi.z) / localWo.z * snc);
+        pdf = ngi_divf(ngi_divf(D * H.z, 4.0f * dot(localWo, H)), localWo.z);
+        return g.albedo * F * (ngi_divf(ngi_divf(D * G, 4.0f * localWi.z), localWo.z) * snc);
     }
     if (type & NGI_S) {
         if (!forceDegenerated) return mk3(0.0f);                                              // :1057-1060, :1261-1264
@@ -264,7 +264,7 @@ NGI_HD f3 ngi_eval_bsdf(const NgiDevPrim& P, const int type, const NgiGeom& g, c
         }
         float etaI = P.s_eta1, etaT = P.s_eta2;
         if (localWi.z < 0.0f) { const float t = etaI; etaI = etaT; etaT = t; }
-        const float eta = etaI / etaT;
+        const float eta = ngi_divf(etaI, etaT);
         const float refr = transLE ? 1.0f : eta;                                              // refrCorrection, :1095 / :1130
         if (P.s_type == NGI_ST_REFRACTION) {                                                  // :1084-1098, :1288-1291
             pdf = 1.0f;
@@ -290,7 +290,7 @@ NGI_HD int ngi_cdf_sample_reuse(const float* __restrict__ cdf, const int count /
     }
     const int i = clampi(lo - 1, 0, count - 2);
     const float c0 = ngi_ldg(cdf + i), c1 = ngi_ldg(cdf + i + 1);
-    u2 = (u - c0) / (c1 - c0);
+    u2 = fminf(ngi_divf(u - c0, c1 - c0), 1.0f);                                              // (< 1 by construction; the SFU quotient can exceed it by an ulp)
     return i;
 }
 
@@ -314,7 +314,7 @@ NGI_HD void ngi_sample_triangle_mesh(const NgiDevScene& sc, const int first_tri,
                                      const float u0, const float u1, f3& p, f3& n, int& tri, float& bx, float& by, double* pd = nullptr) {
     float u2;
     const int i = ngi_cdf_sample_reuse(sc.cdf + cdf_offset, num_tris + 1, u0, u2);
-    const float s = sqrtf(fmaxf(0.0f, u2));                                                   // UniformSampleTriangle, rt.hpp:129-133
+    const float s = ngi_sqrtf(fmaxf(0.0f, u2));                                                   // UniformSampleTriangle, rt.hpp:129-133
     bx = 1.0f - s; by = u1 * s;
     tri = first_tri + i;
     const float4* r = sc.shade_tris + 5 * (size_t)tri;
@@ -341,7 +341,7 @@ NGI_HD NgiLightSample ngi_sample_light(const NgiDevScene& sc, const float uPick,
     const int li = clampi((int)(uPick * (float)n), 0, n - 1);
     ls.prim = (int)ngi_ldg(sc.light_prims + li);
     const NgiDevPrim& L = sc.prims[ls.prim];
-    const float pdfL = 1.0f / (float)n;                                                       // rt.hpp:2338-2344
+    const float pdfL = ngi_rcpf((float)n);                                                      // rt.hpp:2338-2344
     ls.le = L.l_le;
     ls.l_type = L.l_type;
     if (L.l_type == NGI_LT_AREA) {

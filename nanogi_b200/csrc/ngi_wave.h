@@ -217,7 +217,7 @@ NGI_HD void ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const uns
             if (ls.valid) {
                 const f3 diff = mk3((float)((double)ls.p.x - px), (float)((double)ls.p.y - py), (float)((double)ls.p.z - pz));
                 const float dist2 = dot(diff, diff);
-                const float dist = sqrtf(dist2);
+                const float dist = ngi_sqrtf(dist2);
                 const f3 ppL = diff / dist;                                                   // :680
                 f3 fsE; int index = aux;
                 float g1 = 1.0f;
@@ -245,8 +245,8 @@ NGI_HD void ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const uns
                     if (cl <= 0.0f) fsL = mk3(0.0f);                                          // rt.hpp:922-927
                     g2 = fabsf(cl);                                                           // rt.hpp:2372
                 }
-                const float G = g1 * g2 / dist2;                                              // :683
-                const f3 C = thr * fsE * fsL * (G / ls.pdf);                                  // :686 (V applied by the shadow kernel)
+                const float G = ngi_divf(g1 * g2, dist2);                                     // :683
+                const f3 C = thr * fsE * fsL * ngi_divf(G, ls.pdf);                                  // :686 (V applied by the shadow kernel)
                 if (!is_zero(C)) {
                     out.shadow = true;
                     out.so = mk3((float)px, (float)py, (float)pz);                            // rt.hpp:2166-2168
@@ -264,7 +264,7 @@ NGI_HD void ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const uns
         const float pdfPE = L0.l_type == NGI_LT_POINT ? 1.0f : L0.l_inv_area;                 // :1017 — sic, the LIGHT's position pdf
         const f3 diff = mk3((float)(sp.px - px), (float)(sp.py - py), (float)(sp.pz - pz));
         const float dist2 = dot(diff, diff);
-        const float dist = sqrtf(dist2);
+        const float dist = ngi_sqrtf(dist2);
         const f3 ppE = diff / dist;                                                           // :1026
         f3 fsL; float g1 = 1.0f;
         if (KIND == NGI_VTX_LIGHT) {                                                          // :1027, EvaluateDirection(L, forceDegenerated = false)
@@ -287,8 +287,8 @@ NGI_HD void ngi_vertex(const NgiDevScene& sc, const NgiWaveParams& wp, const uns
             g2 = fabsf(ce);
             index = sp.pixel;
         }
-        const float G = g1 * g2 / dist2;                                                      // :1029
-        const f3 C = thr * fsL * fsE * (G / pdfPE);                                           // :1032 (LeP = 1, pdfE = 1; V by the shadow kernel)
+        const float G = ngi_divf(g1 * g2, dist2);                                             // :1029
+        const f3 C = thr * fsL * fsE * ngi_divf(G, pdfPE);                                           // :1032 (LeP = 1, pdfE = 1; V by the shadow kernel)
         if (!is_zero(C)) {                                                                    // :1040
             out.shadow = true;
             out.so = mk3((float)px, (float)py, (float)pz);
@@ -449,7 +449,7 @@ NGI_HD void ngi_logic_eye(const NgiDevScene& sc, const NgiWaveParams& wp, const 
                 const NgiSensorPoint sp = ngi_sample_sensor(sc, wp, u01(rc[1]), u01(rc[2]));
                 g.sn = g.gn = sp.n;
                 ngi_tangent_space(g);
-                ngi_vertex<NGI_VTX_EYE, true>(sc, wp, slot, sample, mk3(1.0f / E.inv_area), sp.pixel, 1, NGI_E, g, mk3(0.0f), sp.px, sp.py, sp.pz,
+                ngi_vertex<NGI_VTX_EYE, true>(sc, wp, slot, sample, mk3(ngi_rcpf(E.inv_area)), sp.pixel, 1, NGI_E, g, mk3(0.0f), sp.px, sp.py, sp.pz,
                                                E.prim, mk3(0.0f), 0, 0, out);
             }
         } else if (sc.n_lights > 0) {
@@ -460,7 +460,7 @@ NGI_HD void ngi_logic_eye(const NgiDevScene& sc, const NgiWaveParams& wp, const 
             g.sn = g.gn = ls.n;
             if (!ls.degenerate) ngi_tangent_space(g);
             // throughput = EvaluatePosition / pdfPL / pdfL (:830 / :980)
-            ngi_vertex<NGI_VTX_LIGHT, true>(sc, wp, slot, sample, mk3(1.0f / ls.pdf), ls.prim, 1, NGI_L, g, mk3(0.0f),
+            ngi_vertex<NGI_VTX_LIGHT, true>(sc, wp, slot, sample, mk3(ngi_rcpf(ls.pdf)), ls.prim, 1, NGI_L, g, mk3(0.0f),
                                             pd[0], pd[1], pd[2], ls.prim, ls.le, ls.l_type, ls.degenerate, out);
         }
     }

@@ -198,24 +198,27 @@ def test_gpu_equals_simulator_light_tracing(cornell):
 
 def test_gpu_equals_simulator_sample_for_sample(cornell):
     """The CUDA kernels and the CPU-stepped device code are the same program. The triangle test is bit-identical
-    (explicit roundings); the shading arithmetic is not (nvcc contracts a*b+c into FMAs, the host build of the
-    same headers uses -ffp-contract=off). Away from the fp32 self-intersection regime (scene scaled to unit size)
-    a last-bit difference almost never changes a branch: ray counts agree to 1e-4 and <= 1 % of the pixels differ.
-    At Cornell scale (coordinates ~550, absolute epsilon 1e-4 ~ 1.6 ulp) a last-bit change of a shadow-ray direction
-    flips grazing self-hits, so ~0.2 % of the samples (measured: 7 % of the pixels at 29 spp) differ — same counts."""
+    (explicit roundings); the shading arithmetic is not: nvcc contracts a*b+c into FMAs and takes divisions, square roots
+    and sin / cos from the SFU (<= 2 ulp, NGI_FAST_SHADE), the host build of the same headers uses IEEE operations.
+    Away from the fp32 self-intersection regime (scene scaled to unit size) a last-bit difference almost never changes
+    a branch: identical ray counts (measured) and <= 1 % of the pixels differ (measured: 0 - 0.2 %).
+    At Cornell scale (coordinates ~550, absolute epsilon 1e-4 ~ 1.6 ulp) the last bit of a direction decides grazing
+    self-hits: ~1 % of the samples differ (measured, profiles/r02_sim_vs_gpu_sfu.txt: 27 - 28 % of the pixels of a 29-spp
+    ptdirect image, ray counts within 2 - 4e-4), without bias — the self-intersection-rate tests and the image acceptance
+    tests are the statistical check of that regime."""
     from tests.hostsim import pysim
     small = scenes.to_scene_data(scaled_spec(scenes.cornell_box(), 0.01), 1.0)
-    for sd, max_bad in ((small, 0.01), (cornell, 0.15)):
+    for sd, max_bad, count_tol, mean_tol in ((small, 0.01, 1e-4, 0.01), (cornell, 0.5, 1e-3, 0.03)):
         g = capi.GpuScene(sd, 0)
         sim = pysim.SimScene(sd)
         for renderer in ("pt", "ptdirect"):
             fg, sg = g.render(renderer, 30000, 32, 32, seed=12, max_num_vertices=8)
             fs, ss = sim.render(renderer, 30000, 32, 32, seed=12, max_num_vertices=8)
-            assert abs(sg.extend_rays - ss["extend_rays"]) <= max(2, 1e-4 * ss["extend_rays"]), (sg.extend_rays, ss["extend_rays"])
-            assert abs(sg.shadow_rays - ss["shadow_rays"]) <= max(2, 1e-4 * ss["shadow_rays"]), (sg.shadow_rays, ss["shadow_rays"])
+            assert abs(sg.extend_rays - ss["extend_rays"]) <= max(2, count_tol * ss["extend_rays"]), (sg.extend_rays, ss["extend_rays"])
+            assert abs(sg.shadow_rays - ss["shadow_rays"]) <= max(2, count_tol * ss["shadow_rays"]), (sg.shadow_rays, ss["shadow_rays"])
             close = np.isclose(fg, fs, rtol=2e-3, atol=1e-5 * fs.max()).all(axis=2)
             assert (~close).mean() <= max_bad, f"{renderer}: {(~close).sum()} pixels differ"
-            assert abs(fg.mean() - fs.mean()) < 0.01 * fs.mean()
+            assert abs(fg.mean() - fs.mean()) < mean_tol * fs.mean()
         g.close()
 
 

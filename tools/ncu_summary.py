@@ -5,6 +5,7 @@
     python tools/ncu_summary.py full     gpurun_out/prof_<tag>.ncu-rep  > profiles/<round>_ncu_<tag>.txt
     python tools/ncu_summary.py source   gpurun_out/prof_<tag>.ncu-rep <kernel-id> [top]   (hot SASS/source lines)
     python tools/ncu_summary.py blocks   gpurun_out/prof_<tag>.ncu-rep <kernel name>        (issue share / active lanes per basic block)
+    python tools/ncu_summary.py lines    gpurun_out/prof_<tag>.ncu-rep <launch index> [top]  (executed warp instructions per CUDA source line)
 """
 import collections
 import csv
@@ -112,6 +113,35 @@ def source(path, kid, top=40):
         print(f"{int(r[s].replace(',', '')) / tot * 100:5.1f}%  {r[0][:14]:14s} {r[1][:110]}")
 
 
+def lines(path, launch, top=40):
+    """executed warp instructions, active lanes and stall samples per CUDA source line of one captured launch (needs -lineinfo + --import-source)"""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass", "--launch-skip", str(launch), "--launch-count", "1"],
+                         capture_output=True, text=True).stdout
+    cur, fn, agg, tw, tt = None, None, [], 0, 0
+    for r in csv.reader(io.StringIO(out)):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+        elif r[0] == "Function Name":
+            fn = r[1]
+        elif r[0] not in ("Line No", ""):
+            try:
+                w, t, smp = int(r[7]), int(r[8]), int(r[6])
+            except (ValueError, IndexError):
+                continue
+            agg.append((w, t, smp, cur, r[0], r[1].strip()[:100]))
+            tw += w
+            tt += t
+    print(f"# {path} launch {launch}: {fn}")
+    print(f"# warp instructions {tw}, thread instructions {tt}, active lanes {tt / max(tw, 1):.1f}")
+    print("# share  cumulative  lanes  stall-samples  file:line  source")
+    cum = 0
+    for w, t, smp, f, ln, src in sorted(agg, reverse=True)[:int(top)]:
+        cum += w
+        print(f"{100 * w / tw:5.1f}%  {100 * cum / tw:5.1f}%  {t / max(w, 1):5.1f}  {smp:5d}  {f}:{ln}  {src}")
+
+
 def blocks(path, kernel, min_share=0.004):
     """Basic-block profile of one kernel from the source page of an `--import-source on` capture: for every run of SASS
     instructions with the same execution count, its share of all issued warp instructions, the average number of active
@@ -170,5 +200,7 @@ if __name__ == "__main__":
         full(sys.argv[2])
     elif mode == "blocks":
         blocks(sys.argv[2], sys.argv[3])
+    elif mode == "lines":
+        lines(*sys.argv[2:])
     else:
         source(*sys.argv[2:])
