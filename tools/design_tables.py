@@ -65,7 +65,7 @@ def tables(prefix):
     print("|---|---|---|---|---|---|---|")
     base = None
     for n in (1, 2, 4, 8):
-        for pat in (f"r02_bench_c3_n{n}_n8v.json", f"r02_bench_c3_n{n}_n8.json", f"r02_bench_c3_n{n}_s44.json"):
+        for pat in (f"r02_bench_c3_n{n}_f5.json", f"r02_bench_c3_n{n}_n8v.json", f"r02_bench_c3_n{n}_n8.json", f"r02_bench_c3_n{n}_s44.json"):
             j = line(pat)
             if j:
                 if n == 1:
