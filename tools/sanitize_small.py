@@ -18,7 +18,32 @@ from nanogi_b200 import capi, scenes  # noqa: E402
 from oracle import pyoracle  # noqa: E402
 
 
+def quick():
+    """`--quick`: the shared-memory users only (trace pool of k_trace8 / k_extend / k_shadow / k_bdw_*, block_reserve of the logic kernels) on the
+    smallest workload that reaches every phase — racecheck instruments every shared access and needs ~1 s per persistent launch; run it with
+    NGI_TRACE_GRID_PCT=6 NGI_LANES=1 so that the trace grids are one CTA per SM."""
+    sd = scenes.to_scene_data(scenes.cornell_spheres(), 1.0)
+    g = capi.GpuScene(sd, 0)
+    orc = pyoracle.OracleScene(sd)
+    rays = scenes.random_rays(sd, 3000, 3)
+    ho, hg = orc.trace(rays, 0), g.trace(rays, False, 0)
+    assert np.array_equal(hg["tri"], ho["tri"]) and np.array_equal(hg["t"], ho["t"])
+    occ = scenes.random_rays(sd, 3000, 4, occlusion=True)
+    assert np.array_equal(g.trace(occ, True, 0)["tri"], orc.trace(occ, 1)["tri"])
+    print("trace ok", flush=True)
+    f, st = g.render("ptdirect", 3000, 16, 16, max_num_vertices=5, seed=3, wave_capacity=1024)
+    assert np.isfinite(f).all() and st.paths == 3000
+    print("ptdirect ok", flush=True)
+    f, st = g.render("bdpt", 400, 16, 16, max_num_vertices=4, seed=3)
+    assert np.isfinite(f).all() and st.paths == 400
+    print("bdpt ok", flush=True)
+    g.close()
+    print("sanitize_small quick OK")
+
+
 def main():
+    if "--quick" in sys.argv:
+        return quick()
     for name, gen in (("cornell_spheres", scenes.cornell_spheres), ("cornell_branches", lambda: scenes.cornell_branches(light_res=8))):
         sd = scenes.to_scene_data(gen(), 1.0)
         g = capi.GpuScene(sd, 0)
